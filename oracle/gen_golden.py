@@ -1,0 +1,365 @@
+"""TEST INFRASTRUCTURE: generate the golden vectors under tests/golden/ by running the UNMODIFIED reference
+(/root/reference, imported through oracle/refshim.py) in this container.
+
+    python -m oracle.gen_golden            # rewrites tests/golden/*.json.gz
+
+The reference cannot travel to the GPU box, the vectors can.  tests/test_oracle_golden.py pins the C oracle against
+them (CPU), tests/test_gpu_parity.py pins the CUDA path against them and against the oracle (GPU).
+"""
+from __future__ import annotations
+
+import gzip
+import json
+import sys
+from datetime import datetime, timedelta
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+from oracle import refshim  # noqa: E402
+
+GOLDEN = ROOT / "tests" / "golden"
+FIXTURE_DIR = Path("/root/reference/test_data")
+MSG_CSV = FIXTURE_DIR / "MSFT_2012-06-21_34200000_37800000_message_50.csv"
+BOOK_CSV = FIXTURE_DIR / "MSFT_2012-06-21_34200000_37800000_orderbook_50.csv"
+DAY = datetime(2012, 6, 21)
+
+
+def save(name: str, obj) -> None:
+    GOLDEN.mkdir(parents=True, exist_ok=True)
+    with gzip.GzipFile(GOLDEN / name, "wb", mtime=0) as f:
+        f.write(json.dumps(obj, separators=(",", ":")).encode())
+    print("wrote", name, (GOLDEN / name).stat().st_size, "bytes")
+
+
+def dump_book(orderbook):
+    """Canonical L3 dump: per side (buy best-first, sell best-first) [price, volume, kind, ext_id];
+    kind 0 = snapshot aggregate (internal_id -1), 1 = external order, 2 = agent order."""
+    out = []
+    for direction in ("buy", "sell"):
+        side = getattr(orderbook, direction)
+        prices = list(reversed(side)) if direction == "buy" else list(side)
+        rows = []
+        for p in prices:
+            for o in side[p]:
+                if not o.is_external:
+                    rows.append([int(p), int(o.volume), 2, 0])
+                elif o.internal_id == -1:
+                    rows.append([int(p), int(o.volume), 0, 0])
+                else:
+                    rows.append([int(p), int(o.volume), 1, int(o.external_id)])
+        out.append(rows)
+    return out
+
+
+def dump_fills(filled):
+    from rl4mm.orderbook.models import MarketOrder
+
+    out = []
+    for lst, orders in ((0, filled.internal), (1, filled.external)):
+        for o in orders:
+            out.append([lst, 0 if o.direction == "buy" else 1, int(o.price), int(o.volume), int(isinstance(o, MarketOrder))])
+    return out  # NOTE: internal and external lists are separate in the reference; order is kept within each list
+
+
+def make_db(snapshot_freq="S", tie_order="reference"):
+    return refshim.InMemoryDatabase(MSG_CSV, BOOK_CSV, "MSFT", DAY, 50, snapshot_freq, 1000, tie_order)
+
+
+def make_sim(db, outer_levels=20, preload=False, episode_length=None, warm_up=timedelta(0)):
+    from rl4mm.orderbook.Exchange import Exchange
+    from rl4mm.simulation.HistoricalOrderGenerator import HistoricalOrderGenerator
+    from rl4mm.simulation.OrderbookSimulator import OrderbookSimulator
+
+    gen = HistoricalOrderGenerator("MSFT", db, preload_orders=preload)
+    return OrderbookSimulator("MSFT", Exchange("MSFT"), [gen], 50, db, preload_orders=preload,
+                              episode_length=episode_length, warm_up=warm_up, outer_levels=outer_levels)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def golden_fixture_replay():
+    """G1: OrderbookSimulator.forward_step over the MSFT fixture in 0.1 s steps; L3 book + fills after every step."""
+    cases = []
+    for outer_levels in (20, 48):
+        for tie in ("reference", "file"):
+            sim = make_sim(make_db("S", tie), outer_levels)
+            start = DAY + timedelta(hours=10)
+            sim.reset_episode(start)
+            steps = [dict(book=dump_book(sim.exchange.central_orderbook), fills=[],
+                          min_buy=int(sim.min_buy_price), max_sell=int(sim.max_sell_price))]
+            now = start
+            for _ in range(27):
+                now += timedelta(seconds=0.1)
+                filled = sim.forward_step(now)
+                steps.append(dict(book=dump_book(sim.exchange.central_orderbook), fills=dump_fills(filled),
+                                  min_buy=int(sim.min_buy_price), max_sell=int(sim.max_sell_price)))
+            cases.append(dict(outer_levels=outer_levels, tie_order=tie, start_seconds=36000, steps=steps))
+    save("fixture_replay.json.gz", cases)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def feature_specs():
+    """(reference constructor, abi description) pairs for a feature set with windows that fit the 3 s fixture."""
+    from rl4mm.features import Features as F
+
+    td = timedelta
+    return [
+        (lambda: F.Spread(), dict(kind="SPREAD", lookback=0, update_us=100000, min=0, max=5000)),
+        (lambda: F.BookImbalance(), dict(kind="BOOK_IMBALANCE", lookback=0, update_us=100000, min=-1, max=1)),
+        (lambda: F.PriceMove(name="pm1", update_frequency=td(seconds=0.1), lookback_periods=1),
+         dict(kind="PRICE_MOVE", lookback=1, update_us=100000, min=-10000, max=10000)),
+        (lambda: F.PriceMove(name="pm3", update_frequency=td(seconds=0.2), lookback_periods=3),
+         dict(kind="PRICE_MOVE", lookback=3, update_us=200000, min=-10000, max=10000)),
+        (lambda: F.PriceRange(update_frequency=td(seconds=0.1), lookback_periods=3),
+         dict(kind="PRICE_RANGE", lookback=3, update_us=100000, min=0, max=10000)),
+        (lambda: F.Volatility(name="v4", update_frequency=td(seconds=0.1), lookback_periods=4, max_value=1e-9),
+         dict(kind="VOLATILITY", lookback=4, update_us=100000, min=0, max=1e-9)),
+        (lambda: F.Price(update_frequency=td(seconds=0.5)),
+         dict(kind="PRICE", lookback=0, update_us=500000, min=0, max=100000000)),
+        (lambda: F.TradeDirectionImbalance(update_frequency=td(seconds=0.1), lookback_periods=5),
+         dict(kind="TRADE_DIR_IMBALANCE", lookback=5, update_us=100000, min=-1, max=1, iparam=0)),
+        (lambda: F.TradeVolumeImbalance(update_frequency=td(seconds=0.1), lookback_periods=5, track_internal=True),
+         dict(kind="TRADE_VOL_IMBALANCE", lookback=5, update_us=100000, min=-1, max=1, iparam=1)),
+        (lambda: F.Inventory(), dict(kind="INVENTORY", lookback=0, update_us=100000, min=-1000000, max=1000000)),
+        (lambda: F.EpisodeProportion(update_frequency=td(seconds=0.1), episode_length=td(seconds=1.5)),
+         dict(kind="EPISODE_PROPORTION", lookback=0, update_us=100000, min=0, max=1, dparam=0.1 / 1.5)),
+        (lambda: F.TimeOfDay(update_frequency=td(seconds=1), n_buckets=10),
+         dict(kind="TIME_OF_DAY", lookback=0, update_us=1000000, min=0, max=9, iparam=10)),
+        # the two features of the reference's own env test (testHistoricalOrderbookEnvironment.py:43); 1 s windows
+        (lambda: F.PriceMove(lookback_periods=1),
+         dict(kind="PRICE_MOVE", lookback=1, update_us=1000000, min=-10000, max=10000)),
+        (lambda: F.PriceRange(lookback_periods=1),
+         dict(kind="PRICE_RANGE", lookback=1, update_us=1000000, min=0, max=10000)),
+    ]
+
+
+def run_env_case(name, actions, env_kwargs, reward_step, reward_term, features=None, episode_seconds=1.5,
+                 start_seconds=36001.0, n_episodes=1, outer_levels=20, portfolio=None):
+    from rl4mm.features.Features import Portfolio
+    from rl4mm.gym.HistoricalOrderbookEnvironment import HistoricalOrderbookEnvironment
+    from rl4mm.rewards.RewardFunctions import InventoryAdjustedPnL, PnL
+
+    def reward(spec):
+        if spec[0] == "PnL":
+            return PnL()
+        return InventoryAdjustedPnL(inventory_aversion=spec[1], asymmetrically_dampened=spec[2])
+
+    specs = feature_specs() if features is None else [feature_specs()[i] for i in features]
+    feats = [mk() for mk, _ in specs]
+    max_window = max(f.window_size for f in feats)
+    episode_length = timedelta(seconds=episode_seconds)
+    db = make_db("S", "reference")
+    sim = make_sim(db, outer_levels, preload=True, episode_length=episode_length, warm_up=max_window)
+    start_td = timedelta(seconds=start_seconds)
+    env = HistoricalOrderbookEnvironment(
+        features=feats, ticker="MSFT", step_size=timedelta(seconds=0.1), episode_length=episode_length,
+        initial_portfolio=Portfolio(*portfolio) if portfolio else None, min_date=DAY, max_date=DAY,
+        min_start_timedelta=start_td, max_end_timedelta=start_td + episode_length, simulator=sim,
+        per_step_reward_function=reward(reward_step), terminal_reward_function=reward(reward_term), n_levels=50,
+        **env_kwargs,
+    )
+    episodes = []
+    k = 0
+    for _ in range(n_episodes):
+        obs0 = env.reset()
+        ep = dict(reset_obs=[float(x) for x in obs0], reset_book=dump_book(env.central_orderbook),
+                  reset_inventory=int(env.state.portfolio.inventory), reset_cash=float(env.state.portfolio.cash),
+                  steps=[])
+        while True:
+            a = actions[k % len(actions)]
+            k += 1
+            orders = None
+            obs, r, done, _ = env.step(np.array(a, dtype=float))
+            ep["steps"].append(dict(
+                action=[float(x) for x in a], obs=[float(x) for x in obs], reward=float(r), done=bool(done),
+                inventory=int(env.state.portfolio.inventory), cash=float(env.state.portfolio.cash),
+                price=float(env.state.price), book=dump_book(env.central_orderbook),
+                agent_book=dump_book(env.internal_orderbook), fills=dump_fills(env.state.filled_orders),
+            ))
+            if done:
+                break
+        episodes.append(ep)
+    return dict(
+        name=name, env_kwargs={k_: v for k_, v in env_kwargs.items()}, reward_step=reward_step, reward_term=reward_term,
+        features=[d for _, d in specs], episode_steps=int(round(episode_seconds * 10)),
+        warmup_steps=int(max_window / timedelta(seconds=0.1)), start_seconds=start_seconds, outer_levels=outer_levels,
+        portfolio=list(portfolio) if portfolio else [0, 1000], episodes=episodes,
+    )
+
+
+def golden_env_episodes():
+    """G2: HistoricalOrderbookEnvironment reset/step traces on the MSFT fixture."""
+    rng = np.random.default_rng(1234)
+    rand4 = rng.uniform(0.0, 10.0, size=(64, 4)).tolist()
+    rand5 = np.c_[rng.uniform(0.0, 10.0, size=(64, 4)), rng.uniform(0, 60, size=64)].tolist()
+    rand2 = rng.uniform(0.0, 10.0, size=(64, 2)).tolist()
+    cases = [
+        run_env_case("fixed_1212_pnl", [[1, 2, 1, 2]], {}, ("PnL",), ("PnL",)),
+        run_env_case("fixed_1111_default_rewards", [[1, 1, 1, 1]], {}, ("IA", 1e-4, False), ("IA", 0.1, False)),
+        run_env_case("random_asym", rand4, {}, ("IA", 0.01, True), ("IA", 0.5, True), n_episodes=2),
+        run_env_case("random_two_episodes_carryover", rand4[7:], {"inc_prev_action_in_obs": True}, ("PnL",),
+                     ("IA", 0.1, False), n_episodes=3, start_seconds=36000.0 + 1.0, episode_seconds=1.0),
+        run_env_case("enter_spread", rand4[20:], {"enter_spread": True}, ("PnL",), ("PnL",)),
+        run_env_case("market_order_clearing", rand5,
+                     {"market_order_clearing": True, "market_order_fraction_of_inventory": 0.3, "max_inventory": 60},
+                     ("PnL",), ("PnL",), n_episodes=2),
+        run_env_case("concentration", rand2, {"concentration": 10.0}, ("PnL",), ("PnL",)),
+        run_env_case("quote_levels_3_8", rand4[30:], {"min_quote_level": 3, "max_quote_level": 8}, ("PnL",), ("PnL",)),
+        run_env_case("float_cash", rand4[40:], {}, ("PnL",), ("PnL",), portfolio=(25, 1e12)),
+        run_env_case("reference_test_features", [[1, 2, 1, 2]], {}, ("IA", 1e-4, False), ("IA", 0.1, False),
+                     features=[9, 0, 12, 13], episode_seconds=1.0, start_seconds=36001.0),
+    ]
+    save("env_episodes.json.gz", cases)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def golden_beta_ladders():
+    """G3: BetaOrderDistributor lot sizes (scipy.stats.beta.pdf + np.round half-to-even)."""
+    from rl4mm.gym.action_interpretation.OrderDistributors import BetaOrderDistributor
+
+    rng = np.random.default_rng(99)
+    out = []
+    for Q, vol, conc in ((10, 100, None), (5, 100, None), (8, 37, None), (16, 250, None), (10, 100, 10.0), (10, 100, 25.0)):
+        dist = BetaOrderDistributor(Q, active_volume=vol, concentration=conc)
+        n = 2 if conc is not None else 4
+        acts = [list(map(float, a)) for a in rng.uniform(0, 10 if conc is None else conc, size=(150, n))]
+        acts += [[float(i), float(j)] * (n // 2) for i in range(0, 11, 2) for j in range(0, 11, 2)] if conc is None else \
+                [[float(i), float(j)] for i in range(0, 11, 2) for j in range(0, 11, 2)]
+        rows = []
+        for a in acts:
+            d = dist.convert_action(np.array(a))
+            rows.append(dict(action=a, buy=[int(x) for x in d["buy"]], sell=[int(x) for x in d["sell"]]))
+        out.append(dict(quote_levels=Q, active_volume=vol, concentration=conc, cases=rows))
+    save("beta_ladders.json.gz", out)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def golden_exchange_fuzz():
+    """G5: random order sequences (external + agent, unknown ids, over-size cancels, self-matches, volume-less
+    deletions) through the reference Exchange; fills per order and the final L3 books."""
+
+    from rl4mm.orderbook.Exchange import EmptyOrderbookError, Exchange
+    from rl4mm.orderbook.models import Cancellation, Deletion, LimitOrder, MarketOrder
+
+    rng = np.random.default_rng(7)
+    ts = datetime(2012, 6, 21, 12)
+    cases = []
+    for case in range(40):
+        ex = Exchange("MSFT")
+        mid = 300000
+        # snapshot aggregates on both sides (internal_id -1)
+        init = []
+        for k in range(1, 6):
+            for direction, price in (("buy", mid - 100 * k), ("sell", mid + 100 * k)):
+                if rng.random() < 0.8:
+                    init.append(LimitOrder(ts, direction, "MSFT", -1, None, True, price, int(rng.integers(1, 9)) * 100))
+        ex.central_orderbook = ex.get_initial_orderbook_from_orders(init)
+        seq = []
+        next_ext = 1
+        live_ext = []     # (ext_id, direction, price)
+        agent_live = []   # (internal_id, direction, price)
+        dead = False
+        for _ in range(int(rng.integers(30, 120))):
+            u = rng.random()
+            is_agent = rng.random() < 0.3
+            direction = "buy" if rng.random() < 0.5 else "sell"
+            price = int(mid + 100 * rng.integers(-7, 8))
+            vol = int(rng.integers(1, 12)) * 50
+            rec = None
+            if u < 0.45:
+                if is_agent:
+                    order = LimitOrder(ts, direction, "MSFT", None, None, False, price, vol)
+                    rec = dict(type=1, dir=direction, price=price, vol=vol, ext=False, ref=0)
+                else:
+                    order = LimitOrder(ts, direction, "MSFT", None, next_ext, True, price, vol)
+                    rec = dict(type=1, dir=direction, price=price, vol=vol, ext=True, ref=next_ext)
+                    live_ext.append((next_ext, direction, price))
+                    next_ext += 1
+            elif u < 0.60:
+                order = MarketOrder(ts, direction, "MSFT", None, None if is_agent else next_ext, not is_agent, vol)
+                rec = dict(type=4, dir=direction, price=0, vol=vol, ext=not is_agent, ref=0 if is_agent else next_ext)
+                if not is_agent:
+                    next_ext += 1
+            else:
+                ctype = Cancellation if u < 0.8 else Deletion
+                t = 2 if u < 0.8 else 3
+                if is_agent and agent_live:
+                    iid, d_, p_ = agent_live[int(rng.integers(len(agent_live)))]
+                    v = None if (t == 3 and rng.random() < 0.5) else vol
+                    order = ctype(ts, d_, "MSFT", iid, None, False, p_, v)
+                    rec = dict(type=t, dir=d_, price=p_, vol=0 if v is None else v, ext=False, ref=-1, agent_index=iid)
+                else:
+                    r = rng.random()
+                    if live_ext and r < 0.7:
+                        e, d_, p_ = live_ext[int(rng.integers(len(live_ext)))]
+                        if rng.random() < 0.1:
+                            p_ += 100  # wrong price level
+                    else:
+                        e, d_, p_ = int(10_000 + rng.integers(100)), direction, price  # unknown id => aggregates
+                    v = vol
+                    if t == 3 and r < 0.35 and live_ext:
+                        v = None  # only for ids that exist (the reference asserts on aggregates)
+                        # make sure the level's head is not an aggregate when the order is gone
+                    order = ctype(ts, d_, "MSFT", None, e, True, p_, v)
+                    rec = dict(type=t, dir=d_, price=p_, vol=0 if v is None else v, ext=True, ref=e)
+            before_counter = ex.order_id_convertor.counter
+            try:
+                filled = ex.process_order(order)
+            except EmptyOrderbookError:
+                rec["raised"] = "EmptyOrderbookError"
+                seq.append(rec)
+                dead = True
+                break
+            except AssertionError:
+                rec["raised"] = "AssertionError"
+                seq.append(rec)
+                continue
+            rec["fills"] = dump_fills(filled) if filled is not None else []
+            if rec["type"] == 1 and not rec["ext"] and ex.order_id_convertor.counter > before_counter:
+                # the agent order (or its remainder) rested and got this internal id
+                agent_live.append((ex.order_id_convertor.counter, direction, price))
+                rec["rested_id"] = ex.order_id_convertor.counter
+            seq.append(rec)
+        cases.append(dict(init=[[0 if o.direction == "buy" else 1, int(o.price), int(o.volume)] for o in init],
+                          orders=seq, dead=dead, book=dump_book(ex.central_orderbook),
+                          agent_book=dump_book(ex.internal_orderbook)))
+    save("exchange_fuzz.json.gz", cases)
+
+
+def golden_packed_fixture():
+    """The MSFT 2012-06-21 fixture (first 1000 LOBSTER rows, 50 levels) packed by rl4mm_b200.packing, so that the GPU
+    box (which has no /root/reference) can replay it."""
+    from rl4mm_b200.packing import pack_lobster
+
+    arrays = {}
+    for tie in ("reference", "file"):
+        s = pack_lobster(MSG_CSV, BOOK_CSV, 50, max_rows=1000, tie_order=tie)
+        arrays[f"msgs_{tie}"] = s.msgs
+        arrays.update(step_off=s.step_off, snapshots=s.snapshots, snap_valid=s.snap_valid, ext_ids=s.ext_ids,
+                      t0_us=np.int64(s.t0_us), step_us=np.int64(s.step_us))
+    np.savez_compressed(GOLDEN / "msft_fixture_packed.npz", **arrays)
+
+
+def main():
+    refshim.install()
+    golden_packed_fixture()
+    import warnings
+
+    warnings.simplefilter("ignore")
+    import contextlib
+    import io
+
+    with contextlib.redirect_stdout(io.StringIO()):  # the reference prints on resync / clamping
+        g1 = golden_fixture_replay
+        g1()
+        golden_env_episodes()
+        golden_beta_ladders()
+        golden_exchange_fuzz()
+    for p in sorted(GOLDEN.glob("*.gz")):
+        print(p.name, p.stat().st_size)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,208 @@
+"""LOBSTER message / orderbook files -> packed, device-ready stream buffers.
+
+This replaces ``rl4mm/database`` for the hot path: instead of loading the
+CSVs into Postgres and querying a range per episode / per step, a ticker-day is packed ONCE into
+
+* ``msgs``      16-byte records in replay order (hidden executions dropped, execution direction flipped),
+* ``step_off``  CSR offsets of the messages of every ``step_us`` grid interval ``(t0 + k*step, t0 + (k+1)*step]``,
+* ``snapshots`` the L-level book at every whole second (``get_last_snapshot`` with ``book_snapshot_freq="S"``),
+
+and kept resident in HBM.  The semantics restated here, with the reference lines they follow:
+
+* type map 1 limit / 2 cancellation / 3 deletion / 4 market / 5 market_hidden / 6 cross_trade / 7 trading_halt --
+  rl4mm/database/database_population_helpers.py:151-160;
+* direction: +1 buy / -1 sell, flipped for executions -- :132-136;
+* timestamps are SQL ``DateTime`` => truncated to microseconds -- rl4mm/database/models.py:14;
+* range query ``start < ts <= end`` ordered by ``(timestamp, id)`` where ``id`` is the STRING
+  ``"{freq}_L{levels}_NASDAQ_{ticker}_{date}_{row}"`` => same-microsecond ties are ordered lexicographically by the
+  decimal row number -- rl4mm/database/HistoricalDatabase.py:103-119, database_population_helpers.py:163-181;
+* hidden executions dropped, cross trades rejected -- rl4mm/simulation/HistoricalOrderGenerator.py:49-57;
+* snapshot at second T = orderbook row of the last message with time <= T --
+  database_population_helpers.py:45-62,139-148, HistoricalDatabase.py:46-62.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+
+from . import abi
+
+LOBSTER_DUMMY = 9_999_999_999
+
+
+@dataclass
+class PackedStream:
+    msgs: np.ndarray        # abi.MSG_DTYPE [n_msgs]
+    step_off: np.ndarray    # uint32 [n_grid_steps + 1]
+    snapshots: np.ndarray   # int32 [n_seconds + 1, 2, n_levels, 2]  (side, level, (price, volume))
+    snap_valid: np.ndarray  # uint8 [n_seconds + 1]
+    t0_us: int              # grid origin, microseconds after midnight (whole second)
+    step_us: int
+    n_levels: int
+    ext_ids: np.ndarray = field(default_factory=lambda: np.zeros(1, np.int64))  # ref -> original external id
+    ticker: str = ""
+    date: str = ""
+
+    @property
+    def n_msgs(self) -> int:
+        return len(self.msgs)
+
+    @property
+    def n_grid_steps(self) -> int:
+        return len(self.step_off) - 1
+
+    @property
+    def n_seconds(self) -> int:
+        return len(self.snap_valid) - 1
+
+    @property
+    def steps_per_second(self) -> int:
+        return 1_000_000 // self.step_us
+
+    def step_of_time(self, seconds_after_midnight: float) -> int:
+        """Grid step index whose boundary is the given clock time (must lie on the grid)."""
+        us = int(round(seconds_after_midnight * 1_000_000)) - self.t0_us
+        if us % self.step_us:
+            raise ValueError("time is not on the step grid")
+        return us // self.step_us
+
+    def validate(self) -> None:
+        assert self.msgs.dtype == abi.MSG_DTYPE and self.msgs.flags.c_contiguous
+        assert self.step_off.dtype == np.uint32 and self.step_off[0] == 0 and self.step_off[-1] == len(self.msgs)
+        assert np.all(np.diff(self.step_off.astype(np.int64)) >= 0)
+        assert self.snapshots.dtype == np.int32 and self.snapshots.shape == (self.n_seconds + 1, 2, self.n_levels, 2)
+        assert self.t0_us % 1_000_000 == 0 and 1_000_000 % self.step_us == 0
+        assert self.n_seconds * self.steps_per_second >= self.n_grid_steps
+
+
+def parse_time_ns(text: str) -> int:
+    """Exact decimal parse of a LOBSTER ``seconds.after.midnight`` field into integer nanoseconds."""
+    if "." in text:
+        sec, frac = text.split(".")
+    else:
+        sec, frac = text, ""
+    return int(sec) * 1_000_000_000 + int((frac + "000000000")[:9])
+
+
+def _lexicographic_tie_order(ts_us: np.ndarray, row_ids: np.ndarray) -> np.ndarray:
+    """Permutation that sorts by (ts_us, str(row_id)) -- the reference's ``ORDER BY timestamp, id`` on a string id."""
+    order = np.argsort(ts_us, kind="stable")
+    t = ts_us[order]
+    run_start = np.flatnonzero(np.r_[True, t[1:] != t[:-1]])
+    run_end = np.r_[run_start[1:], len(t)]
+    for a, b in zip(run_start[run_end - run_start > 1], run_end[run_end - run_start > 1]):
+        seg = order[a:b]
+        order[a:b] = seg[np.argsort(np.array([str(int(r)) for r in row_ids[seg]]), kind="stable")]
+    return order
+
+
+def pack_arrays(
+    time_ns: np.ndarray,
+    msg_type: np.ndarray,
+    ext_id: np.ndarray,
+    size: np.ndarray,
+    price: np.ndarray,
+    direction: np.ndarray,
+    book_rows: np.ndarray,
+    n_levels: int,
+    step_us: int = 100_000,
+    t0_us: Optional[int] = None,
+    tie_order: str = "reference",
+    db_batch_size: int = 1_000_000,
+    ticker: str = "",
+    date: str = "",
+) -> PackedStream:
+    """Pack raw LOBSTER columns.  ``book_rows`` is the orderbook file as int64 [n_rows, 4*n_levels] (one row per
+    message row, columns ask price, ask size, bid price, bid size per level -- rl4mm/orderbook/helpers.py:52-55)."""
+    time_ns = np.asarray(time_ns, np.int64)
+    msg_type = np.asarray(msg_type, np.int64)
+    n = len(time_ns)
+    assert np.all(np.diff(time_ns) >= 0), "LOBSTER messages must be time ordered"
+    assert book_rows.shape == (n, 4 * n_levels)
+    if 1_000_000 % step_us:
+        raise ValueError("step_us must divide one second")
+    ts_us = time_ns // 1000
+    if t0_us is None:
+        t0_us = int(ts_us[0] // 1_000_000) * 1_000_000
+    if t0_us % 1_000_000:
+        raise ValueError("t0_us must be a whole second")
+    last_us = int(ts_us[-1])
+    n_grid = max(1, -(-(last_us - t0_us) // step_us))
+    n_seconds = -(-(n_grid * step_us) // 1_000_000)
+    n_grid = n_seconds * (1_000_000 // step_us)
+
+    # --- replay order ------------------------------------------------------------------------------------------
+    row_ids = np.arange(n, dtype=np.int64)
+    row_ids = row_ids + (row_ids // db_batch_size) * db_batch_size  # message.name + start_index (:171)
+    if tie_order == "reference":
+        order = _lexicographic_tie_order(ts_us, row_ids)
+    elif tie_order == "file":
+        order = np.arange(n)
+    else:
+        raise ValueError(tie_order)
+    keep = order[(ts_us[order] > t0_us) & (msg_type[order] != 5)]
+    bad = np.isin(msg_type[keep], (6, 7))
+    if bad.any():
+        raise ValueError("cross_trade / trading_halt messages inside the replay range (the reference asserts / crashes: "
+                         "HistoricalOrderGenerator.py:52-56, create_order.py:9-24)")
+    if not np.isin(msg_type[keep], (1, 2, 3, 4)).all():
+        raise ValueError("unknown LOBSTER message type")
+    mt = msg_type[keep]
+    d = np.asarray(direction, np.int64)[keep]
+    is_exec = mt == 4
+    side = np.where(d == 1, abi.BUY, abi.SELL)
+    side = np.where(is_exec, 1 - side, side)  # executions carry the aggressor's direction
+    ids = np.asarray(ext_id, np.int64)[keep]
+    uniq, inv = np.unique(ids, return_inverse=True)
+    if len(uniq) + 1 >= 2**31:
+        raise ValueError("too many distinct order ids")
+    msgs = np.zeros(len(keep), abi.MSG_DTYPE)
+    pr = np.asarray(price, np.int64)[keep]
+    sz = np.asarray(size, np.int64)[keep]
+    if pr.max(initial=0) >= 2**31 or sz.max(initial=0) >= 2**31:
+        raise ValueError("price / size does not fit int32")
+    msgs["price"] = pr
+    msgs["volume"] = sz
+    msgs["ref"] = inv + 1
+    msgs["meta"] = mt.astype(np.uint32) | (side.astype(np.uint32) << 3)
+    step_idx = -(-(ts_us[keep] - t0_us) // step_us) - 1  # ts in (t0 + k*step, t0 + (k+1)*step]  =>  k
+    assert step_idx.min(initial=0) >= 0 and step_idx.max(initial=0) < n_grid
+    step_off = np.zeros(n_grid + 1, np.uint32)
+    step_off[1:] = np.cumsum(np.bincount(step_idx, minlength=n_grid))
+
+    # --- per-second snapshots ----------------------------------------------------------------------------------
+    sec_ns = (t0_us + np.arange(n_seconds + 1, dtype=np.int64) * 1_000_000) * 1000
+    idx = np.searchsorted(time_ns, sec_ns, side="right") - 1
+    snap_valid = (idx >= 0).astype(np.uint8)
+    rows = np.asarray(book_rows, np.int64)[np.maximum(idx, 0)].reshape(n_seconds + 1, n_levels, 4)
+    snapshots = np.zeros((n_seconds + 1, 2, n_levels, 2), np.int32)
+    for s, (pc, vc) in ((abi.SELL, (0, 1)), (abi.BUY, (2, 3))):
+        p, v = rows[:, :, pc], rows[:, :, vc]
+        dummy = (np.abs(p) >= LOBSTER_DUMMY)
+        snapshots[:, s, :, 0] = np.where(dummy, abi.NO_PRICE, p)
+        snapshots[:, s, :, 1] = np.where(dummy, 0, v)
+    out = PackedStream(msgs, step_off, snapshots, snap_valid, int(t0_us), int(step_us), n_levels,
+                       np.r_[np.int64(0), uniq], ticker, date)
+    out.validate()
+    return out
+
+
+def pack_lobster(message_csv, orderbook_csv, n_levels: int, max_rows: Optional[int] = None, **kw) -> PackedStream:
+    """Pack a LOBSTER ``*_message_L.csv`` / ``*_orderbook_L.csv`` pair (populate_database.py:71-78 column layout)."""
+    t, ty, oid, sz, pr, di = [], [], [], [], [], []
+    with open(message_csv) as f:
+        for i, line in enumerate(f):
+            if max_rows is not None and i >= max_rows:
+                break
+            p = line.rstrip("\n").split(",")
+            t.append(parse_time_ns(p[0]))
+            ty.append(int(p[1]))
+            oid.append(int(p[2]))
+            sz.append(int(p[3]))
+            pr.append(int(p[4]))
+            di.append(int(p[5]))
+    books = np.loadtxt(orderbook_csv, delimiter=",", dtype=np.int64, max_rows=len(t), ndmin=2)
+    return pack_arrays(np.array(t), np.array(ty), np.array(oid), np.array(sz), np.array(pr), np.array(di), books,
+                       n_levels, **kw)
