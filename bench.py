@@ -1,0 +1,304 @@
+#!/usr/bin/env python
+"""Benchmark of the LOB simulation step (BASELINE.json metric: LOB messages/s and env steps/s, whole box).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload replay|rollout]
+
+Workload at N=1 = BASELINE.json configs[1]: a synthetic SPY-shaped day (10 levels, 1e7 messages, seed 0) replayed
+through 4096 batched books on one B200 (weak scaling: 4096 books per GPU).  One bench "step" = every book advances
+`--segment-steps` simulation steps (default 2340 x 0.1 s = 1% of the day, ~1e5 messages per book).
+
+Timed region per step: CUDA events on the launching stream around the replay launch, inputs resident in HBM
+(`value`); the same step through the host-buffer C-ABI call (`lobsim_replay_host`: H2D of the segment's messages
+from pinned memory, replay, D2H of one 80-byte state record per book) gives `e2e`.  L2 is flushed between timed
+iterations.  Multi-GPU: one process per GPU (torchrun), books sharded by rank, no data-path collective; the time is
+the max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+ALGO_BYTES_PER_MSG = 16          # packed record
+ALGO_BYTES_PER_STEP_REPLAY = 4   # CSR step offset
+ALGO_BYTES_PER_STEP_ENV = 65     # action 4x4 B + obs 10x4 B + reward 4 B + done 1 B + CSR offset 4 B
+S_STATE_L10 = 1216               # SURVEY.md section 8d book-state size for L=10 (round trip per launch)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="replay", choices=["replay", "rollout"])
+    ap.add_argument("--envs-per-gpu", type=int, default=4096)
+    ap.add_argument("--n-msgs", type=int, default=10_000_000)
+    ap.add_argument("--segment-steps", type=int, default=2340)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_stream(args):
+    from rl4mm_b200 import synthetic
+
+    return synthetic.generate(synthetic.spy_day(seed=0, n_msgs=args.n_msgs, duration_s=23_400))
+
+
+def cpu_oracle_throughput(stream, sample_steps: int, threads: int, reps: int = 1):
+    """The oracle (C port of the reference algorithm) on the host cores: `threads` books replay the first
+    `sample_steps` grid steps of the stream concurrently (ctypes releases the GIL)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from oracle.oracle import Oracle
+    from rl4mm_b200 import abi
+
+    cfg = abi.default_cfg(n_levels=stream.n_levels, outer_levels=20)
+    oracles = [Oracle(cfg, stream) for _ in range(threads)]
+    msgs = int(stream.step_off[sample_steps])
+
+    def work(o):
+        for _ in range(reps):
+            o.reset_book(0)
+            o.replay(sample_steps)
+        return int(o.state()["err"])
+
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(work, oracles[:1]))  # warm the caches / page in
+        t0 = time.perf_counter()
+        errs = list(ex.map(work, oracles))
+        dt = time.perf_counter() - t0
+    assert not any(errs), errs
+    return threads * reps * msgs / dt, threads * reps * sample_steps / dt, dt, msgs
+
+
+def run_reference(args):
+    """--impl reference: the reference's algorithm on the host cores (the reference itself is pure Python and cannot
+    be compiled; oracle/lob_oracle.c is its C restatement, pinned against the reference by tests/golden/)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    stream = make_stream(args)
+    threads = os.cpu_count() or 1
+    sample_steps = min(stream.n_grid_steps, args.segment_steps * 20)
+    for _ in range(max(args.warmup, 1)):
+        cpu_oracle_throughput(stream, sample_steps, threads)
+    vals, steps_s, t_all = [], [], 0.0
+    for _ in range(args.steps):
+        v, s, dt, msgs = cpu_oracle_throughput(stream, sample_steps, threads)
+        vals.append(v); steps_s.append(s); t_all += dt
+    value = float(np.mean(vals))
+    sample = f"{threads} books x first {sample_steps} grid steps ({msgs} messages each) per step, C port of the reference algorithm"
+    line = {
+        "impl": "reference", "metric": "lob_messages_per_sec", "value": value, "unit": "messages/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_all / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": workload_config(args, stream),
+        "env_steps_per_sec": float(np.mean(steps_s)),
+        "cpu_baseline": {"value": value, "unit": "messages/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "messages/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, stream):
+    return {
+        "workload": "configs[1]: synthetic SPY-shaped day (10 levels, %d messages, seed 0) replayed through %d "
+                    "batched books per GPU" % (stream.n_msgs, args.envs_per_gpu),
+        "envs_per_gpu": args.envs_per_gpu, "n_levels": stream.n_levels, "segment_steps": args.segment_steps,
+        "step_us": stream.step_us, "mode": args.workload, "l2": "flushed between timed iterations (256 MiB write)",
+        "parallelism": f"books sharded over {args.gpus} GPU(s), no data-path collective",
+    }
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    from rl4mm_b200 import abi
+    from rl4mm_b200.device import LobSim
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (the hot path has no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    stream = make_stream(args)
+    n_envs = args.envs_per_gpu
+    cfg = abi.default_cfg(n_envs=n_envs, n_levels=stream.n_levels, outer_levels=20, max_levels_per_side=64,
+                          max_orders_per_side=256, max_agent_orders=32)
+    sim = LobSim(cfg, local_rank)
+    ds = sim.load_stream(0, stream)
+    seg = args.segment_steps
+    total = args.warmup + args.steps
+    assert total * seg <= stream.n_grid_steps, "not enough stream for warmup + steps segments"
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    cur = torch.cuda.current_stream(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident arm -----------------------------------------------------------------------------------------
+    sim.reset_book(0, 0)
+    for i in range(args.warmup):
+        sim.replay(seg)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = sim.launch_count
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for i in range(args.steps):
+        flush.zero_()
+        ev[i][0].record(cur)
+        sim.replay(seg)
+        ev[i][1].record(cur)
+    barrier()
+    launches = sim.launch_count - launches0
+    clocks = sampler.stop()
+    ms = [a.elapsed_time(b) for a, b in ev]
+    t_dev = sum(ms) / 1e3
+    first = args.warmup * seg
+    msgs_per_env = int(stream.step_off[first + args.steps * seg]) - int(stream.step_off[first])
+    state = sim.state()
+    assert np.all(state["err"] == 0), "error flags raised during the bench: %s" % np.unique(state["err"])
+    assert np.all(state["now_step"] == total * seg)
+    # every book replayed the same stream: they must be identical, and equal to the historical book
+    assert len(np.unique(state[["best_buy", "best_sell", "best_buy_volume", "best_sell_volume"]])) == 1
+    snap = stream.snapshots[total * seg // stream.steps_per_second]
+    assert state["best_buy"][0] == snap[0, 0, 0] and state["best_sell"][0] == snap[1, 0, 0]
+
+    # ---- end-to-end arm: host buffers through lobsim_replay_host ---------------------------------------------------
+    pinned = torch.from_numpy(stream.msgs.view(np.uint8).reshape(-1, 16)).pin_memory()
+    host_msgs = pinned.numpy().view(abi.MSG_DTYPE).reshape(-1)
+    state_out_t = torch.empty((n_envs, abi.ENV_STATE_DTYPE.itemsize), dtype=torch.uint8).pin_memory()
+    state_out = state_out_t.numpy().view(abi.ENV_STATE_DTYPE).reshape(-1)
+    sim.reset_book(0, 0)
+    h2d = d2h = 0
+    t_e2e = 0.0
+    for i in range(total):
+        a, b = int(stream.step_off[i * seg]), int(stream.step_off[(i + 1) * seg])
+        if i == args.warmup:
+            barrier()
+        flush.zero_()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        sim.replay_host(0, host_msgs[a:b], a, seg, state_out)
+        dt = time.perf_counter() - t0
+        if i >= args.warmup:
+            t_e2e += dt
+            h2d += (b - a) * 16
+            d2h += state_out.nbytes
+    assert np.all(state_out["err"] == 0) and np.all(state_out["now_step"] == total * seg)
+
+    # ---- reduce over ranks: max time ------------------------------------------------------------------------------------
+    times = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    t_dev, t_e2e = (float(x) for x in times.cpu())
+    env_msgs = msgs_per_env * n_envs * world
+    env_steps = args.steps * seg * n_envs * world
+    value = env_msgs / t_dev
+    peak, peak_src = measured_peaks()
+    algo_bytes_launch = (ALGO_BYTES_PER_MSG * msgs_per_env / args.steps + ALGO_BYTES_PER_STEP_REPLAY * seg
+                         + 2 * S_STATE_L10) * n_envs
+    achieved = algo_bytes_launch / (t_dev / args.steps) / 1e9  # per GPU (max-over-ranks time)
+    line = {
+        "metric": "lob_messages_per_sec", "value": value, "unit": "messages/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": workload_config(args, stream),
+        "env_steps_per_sec": env_steps / t_dev,
+        "e2e": {"value": env_msgs / t_e2e, "unit": "messages/s", "h2d_bytes_per_step": h2d // args.steps,
+                "d2h_bytes_per_step": d2h // args.steps, "api": "lobsim_replay_host (C ABI, pinned host buffers)"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src, "kernel": "k_advance<false>",
+                     "algorithmic_bytes_per_launch": algo_bytes_launch,
+                     "note": "16 B per env-message + 4 B per env-step + 2 x 1216 B book state per book per launch; "
+                             "per-book processing is serially dependent, so this path is issue/latency-bound far "
+                             "below the HBM roofline (see DESIGN.md)"},
+    }
+    if rank == 0 and not args.no_cpu_baseline and world == 1:
+        threads = os.cpu_count() or 1
+        sample_steps = min(stream.n_grid_steps, seg * 20)
+        v, s, dt, m = cpu_oracle_throughput(stream, sample_steps, threads, reps=2)
+        line["cpu_baseline"] = {"value": v, "unit": "messages/s", "cores": threads, "kind": "port",
+                                "sample": f"{threads} books x 2 replays of the first {sample_steps} grid steps "
+                                          f"({m} messages) on {threads} host threads, {dt:.2f} s wall"}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

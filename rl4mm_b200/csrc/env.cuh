@@ -1,0 +1,399 @@
+// env.cuh -- simulator / gym-environment layer on top of book.cuh: outer-level resync, the agent's action ->
+// orders conversion, features and rewards.  Everything is warp-collective (uniform control flow) except the feature
+// updates, which run one feature per lane.
+#pragma once
+#include <math.h>
+
+#include "book.cuh"
+
+struct __align__(16) FeatState {
+  double cur;        // Feature.current_value
+  long long total;   // total_trades / total_volume
+  long long diff;    // trade_diff / volume_imbalance
+  int32_t len;       // deque length (bit 30: running sums valid)
+  int32_t head;      // circular write position
+};
+static_assert(sizeof(FeatState) == 32, "FeatState must be 32 bytes");
+#define FEAT_SUMS_VALID (1 << 30)
+
+struct EnvConst { // what the device needs of lobsim_cfg_t, by value in the kernel parameters
+  lobsim_cfg_t cfg;
+  int32_t ring_off[LOBSIM_MAX_FEATURES]; // slot offset of each feature's ring inside an env's ring block
+  int32_t ring_stride;                   // slots per env
+  int32_t action_dim, obs_dim;
+};
+
+__device__ __forceinline__ long long now_us_of(const lobsim_stream_t& st, const lobsim_cfg_t& c, int now_step) {
+  return st.t0_us + (long long)now_step * c.step_us;
+}
+
+// a[i] for a register-resident 5-vector and a runtime index (keeps the array out of local memory)
+__device__ __forceinline__ double pick5(const double* a, int i) {
+  double r = a[0];
+#pragma unroll
+  for (int k = 1; k < 5; k++) r = (i == k) ? a[k] : r;
+  return r;
+}
+
+// ---- OrderbookSimulator._near_exiting_initial_price_range, OrderbookSimulator.py:177-183 -------------------------
+__device__ __forceinline__ bool near_exiting(const Book& b, const WarpState& w, const lobsim_cfg_t& c) {
+  const BookHdr* h = b.hdr();
+  double prop = (double)c.outer_levels / (double)c.n_levels;
+  double bb = w.nlv0 ? (double)b.lvp(0)[w.nlv0 - 1] : 0.0;
+  double bs = w.nlv1 ? (double)b.lvp(1)[w.nlv1 - 1] : (double)INFINITY;
+  return bb < (double)h->min_buy + prop * (double)h->init_buy_range || bs > (double)h->max_sell - prop * (double)h->init_sell_range;
+}
+
+// ---- OrderbookSimulator.update_outer_levels, OrderbookSimulator.py:105-135 ---------------------------------------
+// scratch: per-warp shared int2[2*NA] for the agent orders that are cancelled and re-queued behind the aggregates.
+__device__ __forceinline__ void update_outer_levels(const Book& b, WarpState& w, const lobsim_cfg_t& c, const int32_t* __restrict__ row, int2* scratch) {
+  BookHdr* h = b.hdr();
+  const int L = c.n_levels;
+  const int min_buy = h->min_buy, max_sell = h->max_sell;
+  int nrepl = 0, nrepl_buy = 0;
+  for (int side = 0; side < 2; side++) {
+    for (int lvl = 0; lvl < L; lvl++) {
+      int price = __ldg(&row[(side * L + lvl) * 2]), vol = __ldg(&row[(side * L + lvl) * 2 + 1]);
+      if (price == LOBSIM_NO_PRICE) continue;
+      if (!(side == 0 ? price < min_buy : price > max_sell)) continue; // _initial_prices_filter_function :99-103
+      for (int i = 0; i < NAG(w, side);) { // internal orders at this price: cancel now, re-queue later (:116-129)
+        int ap = b.aprice(side)[i], av = b.avol(side)[i];
+        uint32_t id = b.aid(side)[i];
+        __syncwarp();
+        if (ap != price) { i++; continue; }
+        if (b.lane == 0) scratch[nrepl] = make_int2(price, av);
+        nrepl++;
+        int before = NAG(w, side);
+        remove_order(b, w, side, price, av, true, LOBSIM_REF_AGENT | id, true);
+        if (NAG(w, side) == before) agent_remove_at(b, w, side, i); // keep internal and central consistent
+      }
+      bool found;
+      int j = find_level(b, side, NLV(w, side), price, found); // central[dir][price] = deque([aggregate]) :130
+      if (found) {
+        int start = level_start(b, side, j), end = b.lvend(side)[j];
+        __syncwarp();
+        if (end - start > 1) remove_entries(b, w, side, j, start + 1, end - start - 1);
+        if (b.lane == 0) b.ord(side)[start] = make_uint2((unsigned)vol, LOBSIM_REF_AGGREGATE);
+        __syncwarp();
+      } else if (NORD(w, side) < b.L.NO && insert_level(b, w, side, j, price)) {
+        add_order(b, w, side, j, vol, LOBSIM_REF_AGGREGATE);
+      } else w.err |= LOBSIM_ERR_ORDER_OVERFLOW;
+    }
+    if (side == 0) nrepl_buy = nrepl;
+  }
+  __syncwarp();
+  for (int i = 0; i < nrepl; i++) { // :132-133
+    int2 r = scratch[i];
+    submit_or_execute(b, w, i < nrepl_buy ? 0 : 1, r.x, r.y, 0, true, true);
+  }
+  if (b.lane == 0) { // :134-135 (Exchange.orderbook_price_range, Exchange.py:160-170)
+    if (w.nlv0 && b.lvp(0)[0] < h->min_buy) h->min_buy = b.lvp(0)[0];
+    if (w.nlv1 && b.lvp(1)[0] > h->max_sell) h->max_sell = b.lvp(1)[0];
+  }
+  __syncwarp();
+}
+
+// ---- OrderbookSimulator.reset_episode, OrderbookSimulator.py:55-68,156-188 + Exchange.py:172-178 ---------------
+__device__ __forceinline__ void init_book_from_snapshot(const Book& b, WarpState& w, const lobsim_cfg_t& c, const lobsim_stream_t& st, int stream_id, int start_step) {
+  BookHdr* h = b.hdr();
+  const int L = c.n_levels;
+  w.nlv0 = w.nlv1 = w.nord0 = w.nord1 = w.nag0 = w.nag1 = 0;
+  w.err = 0; w.dead = 0;
+  reset_flow(w);
+  long long rel_us = (long long)start_step * c.step_us;
+  long long sec = rel_us / 1000000;
+  bool ok = start_step >= 0 && rel_us % 1000000 == 0 && sec <= (long long)st.n_seconds && st.snap_valid[sec] != 0;
+  if (!ok) { w.err |= LOBSIM_ERR_NO_SNAPSHOT; w.dead = 1; }
+  else {
+    const int32_t* row = st.snapshots + (size_t)sec * 2 * L * 2;
+    for (int side = 0; side < 2; side++) {
+      int nvalid = 0;
+      for (int base = 0; base < L; base += 32) nvalid += __popc(__ballot_sync(FULL_MASK, base + b.lane < L && __ldg(&row[(side * L + base + b.lane) * 2]) != LOBSIM_NO_PRICE));
+      if (nvalid > b.L.NL || nvalid > b.L.NO) { w.err |= LOBSIM_ERR_LEVEL_OVERFLOW; w.dead = 1; nvalid = 0; }
+      int seen = 0;
+      for (int base = 0; base < L; base += 32) {
+        int lvl = base + b.lane;
+        int price = lvl < L ? __ldg(&row[(side * L + lvl) * 2]) : LOBSIM_NO_PRICE;
+        int vol = lvl < L ? __ldg(&row[(side * L + lvl) * 2 + 1]) : 0;
+        unsigned m = __ballot_sync(FULL_MASK, price != LOBSIM_NO_PRICE);
+        if (price != LOBSIM_NO_PRICE && nvalid) {
+          int k = seen + __popc(m & ((1u << b.lane) - 1)); // rank from the best
+          int j = nvalid - 1 - k;                          // worst -> best storage
+          b.lvp(side)[j] = price;
+          b.lvend(side)[j] = (uint16_t)(j + 1);
+          b.ord(side)[j] = make_uint2((unsigned)vol, LOBSIM_REF_AGGREGATE);
+        }
+        seen += __popc(m);
+      }
+      SET_NLV(w, side, nvalid);
+      SET_NORD(w, side, nvalid);
+    }
+  }
+  __syncwarp();
+  if (b.lane == 0) {
+    h->now_step = start_step;
+    h->stream_id = stream_id;
+    // _reset_initial_price_ranges :185-188
+    int bb = w.nlv0 ? b.lvp(0)[w.nlv0 - 1] : 0, wb = w.nlv0 ? b.lvp(0)[0] : 0;
+    int bs = w.nlv1 ? b.lvp(1)[w.nlv1 - 1] : 0, ws = w.nlv1 ? b.lvp(1)[0] : 0;
+    h->min_buy = wb; h->max_sell = ws;
+    h->init_buy_range = bb - wb; h->init_sell_range = ws - bs;
+  }
+  __syncwarp();
+}
+
+// ---- BetaOrderDistributor, rl4mm/gym/action_interpretation/OrderDistributors.py:23-56 ----------------------------
+// lane k < Q returns the lot size of quote level k.  The sum follows numpy's pairwise summation order.
+__device__ __forceinline__ int beta_ladder_lane(double a, double bpar, int Q, int active_volume, int lane) {
+  double x = 1.0 / (double)Q * ((double)lane + 0.5);
+  double A = -INFINITY;
+  if (lane < Q) {
+    double lx = (a - 1.0) == 0.0 ? 0.0 : (a - 1.0) * log(x);
+    double l1 = (bpar - 1.0) == 0.0 ? 0.0 : (bpar - 1.0) * log1p(-x);
+    A = lx + l1;
+  }
+  double amax = A;
+  for (int d = 16; d; d >>= 1) amax = fmax(amax, __shfl_xor_sync(FULL_MASK, amax, d));
+  double e = lane < Q ? exp(A - amax) : 0.0;
+  double s;
+  if (Q >= 8) {
+    double r[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) r[j] = __shfl_sync(FULL_MASK, e, j);
+    int i = 8;
+    for (; i + 8 <= Q; i += 8) {
+#pragma unroll
+      for (int j = 0; j < 8; j++) r[j] += __shfl_sync(FULL_MASK, e, i + j);
+    }
+    s = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    for (; i < Q; i++) s += __shfl_sync(FULL_MASK, e, i);
+  } else {
+    s = 0.0;
+    for (int i = 0; i < Q; i++) s += __shfl_sync(FULL_MASK, e, i);
+  }
+  return lane < Q ? (int)rint(e / s * (double)active_volume) : 0;
+}
+
+// ---- HistoricalOrderbookEnvironment.convert_action_to_orders (HOE.py:206-258) fused with the processing of the
+//      resulting agent orders by Exchange.process_order (OrderbookSimulator.py:76-84: agent orders go first) -------
+__device__ __forceinline__ void agent_orders(const Book& b, WarpState& w, const EnvConst& ec, const double* action /* uniform regs */) {
+  const lobsim_cfg_t& c = ec.cfg;
+  if (w.dead) return;
+  const int Q = c.max_quote_level - c.min_quote_level;
+  const double EPS = 0.000001;
+  double ab, bbp, as, bsp;
+  if (c.concentration >= 0) {
+    ab = action[0] + EPS; bbp = c.concentration - ab + EPS; as = action[1] + EPS; bsp = c.concentration - as + EPS;
+  } else { ab = action[0] + EPS; bbp = action[1] + EPS; as = action[2] + EPS; bsp = action[3] + EPS; }
+  int desired0 = beta_ladder_lane(ab, bbp, Q, c.active_volume, b.lane);
+  int desired1 = beta_ladder_lane(as, bsp, Q, c.active_volume, b.lane);
+  long long absinv = w.inventory < 0 ? -w.inventory : w.inventory;
+  bool clearing = c.market_order_clearing && (double)absinv > pick5(action, ec.action_dim - 1);
+  if (clearing) desired0 = desired1 = 0;
+  if (w.nlv0 == 0 || w.nlv1 == 0) { w.err |= LOBSIM_ERR_EMPTY_BOOK; w.dead = 1; return; }
+  int bb = b.lvp(0)[w.nlv0 - 1], bs = b.lvp(1)[w.nlv1 - 1];
+  const int tick = c.tick_size;
+  if (c.enter_spread) { // _get_best_prices :298-309
+    double mid = (double)(bs + bb) / 2.0;
+    bb = (int)(floor(mid / (double)tick) * (double)tick);
+    bs = (int)(ceil(mid / (double)tick) * (double)tick);
+  }
+  const int price0 = bb - (c.min_quote_level + b.lane) * tick; // ladder price of this lane's quote level
+  const int price1 = bs + (c.min_quote_level + b.lane) * tick;
+  int diff0 = 0, diff1 = 0;
+  if (b.lane < Q) { // _get_current_internal_order_volumes :291-296
+    int cur0 = 0, cur1 = 0;
+    for (int i = 0; i < w.nag0; i++) cur0 += b.aprice(0)[i] == price0 ? b.avol(0)[i] : 0;
+    for (int i = 0; i < w.nag1; i++) cur1 += b.aprice(1)[i] == price1 ? b.avol(1)[i] : 0;
+    diff0 = desired0 - cur0; diff1 = desired1 - cur1;
+  }
+  __syncwarp();
+  for (int side = 0; side < 2 && !w.dead; side++) { // _volume_diff_to_orders :227-258
+    const int myprice = side ? price1 : price0;
+    for (int k = 0; k < Q && !w.dead; k++) {
+      int d = __shfl_sync(FULL_MASK, side ? diff1 : diff0, k);
+      int p = __shfl_sync(FULL_MASK, myprice, k);
+      if (d > 0) submit_or_execute(b, w, side, p, d, 0, true, true);
+      int need = -d;
+      while (need > 0) { // cancel from the back of the agent's queue at this price, :239-249
+        int nag = NAG(w, side), hit = -1;
+        for (int base = (nag - 1) & ~31; base >= 0; base -= 32) {
+          int i = base + b.lane;
+          unsigned m = __ballot_sync(FULL_MASK, i < nag && b.aprice(side)[i] == p);
+          if (m) { hit = base + 31 - __clz(m); break; }
+        }
+        if (hit < 0) break;
+        int av = b.avol(side)[hit];
+        uint32_t id = b.aid(side)[hit];
+        __syncwarp();
+        int v = av < need ? av : need;
+        remove_order(b, w, side, p, v, true, LOBSIM_REF_AGENT | id, true);
+        need -= v;
+      }
+    }
+    for (int i = 0; i < NAG(w, side) && !w.dead;) { // agent orders off the ladder are cancelled in full, :250-257
+      int ap = b.aprice(side)[i], av = b.avol(side)[i];
+      uint32_t id = b.aid(side)[i];
+      __syncwarp();
+      bool on_ladder = __ballot_sync(FULL_MASK, b.lane < Q && myprice == ap) != 0;
+      if (on_ladder) { i++; continue; }
+      int before = NAG(w, side);
+      remove_order(b, w, side, ap, av, true, LOBSIM_REF_AGENT | id, true);
+      if (NAG(w, side) == before) agent_remove_at(b, w, side, i);
+    }
+  }
+  if (clearing && !w.dead) { // _get_inventory_clearing_market_order :260-266
+    int vol = (int)rint((double)absinv * c.market_order_fraction_of_inventory);
+    if (vol <= 0) w.err |= LOBSIM_ERR_BAD_VOLUME;
+    else submit_or_execute(b, w, w.inventory < 0 ? 0 : 1, 0, vol, 0, false, true);
+  }
+}
+
+// ---- agents, rl4mm/agents/baseline_agents.py -----------------------------------------------------------------------
+__device__ __forceinline__ double clamp_to_unit(double x) { const double eps = 0.00001; return fmax(fmin(x, 1 - eps), -1 + eps); }
+__device__ __forceinline__ void agent_action(const lobsim_agent_t& ag, double inventory_obs, double* a) {
+  if (ag.kind == LOBSIM_AGENT_FIXED) {
+#pragma unroll
+    for (int i = 0; i < 5; i++) a[i] = ag.fixed_action[i];
+  } else { // Teradactyl.get_action :76-87
+    double denom = ag.max_inventory > 0 ? ag.max_inventory : 100.0;
+    double wd = ag.default_omega, ob, oa;
+    double cu = clamp_to_unit(inventory_obs / denom);
+    if (inventory_obs >= 0) {
+      ob = wd * (1 + (1 / wd - 1) * pow(cu, ag.exponent));
+      oa = wd * (1 - pow(cu, ag.exponent));
+    } else {
+      ob = wd * (1 - pow(fabs(cu), ag.exponent));
+      oa = wd * (1 + (1 / wd - 1) * pow(fabs(cu), ag.exponent));
+    }
+    double kappa = (ag.max_kappa - ag.default_kappa) * pow(fabs(inventory_obs / ag.max_inventory), ag.exponent) + ag.default_kappa;
+    a[0] = (ob * (kappa - 2)) + 1; a[1] = (1 - ob) * (kappa - 2) + 1;
+    a[2] = (oa * (kappa - 2)) + 1; a[3] = (1 - oa) * (kappa - 2) + 1;
+    a[4] = ag.max_inventory * 2;
+  }
+}
+
+// ---- rewards, rl4mm/rewards/RewardFunctions.py:97-118 ----------------------------------------------------------------
+__device__ __forceinline__ double reward_calc(const lobsim_reward_t& r, double cash0, long long inv0, double p0, double cash1, long long inv1, double p1) {
+  double cur = cash0 + (double)inv0 * p0;
+  double nxt = cash1 + (double)inv1 * p1;
+  double pnl = nxt - cur;
+  if (r.kind == LOBSIM_REWARD_PNL) return pnl;
+  double delta = p1 - p0;
+  double term = r.inventory_aversion * (double)inv1 * delta;
+  if (r.asymmetric) term = term > 0.0 ? term : 0.0;
+  return pnl - term;
+}
+
+// ---- features, rl4mm/features/Features.py : one feature per lane ----------------------------------------------------
+struct StepView { // uniform inputs of the feature updates
+  int have_tops; int bb, bs, bv, sv;
+  double price; long long inventory; long long now_us;
+  int n_ext0, n_ext1, vol_ext0, vol_ext1, n_int0, n_int1, vol_int0, vol_int1;
+};
+
+// Feature._update of the concrete classes; `ring` is this (env, feature)'s circular buffer in global memory
+__device__ __forceinline__ void feature_update_raw(const lobsim_feature_t& fc, FeatState& f, double* ring, const StepView& v) {
+  const int k = fc.lookback;
+  switch (fc.kind) {
+    case LOBSIM_FEAT_SPREAD: f.cur = v.have_tops ? (double)(v.bs - v.bb) : NAN; break;
+    case LOBSIM_FEAT_BOOK_IMBALANCE: f.cur = v.have_tops ? (double)(v.bv - v.sv) / (double)(v.bv + v.sv) : NAN; break;
+    case LOBSIM_FEAT_PRICE: f.cur = v.price; break;
+    case LOBSIM_FEAT_INVENTORY: f.cur = (double)v.inventory; break;
+    case LOBSIM_FEAT_EPISODE_PROPORTION: f.cur += fc.dparam; break;
+    case LOBSIM_FEAT_TIME_OF_DAY: {
+      const long long min_time = 10LL * 3600 * 1000000, max_time = (15LL * 3600 + 1800) * 1000000;
+      long long tot = max_time - min_time, nb = fc.iparam;
+      long long bucket = tot / nb, rem = tot % nb;
+      if (2 * rem > nb || (2 * rem == nb && (bucket & 1))) bucket++;
+      long long d = v.now_us - min_time;
+      long long q = d >= 0 ? d / bucket : -((-d + bucket - 1) / bucket);
+      f.cur = (double)(q > 0 ? q : 0);
+      break;
+    }
+    case LOBSIM_FEAT_PRICE_MOVE:
+    case LOBSIM_FEAT_PRICE_RANGE: { // deque(maxlen=k+1).appendleft(price)
+      const int cap = k + 1;
+      ring[f.head] = v.price;
+      f.head = f.head + 1 == cap ? 0 : f.head + 1;
+      if (f.len < cap) f.len++;
+      if (fc.kind == LOBSIM_FEAT_PRICE_MOVE) {
+        double oldest = f.len < cap ? ring[0] : ring[f.head];
+        f.cur = v.price - oldest;
+      } else {
+        double mx = v.price, mn = v.price;
+        for (int i = 0; i < f.len; i++) { double x = ring[i]; mx = fmax(mx, x); mn = fmin(mn, x); }
+        f.cur = mx - mn;
+      }
+      break;
+    }
+    case LOBSIM_FEAT_VOLATILITY: {
+      const int cap = k + 1;
+      if (f.len < k) { ring[f.len++] = v.price; f.head = f.len == cap ? 0 : f.len; f.cur = 0.0; }
+      else if (f.len == k) {
+        ring[f.len++] = v.price; f.head = 0;
+        double s = 0.0, first = ring[0];
+        for (int i = 0; i < k; i++) { double r = (ring[i + 1] - ring[i]) / first; s += r * r; }
+        f.cur = s / (double)k;
+      } else {
+        int h = f.head, h1 = h + 1 == cap ? 0 : h + 1, hn = h == 0 ? cap - 1 : h - 1;
+        double oldest = ring[h], second = ring[h1], newest = ring[hn];
+        double oldest_ret = (second - oldest) / oldest;
+        double new_ret = (v.price - newest) / newest;
+        ring[h] = v.price; f.head = h1;
+        double ss = f.cur * (double)k - oldest_ret * oldest_ret + new_ret * new_ret;
+        f.cur = ss / (double)k;
+      }
+      break;
+    }
+    case LOBSIM_FEAT_TRADE_DIR_IMBALANCE:
+    case LOBSIM_FEAT_TRADE_VOL_IMBALANCE: {
+      int nb, ns;
+      if (fc.kind == LOBSIM_FEAT_TRADE_DIR_IMBALANCE) { nb = v.n_ext0; ns = v.n_ext1; if (fc.iparam) { nb += v.n_int0; ns += v.n_int1; } }
+      else { nb = v.vol_ext0; ns = v.vol_ext1; if (fc.iparam) { nb += v.vol_int0; ns += v.vol_int1; } }
+      int2* pr = reinterpret_cast<int2*>(ring);
+      int len = f.len & ~FEAT_SUMS_VALID;
+      if (len < k) {
+        pr[len] = make_int2(nb, ns);
+        f.len = (f.len & FEAT_SUMS_VALID) | (len + 1);
+        f.head = len + 1 == k ? 0 : len + 1;
+        f.cur = 0.0;
+      } else {
+        int h = f.head;
+        int2 old = pr[h];
+        pr[h] = make_int2(nb, ns);
+        f.head = h + 1 == k ? 0 : h + 1;
+        if (f.total == 0) {
+          if (f.len & FEAT_SUMS_VALID) { f.total = (long long)nb + ns; f.diff = (long long)nb - ns; } // window was all zero
+          else {
+            long long sb = 0, ss = 0;
+            for (int i = 0; i < k; i++) { int2 e = pr[i]; sb += e.x; ss += e.y; }
+            f.total = sb + ss; f.diff = sb - ss; f.len |= FEAT_SUMS_VALID;
+          }
+        } else {
+          f.total -= (long long)old.x + old.y; f.total += (long long)nb + ns;
+          f.diff -= (long long)old.x - old.y; f.diff += (long long)nb - ns;
+        }
+        f.cur = f.total != 0 ? (double)f.diff / (double)f.total : 0.5;
+      }
+      break;
+    }
+    default: break;
+  }
+}
+
+// Feature.reset/_reset, Features.py:92-96
+__device__ __forceinline__ void feature_reset(const lobsim_feature_t& fc, FeatState& f, double* ring, const StepView& v) {
+  f.len = 0; f.head = 0; f.total = 0; f.diff = 0;
+  feature_update_raw(fc, f, ring, v);
+  if (fc.kind == LOBSIM_FEAT_EPISODE_PROPORTION) f.cur = 0.0;
+}
+
+// Feature.update, Features.py:80-86,102-105
+__device__ __forceinline__ void feature_update(const lobsim_feature_t& fc, FeatState& f, double* ring, const StepView& v, long long episode_start_us) {
+  long long first_usage = episode_start_us - (long long)fc.lookback * fc.update_us;
+  if (v.now_us < first_usage) return;
+  if ((v.now_us % 60000000LL) % fc.update_us != 0) return;
+  feature_update_raw(fc, f, ring, v);
+  f.cur = fmax(fmin(f.cur, fc.max_value), fc.min_value);
+}

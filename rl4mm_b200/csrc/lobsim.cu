@@ -1,0 +1,784 @@
+// lobsim.cu -- kernels and the C ABI (include/lobsim.h) of the B200-native LOB simulation step.
+//
+// Kernel design:
+//   * one warp per book; a CTA is `warps_per_cta` independent warps, no block-level synchronisation at all;
+//   * the book blob lives in shared memory for the whole launch: HBM -> smem by one TMA bulk copy
+//     (cp.async.bulk + mbarrier) at the start, smem -> HBM by one bulk store at the end;
+//   * historical messages are streamed by TMA bulk copies of 512-byte tiles (32 x 16 B records) into a per-warp
+//     double buffer, prefetched one tile ahead; all 32 lanes read a record with one broadcast LDS.128;
+//   * book operations are warp-collective (ballot / popc / ffs level and order search, <=32-entry shifts);
+//   * features run one per lane, the reward and the rollout tensors are written straight from the kernel.
+// fp64 everywhere the reference uses Python floats, compiled with --fmad=false (no FMA contraction).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "env.cuh"
+#include "lobsim.h"
+
+// ====================================================================================================================
+//  PTX helpers: mbarrier + TMA bulk copies (sm_90+; SASS: UBLKCP / SYNCS)
+// ====================================================================================================================
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ void tma_load(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tma_store(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+// ====================================================================================================================
+//  kernel parameters
+// ====================================================================================================================
+#define MSG_TILE 32                      // records per TMA tile
+#define MSG_TILE_BYTES (MSG_TILE * 16)
+
+struct AdvParams {
+  unsigned char* blobs;             // [n_envs][blob_bytes]
+  FeatState* fstate;                // [n_envs][LOBSIM_MAX_FEATURES]
+  double* rings;                    // [n_envs][ring_stride]
+  const lobsim_stream_t* streams;   // device array [n_streams]
+  int32_t n_streams;
+  lobsim_fill_t* fill_log;          // [n_envs][fill_cap] or null
+  int32_t* fill_count;              // [n_envs]
+  int32_t fill_cap;
+  int32_t n_envs;                   // total envs of the handle
+  int32_t n_sel;                    // number of envs this launch works on
+  const int32_t* env_ids;           // [n_sel] or null (identity)
+  int32_t T;                        // simulation steps to run
+  int32_t reset_mode;               // 0 none, 1 book reset only, 2 full env reset (+ warm-up of T steps)
+  const int32_t* reset_stream_ids;  // [n_sel]
+  const int32_t* reset_steps;       // [n_sel]: book reset: start step; env reset: episode start step
+  int32_t agent_kind;               // LOBSIM_AGENT_*
+  int32_t out_final_obs_only;       // reset: write obs once, after the warm-up
+  const double* actions_in;         // EXTERNAL: [T][n_sel][action_dim]
+  double* obs; double* act; double* rew; uint8_t* done; // [T][n_sel][...] (any may be null)
+  lobsim_agent_t agent;
+  Layout L;
+  int32_t warp_smem;                // bytes of shared memory per warp
+};
+
+__device__ __forceinline__ unsigned char* warp_smem_base(unsigned char* smem, int warp, int warp_smem) { return smem + (size_t)warp * warp_smem; }
+
+// ====================================================================================================================
+//  the advance kernel: [reset] + T x ([agent orders] + messages of the step + [resync] + [features, reward])
+// ====================================================================================================================
+template <bool kEnv>
+__global__ void __launch_bounds__(128) k_advance(const __grid_constant__ AdvParams p, const __grid_constant__ EnvConst ec) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sel = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (sel >= p.n_sel) return;
+  const int env = p.env_ids ? p.env_ids[sel] : sel;
+  const lobsim_cfg_t& c = ec.cfg;
+
+  unsigned char* base = warp_smem_base(smem, warp, p.warp_smem);
+  Book b; b.blob = base; b.L = p.L; b.lane = lane;
+  unsigned char* msgbuf = base + p.L.blob_bytes;                                   // 2 x 512 B
+  int2* scratch = reinterpret_cast<int2*>(msgbuf + 2 * MSG_TILE_BYTES);             // [2*NA]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(scratch) + 2 * p.L.NA * 8); // 3 barriers
+  unsigned char* gblob = p.blobs + (size_t)env * p.L.blob_bytes;
+
+  // ---- book blob: HBM -> shared memory ---------------------------------------------------------------------------
+  if (lane == 0) {
+    mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
+    fence_mbar_init();
+    mbar_expect_tx(&bars[2], (uint32_t)p.L.blob_bytes);
+    tma_load(base, gblob, (uint32_t)p.L.blob_bytes, &bars[2]);
+  }
+  __syncwarp();
+  mbar_wait(&bars[2], 0);
+
+  WarpState w;
+  load_state(b, w);
+  w.fill_log = p.fill_log ? p.fill_log + (size_t)env * p.fill_cap : nullptr;
+  w.fill_cap = p.fill_cap; w.n_fills = 0;
+  BookHdr* h = b.hdr();
+  FeatState fs; double* ring = nullptr;
+  lobsim_feature_t fc;
+  const int F = c.n_features;
+
+  // ---- reset prologue ----------------------------------------------------------------------------------------------
+  int stream_id = h->stream_id;
+  if (p.reset_mode) {
+    stream_id = p.reset_stream_ids[sel];
+    int start = p.reset_steps[sel] - (p.reset_mode == 2 ? c.warmup_steps : 0);
+    if (stream_id < 0 || stream_id >= p.n_streams) { stream_id = 0; start = -1; }
+    init_book_from_snapshot(b, w, c, p.streams[stream_id], stream_id, start);
+    if (p.reset_mode == 2 && lane == 0) {
+      h->episode_start_step = p.reset_steps[sel];
+      if (!c.portfolio_carryover || !h->has_reset) { h->inventory = c.initial_inventory; h->cash = c.initial_cash; }
+      h->has_reset = 1;
+    }
+    __syncwarp();
+    w.inventory = h->inventory; w.cash = h->cash;
+  }
+  const lobsim_stream_t st = p.streams[stream_id];
+  int now_step = h->now_step;
+  const long long episode_start_us = st.t0_us + (long long)h->episode_start_step * c.step_us;
+
+  if (kEnv) {
+    if (lane < F) {
+      fc = c.features[lane];
+      ring = p.rings + (size_t)env * ec.ring_stride + ec.ring_off[lane];
+      fs = p.fstate[(size_t)env * LOBSIM_MAX_FEATURES + lane];
+    }
+  }
+
+  // price / tops of the current book
+  auto tops = [&](StepView& v) {
+    v.have_tops = w.nlv0 > 0 && w.nlv1 > 0;
+    if (v.have_tops) {
+      v.bb = b.lvp(0)[w.nlv0 - 1]; v.bs = b.lvp(1)[w.nlv1 - 1];
+      v.bv = best_level_volume(b, 0, w.nlv0); v.sv = best_level_volume(b, 1, w.nlv1);
+      double imb; v.price = microprice(v.bb, v.bs, v.bv, v.sv, imb);
+    } else { v.bb = v.bs = v.bv = v.sv = 0; v.price = NAN; }
+  };
+
+  double price = h->price;
+  if (kEnv && p.reset_mode == 2) { // State(...) + _reset_features, HOE.py:152-154,218-221
+    StepView v; tops(v);
+    v.inventory = w.inventory; v.now_us = now_us_of(st, c, now_step);
+    v.n_ext0 = v.n_ext1 = v.vol_ext0 = v.vol_ext1 = v.n_int0 = v.n_int1 = v.vol_int0 = v.vol_int1 = 0;
+    price = v.price;
+    if (lane < F) feature_reset(fc, fs, ring, v);
+  }
+
+  // ---- message pipeline ----------------------------------------------------------------------------------------------
+  const int T = p.T;
+  const bool in_grid = now_step >= 0 && (long long)now_step + T <= (long long)st.n_grid_steps;
+  if (!in_grid && !w.dead && T > 0) { w.err |= LOBSIM_ERR_END_OF_STREAM; w.dead = 1; }
+  unsigned g = 0, g_end_all = 0;
+  if (!w.dead && T > 0) { g = __ldg(&st.step_off[now_step]); g_end_all = __ldg(&st.step_off[now_step + T]); }
+  const unsigned n_msgs_total = (unsigned)st.n_msgs;
+  uint32_t par0 = 0, par1 = 0;     // phase parity of the two tile barriers
+  unsigned next_issue = g / MSG_TILE, next_wait = g / MSG_TILE; // tiles are issued and consumed in order
+  auto issue_tile = [&]() { // uniform; lane 0 talks to the TMA unit
+    const unsigned tile = next_issue, first = tile * MSG_TILE;
+    if (first >= g_end_all) return;
+    if (lane == 0) {
+      unsigned cnt = n_msgs_total - first < MSG_TILE ? n_msgs_total - first : MSG_TILE;
+      uint64_t* bar = &bars[tile & 1];
+      mbar_expect_tx(bar, cnt * 16);
+      tma_load(msgbuf + (tile & 1) * MSG_TILE_BYTES, st.msgs + first, cnt * 16, bar);
+    }
+    next_issue = tile + 1;
+  };
+  auto wait_tile = [&]() { // wait for tile `next_wait`
+    if (next_wait & 1) { mbar_wait(&bars[1], par1); par1 ^= 1; } else { mbar_wait(&bars[0], par0); par0 ^= 1; }
+    next_wait++;
+  };
+  if (g < g_end_all) { issue_tile(); issue_tile(); }
+  __syncwarp();
+
+  double action[5] = {0, 0, 0, 0, 0};
+  for (int t = 0; t < T; t++) {
+    // ---- agent: obs -> action -> orders (processed before the step's history, OrderbookSimulator.py:76-77) -------
+    double cash0 = w.cash, p0 = price; long long inv0 = w.inventory;
+    if (kEnv) {
+      reset_flow(w);
+      if (p.agent_kind != LOBSIM_AGENT_NONE) {
+        if (p.agent_kind == LOBSIM_AGENT_EXTERNAL) {
+          const double* a = p.actions_in + ((size_t)t * p.n_sel + sel) * ec.action_dim;
+#pragma unroll
+          for (int i = 0; i < 5; i++) if (i < ec.action_dim) action[i] = __ldg(&a[i]);
+        } else {
+          double inv_obs = __shfl_sync(FULL_MASK, fs.cur, p.agent.inventory_index & 31);
+          agent_action(p.agent, inv_obs, action);
+        }
+        if (p.act && p.agent_kind != LOBSIM_AGENT_EXTERNAL && lane < ec.action_dim) p.act[((size_t)t * p.n_sel + sel) * ec.action_dim + lane] = pick5(action, lane);
+        agent_orders(b, w, ec, action);
+      }
+    }
+    // ---- historical messages of (now, now + step] ------------------------------------------------------------------
+    if (!w.dead) {
+      const unsigned g_step_end = __ldg(&st.step_off[now_step + 1]);
+      while (g < g_step_end) {
+        const unsigned tile = g / MSG_TILE;
+        if (tile == next_wait) wait_tile();
+        const uint4 m = *reinterpret_cast<const uint4*>(msgbuf + (tile & 1) * MSG_TILE_BYTES + (g % MSG_TILE) * 16);
+        process_message(b, w, (int)m.x, (int)m.y, m.z, m.w);
+        g++;
+        if (g % MSG_TILE == 0) { // tile consumed: refill its buffer with the tile after the next one
+          __syncwarp();
+          issue_tile();
+        }
+        if (w.dead) break;
+      }
+    }
+    if (!w.dead) {
+      now_step++;
+      // ---- resync, OrderbookSimulator.py:86-87 ----------------------------------------------------------------------
+      if (c.resync) {
+        long long rel = (long long)now_step * c.step_us;
+        if (rel % 1000000 == 0 && near_exiting(b, w, c)) {
+          long long sec = rel / 1000000;
+          if (sec <= (long long)st.n_seconds && st.snap_valid[sec]) update_outer_levels(b, w, c, st.snapshots + (size_t)sec * 2 * c.n_levels * 2, scratch);
+        }
+      }
+    }
+    if (kEnv) {
+      // ---- update_internal_state + _update_features + reward, HOE.py:163-178,199-204 -------------------------------
+      StepView v; tops(v);
+      if (!v.have_tops) w.err |= LOBSIM_ERR_EMPTY_BOOK;
+      price = v.price;
+      v.inventory = w.inventory; v.now_us = now_us_of(st, c, now_step);
+      v.n_ext0 = w.n_ext0; v.n_ext1 = w.n_ext1; v.vol_ext0 = w.vol_ext0; v.vol_ext1 = w.vol_ext1;
+      v.n_int0 = w.n_int0; v.n_int1 = w.n_int1; v.vol_int0 = w.vol_int0; v.vol_int1 = w.vol_int1;
+      if (lane < F) feature_update(fc, fs, ring, v, episode_start_us);
+      const bool write_now = !p.out_final_obs_only || t == T - 1;
+      if (p.obs && write_now) {
+        double* o = p.obs + ((size_t)(p.out_final_obs_only ? 0 : t) * p.n_sel + sel) * ec.obs_dim;
+        if (lane < F) o[lane] = fs.cur;
+        if (c.inc_prev_action_in_obs && lane < ec.action_dim) {
+          o[F + lane] = p.agent_kind == LOBSIM_AGENT_NONE ? 0.0 : pick5(action, lane);
+        }
+      }
+      if (p.agent_kind != LOBSIM_AGENT_NONE) {
+        double r = reward_calc(c.step_reward, cash0, inv0, p0, w.cash, w.inventory, price);
+        bool d = now_step >= h->episode_start_step + c.episode_steps; // terminal_time - now < step/2, HOE.py:172
+        if (d) r = reward_calc(c.terminal_reward, cash0, inv0, p0, w.cash, w.inventory, price);
+        if (lane == 0) {
+          if (p.rew) p.rew[(size_t)t * p.n_sel + sel] = r;
+          if (p.done) p.done[(size_t)t * p.n_sel + sel] = d ? 1 : 0;
+        }
+      }
+    }
+  }
+  if (kEnv && T == 0 && p.obs && p.reset_mode == 2) { // reset with no warm-up: obs straight after _reset_features
+    double* o = p.obs + (size_t)sel * ec.obs_dim;
+    if (lane < F) o[lane] = fs.cur;
+    if (c.inc_prev_action_in_obs && lane < ec.action_dim) o[F + lane] = 0.0;
+  }
+
+  while (next_wait < next_issue) wait_tile(); // drain TMA loads still in flight (only after an aborted episode)
+
+  // ---- write back ----------------------------------------------------------------------------------------------------
+  if (kEnv && lane < F) p.fstate[(size_t)env * LOBSIM_MAX_FEATURES + lane] = fs;
+  if (lane == 0) {
+    h->now_step = now_step;
+    h->price = price;
+    if (p.fill_count) p.fill_count[env] = w.n_fills;
+  }
+  store_state(b, w);
+  fence_proxy_async();
+  __syncwarp();
+  if (lane == 0) { tma_store(gblob, base, (uint32_t)p.L.blob_bytes); tma_store_wait(); }
+  __syncwarp();
+}
+
+// ====================================================================================================================
+//  Exchange.process_order for a list of orders (drop-in / test entry point; one warp, sequential)
+// ====================================================================================================================
+struct OrdParams {
+  unsigned char* blobs; Layout L; int32_t n_envs;
+  const lobsim_order_t* orders; int32_t n;
+  lobsim_fill_t* fills; int32_t max_fills; int32_t* n_fills; uint32_t* refs_out;
+};
+
+__global__ void __launch_bounds__(32) k_process_orders(const __grid_constant__ OrdParams p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int lane = threadIdx.x;
+  Book b; b.blob = smem; b.L = p.L; b.lane = lane;
+  WarpState w;
+  int cur_env = -1, total_fills = 0;
+  auto load_env = [&](int env) {
+    const uint4* src = reinterpret_cast<const uint4*>(p.blobs + (size_t)env * p.L.blob_bytes);
+    uint4* dst = reinterpret_cast<uint4*>(smem);
+    for (int i = lane; i < p.L.blob_bytes / 16; i += 32) dst[i] = src[i];
+    __syncwarp();
+    load_state(b, w);
+    w.fill_log = p.fills ? p.fills + total_fills : nullptr;
+    w.fill_cap = p.max_fills - total_fills; w.n_fills = 0;
+  };
+  auto store_env = [&](int env) {
+    store_state(b, w);
+    uint4* dst = reinterpret_cast<uint4*>(p.blobs + (size_t)env * p.L.blob_bytes);
+    const uint4* src = reinterpret_cast<const uint4*>(smem);
+    for (int i = lane; i < p.L.blob_bytes / 16; i += 32) dst[i] = src[i];
+    __syncwarp();
+    total_fills += w.n_fills < w.fill_cap ? w.n_fills : w.fill_cap;
+  };
+  for (int k = 0; k < p.n; k++) {
+    const lobsim_order_t o = p.orders[k];
+    if (o.env < 0 || o.env >= p.n_envs) continue;
+    if (o.env != cur_env) { if (cur_env >= 0) store_env(cur_env); load_env(o.env); cur_env = o.env; }
+    uint32_t id = 0;
+    const bool is_agent = !o.is_external;
+    const bool has_vol = !((o.type == LOBSIM_MSG_DELETE || o.type == LOBSIM_MSG_CANCEL) && o.volume <= 0);
+    if (!w.dead) {
+      if (has_vol && o.volume <= 0) w.err |= LOBSIM_ERR_BAD_VOLUME;
+      else if (o.type == LOBSIM_MSG_LIMIT) id = submit_or_execute(b, w, o.direction, o.price, o.volume, is_agent ? 0u : o.ref, true, is_agent);
+      else if (o.type == LOBSIM_MSG_MARKET) id = submit_or_execute(b, w, o.direction, 0, o.volume, is_agent ? 0u : o.ref, false, is_agent);
+      else remove_order(b, w, o.direction, o.price, o.volume, has_vol, is_agent ? (LOBSIM_REF_AGENT | (o.ref & 0x7fffffffu)) : o.ref, is_agent);
+    }
+    if (p.refs_out && lane == 0) p.refs_out[k] = id;
+  }
+  if (cur_env >= 0) store_env(cur_env);
+  if (lane == 0 && p.n_fills) *p.n_fills = total_fills;
+}
+
+// ====================================================================================================================
+//  per-env state summary (one thread per env, reads the blob in HBM)
+// ====================================================================================================================
+__global__ void k_get_state(const unsigned char* blobs, Layout L, int first, int n, lobsim_env_state_t* out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned char* blob = blobs + (size_t)(first + i) * L.blob_bytes;
+  const BookHdr* h = reinterpret_cast<const BookHdr*>(blob);
+  lobsim_env_state_t s;
+  s.inventory = h->inventory; s.cash = h->cash; s.price = h->price; s.now_step = h->now_step;
+  s.episode_start_step = h->episode_start_step; s.min_buy_price = h->min_buy; s.max_sell_price = h->max_sell;
+  s.err = h->err; s.stream_id = h->stream_id; s.n_agent_orders[0] = h->nag[0]; s.n_agent_orders[1] = h->nag[1];
+  s.next_agent_id = h->next_agent_id; s.reserved = 0;
+  int best[2] = {0, INT32_MAX}, bvol[2] = {0, 0};
+  for (int side = 0; side < 2; side++) {
+    int nlv = h->nlv[side];
+    if (!nlv) continue;
+    const unsigned char* sb = blob + L.side_off + side * L.side_stride;
+    const int32_t* lvp = reinterpret_cast<const int32_t*>(sb);
+    const uint16_t* lvend = reinterpret_cast<const uint16_t*>(sb + L.lvend_off);
+    const uint2* ord = reinterpret_cast<const uint2*>(sb + L.ord_off);
+    best[side] = lvp[nlv - 1];
+    int start = nlv > 1 ? lvend[nlv - 2] : 0, end = lvend[nlv - 1], v = 0;
+    for (int k = start; k < end; k++) v += (int)ord[k].x;
+    bvol[side] = v;
+  }
+  s.best_buy = best[0]; s.best_sell = best[1]; s.best_buy_volume = bvol[0]; s.best_sell_volume = bvol[1];
+  out[i] = s;
+}
+
+__global__ void k_init_blobs(unsigned char* blobs, Layout L, int n, long long inventory, double cash) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  BookHdr* h = reinterpret_cast<BookHdr*>(blobs + (size_t)i * L.blob_bytes);
+  memset(h, 0, sizeof(BookHdr));
+  h->next_agent_id = 1; h->inventory = inventory; h->cash = cash; h->stream_id = 0;
+}
+
+// ====================================================================================================================
+//  host side: handle + C ABI
+// ====================================================================================================================
+static thread_local std::string g_last_error;
+static int fail(int code, const std::string& msg) { g_last_error = msg; return code; }
+#define CUDA_TRY(expr)                                                                                             \
+  do {                                                                                                             \
+    cudaError_t e__ = (expr);                                                                                      \
+    if (e__ != cudaSuccess) return fail(LOBSIM_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));       \
+  } while (0)
+
+struct lobsim {
+  lobsim_cfg_t cfg;
+  EnvConst ec;
+  Layout L;
+  int device;
+  int warps_per_cta;
+  int warp_smem;
+  unsigned char* blobs = nullptr;
+  FeatState* fstate = nullptr;
+  double* rings = nullptr;
+  lobsim_fill_t* fill_log = nullptr;
+  int32_t* fill_count = nullptr;
+  std::vector<lobsim_stream_t> streams;
+  lobsim_stream_t* streams_dev = nullptr;
+  int streams_cap = 0;
+  // staging for the *_host entry points
+  double* st_actions = nullptr; double* st_obs = nullptr; double* st_rew = nullptr; uint8_t* st_done = nullptr;
+  lobsim_env_state_t* st_state = nullptr;
+  lobsim_msg_t* st_msgs = nullptr; uint64_t st_msgs_cap = 0;
+  bool has_reset = false;
+  int64_t launches = 0;
+};
+
+extern "C" {
+
+const char* lobsim_last_error(void) { return g_last_error.c_str(); }
+int lobsim_abi_version(void) { return LOBSIM_ABI_VERSION; }
+int lobsim_action_dim(const lobsim_cfg_t* c) { return (c->concentration >= 0 ? 2 : 4) + (c->market_order_clearing ? 1 : 0); }
+int lobsim_obs_dim(const lobsim_cfg_t* c) { return c->n_features + (c->inc_prev_action_in_obs ? lobsim_action_dim(c) : 0); }
+
+static int validate_cfg(const lobsim_cfg_t* c) {
+  if (!c) return fail(LOBSIM_E_INVALID, "cfg is null");
+  if (c->abi_version != LOBSIM_ABI_VERSION) return fail(LOBSIM_E_INVALID, "abi_version mismatch");
+  if (c->n_envs <= 0 || c->n_levels <= 0 || c->tick_size <= 0 || c->step_us <= 0) return fail(LOBSIM_E_INVALID, "n_envs, n_levels, tick_size, step_us must be positive");
+  if (1000000 % c->step_us) return fail(LOBSIM_E_INVALID, "step_us must divide one second");
+  int Q = c->max_quote_level - c->min_quote_level;
+  if (Q <= 0 || Q > 32) return fail(LOBSIM_E_INVALID, "1 <= max_quote_level - min_quote_level <= 32");
+  if (c->n_features < 0 || c->n_features > LOBSIM_MAX_FEATURES) return fail(LOBSIM_E_INVALID, "too many features");
+  if (c->max_levels_per_side < 4 || c->max_levels_per_side % 4 || c->max_levels_per_side > 4096) return fail(LOBSIM_E_INVALID, "max_levels_per_side must be a multiple of 4 in [4, 4096]");
+  if (c->max_orders_per_side < c->max_levels_per_side || c->max_orders_per_side > 65535) return fail(LOBSIM_E_INVALID, "max_orders_per_side must be in [max_levels_per_side, 65535]");
+  if (c->max_agent_orders < 1 || c->max_agent_orders > 1024) return fail(LOBSIM_E_INVALID, "max_agent_orders must be in [1, 1024]");
+  if (c->n_levels > c->max_levels_per_side) return fail(LOBSIM_E_INVALID, "n_levels exceeds max_levels_per_side");
+  if (c->warmup_steps < 0 || c->episode_steps <= 0) return fail(LOBSIM_E_INVALID, "bad episode_steps / warmup_steps");
+  for (int i = 0; i < c->n_features; i++) {
+    const lobsim_feature_t& f = c->features[i];
+    if (f.kind < 0 || f.kind > LOBSIM_FEAT_TIME_OF_DAY) return fail(LOBSIM_E_INVALID, "unknown feature kind");
+    if (f.update_us <= 0 || f.update_us > 60000000 || f.lookback < 0) return fail(LOBSIM_E_INVALID, "bad feature update_us / lookback");
+    if (f.kind == LOBSIM_FEAT_TIME_OF_DAY && f.iparam <= 0) return fail(LOBSIM_E_INVALID, "TIME_OF_DAY needs n_buckets > 0");
+    if ((f.kind == LOBSIM_FEAT_VOLATILITY || f.kind == LOBSIM_FEAT_TRADE_DIR_IMBALANCE || f.kind == LOBSIM_FEAT_TRADE_VOL_IMBALANCE) && f.lookback < 1)
+      return fail(LOBSIM_E_INVALID, "windowed feature needs lookback >= 1");
+  }
+  return LOBSIM_OK;
+}
+
+int64_t lobsim_state_bytes(const lobsim_cfg_t* c) {
+  if (validate_cfg(c)) return LOBSIM_E_INVALID;
+  return make_layout(c->max_levels_per_side, c->max_orders_per_side, c->max_agent_orders).blob_bytes;
+}
+
+static int warp_smem_bytes(const Layout& L) { return (L.blob_bytes + 2 * MSG_TILE_BYTES + 2 * L.NA * 8 + 32 + 127) & ~127; }
+
+int lobsim_create(const lobsim_cfg_t* cfg, int device, lobsim_t** out) {
+  if (!out) return fail(LOBSIM_E_INVALID, "out is null");
+  int rc = validate_cfg(cfg);
+  if (rc) return rc;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(LOBSIM_E_CUDA, "no CUDA device: the lobsim hot path has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(LOBSIM_E_INVALID, "bad device index");
+  CUDA_TRY(cudaSetDevice(device));
+  lobsim* h = new (std::nothrow) lobsim();
+  if (!h) return fail(LOBSIM_E_NOMEM, "out of host memory");
+  h->cfg = *cfg; h->device = device;
+  h->L = make_layout(cfg->max_levels_per_side, cfg->max_orders_per_side, cfg->max_agent_orders);
+  h->warp_smem = warp_smem_bytes(h->L);
+  int max_smem = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  if (h->warp_smem > max_smem) { delete h; return fail(LOBSIM_E_INVALID, "book capacities exceed the shared memory of one SM"); }
+  h->warps_per_cta = 4;
+  while (h->warps_per_cta > 1 && h->warps_per_cta * h->warp_smem > max_smem) h->warps_per_cta >>= 1;
+  CUDA_TRY(cudaFuncSetAttribute(k_advance<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->warps_per_cta * h->warp_smem));
+  CUDA_TRY(cudaFuncSetAttribute(k_advance<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->warps_per_cta * h->warp_smem));
+  CUDA_TRY(cudaFuncSetAttribute(k_process_orders, cudaFuncAttributeMaxDynamicSharedMemorySize, h->L.blob_bytes));
+  // feature rings
+  memset(&h->ec, 0, sizeof h->ec);
+  h->ec.cfg = *cfg;
+  int slots = 0;
+  for (int i = 0; i < cfg->n_features; i++) { h->ec.ring_off[i] = slots; slots += cfg->features[i].lookback + 2; }
+  h->ec.ring_stride = (slots + 1) & ~1;
+  h->ec.action_dim = lobsim_action_dim(cfg); h->ec.obs_dim = lobsim_obs_dim(cfg);
+  const size_t n = (size_t)cfg->n_envs;
+  CUDA_TRY(cudaMalloc(&h->blobs, n * h->L.blob_bytes));
+  CUDA_TRY(cudaMalloc(&h->fstate, n * LOBSIM_MAX_FEATURES * sizeof(FeatState)));
+  CUDA_TRY(cudaMemset(h->fstate, 0, n * LOBSIM_MAX_FEATURES * sizeof(FeatState)));
+  CUDA_TRY(cudaMalloc(&h->rings, n * (size_t)(h->ec.ring_stride > 0 ? h->ec.ring_stride : 2) * sizeof(double)));
+  CUDA_TRY(cudaMemset(h->blobs, 0, n * h->L.blob_bytes));
+  if (cfg->fill_log_capacity > 0) {
+    CUDA_TRY(cudaMalloc(&h->fill_log, n * (size_t)cfg->fill_log_capacity * sizeof(lobsim_fill_t)));
+    CUDA_TRY(cudaMalloc(&h->fill_count, n * sizeof(int32_t)));
+    CUDA_TRY(cudaMemset(h->fill_count, 0, n * sizeof(int32_t)));
+  }
+  k_init_blobs<<<(cfg->n_envs + 127) / 128, 128>>>(h->blobs, h->L, cfg->n_envs, cfg->initial_inventory, cfg->initial_cash);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaDeviceSynchronize());
+  h->launches++;
+  *out = h;
+  return LOBSIM_OK;
+}
+
+int lobsim_destroy(lobsim_t* h) {
+  if (!h) return LOBSIM_OK;
+  cudaSetDevice(h->device);
+  cudaFree(h->blobs); cudaFree(h->fstate); cudaFree(h->rings); cudaFree(h->fill_log); cudaFree(h->fill_count);
+  cudaFree(h->streams_dev); cudaFree(h->st_actions); cudaFree(h->st_obs); cudaFree(h->st_rew); cudaFree(h->st_done);
+  cudaFree(h->st_state); cudaFree(h->st_msgs);
+  delete h;
+  return LOBSIM_OK;
+}
+
+int lobsim_load_stream(lobsim_t* h, int stream_id, const lobsim_stream_t* s) {
+  if (!h || !s) return fail(LOBSIM_E_INVALID, "null argument");
+  if (stream_id < 0 || stream_id > 65535) return fail(LOBSIM_E_INVALID, "bad stream id");
+  if (!s->step_off || !s->snapshots || !s->snap_valid || (!s->msgs && s->n_msgs)) return fail(LOBSIM_E_INVALID, "stream arrays missing");
+  if (s->t0_us % 1000000) return fail(LOBSIM_E_INVALID, "t0_us must be a whole second");
+  if (s->n_msgs >= 0xffffffffull) return fail(LOBSIM_E_INVALID, "more than 2^32-1 messages in one stream");
+  if (((uintptr_t)s->msgs & 15) != 0) return fail(LOBSIM_E_INVALID, "msgs must be 16-byte aligned");
+  CUDA_TRY(cudaSetDevice(h->device));
+  if ((int)h->streams.size() <= stream_id) {
+    lobsim_stream_t empty; memset(&empty, 0, sizeof empty);
+    h->streams.resize(stream_id + 1, empty);
+  }
+  h->streams[stream_id] = *s;
+  if (h->streams_cap < (int)h->streams.size()) {
+    CUDA_TRY(cudaDeviceSynchronize());
+    cudaFree(h->streams_dev);
+    h->streams_cap = (int)h->streams.size() * 2;
+    CUDA_TRY(cudaMalloc(&h->streams_dev, h->streams_cap * sizeof(lobsim_stream_t)));
+  }
+  CUDA_TRY(cudaMemcpy(h->streams_dev, h->streams.data(), h->streams.size() * sizeof(lobsim_stream_t), cudaMemcpyHostToDevice));
+  return LOBSIM_OK;
+}
+
+static void base_params(lobsim* h, AdvParams& p) {
+  memset(&p, 0, sizeof p);
+  p.blobs = h->blobs; p.fstate = h->fstate; p.rings = h->rings; p.streams = h->streams_dev; p.n_streams = (int)h->streams.size();
+  p.fill_log = h->fill_log; p.fill_count = h->fill_count; p.fill_cap = h->cfg.fill_log_capacity;
+  p.n_envs = h->cfg.n_envs; p.n_sel = h->cfg.n_envs; p.L = h->L; p.warp_smem = h->warp_smem;
+}
+
+} // extern "C"
+
+template <bool kEnv>
+static int launch_advance(lobsim* h, const AdvParams& p, cudaStream_t stream) {
+  if (h->streams.empty()) return fail(LOBSIM_E_STATE, "no stream loaded");
+  CUDA_TRY(cudaSetDevice(h->device));
+  int wpc = h->warps_per_cta;
+  int grid = (p.n_sel + wpc - 1) / wpc;
+  if (grid <= 0) return LOBSIM_OK;
+  k_advance<kEnv><<<grid, wpc * 32, (size_t)wpc * h->warp_smem, stream>>>(p, h->ec);
+  CUDA_TRY(cudaGetLastError());
+  h->launches++;
+  return LOBSIM_OK;
+}
+
+extern "C" {
+
+int lobsim_reset_book(lobsim_t* h, const int32_t* env_ids, int32_t n, const int32_t* stream_ids, const int32_t* start_steps, void* stream) {
+  if (!h || !stream_ids || !start_steps) return fail(LOBSIM_E_INVALID, "null argument");
+  AdvParams p; base_params(h, p);
+  p.env_ids = env_ids; p.n_sel = env_ids ? n : h->cfg.n_envs;
+  p.T = 0; p.reset_mode = 1; p.reset_stream_ids = stream_ids; p.reset_steps = start_steps; p.agent_kind = LOBSIM_AGENT_NONE;
+  return launch_advance<false>(h, p, (cudaStream_t)stream);
+}
+
+int lobsim_reset(lobsim_t* h, const int32_t* env_ids, int32_t n, const int32_t* stream_ids, const int32_t* episode_start_steps, double* obs_out, void* stream) {
+  if (!h || !stream_ids || !episode_start_steps) return fail(LOBSIM_E_INVALID, "null argument");
+  AdvParams p; base_params(h, p);
+  p.env_ids = env_ids; p.n_sel = env_ids ? n : h->cfg.n_envs;
+  p.T = h->cfg.warmup_steps; p.reset_mode = 2; p.reset_stream_ids = stream_ids; p.reset_steps = episode_start_steps;
+  p.agent_kind = LOBSIM_AGENT_NONE; p.obs = obs_out; p.out_final_obs_only = 1;
+  h->has_reset = true;
+  return launch_advance<true>(h, p, (cudaStream_t)stream);
+}
+
+int lobsim_step(lobsim_t* h, const double* actions, double* obs_out, double* reward_out, uint8_t* done_out, void* stream) {
+  if (!h || !actions) return fail(LOBSIM_E_INVALID, "null argument");
+  if (!h->has_reset) return fail(LOBSIM_E_STATE, "step before reset");
+  AdvParams p; base_params(h, p);
+  p.T = 1; p.agent_kind = LOBSIM_AGENT_EXTERNAL; p.actions_in = actions; p.obs = obs_out; p.rew = reward_out; p.done = done_out;
+  return launch_advance<true>(h, p, (cudaStream_t)stream);
+}
+
+static int ensure_staging(lobsim* h) {
+  if (h->st_actions) return LOBSIM_OK;
+  const size_t n = (size_t)h->cfg.n_envs;
+  CUDA_TRY(cudaMalloc(&h->st_actions, n * 8 * sizeof(double)));
+  CUDA_TRY(cudaMalloc(&h->st_obs, n * (LOBSIM_MAX_FEATURES + 8) * sizeof(double)));
+  CUDA_TRY(cudaMalloc(&h->st_rew, n * sizeof(double)));
+  CUDA_TRY(cudaMalloc(&h->st_done, n));
+  CUDA_TRY(cudaMalloc(&h->st_state, n * sizeof(lobsim_env_state_t)));
+  return LOBSIM_OK;
+}
+
+int lobsim_step_host(lobsim_t* h, const double* actions, double* obs_out, double* reward_out, uint8_t* done_out) {
+  if (!h || !actions) return fail(LOBSIM_E_INVALID, "null argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  int rc = ensure_staging(h);
+  if (rc) return rc;
+  const size_t n = (size_t)h->cfg.n_envs;
+  CUDA_TRY(cudaMemcpyAsync(h->st_actions, actions, n * h->ec.action_dim * sizeof(double), cudaMemcpyHostToDevice, 0));
+  rc = lobsim_step(h, h->st_actions, h->st_obs, h->st_rew, h->st_done, nullptr);
+  if (rc) return rc;
+  if (obs_out) CUDA_TRY(cudaMemcpyAsync(obs_out, h->st_obs, n * h->ec.obs_dim * sizeof(double), cudaMemcpyDeviceToHost, 0));
+  if (reward_out) CUDA_TRY(cudaMemcpyAsync(reward_out, h->st_rew, n * sizeof(double), cudaMemcpyDeviceToHost, 0));
+  if (done_out) CUDA_TRY(cudaMemcpyAsync(done_out, h->st_done, n, cudaMemcpyDeviceToHost, 0));
+  CUDA_TRY(cudaStreamSynchronize(0));
+  return LOBSIM_OK;
+}
+
+int lobsim_rollout(lobsim_t* h, int32_t T, const lobsim_agent_t* agent, double* obs, double* act, double* rew, uint8_t* done, void* stream) {
+  if (!h || !agent || T < 0) return fail(LOBSIM_E_INVALID, "bad argument");
+  if (!h->has_reset) return fail(LOBSIM_E_STATE, "rollout before reset");
+  if (agent->kind == LOBSIM_AGENT_EXTERNAL && !act) return fail(LOBSIM_E_INVALID, "EXTERNAL agent needs the act tensor as input");
+  if (agent->kind == LOBSIM_AGENT_TERADACTYL && (agent->inventory_index < 0 || agent->inventory_index >= h->cfg.n_features)) return fail(LOBSIM_E_INVALID, "bad inventory_index");
+  AdvParams p; base_params(h, p);
+  p.T = T; p.agent_kind = agent->kind; p.agent = *agent; p.obs = obs; p.rew = rew; p.done = done;
+  if (agent->kind == LOBSIM_AGENT_EXTERNAL) p.actions_in = act; else p.act = act;
+  return launch_advance<true>(h, p, (cudaStream_t)stream);
+}
+
+int lobsim_replay(lobsim_t* h, int32_t n_steps, void* stream) {
+  if (!h || n_steps < 0) return fail(LOBSIM_E_INVALID, "bad argument");
+  AdvParams p; base_params(h, p);
+  p.T = n_steps; p.agent_kind = LOBSIM_AGENT_NONE;
+  return launch_advance<false>(h, p, (cudaStream_t)stream);
+}
+
+int lobsim_get_state_dev(lobsim_t* h, lobsim_env_state_t* out_dev, void* stream) {
+  if (!h || !out_dev) return fail(LOBSIM_E_INVALID, "null argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  k_get_state<<<(h->cfg.n_envs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->blobs, h->L, 0, h->cfg.n_envs, out_dev);
+  CUDA_TRY(cudaGetLastError());
+  h->launches++;
+  return LOBSIM_OK;
+}
+
+int lobsim_get_state(lobsim_t* h, int32_t first_env, int32_t n, lobsim_env_state_t* out) {
+  if (!h || !out || first_env < 0 || n < 0 || first_env + n > h->cfg.n_envs) return fail(LOBSIM_E_INVALID, "bad argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  int rc = ensure_staging(h);
+  if (rc) return rc;
+  if (n == 0) return LOBSIM_OK;
+  k_get_state<<<(n + 127) / 128, 128>>>(h->blobs, h->L, first_env, n, h->st_state);
+  CUDA_TRY(cudaGetLastError());
+  h->launches++;
+  CUDA_TRY(cudaMemcpy(out, h->st_state, (size_t)n * sizeof(lobsim_env_state_t), cudaMemcpyDeviceToHost));
+  return LOBSIM_OK;
+}
+
+int lobsim_replay_host(lobsim_t* h, int stream_id, const lobsim_msg_t* msgs_host, uint64_t first_msg, uint64_t n_msgs, int32_t n_steps, lobsim_env_state_t* state_out) {
+  if (!h || stream_id < 0 || stream_id >= (int)h->streams.size()) return fail(LOBSIM_E_INVALID, "bad argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  int rc = ensure_staging(h);
+  if (rc) return rc;
+  lobsim_stream_t& s = h->streams[stream_id];
+  if (first_msg + n_msgs > s.n_msgs) return fail(LOBSIM_E_INVALID, "segment outside the stream");
+  if (n_msgs) { // H2D of the segment straight into the resident stream buffer (same layout, same offsets)
+    if (!msgs_host) return fail(LOBSIM_E_INVALID, "msgs_host is null");
+    CUDA_TRY(cudaMemcpyAsync(const_cast<lobsim_msg_t*>(s.msgs) + first_msg, msgs_host, n_msgs * sizeof(lobsim_msg_t), cudaMemcpyHostToDevice, 0));
+  }
+  rc = lobsim_replay(h, n_steps, nullptr);
+  if (rc) return rc;
+  if (state_out) {
+    rc = lobsim_get_state_dev(h, h->st_state, nullptr);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(state_out, h->st_state, (size_t)h->cfg.n_envs * sizeof(lobsim_env_state_t), cudaMemcpyDeviceToHost, 0));
+  }
+  CUDA_TRY(cudaStreamSynchronize(0));
+  return LOBSIM_OK;
+}
+
+int lobsim_process_orders(lobsim_t* h, const lobsim_order_t* orders, int32_t n, lobsim_fill_t* fills_out, int32_t max_fills, int32_t* n_fills_out, uint32_t* refs_out) {
+  if (!h || (!orders && n) || n < 0 || max_fills < 0) return fail(LOBSIM_E_INVALID, "bad argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (n_fills_out) *n_fills_out = 0;
+  if (n == 0) return LOBSIM_OK;
+  lobsim_order_t* d_orders = nullptr; lobsim_fill_t* d_fills = nullptr; int32_t* d_nf = nullptr; uint32_t* d_refs = nullptr;
+  CUDA_TRY(cudaMalloc(&d_orders, (size_t)n * sizeof(lobsim_order_t)));
+  CUDA_TRY(cudaMalloc(&d_fills, (size_t)(max_fills > 0 ? max_fills : 1) * sizeof(lobsim_fill_t)));
+  CUDA_TRY(cudaMalloc(&d_nf, sizeof(int32_t)));
+  CUDA_TRY(cudaMalloc(&d_refs, (size_t)n * sizeof(uint32_t)));
+  CUDA_TRY(cudaMemcpy(d_orders, orders, (size_t)n * sizeof(lobsim_order_t), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemset(d_nf, 0, sizeof(int32_t)));
+  OrdParams p; p.blobs = h->blobs; p.L = h->L; p.n_envs = h->cfg.n_envs; p.orders = d_orders; p.n = n;
+  p.fills = max_fills > 0 ? d_fills : nullptr; p.max_fills = max_fills; p.n_fills = d_nf; p.refs_out = d_refs;
+  k_process_orders<<<1, 32, h->L.blob_bytes>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  h->launches++;
+  int32_t nf = 0;
+  if (e == cudaSuccess) e = cudaMemcpy(&nf, d_nf, sizeof nf, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && fills_out && nf > 0) e = cudaMemcpy(fills_out, d_fills, (size_t)nf * sizeof(lobsim_fill_t), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && refs_out) e = cudaMemcpy(refs_out, d_refs, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost);
+  cudaFree(d_orders); cudaFree(d_fills); cudaFree(d_nf); cudaFree(d_refs);
+  if (e != cudaSuccess) return fail(LOBSIM_E_CUDA, cudaGetErrorString(e));
+  if (n_fills_out) *n_fills_out = nf;
+  return LOBSIM_OK;
+}
+
+// host-side decode of one env's blob (layout = book.cuh)
+static int fetch_blob(lobsim* h, int env, std::vector<unsigned char>& buf) {
+  if (env < 0 || env >= h->cfg.n_envs) return fail(LOBSIM_E_INVALID, "bad env index");
+  CUDA_TRY(cudaSetDevice(h->device));
+  buf.resize(h->L.blob_bytes);
+  CUDA_TRY(cudaMemcpy(buf.data(), h->blobs + (size_t)env * h->L.blob_bytes, h->L.blob_bytes, cudaMemcpyDeviceToHost));
+  return LOBSIM_OK;
+}
+
+int lobsim_dump_book(lobsim_t* h, int32_t env, int32_t side, lobsim_book_entry_t* out, int32_t capacity) {
+  if (!h || side < 0 || side > 1) return fail(LOBSIM_E_INVALID, "bad argument");
+  std::vector<unsigned char> buf;
+  int rc = fetch_blob(h, env, buf);
+  if (rc) return rc;
+  const Layout& L = h->L;
+  const BookHdr* hd = reinterpret_cast<const BookHdr*>(buf.data());
+  const unsigned char* sb = buf.data() + L.side_off + side * L.side_stride;
+  const int32_t* lvp = reinterpret_cast<const int32_t*>(sb);
+  const uint16_t* lvend = reinterpret_cast<const uint16_t*>(sb + L.lvend_off);
+  const uint2* ord = reinterpret_cast<const uint2*>(sb + L.ord_off);
+  int n = 0;
+  for (int k = 0; k < hd->nlv[side]; k++) { // best level first
+    int j = hd->nlv[side] - 1 - k;
+    int start = j > 0 ? lvend[j - 1] : 0, end = lvend[j];
+    for (int i = start; i < end; i++) {
+      if (out && n < capacity) { out[n].price = lvp[j]; out[n].volume = (int32_t)ord[i].x; out[n].ref = ord[i].y; out[n].level = k; }
+      n++;
+    }
+  }
+  return n;
+}
+
+int lobsim_dump_agent_orders(lobsim_t* h, int32_t env, int32_t side, lobsim_book_entry_t* out, int32_t capacity) {
+  if (!h || side < 0 || side > 1) return fail(LOBSIM_E_INVALID, "bad argument");
+  std::vector<unsigned char> buf;
+  int rc = fetch_blob(h, env, buf);
+  if (rc) return rc;
+  const Layout& L = h->L;
+  const BookHdr* hd = reinterpret_cast<const BookHdr*>(buf.data());
+  const int32_t* ap = reinterpret_cast<const int32_t*>(buf.data() + L.agent_off + side * L.NA * 12);
+  const int32_t* av = ap + L.NA;
+  const uint32_t* ai = reinterpret_cast<const uint32_t*>(ap + 2 * L.NA);
+  int n = hd->nag[side];
+  for (int i = 0; i < n && out && i < capacity; i++) { out[i].price = ap[i]; out[i].volume = av[i]; out[i].ref = LOBSIM_REF_AGENT | ai[i]; out[i].level = -1; }
+  return n;
+}
+
+int lobsim_get_fills(lobsim_t* h, int32_t env, lobsim_fill_t* out, int32_t capacity, int32_t* n_out) {
+  if (!h || env < 0 || env >= h->cfg.n_envs || !n_out) return fail(LOBSIM_E_INVALID, "bad argument");
+  *n_out = 0;
+  if (!h->fill_log) return LOBSIM_OK;
+  CUDA_TRY(cudaSetDevice(h->device));
+  int32_t n = 0;
+  CUDA_TRY(cudaMemcpy(&n, h->fill_count + env, sizeof n, cudaMemcpyDeviceToHost));
+  *n_out = n;
+  int m = n < h->cfg.fill_log_capacity ? n : h->cfg.fill_log_capacity;
+  if (m > capacity) m = capacity;
+  if (out && m > 0) CUDA_TRY(cudaMemcpy(out, h->fill_log + (size_t)env * h->cfg.fill_log_capacity, (size_t)m * sizeof(lobsim_fill_t), cudaMemcpyDeviceToHost));
+  return LOBSIM_OK;
+}
+
+int lobsim_errors(lobsim_t* h, uint32_t* err_out) {
+  if (!h || !err_out) return fail(LOBSIM_E_INVALID, "null argument");
+  std::vector<lobsim_env_state_t> st(h->cfg.n_envs);
+  int rc = lobsim_get_state(h, 0, h->cfg.n_envs, st.data());
+  if (rc) return rc;
+  for (int i = 0; i < h->cfg.n_envs; i++) err_out[i] = st[i].err;
+  return LOBSIM_OK;
+}
+
+int64_t lobsim_launch_count(lobsim_t* h) { return h ? h->launches : 0; }
+
+} // extern "C"

@@ -1,0 +1,162 @@
+"""CPU-side checks of the C-ABI library and the host logic (no compute calls: there is no GPU here)."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from rl4mm_b200 import abi
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+@pytest.fixture(scope="module")
+def lobsim_lib():
+    from rl4mm_b200.build import build_all
+
+    build_all()
+    from rl4mm_b200._lib import lib
+
+    return lib()
+
+
+def test_header_symbols_are_exported(lobsim_lib):
+    header = (ROOT / "include" / "lobsim.h").read_text()
+    declared = sorted(set(re.findall(r"\b(lobsim_[a-z_]+)\s*\(", header)))
+    assert len(declared) >= 20
+    from rl4mm_b200._lib import EXPORTED_SYMBOLS
+
+    assert sorted(EXPORTED_SYMBOLS) == declared
+    for name in declared:
+        assert hasattr(lobsim_lib, name), f"{name} declared in include/lobsim.h but not exported by liblobsim.so"
+
+
+def test_abi_version_and_dims(lobsim_lib):
+    assert lobsim_lib.lobsim_abi_version() == abi.ABI_VERSION
+    cfg = abi.default_cfg(features=[abi.feature(abi.FEAT_SPREAD, 0, 100000, 0, 5000)] * 3, inc_prev_action_in_obs=1)
+    assert lobsim_lib.lobsim_action_dim(C.byref(cfg)) == abi.action_dim(cfg) == 4
+    assert lobsim_lib.lobsim_obs_dim(C.byref(cfg)) == abi.obs_dim(cfg) == 7
+    cfg2 = abi.default_cfg(concentration=10.0, market_order_clearing=1)
+    assert lobsim_lib.lobsim_action_dim(C.byref(cfg2)) == 3
+    assert lobsim_lib.lobsim_state_bytes(C.byref(cfg)) % 16 == 0
+
+
+def test_struct_sizes_match_header():
+    """ctypes mirrors must have the C layout: compile a tiny probe with gcc and compare sizeof()."""
+    import subprocess
+    import tempfile
+
+    src = '#include <stdio.h>\n#include "lobsim.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",' \
+          "sizeof(lobsim_msg_t),sizeof(lobsim_feature_t),sizeof(lobsim_reward_t),sizeof(lobsim_agent_t)," \
+          "sizeof(lobsim_cfg_t),sizeof(lobsim_stream_t),sizeof(lobsim_order_t),sizeof(lobsim_fill_t)," \
+          "sizeof(lobsim_book_entry_t),sizeof(lobsim_env_state_t));return 0;}\n"
+    with tempfile.TemporaryDirectory() as d:
+        (Path(d) / "p.c").write_text(src)
+        subprocess.run(["gcc", "-I", str(ROOT / "include"), "-o", f"{d}/p", f"{d}/p.c"], check=True)
+        out = subprocess.run([f"{d}/p"], capture_output=True, text=True, check=True).stdout.split()
+    got = [int(x) for x in out]
+    want = [abi.MSG_DTYPE.itemsize, C.sizeof(abi.Feature), C.sizeof(abi.Reward), C.sizeof(abi.Agent), C.sizeof(abi.Cfg),
+            C.sizeof(abi.Stream), abi.ORDER_DTYPE.itemsize, abi.FILL_DTYPE.itemsize, abi.BOOK_ENTRY_DTYPE.itemsize,
+            abi.ENV_STATE_DTYPE.itemsize]
+    assert got == want
+    assert C.sizeof(abi.Order) == abi.ORDER_DTYPE.itemsize
+
+
+def test_no_cpu_fallback(lobsim_lib):
+    """Without a CUDA device the product must fail loudly, not fall back to the oracle or any CPU path."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    h = C.c_void_p()
+    cfg = abi.default_cfg()
+    rc = lobsim_lib.lobsim_create(C.byref(cfg), 0, C.byref(h))
+    assert rc == abi.E_CUDA and b"no CUDA device" in lobsim_lib.lobsim_last_error()
+    from rl4mm_b200.device import LobSim
+    from rl4mm_b200._lib import LobsimError
+
+    with pytest.raises(LobsimError):
+        LobSim(cfg)
+
+
+def test_invalid_cfg_rejected(lobsim_lib):
+    cfg = abi.default_cfg(max_quote_level=40)
+    assert lobsim_lib.lobsim_state_bytes(C.byref(cfg)) == abi.E_INVALID
+
+
+def test_product_never_imports_oracle():
+    for py in (ROOT / "rl4mm_b200").rglob("*.py"):
+        text = py.read_text()
+        assert "import oracle" not in text and "from oracle" not in text, py
+    for src in (ROOT / "rl4mm_b200" / "csrc").iterdir():
+        assert not re.search(r'#include\s*[<"][^>"]*oracle', src.read_text()), src
+
+
+def test_packer_matches_committed_fixture():
+    """pack_arrays semantics on a hand-made LOBSTER snippet: type map, direction flip, hidden executions dropped,
+    lexicographic tie order, CSR step offsets, per-second snapshots."""
+    from rl4mm_b200.packing import pack_arrays
+
+    L = 2
+    t = np.array([34200_100_000_000, 34200_100_000_500, 34200_100_000_900, 34200_950_000_000, 34201_000_000_000,
+                  34201_050_000_000, 34201_050_000_000, 34201_050_000_000, 34201_050_000_000, 34201_050_000_000,
+                  34201_050_000_000, 34201_050_000_000, 34201_050_000_000, 34201_050_000_000, 34201_050_000_000,
+                  34201_050_000_000], np.int64)
+    n = len(t)
+    ty = np.array([1, 4, 5, 3, 2] + [1] * 11)
+    oid = np.arange(100, 100 + n)
+    size = np.full(n, 10)
+    price = np.full(n, 1000)
+    direction = np.array([1, 1, 1, -1, -1] + [1] * 11)
+    books = np.tile(np.array([1100, 5, 1000, 7, 9999999999, 0, -9999999999, 0], np.int64), (n, 1))
+    books[:, 1] = np.arange(n)  # ask size encodes the row, to check snapshot alignment
+    s = pack_arrays(t, ty, oid, size, price, direction, books, L, step_us=100_000)
+    assert s.t0_us == 34200_000_000 and s.n_grid_steps == 20 and s.n_seconds == 2
+    assert s.n_msgs == n - 1  # the hidden execution is dropped
+    m = s.msgs
+    assert (m["meta"][0] & 7, (m["meta"][0] >> 3) & 1) == (abi.MSG_LIMIT, abi.BUY)
+    assert (m["meta"][1] & 7, (m["meta"][1] >> 3) & 1) == (abi.MSG_MARKET, abi.SELL)   # execution of a buy => sell aggressor
+    assert (m["meta"][2] & 7, (m["meta"][2] >> 3) & 1) == (abi.MSG_DELETE, abi.SELL)
+    assert (m["meta"][3] & 7, (m["meta"][3] >> 3) & 1) == (abi.MSG_CANCEL, abi.SELL)
+    # rows 5..15 share one microsecond: the reference orders them by the STRING row id: "10" < "11" < ... < "15" < "5" ...
+    tied = [int(s.ext_ids[r]) - 100 for r in m["ref"][4:]]
+    assert tied == sorted(range(5, 16), key=str)
+    # 0.1 s (+ sub-microsecond digits) truncates to exactly 0.1 s => step 0 = (0, 0.1 s] holds the first two kept messages, 0.95 s is step 9, 1.0 s exactly is step 9 too
+    assert list(s.step_off[:3]) == [0, 2, 2] and s.step_off[9] == 2 and s.step_off[10] == 4
+    assert s.step_off[11] == n - 1
+    # snapshots: second 0 has no data, second 1 = row 4 (ts == boundary), second 2 = last row
+    assert list(s.snap_valid) == [0, 1, 1]
+    assert s.snapshots[1, abi.SELL, 0, 1] == 4 and s.snapshots[2, abi.SELL, 0, 1] == n - 1
+    assert s.snapshots[1, abi.SELL, 1, 0] == abi.NO_PRICE and s.snapshots[1, abi.BUY, 1, 0] == abi.NO_PRICE
+    assert tuple(s.snapshots[1, abi.BUY, 0]) == (1000, 7)
+    # file order keeps the rows as they are
+    s2 = pack_arrays(t, ty, oid, size, price, direction, books, L, step_us=100_000, tie_order="file")
+    assert [int(s2.ext_ids[r]) - 100 for r in s2.msgs["ref"][4:]] == list(range(5, 16))
+    with pytest.raises(ValueError):
+        pack_arrays(t, np.where(ty == 2, 6, ty), oid, size, price, direction, books, L)
+
+
+def test_synthetic_stream_is_self_consistent():
+    """Replaying a synthetic stream through the oracle from the initial snapshot reproduces every later snapshot's
+    top of book (the generator's own book and the simulator agree), with no error flags."""
+    from oracle.oracle import Oracle
+    from rl4mm_b200 import synthetic
+
+    sc = synthetic.spy_day(seed=1, n_msgs=100_000, duration_s=234)
+    s = synthetic.generate(sc)
+    s2 = synthetic.generate(sc)
+    assert np.array_equal(s.msgs, s2.msgs) and np.array_equal(s.step_off, s2.step_off)  # seeded => reproducible
+    ty = s.msgs["meta"] & 7
+    frac = np.bincount(ty, minlength=5)[1:] / len(ty)
+    assert abs(frac[0] - 0.48) < 0.03 and abs(frac[2] - 0.42) < 0.03 and 0.05 < frac[3] < 0.12
+    o = Oracle(abi.default_cfg(n_levels=10, outer_levels=20), s)
+    o.reset_book(0)
+    for sec in range(1, 235):
+        o.replay(10)
+        st = o.state()
+        assert st["err"] == 0
+        snap = s.snapshots[sec]
+        assert st["best_buy"] == snap[0, 0, 0] and st["best_sell"] == snap[1, 0, 0], sec
+        if sec > 120:  # the initial aggregates near the touch are gone by now: volumes agree too
+            assert st["best_buy_volume"] == snap[0, 0, 1] and st["best_sell_volume"] == snap[1, 0, 1], sec
