@@ -46,6 +46,7 @@ __device__ __forceinline__ bool near_exiting(const Book& b, const WarpState& w, 
 
 // ---- OrderbookSimulator.update_outer_levels, OrderbookSimulator.py:105-135 ---------------------------------------
 // scratch: per-warp shared int2[2*NA] for the agent orders that are cancelled and re-queued behind the aggregates.
+template <bool TR>
 __device__ __forceinline__ void update_outer_levels(const Book& b, WarpState& w, const lobsim_cfg_t& c, const int32_t* __restrict__ row, int2* scratch) {
   BookHdr* h = b.hdr();
   const int L = c.n_levels;
@@ -56,7 +57,7 @@ __device__ __forceinline__ void update_outer_levels(const Book& b, WarpState& w,
       int price = __ldg(&row[(side * L + lvl) * 2]), vol = __ldg(&row[(side * L + lvl) * 2 + 1]);
       if (price == LOBSIM_NO_PRICE) continue;
       if (!(side == 0 ? price < min_buy : price > max_sell)) continue; // _initial_prices_filter_function :99-103
-      for (int i = 0; i < NAG(w, side);) { // internal orders at this price: cancel now, re-queue later (:116-129)
+      for (int i = 0; TR && i < NAG(w, side);) { // internal orders at this price: cancel now, re-queue later (:116-129)
         int ap = b.aprice(side)[i], av = b.avol(side)[i];
         uint32_t id = b.aid(side)[i];
         __syncwarp();
@@ -64,7 +65,7 @@ __device__ __forceinline__ void update_outer_levels(const Book& b, WarpState& w,
         if (b.lane == 0) scratch[nrepl] = make_int2(price, av);
         nrepl++;
         int before = NAG(w, side);
-        remove_order(b, w, side, price, av, true, LOBSIM_REF_AGENT | id, true);
+        remove_order<TR>(b, w, side, price, av, true, LOBSIM_REF_AGENT | id, true);
         if (NAG(w, side) == before) agent_remove_at(b, w, side, i); // keep internal and central consistent
       }
       bool found;
@@ -82,9 +83,9 @@ __device__ __forceinline__ void update_outer_levels(const Book& b, WarpState& w,
     if (side == 0) nrepl_buy = nrepl;
   }
   __syncwarp();
-  for (int i = 0; i < nrepl; i++) { // :132-133
+  for (int i = 0; TR && i < nrepl; i++) { // :132-133
     int2 r = scratch[i];
-    submit_or_execute(b, w, i < nrepl_buy ? 0 : 1, r.x, r.y, 0, true, true);
+    submit_or_execute<TR>(b, w, i < nrepl_buy ? 0 : 1, r.x, r.y, 0, true, true);
   }
   if (b.lane == 0) { // :134-135 (Exchange.orderbook_price_range, Exchange.py:160-170)
     if (w.nlv0 && b.lvp(0)[0] < h->min_buy) h->min_buy = b.lvp(0)[0];
@@ -213,7 +214,7 @@ __device__ __forceinline__ void agent_orders(const Book& b, WarpState& w, const 
     for (int k = 0; k < Q && !w.dead; k++) {
       int d = __shfl_sync(FULL_MASK, side ? diff1 : diff0, k);
       int p = __shfl_sync(FULL_MASK, myprice, k);
-      if (d > 0) submit_or_execute(b, w, side, p, d, 0, true, true);
+      if (d > 0) submit_or_execute<true>(b, w, side, p, d, 0, true, true);
       int need = -d;
       while (need > 0) { // cancel from the back of the agent's queue at this price, :239-249
         int nag = NAG(w, side), hit = -1;
@@ -227,7 +228,7 @@ __device__ __forceinline__ void agent_orders(const Book& b, WarpState& w, const 
         uint32_t id = b.aid(side)[hit];
         __syncwarp();
         int v = av < need ? av : need;
-        remove_order(b, w, side, p, v, true, LOBSIM_REF_AGENT | id, true);
+        remove_order<true>(b, w, side, p, v, true, LOBSIM_REF_AGENT | id, true);
         need -= v;
       }
     }
@@ -238,14 +239,14 @@ __device__ __forceinline__ void agent_orders(const Book& b, WarpState& w, const 
       bool on_ladder = __ballot_sync(FULL_MASK, b.lane < Q && myprice == ap) != 0;
       if (on_ladder) { i++; continue; }
       int before = NAG(w, side);
-      remove_order(b, w, side, ap, av, true, LOBSIM_REF_AGENT | id, true);
+      remove_order<true>(b, w, side, ap, av, true, LOBSIM_REF_AGENT | id, true);
       if (NAG(w, side) == before) agent_remove_at(b, w, side, i);
     }
   }
   if (clearing && !w.dead) { // _get_inventory_clearing_market_order :260-266
     int vol = (int)rint((double)absinv * c.market_order_fraction_of_inventory);
     if (vol <= 0) w.err |= LOBSIM_ERR_BAD_VOLUME;
-    else submit_or_execute(b, w, w.inventory < 0 ? 0 : 1, 0, vol, 0, false, true);
+    else submit_or_execute<true>(b, w, w.inventory < 0 ? 0 : 1, 0, vol, 0, false, true);
   }
 }
 

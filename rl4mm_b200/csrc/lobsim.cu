@@ -97,8 +97,10 @@ __device__ __forceinline__ unsigned char* warp_smem_base(unsigned char* smem, in
 // ====================================================================================================================
 //  the advance kernel: [reset] + T x ([agent orders] + messages of the step + [resync] + [features, reward])
 // ====================================================================================================================
-template <bool kEnv>
-__global__ void __launch_bounds__(128) k_advance(const __grid_constant__ AdvParams p, const __grid_constant__ EnvConst ec) {
+// kEnv: agent + features + rewards (HistoricalOrderbookEnvironment.step); kTrack: fills / flows / agent orders are
+// tracked (always with kEnv; the pure replay fast path <false,false> is used when no agent order can be resting).
+template <bool kEnv, bool kTrack>
+__global__ void __launch_bounds__(128, kEnv ? 3 : (kTrack ? 4 : 7)) k_advance(const __grid_constant__ AdvParams p, const __grid_constant__ EnvConst ec) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int sel = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -124,9 +126,10 @@ __global__ void __launch_bounds__(128) k_advance(const __grid_constant__ AdvPara
   mbar_wait(&bars[2], 0);
 
   WarpState w;
-  load_state(b, w);
+  load_state<kTrack>(b, w);
   w.fill_log = p.fill_log ? p.fill_log + (size_t)env * p.fill_cap : nullptr;
   w.fill_cap = p.fill_cap; w.n_fills = 0;
+  const long long inventory_in = w.inventory; const double cash_in = w.cash;
   BookHdr* h = b.hdr();
   FeatState fs; double* ring = nullptr;
   lobsim_feature_t fc;
@@ -134,7 +137,7 @@ __global__ void __launch_bounds__(128) k_advance(const __grid_constant__ AdvPara
 
   // ---- reset prologue ----------------------------------------------------------------------------------------------
   int stream_id = h->stream_id;
-  if (p.reset_mode) {
+  if (kTrack && p.reset_mode) {
     stream_id = p.reset_stream_ids[sel];
     int start = p.reset_steps[sel] - (p.reset_mode == 2 ? c.warmup_steps : 0);
     if (stream_id < 0 || stream_id >= p.n_streams) { stream_id = 0; start = -1; }
@@ -147,9 +150,12 @@ __global__ void __launch_bounds__(128) k_advance(const __grid_constant__ AdvPara
     __syncwarp();
     w.inventory = h->inventory; w.cash = h->cash;
   }
-  const lobsim_stream_t st = p.streams[stream_id];
+  const lobsim_stream_t* stp = &p.streams[stream_id];
+  const lobsim_msg_t* __restrict__ st_msgs = stp->msgs;
+  const uint32_t* __restrict__ st_step_off = stp->step_off;
+  const long long st_t0_us = kEnv ? stp->t0_us : 0;
   int now_step = h->now_step;
-  const long long episode_start_us = st.t0_us + (long long)h->episode_start_step * c.step_us;
+  const long long episode_start_us = st_t0_us + (long long)h->episode_start_step * c.step_us;
 
   if (kEnv) {
     if (lane < F) {
@@ -172,7 +178,7 @@ __global__ void __launch_bounds__(128) k_advance(const __grid_constant__ AdvPara
   double price = h->price;
   if (kEnv && p.reset_mode == 2) { // State(...) + _reset_features, HOE.py:152-154,218-221
     StepView v; tops(v);
-    v.inventory = w.inventory; v.now_us = now_us_of(st, c, now_step);
+    v.inventory = w.inventory; v.now_us = st_t0_us + (long long)now_step * c.step_us;
     v.n_ext0 = v.n_ext1 = v.vol_ext0 = v.vol_ext1 = v.n_int0 = v.n_int1 = v.vol_int0 = v.vol_int1 = 0;
     price = v.price;
     if (lane < F) feature_reset(fc, fs, ring, v);
@@ -180,26 +186,28 @@ __global__ void __launch_bounds__(128) k_advance(const __grid_constant__ AdvPara
 
   // ---- message pipeline ----------------------------------------------------------------------------------------------
   const int T = p.T;
-  const bool in_grid = now_step >= 0 && (long long)now_step + T <= (long long)st.n_grid_steps;
+  const bool in_grid = now_step >= 0 && (long long)now_step + T <= (long long)stp->n_grid_steps;
   if (!in_grid && !w.dead && T > 0) { w.err |= LOBSIM_ERR_END_OF_STREAM; w.dead = 1; }
   unsigned g = 0, g_end_all = 0;
-  if (!w.dead && T > 0) { g = __ldg(&st.step_off[now_step]); g_end_all = __ldg(&st.step_off[now_step + T]); }
-  const unsigned n_msgs_total = (unsigned)st.n_msgs;
-  uint32_t par0 = 0, par1 = 0;     // phase parity of the two tile barriers
-  unsigned next_issue = g / MSG_TILE, next_wait = g / MSG_TILE; // tiles are issued and consumed in order
+  if (!w.dead && T > 0) { g = __ldg(&st_step_off[now_step]); g_end_all = __ldg(&st_step_off[now_step + T]); }
+  // tiles are MSG_TILE-aligned in the global message index space; `rel` tile r lives in buffer r & 1 and completes
+  // phase (r >> 1) & 1 of that buffer's mbarrier.  Tiles are issued and consumed strictly in order.
+  const unsigned tile0 = g / MSG_TILE;
+  unsigned next_issue = 0, next_wait = 0;
   auto issue_tile = [&]() { // uniform; lane 0 talks to the TMA unit
-    const unsigned tile = next_issue, first = tile * MSG_TILE;
+    const unsigned first = (tile0 + next_issue) * MSG_TILE;
     if (first >= g_end_all) return;
     if (lane == 0) {
-      unsigned cnt = n_msgs_total - first < MSG_TILE ? n_msgs_total - first : MSG_TILE;
-      uint64_t* bar = &bars[tile & 1];
+      const unsigned n_total = (unsigned)stp->n_msgs;
+      unsigned cnt = n_total - first < MSG_TILE ? n_total - first : MSG_TILE;
+      uint64_t* bar = &bars[next_issue & 1];
       mbar_expect_tx(bar, cnt * 16);
-      tma_load(msgbuf + (tile & 1) * MSG_TILE_BYTES, st.msgs + first, cnt * 16, bar);
+      tma_load(msgbuf + (next_issue & 1) * MSG_TILE_BYTES, st_msgs + first, cnt * 16, bar);
     }
-    next_issue = tile + 1;
+    next_issue++;
   };
-  auto wait_tile = [&]() { // wait for tile `next_wait`
-    if (next_wait & 1) { mbar_wait(&bars[1], par1); par1 ^= 1; } else { mbar_wait(&bars[0], par0); par0 ^= 1; }
+  auto wait_tile = [&]() { // wait for relative tile `next_wait`
+    mbar_wait(&bars[next_wait & 1], (next_wait >> 1) & 1);
     next_wait++;
   };
   if (g < g_end_all) { issue_tile(); issue_tile(); }
@@ -226,12 +234,12 @@ __global__ void __launch_bounds__(128) k_advance(const __grid_constant__ AdvPara
     }
     // ---- historical messages of (now, now + step] ------------------------------------------------------------------
     if (!w.dead) {
-      const unsigned g_step_end = __ldg(&st.step_off[now_step + 1]);
+      const unsigned g_step_end = __ldg(&st_step_off[now_step + 1]);
       while (g < g_step_end) {
-        const unsigned tile = g / MSG_TILE;
+        const unsigned tile = g / MSG_TILE - tile0;
         if (tile == next_wait) wait_tile();
         const uint4 m = *reinterpret_cast<const uint4*>(msgbuf + (tile & 1) * MSG_TILE_BYTES + (g % MSG_TILE) * 16);
-        process_message(b, w, (int)m.x, (int)m.y, m.z, m.w);
+        process_message<kTrack>(b, w, (int)m.x, (int)m.y, m.z, m.w);
         g++;
         if (g % MSG_TILE == 0) { // tile consumed: refill its buffer with the tile after the next one
           __syncwarp();
@@ -247,7 +255,7 @@ __global__ void __launch_bounds__(128) k_advance(const __grid_constant__ AdvPara
         long long rel = (long long)now_step * c.step_us;
         if (rel % 1000000 == 0 && near_exiting(b, w, c)) {
           long long sec = rel / 1000000;
-          if (sec <= (long long)st.n_seconds && st.snap_valid[sec]) update_outer_levels(b, w, c, st.snapshots + (size_t)sec * 2 * c.n_levels * 2, scratch);
+          if (sec <= (long long)stp->n_seconds && stp->snap_valid[sec]) update_outer_levels<kTrack>(b, w, c, stp->snapshots + (size_t)sec * 2 * c.n_levels * 2, scratch);
         }
       }
     }
@@ -256,7 +264,7 @@ __global__ void __launch_bounds__(128) k_advance(const __grid_constant__ AdvPara
       StepView v; tops(v);
       if (!v.have_tops) w.err |= LOBSIM_ERR_EMPTY_BOOK;
       price = v.price;
-      v.inventory = w.inventory; v.now_us = now_us_of(st, c, now_step);
+      v.inventory = w.inventory; v.now_us = st_t0_us + (long long)now_step * c.step_us;
       v.n_ext0 = w.n_ext0; v.n_ext1 = w.n_ext1; v.vol_ext0 = w.vol_ext0; v.vol_ext1 = w.vol_ext1;
       v.n_int0 = w.n_int0; v.n_int1 = w.n_int1; v.vol_int0 = w.vol_int0; v.vol_int1 = w.vol_int1;
       if (lane < F) feature_update(fc, fs, ring, v, episode_start_us);
@@ -288,13 +296,15 @@ __global__ void __launch_bounds__(128) k_advance(const __grid_constant__ AdvPara
   while (next_wait < next_issue) wait_tile(); // drain TMA loads still in flight (only after an aborted episode)
 
   // ---- write back ----------------------------------------------------------------------------------------------------
+  // OrderbookSimulator.forward_step only returns the fills: the portfolio belongs to the env (HOE.py:280-289)
+  if (!kEnv && !p.reset_mode) { w.inventory = inventory_in; w.cash = cash_in; }
   if (kEnv && lane < F) p.fstate[(size_t)env * LOBSIM_MAX_FEATURES + lane] = fs;
   if (lane == 0) {
     h->now_step = now_step;
     h->price = price;
     if (p.fill_count) p.fill_count[env] = w.n_fills;
   }
-  store_state(b, w);
+  store_state<kTrack>(b, w);
   fence_proxy_async();
   __syncwarp();
   if (lane == 0) { tma_store(gblob, base, (uint32_t)p.L.blob_bytes); tma_store_wait(); }
@@ -321,12 +331,12 @@ __global__ void __launch_bounds__(32) k_process_orders(const __grid_constant__ O
     uint4* dst = reinterpret_cast<uint4*>(smem);
     for (int i = lane; i < p.L.blob_bytes / 16; i += 32) dst[i] = src[i];
     __syncwarp();
-    load_state(b, w);
+    load_state<true>(b, w);
     w.fill_log = p.fills ? p.fills + total_fills : nullptr;
     w.fill_cap = p.max_fills - total_fills; w.n_fills = 0;
   };
   auto store_env = [&](int env) {
-    store_state(b, w);
+    store_state<true>(b, w);
     uint4* dst = reinterpret_cast<uint4*>(p.blobs + (size_t)env * p.L.blob_bytes);
     const uint4* src = reinterpret_cast<const uint4*>(smem);
     for (int i = lane; i < p.L.blob_bytes / 16; i += 32) dst[i] = src[i];
@@ -342,9 +352,9 @@ __global__ void __launch_bounds__(32) k_process_orders(const __grid_constant__ O
     const bool has_vol = !((o.type == LOBSIM_MSG_DELETE || o.type == LOBSIM_MSG_CANCEL) && o.volume <= 0);
     if (!w.dead) {
       if (has_vol && o.volume <= 0) w.err |= LOBSIM_ERR_BAD_VOLUME;
-      else if (o.type == LOBSIM_MSG_LIMIT) id = submit_or_execute(b, w, o.direction, o.price, o.volume, is_agent ? 0u : o.ref, true, is_agent);
-      else if (o.type == LOBSIM_MSG_MARKET) id = submit_or_execute(b, w, o.direction, 0, o.volume, is_agent ? 0u : o.ref, false, is_agent);
-      else remove_order(b, w, o.direction, o.price, o.volume, has_vol, is_agent ? (LOBSIM_REF_AGENT | (o.ref & 0x7fffffffu)) : o.ref, is_agent);
+      else if (o.type == LOBSIM_MSG_LIMIT) id = submit_or_execute<true>(b, w, o.direction, o.price, o.volume, is_agent ? 0u : o.ref, true, is_agent);
+      else if (o.type == LOBSIM_MSG_MARKET) id = submit_or_execute<true>(b, w, o.direction, 0, o.volume, is_agent ? 0u : o.ref, false, is_agent);
+      else remove_order<true>(b, w, o.direction, o.price, o.volume, has_vol, is_agent ? (LOBSIM_REF_AGENT | (o.ref & 0x7fffffffu)) : o.ref, is_agent);
     }
     if (p.refs_out && lane == 0) p.refs_out[k] = id;
   }
@@ -421,6 +431,7 @@ struct lobsim {
   lobsim_env_state_t* st_state = nullptr;
   lobsim_msg_t* st_msgs = nullptr; uint64_t st_msgs_cap = 0;
   bool has_reset = false;
+  bool agent_orders_possible = false; // an agent order may rest in some book (disables the replay fast path)
   int64_t launches = 0;
 };
 
@@ -480,8 +491,12 @@ int lobsim_create(const lobsim_cfg_t* cfg, int device, lobsim_t** out) {
   if (h->warp_smem > max_smem) { delete h; return fail(LOBSIM_E_INVALID, "book capacities exceed the shared memory of one SM"); }
   h->warps_per_cta = 4;
   while (h->warps_per_cta > 1 && h->warps_per_cta * h->warp_smem > max_smem) h->warps_per_cta >>= 1;
-  CUDA_TRY(cudaFuncSetAttribute(k_advance<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->warps_per_cta * h->warp_smem));
-  CUDA_TRY(cudaFuncSetAttribute(k_advance<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->warps_per_cta * h->warp_smem));
+  CUDA_TRY((cudaFuncSetAttribute(k_advance<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->warps_per_cta * h->warp_smem)));
+  CUDA_TRY((cudaFuncSetAttribute(k_advance<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->warps_per_cta * h->warp_smem)));
+  CUDA_TRY((cudaFuncSetAttribute(k_advance<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->warps_per_cta * h->warp_smem)));
+  CUDA_TRY((cudaFuncSetAttribute(k_advance<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)));
+  CUDA_TRY((cudaFuncSetAttribute(k_advance<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)));
+  CUDA_TRY((cudaFuncSetAttribute(k_advance<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)));
   CUDA_TRY(cudaFuncSetAttribute(k_process_orders, cudaFuncAttributeMaxDynamicSharedMemorySize, h->L.blob_bytes));
   // feature rings
   memset(&h->ec, 0, sizeof h->ec);
@@ -551,14 +566,14 @@ static void base_params(lobsim* h, AdvParams& p) {
 
 } // extern "C"
 
-template <bool kEnv>
+template <bool kEnv, bool kTrack>
 static int launch_advance(lobsim* h, const AdvParams& p, cudaStream_t stream) {
   if (h->streams.empty()) return fail(LOBSIM_E_STATE, "no stream loaded");
   CUDA_TRY(cudaSetDevice(h->device));
   int wpc = h->warps_per_cta;
   int grid = (p.n_sel + wpc - 1) / wpc;
   if (grid <= 0) return LOBSIM_OK;
-  k_advance<kEnv><<<grid, wpc * 32, (size_t)wpc * h->warp_smem, stream>>>(p, h->ec);
+  k_advance<kEnv, kTrack><<<grid, wpc * 32, (size_t)wpc * h->warp_smem, stream>>>(p, h->ec);
   CUDA_TRY(cudaGetLastError());
   h->launches++;
   return LOBSIM_OK;
@@ -571,7 +586,8 @@ int lobsim_reset_book(lobsim_t* h, const int32_t* env_ids, int32_t n, const int3
   AdvParams p; base_params(h, p);
   p.env_ids = env_ids; p.n_sel = env_ids ? n : h->cfg.n_envs;
   p.T = 0; p.reset_mode = 1; p.reset_stream_ids = stream_ids; p.reset_steps = start_steps; p.agent_kind = LOBSIM_AGENT_NONE;
-  return launch_advance<false>(h, p, (cudaStream_t)stream);
+  if (!env_ids) h->agent_orders_possible = false; // every book is a fresh snapshot again
+  return launch_advance<false, true>(h, p, (cudaStream_t)stream);
 }
 
 int lobsim_reset(lobsim_t* h, const int32_t* env_ids, int32_t n, const int32_t* stream_ids, const int32_t* episode_start_steps, double* obs_out, void* stream) {
@@ -581,7 +597,7 @@ int lobsim_reset(lobsim_t* h, const int32_t* env_ids, int32_t n, const int32_t* 
   p.T = h->cfg.warmup_steps; p.reset_mode = 2; p.reset_stream_ids = stream_ids; p.reset_steps = episode_start_steps;
   p.agent_kind = LOBSIM_AGENT_NONE; p.obs = obs_out; p.out_final_obs_only = 1;
   h->has_reset = true;
-  return launch_advance<true>(h, p, (cudaStream_t)stream);
+  return launch_advance<true, true>(h, p, (cudaStream_t)stream);
 }
 
 int lobsim_step(lobsim_t* h, const double* actions, double* obs_out, double* reward_out, uint8_t* done_out, void* stream) {
@@ -589,7 +605,8 @@ int lobsim_step(lobsim_t* h, const double* actions, double* obs_out, double* rew
   if (!h->has_reset) return fail(LOBSIM_E_STATE, "step before reset");
   AdvParams p; base_params(h, p);
   p.T = 1; p.agent_kind = LOBSIM_AGENT_EXTERNAL; p.actions_in = actions; p.obs = obs_out; p.rew = reward_out; p.done = done_out;
-  return launch_advance<true>(h, p, (cudaStream_t)stream);
+  h->agent_orders_possible = true;
+  return launch_advance<true, true>(h, p, (cudaStream_t)stream);
 }
 
 static int ensure_staging(lobsim* h) {
@@ -627,14 +644,17 @@ int lobsim_rollout(lobsim_t* h, int32_t T, const lobsim_agent_t* agent, double* 
   AdvParams p; base_params(h, p);
   p.T = T; p.agent_kind = agent->kind; p.agent = *agent; p.obs = obs; p.rew = rew; p.done = done;
   if (agent->kind == LOBSIM_AGENT_EXTERNAL) p.actions_in = act; else p.act = act;
-  return launch_advance<true>(h, p, (cudaStream_t)stream);
+  if (agent->kind != LOBSIM_AGENT_NONE) h->agent_orders_possible = true;
+  return launch_advance<true, true>(h, p, (cudaStream_t)stream);
 }
 
 int lobsim_replay(lobsim_t* h, int32_t n_steps, void* stream) {
   if (!h || n_steps < 0) return fail(LOBSIM_E_INVALID, "bad argument");
   AdvParams p; base_params(h, p);
   p.T = n_steps; p.agent_kind = LOBSIM_AGENT_NONE;
-  return launch_advance<false>(h, p, (cudaStream_t)stream);
+  // fast path: no fill log requested and no agent order can be resting in any book
+  if (!h->fill_log && !h->agent_orders_possible) return launch_advance<false, false>(h, p, (cudaStream_t)stream);
+  return launch_advance<false, true>(h, p, (cudaStream_t)stream);
 }
 
 int lobsim_get_state_dev(lobsim_t* h, lobsim_env_state_t* out_dev, void* stream) {
@@ -695,6 +715,7 @@ int lobsim_process_orders(lobsim_t* h, const lobsim_order_t* orders, int32_t n, 
   CUDA_TRY(cudaMemset(d_nf, 0, sizeof(int32_t)));
   OrdParams p; p.blobs = h->blobs; p.L = h->L; p.n_envs = h->cfg.n_envs; p.orders = d_orders; p.n = n;
   p.fills = max_fills > 0 ? d_fills : nullptr; p.max_fills = max_fills; p.n_fills = d_nf; p.refs_out = d_refs;
+  h->agent_orders_possible = true;
   k_process_orders<<<1, 32, h->L.blob_bytes>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
