@@ -274,15 +274,29 @@ int lobsim_replay(lobsim_t* h, int32_t n_steps, void* stream);
 int lobsim_replay_host(lobsim_t* h, int stream_id, const lobsim_msg_t* msgs_host, uint64_t first_msg,
                        uint64_t n_msgs, int32_t n_steps, lobsim_env_state_t* state_out_host);
 
+/* exactly ONE OrderbookSimulator.forward_step(until = now + n_steps * step_size) for every env: like lobsim_replay
+ * but the outer-level resync (OrderbookSimulator.py:86-87) is evaluated once, at `until`, as the reference does when
+ * it is stepped over more than one grid interval at a time.                                                     */
+int lobsim_forward_step(lobsim_t* h, int32_t n_steps, void* stream);
+
 /* OrderbookSimulator.reset_episode only (no features, no warm-up): book := snapshot at grid step `start_step`   */
 int lobsim_reset_book(lobsim_t* h, const int32_t* env_ids_dev, int32_t n, const int32_t* stream_ids_dev,
                       const int32_t* start_steps_dev, void* stream);
 
 /* Exchange.process_order (rl4mm/orderbook/Exchange.py:58-69) for a host list of orders, applied in order.
- * fills_out_host (capacity max_fills) receives FilledOrders in emission order, refs_out_host[i] the internal id
- * assigned to order i when it is an agent limit order that rested (0 otherwise).                                */
+ * fills_out_host (capacity max_fills) receives FilledOrders in emission order; refs_out_host[i] is, for a limit order
+ * (or its unfilled remainder) that RESTED in the book -- i.e. whenever the reference's OrderIdConvertor hands out a
+ * new internal id (OrderIDConvertor.py:12-18) --, the agent order id (agent orders) or 0xffffffff (external orders),
+ * and 0 otherwise.                                                                                                */
 int lobsim_process_orders(lobsim_t* h, const lobsim_order_t* orders_host, int32_t n, lobsim_fill_t* fills_out_host,
                           int32_t max_fills, int32_t* n_fills_out, uint32_t* refs_out_host);
+
+/* Exchange(central_orderbook=..., internal_orderbook=...) (Exchange.py:40-49) / `exchange.central_orderbook = book`:
+ * replaces env's books by the given L3 entries (per side: best level first, FIFO order inside a level, exactly the
+ * lobsim_dump_book format; ref = LOBSIM_REF_AGENT | id marks the agent's own orders, which also form the internal
+ * book).  The simulator clock and portfolio are left untouched.                                                 */
+int lobsim_set_book(lobsim_t* h, int32_t env, const lobsim_book_entry_t* buy_host, int32_t n_buy,
+                    const lobsim_book_entry_t* sell_host, int32_t n_sell);
 
 /* L3 dump of one env's central book side, best level first, FIFO order within a level
  * (rl4mm/extras/orderbook_comparison.py:6-19 is the L2 projection of this).  Returns the number of entries.     */

@@ -247,10 +247,8 @@ static void submit_order(lo_t* o, o_msg* m, uint32_t* ref_out) {
   r.iid = ++o->counter; r.vol = m->vol; r.ext = m->ext; r.is_ext = m->is_ext;
   if (m->is_ext) map_put(&o->ext2int, m->ext, r.iid);
   level_append(side_get_or_insert(&o->central.s[m->dir], m->price), r);
-  if (!m->is_ext) {
-    level_append(side_get_or_insert(&o->internal.s[m->dir], m->price), r);
-    if (ref_out) *ref_out = (uint32_t)r.iid;
-  }
+  if (!m->is_ext) level_append(side_get_or_insert(&o->internal.s[m->dir], m->price), r);
+  if (ref_out) *ref_out = m->is_ext ? 0xffffffffu : (uint32_t)r.iid;
 }
 
 /* Exchange.execute_order -- Exchange.py:85-120 */

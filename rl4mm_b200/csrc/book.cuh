@@ -253,7 +253,7 @@ __device__ __forceinline__ void record_external(WarpState& w, int dir, int vol) 
 }
 
 // ---- Exchange.submit_order (no-cross branch), Exchange.py:74-83 ------------------------------------------------
-// returns the agent id given to the order (0 for external orders / on overflow)
+// returns the agent id given to the order, 0xffffffff for an external order that rested, 0 on overflow
 // TR == false is the replay fast path: no agent orders can rest in the book, fills are not recorded.
 template <bool TR>
 __device__ __forceinline__ uint32_t rest_order(const Book& b, WarpState& w, int side, int price, int vol, uint32_t ref, bool is_agent) {
@@ -273,7 +273,7 @@ __device__ __forceinline__ uint32_t rest_order(const Book& b, WarpState& w, int 
     __syncwarp();
   }
   add_order(b, w, side, j, vol, ref);
-  return id;
+  return is_agent ? id : 0xffffffffu; // external order rested (the reference assigns it an internal id here)
 }
 
 // ---- Exchange.submit_order / execute_order, Exchange.py:71-120 --------------------------------------------------

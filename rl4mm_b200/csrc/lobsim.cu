@@ -14,7 +14,9 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <mutex>
+#include <utility>
 #include <new>
 #include <string>
 #include <vector>
@@ -85,6 +87,7 @@ struct AdvParams {
   const int32_t* reset_steps;       // [n_sel]: book reset: start step; env reset: episode start step
   int32_t agent_kind;               // LOBSIM_AGENT_*
   int32_t out_final_obs_only;       // reset: write obs once, after the warm-up
+  int32_t resync_last_only;         // forward_step over several grid steps: resync check only at the end
   const double* actions_in;         // EXTERNAL: [T][n_sel][action_dim]
   double* obs; double* act; double* rew; uint8_t* done; // [T][n_sel][...] (any may be null)
   lobsim_agent_t agent;
@@ -251,7 +254,7 @@ __global__ void __launch_bounds__(128, kEnv ? 3 : (kTrack ? 4 : 7)) k_advance(co
     if (!w.dead) {
       now_step++;
       // ---- resync, OrderbookSimulator.py:86-87 ----------------------------------------------------------------------
-      if (c.resync) {
+      if (c.resync && (!p.resync_last_only || t == T - 1)) {
         long long rel = (long long)now_step * c.step_us;
         if (rel % 1000000 == 0 && near_exiting(b, w, c)) {
           long long sec = rel / 1000000;
@@ -655,6 +658,71 @@ int lobsim_replay(lobsim_t* h, int32_t n_steps, void* stream) {
   // fast path: no fill log requested and no agent order can be resting in any book
   if (!h->fill_log && !h->agent_orders_possible) return launch_advance<false, false>(h, p, (cudaStream_t)stream);
   return launch_advance<false, true>(h, p, (cudaStream_t)stream);
+}
+
+int lobsim_forward_step(lobsim_t* h, int32_t n_steps, void* stream) {
+  if (!h || n_steps < 0) return fail(LOBSIM_E_INVALID, "bad argument");
+  AdvParams p; base_params(h, p);
+  p.T = n_steps; p.agent_kind = LOBSIM_AGENT_NONE; p.resync_last_only = 1;
+  return launch_advance<false, true>(h, p, (cudaStream_t)stream);
+}
+
+int lobsim_set_book(lobsim_t* h, int32_t env, const lobsim_book_entry_t* buy, int32_t n_buy, const lobsim_book_entry_t* sell, int32_t n_sell) {
+  if (!h || env < 0 || env >= h->cfg.n_envs || n_buy < 0 || n_sell < 0 || (!buy && n_buy) || (!sell && n_sell)) return fail(LOBSIM_E_INVALID, "bad argument");
+  const Layout& L = h->L;
+  if (n_buy > L.NO || n_sell > L.NO) return fail(LOBSIM_E_INVALID, "more orders than max_orders_per_side");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  std::vector<unsigned char> buf(L.blob_bytes);
+  unsigned char* gblob = h->blobs + (size_t)env * L.blob_bytes;
+  CUDA_TRY(cudaMemcpy(buf.data(), gblob, L.blob_bytes, cudaMemcpyDeviceToHost));
+  BookHdr* hd = reinterpret_cast<BookHdr*>(buf.data());
+  uint32_t max_agent_id = 0;
+  for (int side = 0; side < 2; side++) {
+    const lobsim_book_entry_t* e = side ? sell : buy;
+    const int n = side ? n_sell : n_buy;
+    unsigned char* sb = buf.data() + L.side_off + side * L.side_stride;
+    int32_t* lvp = reinterpret_cast<int32_t*>(sb);
+    uint16_t* lvend = reinterpret_cast<uint16_t*>(sb + L.lvend_off);
+    uint2* ord = reinterpret_cast<uint2*>(sb + L.ord_off);
+    int32_t* ap = reinterpret_cast<int32_t*>(buf.data() + L.agent_off + side * L.NA * 12);
+    int32_t* av = ap + L.NA;
+    uint32_t* ai = reinterpret_cast<uint32_t*>(ap + 2 * L.NA);
+    // entries arrive best level first; storage is worst level first => walk the levels backwards
+    std::vector<std::pair<int, int>> levels; // [first, last) index ranges of equal price, best first
+    for (int i = 0; i < n;) {
+      int j = i;
+      while (j < n && e[j].price == e[i].price) j++;
+      if (!levels.empty()) {
+        int prev = e[levels.back().first].price;
+        if (side == 0 ? e[i].price >= prev : e[i].price <= prev) return fail(LOBSIM_E_INVALID, "entries must be sorted best level first");
+      }
+      levels.push_back({i, j});
+      i = j;
+    }
+    if ((int)levels.size() > L.NL) return fail(LOBSIM_E_INVALID, "more levels than max_levels_per_side");
+    int nlv = (int)levels.size(), pos = 0, nag = 0;
+    std::vector<std::pair<uint32_t, int>> agent; // (id, entry index)
+    for (int k = nlv - 1; k >= 0; k--) {
+      int j = nlv - 1 - k;
+      lvp[j] = e[levels[k].first].price;
+      for (int i = levels[k].first; i < levels[k].second; i++) {
+        if (e[i].volume < 0) return fail(LOBSIM_E_INVALID, "negative volume");
+        ord[pos++] = make_uint2((unsigned)e[i].volume, e[i].ref);
+        if (e[i].ref & LOBSIM_REF_AGENT) agent.push_back({e[i].ref & 0x7fffffffu, i});
+      }
+      lvend[j] = (uint16_t)pos;
+    }
+    if ((int)agent.size() > L.NA) return fail(LOBSIM_E_INVALID, "more agent orders than max_agent_orders");
+    std::sort(agent.begin(), agent.end());
+    for (auto& a : agent) { ap[nag] = e[a.second].price; av[nag] = e[a.second].volume; ai[nag] = a.first; nag++; if (a.first > max_agent_id) max_agent_id = a.first; }
+    hd->nlv[side] = nlv; hd->nord[side] = pos; hd->nag[side] = nag;
+  }
+  if (hd->next_agent_id <= max_agent_id) hd->next_agent_id = max_agent_id + 1;
+  hd->dead = 0; hd->err = 0;
+  CUDA_TRY(cudaMemcpy(gblob, buf.data(), L.blob_bytes, cudaMemcpyHostToDevice));
+  h->agent_orders_possible = true;
+  return LOBSIM_OK;
 }
 
 int lobsim_get_state_dev(lobsim_t* h, lobsim_env_state_t* out_dev, void* stream) {

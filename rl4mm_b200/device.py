@@ -129,6 +129,15 @@ class LobSim:
     def replay(self, n_steps: int, stream=None) -> None:
         check(lib().lobsim_replay(self._h, int(n_steps), self._stream_arg(stream)))
 
+    def forward_step(self, n_steps: int, stream=None) -> None:
+        """One OrderbookSimulator.forward_step over ``n_steps`` grid steps (resync evaluated once, at the end)."""
+        check(lib().lobsim_forward_step(self._h, int(n_steps), self._stream_arg(stream)))
+
+    def set_book(self, env: int, buy: np.ndarray, sell: np.ndarray) -> None:
+        buy = np.ascontiguousarray(buy, dtype=abi.BOOK_ENTRY_DTYPE)
+        sell = np.ascontiguousarray(sell, dtype=abi.BOOK_ENTRY_DTYPE)
+        check(lib().lobsim_set_book(self._h, env, np_ptr(buy), len(buy), np_ptr(sell), len(sell)))
+
     def replay_host(self, stream_id: int, msgs_host: np.ndarray, first_msg: int, n_steps: int,
                     state_out: Optional[np.ndarray] = None) -> None:
         """Upload ``msgs_host`` (a slice of the stream starting at message ``first_msg``) and replay ``n_steps``."""

@@ -160,3 +160,19 @@ def test_synthetic_stream_is_self_consistent():
         assert st["best_buy"] == snap[0, 0, 0] and st["best_sell"] == snap[1, 0, 0], sec
         if sec > 120:  # the initial aggregates near the touch are gone by now: volumes agree too
             assert st["best_buy_volume"] == snap[0, 0, 1] and st["best_sell_volume"] == snap[1, 0, 1], sec
+
+
+def test_host_beta_distributor_matches_reference_lots():
+    """rl4mm_b200.gym.BetaOrderDistributor (the host twin of the kernel's ladder) against scipy's lot sizes."""
+    import parity_helpers as H
+    from rl4mm_b200.gym import BetaOrderDistributor
+
+    n = 0
+    for grp in H.load_golden("beta_ladders.json.gz"):
+        d = BetaOrderDistributor(grp["quote_levels"], grp["active_volume"], grp["concentration"])
+        acts = np.array([c["action"] for c in grp["cases"]])
+        out = d.convert_action(acts)
+        for i, c in enumerate(grp["cases"]):
+            assert list(out["buy"][i]) == c["buy"] and list(out["sell"][i]) == c["sell"], (grp["quote_levels"], c["action"])
+            n += 1
+    assert n > 900
