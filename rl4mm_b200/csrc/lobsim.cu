@@ -215,6 +215,7 @@ __global__ void __launch_bounds__(128, kEnv ? 3 : (kTrack ? 4 : 7)) k_advance(co
   };
   if (g < g_end_all) { issue_tile(); issue_tile(); }
   __syncwarp();
+  if (!kTrack) refresh_best(b, w);
 
   double action[5] = {0, 0, 0, 0, 0};
   for (int t = 0; t < T; t++) {
@@ -241,14 +242,20 @@ __global__ void __launch_bounds__(128, kEnv ? 3 : (kTrack ? 4 : 7)) k_advance(co
       while (g < g_step_end) {
         const unsigned tile = g / MSG_TILE - tile0;
         if (tile == next_wait) wait_tile();
-        const uint4 m = *reinterpret_cast<const uint4*>(msgbuf + (tile & 1) * MSG_TILE_BYTES + (g % MSG_TILE) * 16);
-        process_message<kTrack>(b, w, (int)m.x, (int)m.y, m.z, m.w);
-        g++;
-        if (g % MSG_TILE == 0) { // tile consumed: refill its buffer with the tile after the next one
+        const unsigned tile_end = (g / MSG_TILE + 1) * MSG_TILE;
+        const unsigned lim = g_step_end < tile_end ? g_step_end : tile_end;
+        const uint4* buf = reinterpret_cast<const uint4*>(msgbuf + (tile & 1) * MSG_TILE_BYTES);
+        for (; g < lim; g++) {
+          const uint4 m = buf[g % MSG_TILE];
+          if (kTrack) process_message<true>(b, w, (int)m.x, (int)m.y, m.z, m.w);
+          else process_message_fast(b, w, (int)m.x, (int)m.y, m.z, m.w);
+          if (w.dead) break;
+        }
+        if (w.dead) break;
+        if (g == tile_end) { // tile consumed: refill its buffer with the tile after the next one
           __syncwarp();
           issue_tile();
         }
-        if (w.dead) break;
       }
     }
     if (!w.dead) {
@@ -258,7 +265,10 @@ __global__ void __launch_bounds__(128, kEnv ? 3 : (kTrack ? 4 : 7)) k_advance(co
         long long rel = (long long)now_step * c.step_us;
         if (rel % 1000000 == 0 && near_exiting(b, w, c)) {
           long long sec = rel / 1000000;
-          if (sec <= (long long)stp->n_seconds && stp->snap_valid[sec]) update_outer_levels<kTrack>(b, w, c, stp->snapshots + (size_t)sec * 2 * c.n_levels * 2, scratch);
+          if (sec <= (long long)stp->n_seconds && stp->snap_valid[sec]) {
+            update_outer_levels<kTrack>(b, w, c, stp->snapshots + (size_t)sec * 2 * c.n_levels * 2, scratch);
+            if (!kTrack) refresh_best(b, w);
+          }
         }
       }
     }
