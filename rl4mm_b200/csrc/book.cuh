@@ -27,8 +27,7 @@
 #define FULL_MASK 0xffffffffu
 
 struct __align__(16) BookHdr {
-  int32_t nlv[2];
-  int32_t nord[2];
+  int32_t cnt[2][2]; // cnt[side] = {number of levels, number of orders}
   int32_t nag[2];
   uint32_t next_agent_id;
   uint32_t err;
@@ -76,8 +75,6 @@ struct WarpState {
   double cash;
   // flow of the current step: [recorded direction]
   int n_ext0, n_ext1, vol_ext0, vol_ext1, n_int0, n_int1, vol_int0, vol_int1;
-  // cached best prices (replay fast path only): INT32_MIN / INT32_MAX when the side is empty
-  int best0, best1;
   // optional fill log (global memory)
   lobsim_fill_t* fill_log;
   int fill_cap, n_fills;
@@ -367,186 +364,6 @@ __device__ __forceinline__ void process_message(const Book& b, WarpState& w, int
   else remove_order<TR>(b, w, side, price, vol, true, ref, false);
 }
 
-// =====================================================================================================================
-//  Replay fast path.  Same semantics as process_message<false>, specialised for the overwhelmingly common shapes --
-//  the touched level is among the 32 best, at most 32 queue entries have to move, no capacity is exhausted -- as
-//  straight-line warp-wide code (no search / shift loops).  Anything else falls back, BEFORE mutating the book, to
-//  the general routines above.  The best prices are cached in registers (w.best0 / w.best1).
-// =====================================================================================================================
-__device__ __forceinline__ void refresh_best(const Book& b, WarpState& w) {
-  __syncwarp();
-  w.best0 = w.nlv0 ? b.lvp(0)[w.nlv0 - 1] : INT32_MIN;
-  w.best1 = w.nlv1 ? b.lvp(1)[w.nlv1 - 1] : INT32_MAX;
-}
-
-__device__ __forceinline__ void process_message_fast(const Book& b, WarpState& w, int price, int vol, uint32_t ref, uint32_t meta) {
-  const int type = (int)LOBSIM_META_TYPE(meta), side = (int)LOBSIM_META_DIR(meta);
-  const int lane = b.lane;
-  if (vol <= 0) { w.err |= LOBSIM_ERR_BAD_VOLUME; return; }
-  if (type == LOBSIM_MSG_MARKET || (type == LOBSIM_MSG_LIMIT && (side == 0 ? price >= w.best1 : price <= w.best0))) {
-    // ---- execution against the opposite best queue (Exchange.py:85-120) -------------------------------------------
-    const int opp = side ^ 1;
-    unsigned char* sb = b.blob + b.L.side_off + opp * b.L.side_stride;
-    int32_t* P = reinterpret_cast<int32_t*>(sb);
-    uint16_t* LE = reinterpret_cast<uint16_t*>(sb + b.L.lvend_off);
-    uint2* O = reinterpret_cast<uint2*>(sb + b.L.ord_off);
-    int rem = vol;
-    int nl = NLV(w, opp), n = NORD(w, opp);
-    while (rem > 0) {
-      if (nl == 0) {
-        if (type == LOBSIM_MSG_MARKET) { w.err |= LOBSIM_ERR_EMPTY_BOOK; w.dead = 1; }
-        break;
-      }
-      const int j = nl - 1;
-      const int bp = GET2(opp, w.best0, w.best1);
-      if (type == LOBSIM_MSG_LIMIT && !(side == 0 ? price >= bp : price <= bp)) break;
-      const int start = j > 0 ? (int)LE[j - 1] : 0;     // the best level is the last segment: [start, n)
-      const int len = n - start;
-      uint2 e = make_uint2(0u, 0u);
-      if (lane < len) e = O[start + lane];               // first 32 entries of the best queue
-      const int hv = (int)__shfl_sync(FULL_MASK, e.x, 0);
-      if (rem < hv) {                                    // partial fill of the head
-        if (lane == 0) O[start].x = (unsigned)(hv - rem);
-        rem = 0;
-        break;
-      }
-      rem -= hv;                                         // the head is consumed
-      if (len > 33) {                                    // rare: long queue, general shift
-        __syncwarp();
-        shift_down(O, start, 1, n, lane);
-      } else {
-        uint2 e32 = make_uint2(0u, 0u);
-        if (len == 33 && lane == 0) e32 = O[start + 32];
-        __syncwarp();
-        if (lane >= 1 && lane < len) O[start + lane - 1] = e;
-        if (len == 33 && lane == 0) O[start + 31] = e32;
-      }
-      n -= 1;
-      if (len == 1) {                                    // level emptied: it is the last one, nothing to shift
-        nl -= 1;
-        __syncwarp();
-        const int nb = nl ? P[nl - 1] : (opp ? INT32_MAX : INT32_MIN);
-        if (opp) w.best1 = nb; else w.best0 = nb;
-      } else if (lane == 0) LE[j] = (uint16_t)n;
-      __syncwarp();
-    }
-    __syncwarp();
-    SET_NLV(w, opp, nl); SET_NORD(w, opp, n);
-    if (rem > 0 && type == LOBSIM_MSG_LIMIT && !w.dead) {
-      // the remainder rests (Exchange.py:116-119): handled by the general path (rare)
-      rest_order<false>(b, w, side, price, rem, ref, false);
-      refresh_best(b, w);
-    }
-    return;
-  }
-  unsigned char* sb = b.blob + b.L.side_off + side * b.L.side_stride;
-  int32_t* P = reinterpret_cast<int32_t*>(sb);
-  uint16_t* LE = reinterpret_cast<uint16_t*>(sb + b.L.lvend_off);
-  uint2* O = reinterpret_cast<uint2*>(sb + b.L.ord_off);
-  const int nlv = NLV(w, side), nord = NORD(w, side);
-  // ---- level search among the 32 best levels ----------------------------------------------------------------------
-  const int idx = nlv - 1 - lane;
-  const int tkey = side ? -price : price;
-  int k = INT32_MIN;
-  if (idx >= 0) { const int p = P[idx]; k = side ? -p : p; }
-  const unsigned eq = __ballot_sync(FULL_MASK, k == tkey);
-  const unsigned gt = __ballot_sync(FULL_MASK, k > tkey);
-  if (type == LOBSIM_MSG_LIMIT) {
-    // ---- a non-crossing limit order rests (Exchange.py:74-83) -------------------------------------------------------
-    const int c = __popc(gt);
-    if ((!eq && (c == 32 || nlv >= b.L.NL)) || nord >= b.L.NO) { // deep level or a capacity limit: general path
-      rest_order<false>(b, w, side, price, vol, ref, false);
-      refresh_best(b, w);
-      return;
-    }
-    int j, pos;
-    if (eq) {
-      j = nlv - __ffs(eq);                              // = nlv - 1 - (ffs - 1)
-      pos = LE[j];
-    } else {
-      j = nlv - c;                                      // insertion index; the c better levels move up by one
-      pos = j > 0 ? (int)LE[j - 1] : 0;
-      int pv = 0; unsigned short ev = 0;
-      const int i = j + lane;
-      if (i < nlv) { pv = P[i]; ev = LE[i]; }
-      __syncwarp();
-      if (i < nlv) { P[i + 1] = pv; LE[i + 1] = ev; }
-      if (lane == 0) { P[j] = price; LE[j] = (uint16_t)pos; }
-      if (c == 0) { if (side) w.best1 = price; else w.best0 = price; }
-      __syncwarp();
-    }
-    const int nlv2 = eq ? nlv : nlv + 1;
-    const int above = nord - pos;                        // entries of better levels that move up by one
-    if (above > 32) { __syncwarp(); shift_up1(O, pos, nord, lane); }
-    else {
-      uint2 v = make_uint2(0u, 0u);
-      if (lane < above) v = O[pos + lane];
-      __syncwarp();
-      if (lane < above) O[pos + lane + 1] = v;
-    }
-    if (lane == 0) O[pos] = make_uint2((unsigned)vol, ref);
-    { const int i = j + lane; if (i < nlv2) LE[i] = (uint16_t)(LE[i] + 1); }   // nlv2 - j <= 32
-    __syncwarp();
-    SET_NLV(w, side, nlv2); SET_NORD(w, side, nord + 1);
-    return;
-  }
-  // ---- cancellation / deletion (Exchange.py:122-147) ------------------------------------------------------------------
-  if (!eq) {
-    if (__popc(gt) == 32) { remove_order<false>(b, w, side, price, vol, true, ref, false); refresh_best(b, w); }
-    return;                                              // level absent: nothing to do (:129-132)
-  }
-  const int j = nlv - __ffs(eq);
-  const int start = j > 0 ? (int)LE[j - 1] : 0, end = LE[j];
-  const int len = end - start;
-  if (len > 32 || nord - start > 64) {                   // long queue / long shift: general path
-    remove_order<false>(b, w, side, price, vol, true, ref, false);
-    refresh_best(b, w);
-    return;
-  }
-  uint2 e = make_uint2(0u, 0xffffffffu);
-  if (lane < len) e = O[start + lane];
-  const unsigned m = __ballot_sync(FULL_MASK, lane < len && e.y == ref);
-  int l;
-  if (m) l = __ffs(m) - 1;
-  else {
-    if (__shfl_sync(FULL_MASK, e.y, 0) != LOBSIM_REF_AGGREGATE) return;  // already filled (:138-139)
-    l = 0;                                                              // hit the aggregate at the head (:133-137)
-  }
-  const int cur = (int)__shfl_sync(FULL_MASK, e.x, l);
-  const int pos = start + l;
-  if (vol < cur) {                                       // partial: reduce in place
-    if (lane == l) O[pos].x = (unsigned)(cur - vol);
-    __syncwarp();
-    return;
-  }
-  // full removal: entries (pos, nord) move down by one (at most 63 of them)
-  const int tail = nord - pos - 1;
-  uint2 v0 = make_uint2(0u, 0u), v1 = make_uint2(0u, 0u);
-  if (lane < tail) v0 = O[pos + 1 + lane];
-  if (lane + 32 < tail) v1 = O[pos + 33 + lane];
-  __syncwarp();
-  if (lane < tail) O[pos + lane] = v0;
-  if (lane + 32 < tail) O[pos + 32 + lane] = v1;
-  const int above_levels = nlv - j;                      // <= 32
-  if (len == 1) {                                        // the level disappears: better levels move down by one
-    int pv = 0; unsigned short ev = 0;
-    const int i = j + 1 + lane;
-    if (i < nlv) { pv = P[i]; ev = LE[i]; }
-    __syncwarp();
-    if (i < nlv) { P[i - 1] = pv; LE[i - 1] = (uint16_t)(ev - 1); }
-    SET_NLV(w, side, nlv - 1);
-    if (j == nlv - 1) {                                  // it was the best level
-      __syncwarp();
-      const int nb = nlv - 1 > 0 ? P[nlv - 2] : (side ? INT32_MAX : INT32_MIN);
-      if (side) w.best1 = nb; else w.best0 = nb;
-    }
-  } else {
-    if (lane < above_levels) LE[j + lane] = (uint16_t)(LE[j + lane] - 1);
-  }
-  __syncwarp();
-  SET_NORD(w, side, nord - 1);
-}
-
 // ---- Orderbook properties, rl4mm/orderbook/models.py:72-101 -------------------------------------------------------
 __device__ __forceinline__ int best_level_volume(const Book& b, int side, int nlv) {
   int j = nlv - 1;
@@ -569,7 +386,7 @@ __device__ __forceinline__ double microprice(int bb, int bs, int bv, int sv, dou
 template <bool FULL>
 __device__ __forceinline__ void load_state(const Book& b, WarpState& w) {
   const BookHdr* h = b.hdr();
-  w.nlv0 = h->nlv[0]; w.nlv1 = h->nlv[1]; w.nord0 = h->nord[0]; w.nord1 = h->nord[1];
+  w.nlv0 = h->cnt[0][0]; w.nlv1 = h->cnt[1][0]; w.nord0 = h->cnt[0][1]; w.nord1 = h->cnt[1][1];
   w.err = h->err; w.dead = h->dead;
   w.nag0 = w.nag1 = 0; w.next_agent_id = 0; w.inventory = 0; w.cash = 0.0;
   if (FULL) { w.nag0 = h->nag[0]; w.nag1 = h->nag[1]; w.next_agent_id = h->next_agent_id; w.inventory = h->inventory; w.cash = h->cash; }
@@ -580,7 +397,7 @@ __device__ __forceinline__ void store_state(const Book& b, const WarpState& w) {
   __syncwarp();
   if (b.lane == 0) {
     BookHdr* h = b.hdr();
-    h->nlv[0] = w.nlv0; h->nlv[1] = w.nlv1; h->nord[0] = w.nord0; h->nord[1] = w.nord1;
+    h->cnt[0][0] = w.nlv0; h->cnt[1][0] = w.nlv1; h->cnt[0][1] = w.nord0; h->cnt[1][1] = w.nord1;
     h->err = w.err; h->dead = w.dead;
     if (FULL) { h->nag[0] = w.nag0; h->nag[1] = w.nag1; h->next_agent_id = w.next_agent_id; h->inventory = w.inventory; h->cash = w.cash; }
   }

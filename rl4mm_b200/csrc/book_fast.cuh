@@ -1,0 +1,245 @@
+// book_fast.cuh -- the replay fast path (k_advance<false,false>): same semantics as process_message<false> in
+// book.cuh, specialised for the overwhelmingly common shapes -- the touched level is among the 32 best, at most 32
+// (64 for removals) queue entries have to move, no capacity is exhausted -- as straight-line warp-wide code without
+// search / shift loops.  Anything else falls back, BEFORE mutating the book, to the general routines.
+//
+// Differences from the general path, all for instruction count (the kernel is issue-bound):
+//   * the layout is a compile-time constant (StaticLayout<NL,NO,NA>), so every array access is base + immediate;
+//   * the per-side counters {nlv, nord} stay in the shared-memory header and are read / written with one 64-bit
+//     access keyed by the side, instead of living in registers behind per-side selects;
+//   * the best price of each side is cached in registers for the crossing test.
+#pragma once
+#include "book.cuh"
+
+template <int NL_, int NO_, int NA_>
+struct StaticLayout {
+  static constexpr int NL = NL_, NO = NO_, NA = NA_;
+  static constexpr int side_off = (int)sizeof(BookHdr);
+  static constexpr int lvend_off = NL * 4;
+  static constexpr int ord_off = (NL * 4 + NL * 2 + 7) & ~7;
+  static constexpr int side_stride = (ord_off + NO * 8 + 15) & ~15;
+  static constexpr int agent_off = side_off + 2 * side_stride;
+  static constexpr int blob_bytes = (agent_off + 2 * NA * 12 + 15) & ~15;
+  __host__ __device__ static bool matches(const Layout& l) {
+    return l.NL == NL && l.NO == NO && l.NA == NA && l.side_off == side_off && l.lvend_off == lvend_off && l.ord_off == ord_off &&
+           l.side_stride == side_stride && l.agent_off == agent_off && l.blob_bytes == blob_bytes;
+  }
+};
+
+struct FastState {
+  int best0, best1; // INT32_MIN / INT32_MAX when the side is empty
+  uint32_t err;
+  int dead;
+};
+
+template <class LT>
+struct FastBook {
+  unsigned char* blob;
+  int lane;
+  __device__ __forceinline__ int2* cnt(int s) const { return reinterpret_cast<int2*>(blob) + s; }
+  __device__ __forceinline__ unsigned char* side(int s) const { return blob + LT::side_off + s * LT::side_stride; }
+  static __device__ __forceinline__ int32_t* P(unsigned char* sb) { return reinterpret_cast<int32_t*>(sb); }
+  static __device__ __forceinline__ uint16_t* LE(unsigned char* sb) { return reinterpret_cast<uint16_t*>(sb + LT::lvend_off); }
+  static __device__ __forceinline__ uint2* O(unsigned char* sb) { return reinterpret_cast<uint2*>(sb + LT::ord_off); }
+};
+
+// general-path fallbacks: run a book.cuh routine on a WarpState materialised from the header.  They are real
+// (noinline) functions taking everything BY VALUE, so that no hot-path variable has its address taken; they return
+// the updated (err | dead << 31) word and the caller re-reads the best prices from shared memory.
+__device__ __forceinline__ uint32_t pack_errdead(uint32_t err, int dead) { return err | ((uint32_t)dead << 31); }
+
+__device__ __noinline__ uint32_t fallback_rest(unsigned char* blob, const Layout* L, int lane, int side, int price, int vol, uint32_t ref, uint32_t errdead) {
+  Book b; b.blob = blob; b.L = *L; b.lane = lane;
+  WarpState w;
+  __syncwarp();
+  load_state<false>(b, w);
+  w.err = errdead & 0x7fffffffu; w.dead = (int)(errdead >> 31); w.fill_log = nullptr; w.fill_cap = 0; w.n_fills = 0;
+  rest_order<false>(b, w, side, price, vol, ref, false);
+  store_state<false>(b, w);
+  return pack_errdead(w.err, w.dead);
+}
+__device__ __noinline__ uint32_t fallback_remove(unsigned char* blob, const Layout* L, int lane, int side, int price, int vol, uint32_t ref, uint32_t errdead) {
+  Book b; b.blob = blob; b.L = *L; b.lane = lane;
+  WarpState w;
+  __syncwarp();
+  load_state<false>(b, w);
+  w.err = errdead & 0x7fffffffu; w.dead = (int)(errdead >> 31); w.fill_log = nullptr; w.fill_cap = 0; w.n_fills = 0;
+  remove_order<false>(b, w, side, price, vol, true, ref, false);
+  store_state<false>(b, w);
+  return pack_errdead(w.err, w.dead);
+}
+
+template <class LT>
+__device__ __forceinline__ void fast_refresh_best(const FastBook<LT>& fb, FastState& f) {
+  __syncwarp();
+  const int n0 = fb.cnt(0)->x, n1 = fb.cnt(1)->x;
+  f.best0 = n0 ? fb.P(fb.side(0))[n0 - 1] : INT32_MIN;
+  f.best1 = n1 ? fb.P(fb.side(1))[n1 - 1] : INT32_MAX;
+}
+
+template <class LT>
+__device__ __forceinline__ void fast_message(const FastBook<LT>& fb, FastState& f, const Layout* L, int price, int vol, uint32_t ref, uint32_t meta) {
+  const int type = (int)(meta & 7u), side = (int)((meta >> 3) & 1u);
+  const int lane = fb.lane;
+  if (vol <= 0) { f.err |= LOBSIM_ERR_BAD_VOLUME; return; }
+  const bool crosses = side ? price <= f.best0 : price >= f.best1;
+  if (type == LOBSIM_MSG_MARKET || (type == LOBSIM_MSG_LIMIT && crosses)) {
+    // ---- execution against the opposite best queue (Exchange.py:85-120) -------------------------------------------
+    const int opp = side ^ 1;
+    unsigned char* sb = fb.side(opp);
+    int2 c = *fb.cnt(opp);
+    int rem = vol;
+#pragma unroll 1
+    while (rem > 0) {
+      if (c.x == 0) {
+        if (type == LOBSIM_MSG_MARKET) { f.err |= LOBSIM_ERR_EMPTY_BOOK; f.dead = 1; } // EmptyOrderbookError :183-186
+        break;
+      }
+      const int bp = opp ? f.best1 : f.best0;
+      if (type == LOBSIM_MSG_LIMIT && !(side ? price <= bp : price >= bp)) break;
+      const int j = c.x - 1;
+      const int start = j > 0 ? (int)fb.LE(sb)[j - 1] : 0;   // the best level is the last segment: [start, nord)
+      const int len = c.y - start;
+      uint2 e = make_uint2(0u, 0u);
+      if (lane < len) e = fb.O(sb)[start + lane];           // first 32 entries of the best queue
+      const int hv = (int)__shfl_sync(FULL_MASK, e.x, 0);
+      if (rem < hv) {                                        // partial fill of the head
+        if (lane == 0) fb.O(sb)[start].x = (unsigned)(hv - rem);
+        rem = 0;
+        break;
+      }
+      rem -= hv;                                             // the head is consumed
+      if (len > 33) { __syncwarp(); shift_down(fb.O(sb), start, 1, c.y, lane); }
+      else {
+        uint2 e32 = make_uint2(0u, 0u);
+        if (len == 33 && lane == 0) e32 = fb.O(sb)[start + 32];
+        __syncwarp();
+        if (lane >= 1 && lane < len) fb.O(sb)[start + lane - 1] = e;
+        if (len == 33 && lane == 0) fb.O(sb)[start + 31] = e32;
+      }
+      c.y -= 1;
+      if (len == 1) {                                        // level emptied: it is the last one, nothing to shift
+        c.x -= 1;
+        const int nb = c.x ? fb.P(sb)[c.x - 1] : (opp ? INT32_MAX : INT32_MIN);
+        if (opp) f.best1 = nb; else f.best0 = nb;
+      } else if (lane == 0) fb.LE(sb)[j] = (uint16_t)c.y;
+      __syncwarp();
+    }
+    if (lane == 0) *fb.cnt(opp) = c;
+    __syncwarp();
+    if (rem > 0 && type == LOBSIM_MSG_LIMIT && !f.dead) {    // the remainder rests (Exchange.py:116-119); rare
+      const uint32_t ed = fallback_rest(fb.blob, L, lane, side, price, rem, ref, pack_errdead(f.err, f.dead));
+      f.err = ed & 0x7fffffffu; f.dead = (int)(ed >> 31);
+      fast_refresh_best(fb, f);
+    }
+    return;
+  }
+  unsigned char* sb = fb.side(side);
+  const int2 c = *fb.cnt(side);
+  const int nlv = c.x, nord = c.y;
+  // ---- level search among the 32 best levels (prices compared as keys: bids p, asks -p) ---------------------------
+  const int sm = -side;                                      // 0 or 0xffffffff
+  const int idx = nlv - 1 - lane;
+  const int tkey = (price ^ sm) - sm;
+  int k = INT32_MIN;
+  if (idx >= 0) k = (fb.P(sb)[idx] ^ sm) - sm;
+  const unsigned eq = __ballot_sync(FULL_MASK, k == tkey);
+  const unsigned gt = __ballot_sync(FULL_MASK, k > tkey);
+  if (type == LOBSIM_MSG_LIMIT) {
+    // ---- a non-crossing limit order rests (Exchange.py:74-83) -------------------------------------------------------
+    const int cb = __popc(gt);
+    if ((!eq && (cb == 32 || nlv >= LT::NL)) || nord >= LT::NO) { // deep level or a capacity limit: general path
+      const uint32_t ed = fallback_rest(fb.blob, L, lane, side, price, vol, ref, pack_errdead(f.err, f.dead));
+      f.err = ed & 0x7fffffffu; f.dead = (int)(ed >> 31);
+      fast_refresh_best(fb, f);
+      return;
+    }
+    int j, pos;
+    if (eq) {
+      j = nlv - __ffs(eq);
+      pos = fb.LE(sb)[j];
+    } else {
+      j = nlv - cb;                                          // insertion index; the cb better levels move up by one
+      pos = j > 0 ? (int)fb.LE(sb)[j - 1] : 0;
+      int pv = 0; unsigned short ev = 0;
+      const int i = j + lane;
+      if (i < nlv) { pv = fb.P(sb)[i]; ev = fb.LE(sb)[i]; }
+      __syncwarp();
+      if (i < nlv) { fb.P(sb)[i + 1] = pv; fb.LE(sb)[i + 1] = ev; }
+      if (lane == 0) { fb.P(sb)[j] = price; fb.LE(sb)[j] = (uint16_t)pos; }
+      if (cb == 0) { if (side) f.best1 = price; else f.best0 = price; }
+      __syncwarp();
+    }
+    const int nlv2 = eq ? nlv : nlv + 1;
+    const int above = nord - pos;                            // entries of better levels that move up by one
+    if (above > 32) { __syncwarp(); shift_up1(fb.O(sb), pos, nord, lane); }
+    else if (above > 0) {
+      uint2 v = make_uint2(0u, 0u);
+      if (lane < above) v = fb.O(sb)[pos + lane];
+      __syncwarp();
+      if (lane < above) fb.O(sb)[pos + lane + 1] = v;
+    }
+    if (lane == 0) { fb.O(sb)[pos] = make_uint2((unsigned)vol, ref); *fb.cnt(side) = make_int2(nlv2, nord + 1); }
+    { const int i = j + lane; if (i < nlv2) fb.LE(sb)[i] = (uint16_t)(fb.LE(sb)[i] + 1); }   // nlv2 - j <= 32
+    __syncwarp();
+    return;
+  }
+  // ---- cancellation / deletion (Exchange.py:122-147) ------------------------------------------------------------------
+  if (!eq) {
+    if (__popc(gt) == 32) {                                  // the level may be deeper than the 32 best
+      const uint32_t ed = fallback_remove(fb.blob, L, lane, side, price, vol, ref, pack_errdead(f.err, f.dead));
+      f.err = ed & 0x7fffffffu; f.dead = (int)(ed >> 31);
+      fast_refresh_best(fb, f);
+    }
+    return;                                                  // level absent: nothing to do (:129-132)
+  }
+  const int j = nlv - __ffs(eq);
+  const int start = j > 0 ? (int)fb.LE(sb)[j - 1] : 0, end = fb.LE(sb)[j];
+  const int len = end - start;
+  if (len > 32 || nord - start > 64) {                       // long queue / long shift: general path
+    const uint32_t ed = fallback_remove(fb.blob, L, lane, side, price, vol, ref, pack_errdead(f.err, f.dead));
+    f.err = ed & 0x7fffffffu; f.dead = (int)(ed >> 31);
+    fast_refresh_best(fb, f);
+    return;
+  }
+  uint2 e = make_uint2(0u, 0xffffffffu);
+  if (lane < len) e = fb.O(sb)[start + lane];
+  const unsigned m = __ballot_sync(FULL_MASK, lane < len && e.y == ref);   // _find_queue_position :196-217
+  int l;
+  if (m) l = __ffs(m) - 1;
+  else {
+    if (__shfl_sync(FULL_MASK, e.y, 0) != LOBSIM_REF_AGGREGATE) return;    // already filled (:138-139)
+    l = 0;                                                                // hit the aggregate at the head (:133-137)
+  }
+  const int cur = (int)__shfl_sync(FULL_MASK, e.x, l);
+  const int pos = start + l;
+  if (vol < cur) {                                           // partial: reduce in place
+    if (lane == l) fb.O(sb)[pos].x = (unsigned)(cur - vol);
+    __syncwarp();
+    return;
+  }
+  // full removal (over-size requests remove the resting volume, :142-146): entries (pos, nord) move down by one
+  const int tail = nord - pos - 1;                           // <= 63
+  uint2 v0 = make_uint2(0u, 0u), v1 = make_uint2(0u, 0u);
+  if (lane < tail) v0 = fb.O(sb)[pos + 1 + lane];
+  if (lane + 32 < tail) v1 = fb.O(sb)[pos + 33 + lane];
+  __syncwarp();
+  if (lane < tail) fb.O(sb)[pos + lane] = v0;
+  if (lane + 32 < tail) fb.O(sb)[pos + 32 + lane] = v1;
+  if (len == 1) {                                            // the level disappears: better levels move down by one
+    int pv = 0; unsigned short ev = 0;
+    const int i = j + 1 + lane;
+    if (i < nlv) { pv = fb.P(sb)[i]; ev = fb.LE(sb)[i]; }
+    __syncwarp();
+    if (i < nlv) { fb.P(sb)[i - 1] = pv; fb.LE(sb)[i - 1] = (uint16_t)(ev - 1); }
+    if (lane == 0) *fb.cnt(side) = make_int2(nlv - 1, nord - 1);
+    if (j == nlv - 1) {                                      // it was the best level
+      const int nb = nlv > 1 ? fb.P(sb)[nlv - 2] : (side ? INT32_MAX : INT32_MIN);
+      if (side) f.best1 = nb; else f.best0 = nb;
+    }
+  } else {
+    if (lane < nlv - j) fb.LE(sb)[j + lane] = (uint16_t)(fb.LE(sb)[j + lane] - 1);   // nlv - j <= 32
+    if (lane == 0) *fb.cnt(side) = make_int2(nlv, nord - 1);
+  }
+  __syncwarp();
+}

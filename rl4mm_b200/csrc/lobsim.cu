@@ -21,6 +21,7 @@
 #include <string>
 #include <vector>
 
+#include "book_fast.cuh"
 #include "env.cuh"
 #include "lobsim.h"
 
@@ -103,7 +104,7 @@ __device__ __forceinline__ unsigned char* warp_smem_base(unsigned char* smem, in
 // kEnv: agent + features + rewards (HistoricalOrderbookEnvironment.step); kTrack: fills / flows / agent orders are
 // tracked (always with kEnv; the pure replay fast path <false,false> is used when no agent order can be resting).
 template <bool kEnv, bool kTrack>
-__global__ void __launch_bounds__(128, kEnv ? 3 : (kTrack ? 4 : 7)) k_advance(const __grid_constant__ AdvParams p, const __grid_constant__ EnvConst ec) {
+__global__ void __launch_bounds__(128, kEnv ? 3 : 4) k_advance(const __grid_constant__ AdvParams p, const __grid_constant__ EnvConst ec) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int sel = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -215,7 +216,6 @@ __global__ void __launch_bounds__(128, kEnv ? 3 : (kTrack ? 4 : 7)) k_advance(co
   };
   if (g < g_end_all) { issue_tile(); issue_tile(); }
   __syncwarp();
-  if (!kTrack) refresh_best(b, w);
 
   double action[5] = {0, 0, 0, 0, 0};
   for (int t = 0; t < T; t++) {
@@ -247,8 +247,7 @@ __global__ void __launch_bounds__(128, kEnv ? 3 : (kTrack ? 4 : 7)) k_advance(co
         const uint4* buf = reinterpret_cast<const uint4*>(msgbuf + (tile & 1) * MSG_TILE_BYTES);
         for (; g < lim; g++) {
           const uint4 m = buf[g % MSG_TILE];
-          if (kTrack) process_message<true>(b, w, (int)m.x, (int)m.y, m.z, m.w);
-          else process_message_fast(b, w, (int)m.x, (int)m.y, m.z, m.w);
+          process_message<kTrack>(b, w, (int)m.x, (int)m.y, m.z, m.w);
           if (w.dead) break;
         }
         if (w.dead) break;
@@ -267,8 +266,7 @@ __global__ void __launch_bounds__(128, kEnv ? 3 : (kTrack ? 4 : 7)) k_advance(co
           long long sec = rel / 1000000;
           if (sec <= (long long)stp->n_seconds && stp->snap_valid[sec]) {
             update_outer_levels<kTrack>(b, w, c, stp->snapshots + (size_t)sec * 2 * c.n_levels * 2, scratch);
-            if (!kTrack) refresh_best(b, w);
-          }
+                    }
         }
       }
     }
@@ -323,6 +321,129 @@ __global__ void __launch_bounds__(128, kEnv ? 3 : (kTrack ? 4 : 7)) k_advance(co
   if (lane == 0) { tma_store(gblob, base, (uint32_t)p.L.blob_bytes); tma_store_wait(); }
   __syncwarp();
 }
+
+// ====================================================================================================================
+//  the replay fast kernel: T x (messages of the step + [resync]) with the straight-line message path of book_fast.cuh.
+//  Used by lobsim_replay when no fill log is requested, no agent order can be resting and the book capacities match
+//  one of the compiled StaticLayouts.  72 registers => 7 CTAs x 4 warps = 28 books resident per SM.
+// ====================================================================================================================
+__device__ __noinline__ uint32_t fallback_resync(unsigned char* blob, const Layout* L, int lane, const lobsim_cfg_t* c, const int32_t* row, int2* scratch, uint32_t errdead) {
+  Book b; b.blob = blob; b.L = *L; b.lane = lane;
+  WarpState w;
+  __syncwarp();
+  load_state<false>(b, w);
+  w.err = errdead & 0x7fffffffu; w.dead = (int)(errdead >> 31); w.fill_log = nullptr; w.fill_cap = 0; w.n_fills = 0;
+  update_outer_levels<false>(b, w, *c, row, scratch);
+  store_state<false>(b, w);
+  return pack_errdead(w.err, w.dead);
+}
+
+template <class LT>
+__global__ void __launch_bounds__(128, 7) k_replay_fast(const __grid_constant__ AdvParams p, const __grid_constant__ EnvConst ec) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int env = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (env >= p.n_sel) return;
+  const lobsim_cfg_t& c = ec.cfg;
+  unsigned char* base = warp_smem_base(smem, warp, p.warp_smem);
+  unsigned char* msgbuf = base + LT::blob_bytes;
+  int2* scratch = reinterpret_cast<int2*>(msgbuf + 2 * MSG_TILE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(scratch) + 2 * LT::NA * 8);
+  unsigned char* gblob = p.blobs + (size_t)env * LT::blob_bytes;
+  if (lane == 0) {
+    mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
+    fence_mbar_init();
+    mbar_expect_tx(&bars[2], (uint32_t)LT::blob_bytes);
+    tma_load(base, gblob, (uint32_t)LT::blob_bytes, &bars[2]);
+  }
+  __syncwarp();
+  mbar_wait(&bars[2], 0);
+
+  FastBook<LT> fb; fb.blob = base; fb.lane = lane;
+  BookHdr* h = reinterpret_cast<BookHdr*>(base);
+  FastState f; f.err = h->err; f.dead = h->dead;
+  fast_refresh_best(fb, f);
+  const lobsim_stream_t* stp = &p.streams[h->stream_id];
+  const lobsim_msg_t* __restrict__ st_msgs = stp->msgs;
+  const uint32_t* __restrict__ st_step_off = stp->step_off;
+  int now_step = h->now_step;
+  const int T = p.T;
+  if (!(now_step >= 0 && (long long)now_step + T <= (long long)stp->n_grid_steps) && !f.dead && T > 0) { f.err |= LOBSIM_ERR_END_OF_STREAM; f.dead = 1; }
+  unsigned g = 0, g_end_all = 0;
+  if (!f.dead && T > 0) { g = __ldg(&st_step_off[now_step]); g_end_all = __ldg(&st_step_off[now_step + T]); }
+  const unsigned tile0 = g / MSG_TILE;
+  unsigned next_issue = 0, next_wait = 0;
+  auto issue_tile = [&]() {
+    const unsigned first = (tile0 + next_issue) * MSG_TILE;
+    if (first >= g_end_all) return;
+    if (lane == 0) {
+      const unsigned n_total = (unsigned)stp->n_msgs;
+      const unsigned cnt = n_total - first < MSG_TILE ? n_total - first : MSG_TILE;
+      uint64_t* bar = &bars[next_issue & 1];
+      mbar_expect_tx(bar, cnt * 16);
+      tma_load(msgbuf + (next_issue & 1) * MSG_TILE_BYTES, st_msgs + first, cnt * 16, bar);
+    }
+    next_issue++;
+  };
+  auto wait_tile = [&]() { mbar_wait(&bars[next_wait & 1], (next_wait >> 1) & 1); next_wait++; };
+  if (g < g_end_all) { issue_tile(); issue_tile(); }
+  __syncwarp();
+  const int steps_per_sec = (int)(1000000 / c.step_us);
+  int sub = now_step >= 0 ? now_step % steps_per_sec : 0;   // position inside the current second
+
+#pragma unroll 1
+  for (int t = 0; t < T && !f.dead; t++) {
+    const unsigned g_step_end = __ldg(&st_step_off[now_step + 1]);
+#pragma unroll 1
+    while (g < g_step_end) {
+      const unsigned tile = g / MSG_TILE - tile0;
+      if (tile == next_wait) wait_tile();
+      const unsigned tile_end = (g / MSG_TILE + 1) * MSG_TILE;
+      const unsigned lim = g_step_end < tile_end ? g_step_end : tile_end;
+      const uint4* mp = reinterpret_cast<const uint4*>(msgbuf + (tile & 1) * MSG_TILE_BYTES) + (g % MSG_TILE);
+      const unsigned cnt = lim - g;
+#pragma unroll 1
+      for (unsigned i = 0; i < cnt; i++) {
+        const uint4 m = mp[i];
+        fast_message(fb, f, &p.L, (int)m.x, (int)m.y, m.z, m.w);
+        if (f.dead) break;
+      }
+      if (f.dead) break;
+      g = lim;
+      if (g == tile_end) { __syncwarp(); issue_tile(); }
+    }
+    if (f.dead) break;
+    now_step++;
+    if (++sub == steps_per_sec) {                            // whole second: outer-level resync, OrderbookSimulator.py:86-87
+      sub = 0;
+      if (c.resync && (!p.resync_last_only || t == T - 1)) {
+        const double prop = (double)c.outer_levels / (double)c.n_levels;
+        const double bb = f.best0 == INT32_MIN ? 0.0 : (double)f.best0;
+        const double bs = f.best1 == INT32_MAX ? (double)INFINITY : (double)f.best1;
+        if (bb < (double)h->min_buy + prop * (double)h->init_buy_range || bs > (double)h->max_sell - prop * (double)h->init_sell_range) {
+          const long long sec = (long long)now_step / steps_per_sec;
+          if (sec <= (long long)stp->n_seconds && stp->snap_valid[sec]) {
+            const int32_t* row = stp->snapshots + (size_t)sec * 2 * c.n_levels * 2;
+            const uint32_t ed = fallback_resync(base, &p.L, lane, &ec.cfg, row, scratch, pack_errdead(f.err, f.dead));
+            f.err = ed & 0x7fffffffu; f.dead = (int)(ed >> 31);
+            fast_refresh_best(fb, f);
+          }
+        }
+      }
+    }
+  }
+  while (next_wait < next_issue) wait_tile();                // drain TMA loads still in flight (aborted episode)
+  __syncwarp();
+  if (lane == 0) { h->now_step = now_step; h->err = f.err; h->dead = f.dead; }
+  __syncwarp();
+  fence_proxy_async();
+  __syncwarp();
+  if (lane == 0) { tma_store(gblob, base, (uint32_t)LT::blob_bytes); tma_store_wait(); }
+  __syncwarp();
+}
+
+typedef StaticLayout<64, 256, 32> FastLayoutA;   // BASELINE config 2 (10-level books)
+typedef StaticLayout<128, 512, 64> FastLayoutB;  // the default capacities (50-level books)
 
 // ====================================================================================================================
 //  Exchange.process_order for a list of orders (drop-in / test entry point; one warp, sequential)
@@ -390,7 +511,7 @@ __global__ void k_get_state(const unsigned char* blobs, Layout L, int first, int
   s.next_agent_id = h->next_agent_id; s.reserved = 0;
   int best[2] = {0, INT32_MAX}, bvol[2] = {0, 0};
   for (int side = 0; side < 2; side++) {
-    int nlv = h->nlv[side];
+    int nlv = h->cnt[side][0];
     if (!nlv) continue;
     const unsigned char* sb = blob + L.side_off + side * L.side_stride;
     const int32_t* lvp = reinterpret_cast<const int32_t*>(sb);
@@ -506,10 +627,12 @@ int lobsim_create(const lobsim_cfg_t* cfg, int device, lobsim_t** out) {
   while (h->warps_per_cta > 1 && h->warps_per_cta * h->warp_smem > max_smem) h->warps_per_cta >>= 1;
   CUDA_TRY((cudaFuncSetAttribute(k_advance<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->warps_per_cta * h->warp_smem)));
   CUDA_TRY((cudaFuncSetAttribute(k_advance<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->warps_per_cta * h->warp_smem)));
-  CUDA_TRY((cudaFuncSetAttribute(k_advance<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->warps_per_cta * h->warp_smem)));
+  CUDA_TRY((cudaFuncSetAttribute(k_replay_fast<FastLayoutA>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->warps_per_cta * h->warp_smem)));
+  CUDA_TRY((cudaFuncSetAttribute(k_replay_fast<FastLayoutB>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->warps_per_cta * h->warp_smem)));
   CUDA_TRY((cudaFuncSetAttribute(k_advance<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)));
   CUDA_TRY((cudaFuncSetAttribute(k_advance<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)));
-  CUDA_TRY((cudaFuncSetAttribute(k_advance<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)));
+  CUDA_TRY((cudaFuncSetAttribute(k_replay_fast<FastLayoutA>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)));
+  CUDA_TRY((cudaFuncSetAttribute(k_replay_fast<FastLayoutB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)));
   CUDA_TRY(cudaFuncSetAttribute(k_process_orders, cudaFuncAttributeMaxDynamicSharedMemorySize, h->L.blob_bytes));
   // feature rings
   memset(&h->ec, 0, sizeof h->ec);
@@ -592,6 +715,19 @@ static int launch_advance(lobsim* h, const AdvParams& p, cudaStream_t stream) {
   return LOBSIM_OK;
 }
 
+static int launch_replay_fast(lobsim* h, const AdvParams& p, cudaStream_t stream) {
+  if (h->streams.empty()) return fail(LOBSIM_E_STATE, "no stream loaded");
+  const bool a = FastLayoutA::matches(h->L), b = FastLayoutB::matches(h->L);
+  if (!a && !b) return 1;
+  CUDA_TRY(cudaSetDevice(h->device));
+  const int wpc = h->warps_per_cta, grid = (p.n_sel + wpc - 1) / wpc;
+  if (a) k_replay_fast<FastLayoutA><<<grid, wpc * 32, (size_t)wpc * h->warp_smem, stream>>>(p, h->ec);
+  else k_replay_fast<FastLayoutB><<<grid, wpc * 32, (size_t)wpc * h->warp_smem, stream>>>(p, h->ec);
+  CUDA_TRY(cudaGetLastError());
+  h->launches++;
+  return LOBSIM_OK;
+}
+
 extern "C" {
 
 int lobsim_reset_book(lobsim_t* h, const int32_t* env_ids, int32_t n, const int32_t* stream_ids, const int32_t* start_steps, void* stream) {
@@ -666,7 +802,10 @@ int lobsim_replay(lobsim_t* h, int32_t n_steps, void* stream) {
   AdvParams p; base_params(h, p);
   p.T = n_steps; p.agent_kind = LOBSIM_AGENT_NONE;
   // fast path: no fill log requested and no agent order can be resting in any book
-  if (!h->fill_log && !h->agent_orders_possible) return launch_advance<false, false>(h, p, (cudaStream_t)stream);
+  if (!h->fill_log && !h->agent_orders_possible) {
+    int rc = launch_replay_fast(h, p, (cudaStream_t)stream);
+    if (rc != 1) return rc; // 1: no compiled StaticLayout matches these capacities
+  }
   return launch_advance<false, true>(h, p, (cudaStream_t)stream);
 }
 
@@ -726,7 +865,7 @@ int lobsim_set_book(lobsim_t* h, int32_t env, const lobsim_book_entry_t* buy, in
     if ((int)agent.size() > L.NA) return fail(LOBSIM_E_INVALID, "more agent orders than max_agent_orders");
     std::sort(agent.begin(), agent.end());
     for (auto& a : agent) { ap[nag] = e[a.second].price; av[nag] = e[a.second].volume; ai[nag] = a.first; nag++; if (a.first > max_agent_id) max_agent_id = a.first; }
-    hd->nlv[side] = nlv; hd->nord[side] = pos; hd->nag[side] = nag;
+    hd->cnt[side][0] = nlv; hd->cnt[side][1] = pos; hd->nag[side] = nag;
   }
   if (hd->next_agent_id <= max_agent_id) hd->next_agent_id = max_agent_id + 1;
   hd->dead = 0; hd->err = 0;
@@ -829,8 +968,8 @@ int lobsim_dump_book(lobsim_t* h, int32_t env, int32_t side, lobsim_book_entry_t
   const uint16_t* lvend = reinterpret_cast<const uint16_t*>(sb + L.lvend_off);
   const uint2* ord = reinterpret_cast<const uint2*>(sb + L.ord_off);
   int n = 0;
-  for (int k = 0; k < hd->nlv[side]; k++) { // best level first
-    int j = hd->nlv[side] - 1 - k;
+  for (int k = 0; k < hd->cnt[side][0]; k++) { // best level first
+    int j = hd->cnt[side][0] - 1 - k;
     int start = j > 0 ? lvend[j - 1] : 0, end = lvend[j];
     for (int i = start; i < end; i++) {
       if (out && n < capacity) { out[n].price = lvp[j]; out[n].volume = (int32_t)ord[i].x; out[n].ref = ord[i].y; out[n].level = k; }

@@ -3,5 +3,5 @@ cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
 timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke.log
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_advance -s 4 -c 1 -f -o gpurun_out/prof_replay python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_replay_fast -s 4 -c 1 -f -o gpurun_out/prof_replay python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
 tail -3 gpurun_out/smoke.log; tail -3 gpurun_out/ncu_full.log; ls -la gpurun_out
