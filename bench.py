@@ -169,10 +169,122 @@ def workload_config(args, stream):
     }
 
 
+def run_rollout(args):
+    """BASELINE.json configs[2]: HistoricalOrderbookEnvironment rollouts with a Beta-policy (torch MLP 2x64 tanh ->
+    sigmoid x 10) between steps, PnL reward, default full_state features, `--envs-per-gpu` envs (65536 in the config).
+    One bench step = T = 128 env steps of every env: policy forward (torch) + lobsim_step (one launch) per env step."""
+    import torch
+    import torch.distributed as dist
+
+    from rl4mm_b200 import abi, parallel
+    from rl4mm_b200.device import LobSim
+    from rl4mm_b200.features import _us
+    from rl4mm_b200.gym import HistoricalOrderbookEnvironment
+    from datetime import timedelta
+
+    rank, world, local_rank = parallel.init_from_env()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    stream = make_stream(args)
+    n_envs, T = args.envs_per_gpu, 128
+    feats = HistoricalOrderbookEnvironment.get_default_features(timedelta(seconds=0.1), timedelta(minutes=30))
+    warm = int(max(f.window_size for f in feats) / timedelta(seconds=0.1))
+    cfg = abi.default_cfg(n_envs=n_envs, n_levels=stream.n_levels, episode_steps=18000, warmup_steps=warm,
+                          features=[f.to_abi() for f in feats], step_reward=abi.Reward(abi.REWARD_PNL, 0, 0.0),
+                          terminal_reward=abi.Reward(abi.REWARD_PNL, 0, 0.0), initial_cash=1000.0,
+                          max_levels_per_side=64, max_orders_per_side=256, max_agent_orders=64, outer_levels=20)
+    sim = LobSim(cfg, local_rank)
+    sim.load_stream(0, stream)
+    rng = np.random.default_rng(1234 + rank)
+    sps = stream.steps_per_second
+    # episode starts on whole seconds in [10:00, 15:00] (grid origin 09:30)
+    starts = ((1800 + rng.integers(0, 5 * 3600, size=n_envs)) * sps).astype(np.int32)
+    obs = sim.reset(0, starts)
+    torch.manual_seed(0)
+    policy = torch.nn.Sequential(torch.nn.Linear(obs.shape[1], 64), torch.nn.Tanh(), torch.nn.Linear(64, 64), torch.nn.Tanh(),
+                                 torch.nn.Linear(64, 4)).to(dev).double()
+    scale = torch.tensor([1e-2, 1e-2, 1e-2, 1e3, 1e3, 1e-2, 1.0, 0.1, 1.0, 1.0], device=dev, dtype=torch.float64)
+
+    def act(o):
+        with torch.no_grad():
+            return torch.sigmoid(policy(o * scale)) * 10.0
+
+    def rollout(o):
+        for _ in range(T):
+            o, r, d = sim.step(act(o))
+        return o
+
+    cur = torch.cuda.current_stream(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for _ in range(args.warmup):
+        obs = rollout(obs)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = sim.launch_count
+    now0 = sim.state()["now_step"].astype(np.int64)
+    ev = []
+    for _ in range(args.steps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(cur)
+        obs = rollout(obs)
+        b.record(cur)
+        ev.append((a, b))
+    torch.cuda.synchronize(dev)
+    launches = sim.launch_count - l0
+    clocks = sampler.stop()
+    st = sim.state()
+    assert np.all(st["err"] == 0), np.unique(st["err"])
+    t_dev = parallel.max_over_ranks(sum(a.elapsed_time(b) for a, b in ev) / 1e3, dev)
+    off = stream.step_off.astype(np.int64)
+    msgs = int((off[st["now_step"]] - off[now0]).sum())
+    # end-to-end: host actions in, host obs/reward/done out through lobsim_step_host (pinned buffers)
+    a_host = torch.empty((n_envs, 4), dtype=torch.float64).pin_memory()
+    o_host = torch.empty((n_envs, obs.shape[1]), dtype=torch.float64).pin_memory()
+    r_host = torch.empty(n_envs, dtype=torch.float64).pin_memory()
+    d_host = torch.empty(n_envs, dtype=torch.uint8).pin_memory()
+    a_host.copy_(act(obs))
+    torch.cuda.synchronize(dev)
+    n_e2e = 32
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        sim.step_host(a_host.numpy(), o_host.numpy(), r_host.numpy(), d_host.numpy())
+    t_e2e = parallel.max_over_ranks(time.perf_counter() - t0, dev)
+    env_steps = args.steps * T * n_envs * world
+    peak, peak_src = measured_peaks()
+    algo = (ALGO_BYTES_PER_MSG * msgs / (args.steps * T) + (ALGO_BYTES_PER_STEP_ENV + 2 * S_STATE_L10) * n_envs)
+    achieved = algo / (t_dev / (args.steps * T)) / 1e9
+    line = {
+        "metric": "env_steps_per_sec", "value": env_steps / t_dev, "unit": "env steps/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "configs[2]: HistoricalOrderbookEnvironment rollouts, torch MLP Beta policy between steps, "
+                               "PnL reward, default full_state features (F=10), %d envs per GPU, T=128 env steps per bench step" % n_envs,
+                   "envs_per_gpu": n_envs, "n_levels": stream.n_levels, "T": T, "l2": "flushed between timed iterations (256 MiB write)"},
+        "lob_messages_per_sec": msgs * world / t_dev,
+        "e2e": {"value": n_e2e * n_envs * world / t_e2e, "unit": "env steps/s", "h2d_bytes_per_step": a_host.numel() * 8,
+                "d2h_bytes_per_step": o_host.numel() * 8 + r_host.numel() * 8 + d_host.numel(),
+                "api": "lobsim_step_host (C ABI, pinned host buffers), policy excluded"},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "peak_source": peak_src, "kernel": "k_advance<true,true> (one launch per env step; includes the torch policy time)",
+                     "algorithmic_bytes_per_launch": algo},
+    }
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "rollout":
+        return run_rollout(args)
 
     import torch
     import torch.distributed as dist

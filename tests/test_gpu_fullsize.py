@@ -1,0 +1,135 @@
+"""Size-independent properties at BASELINE.json's full sizes (the oracle is too slow to sweep these sizes; it is used
+on a sample of books only):
+
+* replay of a whole synthetic day through thousands of books: every replica ends bit-identical, the simulated top of
+  book equals the generator's own snapshot at every checkpoint (the generator keeps an independent book), no error
+  flag, and a second pass from the same snapshot reproduces the same state (determinism / idempotence of reset);
+* a sample of books is compared with the CPU oracle (full L3) at the end;
+* env rollouts at 65 536 books: replicas with equal start and actions stay identical, distinct starts differ, no errors.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+from rl4mm_b200 import abi
+
+pytestmark = pytest.mark.gpu
+
+
+def _sim(cfg, streams):
+    import torch
+
+    assert torch.cuda.is_available()
+    from rl4mm_b200.device import LobSim
+
+    sim = LobSim(cfg, 0)
+    for i, s in enumerate(streams):
+        sim.load_stream(i, s)
+    return sim
+
+
+def test_config2_full_day_replay_4096_books():
+    from oracle.oracle import Oracle
+    from rl4mm_b200 import synthetic
+
+    s = synthetic.generate(synthetic.spy_day(seed=0, n_msgs=10_000_000, duration_s=23_400))
+    n = 4096
+    cfg = abi.default_cfg(n_envs=n, n_levels=10, outer_levels=20, max_levels_per_side=64, max_orders_per_side=256,
+                          max_agent_orders=32)
+    sim = _sim(cfg, [s])
+    finals = []
+    for attempt in range(2):
+        sim.reset_book(0, 0)
+        for chunk in range(10):
+            sim.replay(23_400)
+            st = sim.state()
+            assert np.all(st["err"] == 0), np.unique(st["err"])
+            sec = (chunk + 1) * 2340
+            assert np.all(st["now_step"] == sec * 10)
+            # every replica identical
+            for f in ("best_buy", "best_sell", "best_buy_volume", "best_sell_volume", "min_buy_price", "max_sell_price"):
+                assert np.all(st[f] == st[f][0]), (chunk, f)
+            # the simulated top of book is the historical one (independent book inside the generator)
+            snap = s.snapshots[sec]
+            assert st["best_buy"][0] == snap[0, 0, 0] and st["best_sell"][0] == snap[1, 0, 0], chunk
+            assert st["best_buy_volume"][0] == snap[0, 0, 1] and st["best_sell_volume"][0] == snap[1, 0, 1], chunk
+        finals.append((sim.dump_book(0, 0), sim.dump_book(0, 1), sim.dump_book(n - 1, 0), sim.dump_book(n - 1, 1)))
+    for a, b in zip(finals[0], finals[1]):
+        assert np.array_equal(a, b)                      # second pass reproduces the first
+    assert np.array_equal(finals[0][0], finals[0][2]) and np.array_equal(finals[0][1], finals[0][3])
+    # L2 of the final book == the generator's final snapshot on the 10 best levels
+    for side in (0, 1):
+        d = finals[0][side]
+        l2 = {}
+        for e in d:
+            l2[int(e["price"])] = l2.get(int(e["price"]), 0) + int(e["volume"])
+        top = sorted(l2, reverse=(side == 0))[:10]
+        exp = [(int(p), int(v)) for p, v in s.snapshots[-1, side] if p != abi.NO_PRICE]
+        assert [(p, l2[p]) for p in top][: len(exp)] == exp[: len(top)]
+    # and the full L3 book equals the CPU oracle's (one book is enough: all replicas are identical)
+    o = Oracle(abi.default_cfg(n_levels=10, outer_levels=20), s)
+    o.reset_book(0)
+    o.replay(234_000)
+    for side in (0, 1):
+        assert np.array_equal(finals[0][side][["price", "volume", "ref"]], o.dump_book(side)[["price", "volume", "ref"]])
+
+
+def test_config5_multi_ticker_heavy_cancel_general_path():
+    """50-level books, deep queues, heavy cancel / modify flow, several tickers: exercises the general
+    (runtime-layout) replay kernel; a sample of books is checked against the oracle."""
+    from oracle.oracle import Oracle
+    from rl4mm_b200 import synthetic
+
+    streams = [synthetic.generate(synthetic.heavy_cancel_ticker(seed=k, n_msgs=1_000_000, duration_s=4680)) for k in range(3)]
+    n = 1536
+    cfg = abi.default_cfg(n_envs=n, n_levels=50, outer_levels=20, max_levels_per_side=128, max_orders_per_side=1536,
+                          max_agent_orders=32)
+    sim = _sim(cfg, streams)
+    sid = (np.arange(n) % 3).astype(np.int32)
+    start = ((np.arange(n) // 3) % 4 * 1000).astype(np.int32)   # four different start seconds per ticker
+    sim.reset_book(sid, start)
+    sim.replay(20_000)
+    st = sim.state()
+    assert np.all(st["err"] == 0), np.unique(st["err"])
+    for k in range(12):  # envs with the same (ticker, start) are replicas
+        grp = np.flatnonzero((sid == k % 3) & (start == (k // 3) * 1000))
+        for f in ("best_buy", "best_sell", "best_buy_volume", "best_sell_volume"):
+            assert np.all(st[f][grp] == st[f][grp[0]])
+    for env in (0, 1, 2, 700, 1535):
+        o = Oracle(abi.default_cfg(n_levels=50, outer_levels=20), streams[int(sid[env])])
+        o.reset_book(int(start[env]))
+        o.replay(20_000)
+        for side in (0, 1):
+            assert np.array_equal(sim.dump_book(env, side)[["price", "volume", "ref"]], o.dump_book(side)[["price", "volume", "ref"]]), (env, side)
+
+
+def test_config3_rollout_65536_envs():
+    import torch
+
+    from rl4mm_b200 import synthetic
+
+    s = synthetic.generate(synthetic.spy_day(seed=0, n_msgs=2_000_000, duration_s=4680))
+    n = 65_536
+    feats = [abi.feature(abi.FEAT_SPREAD, 0, 100000, 0, 5000), abi.feature(abi.FEAT_BOOK_IMBALANCE, 0, 100000, -1, 1),
+             abi.feature(abi.FEAT_INVENTORY, 0, 100000, -1e6, 1e6), abi.feature(abi.FEAT_VOLATILITY, 100, 100000, 0, 1),
+             abi.feature(abi.FEAT_TRADE_VOL_IMBALANCE, 100, 100000, -1, 1)]
+    cfg = abi.default_cfg(n_envs=n, n_levels=10, episode_steps=64, warmup_steps=100, features=feats,
+                          step_reward=abi.Reward(abi.REWARD_PNL, 0, 0), terminal_reward=abi.Reward(abi.REWARD_PNL, 0, 0),
+                          max_levels_per_side=64, max_orders_per_side=256, max_agent_orders=64, portfolio_carryover=0)
+    sim = _sim(cfg, [s])
+    # pairs of replicas: env 2k and 2k+1 share the start; starts are spread over the first hour
+    starts = (100 + (np.arange(n) // 2) % 3000).astype(np.int32) * 10
+    obs0 = sim.reset(0, starts)
+    agent = abi.Agent(kind=abi.AGENT_FIXED, fixed_action=(ctypes.c_double * 5)(2, 3, 2, 3, 0))
+    obs, act, rew, done = sim.rollout(64, agent)
+    st = sim.state()
+    assert np.all(st["err"] == 0), np.unique(st["err"])
+    assert torch.equal(obs[:, 0::2], obs[:, 1::2]) and torch.equal(rew[:, 0::2], rew[:, 1::2])
+    assert bool(done[-1].all()) and not bool(done[:-1].any())
+    assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
+    assert len(np.unique(st["price"])) > 1000            # distinct starts really differ
+    # PnL telescopes: sum of step rewards == final mark-to-market - initial (portfolio reset at episode start)
+    total = rew.sum(0).cpu().numpy()
+    mtm = st["cash"] + st["inventory"] * st["price"]
+    assert np.allclose(total, mtm - 1000.0, rtol=1e-9, atol=1e-3)

@@ -1,6 +1,7 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q --maxfail=10 --tb=short --timeout 300 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+timeout 1200 python -m pytest tests -m gpu -q --maxfail=10 --tb=short --timeout 600 --durations=5 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
 timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.log 2>&1; echo "bench rc=$?" >> gpurun_out/bench.log
-tail -15 gpurun_out/pytest_gpu.log; tail -3 gpurun_out/bench.log | cut -c1-1500
+timeout 900 python bench.py --workload rollout --envs-per-gpu 65536 --steps 3 --warmup 3 > gpurun_out/bench_rollout.log 2>&1; echo "rollout rc=$?" >> gpurun_out/bench_rollout.log
+tail -25 gpurun_out/pytest_gpu.log; tail -3 gpurun_out/bench.log | cut -c1-300; tail -5 gpurun_out/bench_rollout.log | cut -c1-900
