@@ -80,6 +80,8 @@ struct WarpState {
   int fill_cap, n_fills;
 };
 
+static_assert(sizeof(WarpState) <= 128, "WarpState must fit the 128-byte per-warp shared slot");
+
 struct Book {
   unsigned char* blob; // shared memory
   Layout L;
@@ -353,15 +355,13 @@ __device__ __forceinline__ void remove_order(const Book& b, WarpState& w, int si
   if (is_agent && !aggregate) agent_reduce(b, w, side, ref & 0x7fffffffu, rv, false);
 }
 
-// ---- Exchange.process_order for a packed historical message, Exchange.py:58-69 -----------------------------------
+// ---- Exchange.process_order, Exchange.py:58-69: the ONE call site of the general book routines in a kernel ---------
 template <bool TR>
-__device__ __forceinline__ void process_message(const Book& b, WarpState& w, int price, int vol, uint32_t ref, uint32_t meta) {
+__device__ __forceinline__ void process_order(const Book& b, WarpState& w, int type, int side, int price, int vol, uint32_t ref, bool is_agent) {
   if (w.dead) return;
-  int type = (int)LOBSIM_META_TYPE(meta), side = (int)LOBSIM_META_DIR(meta);
   if (vol <= 0) { w.err |= LOBSIM_ERR_BAD_VOLUME; return; }
-  if (type == LOBSIM_MSG_LIMIT) submit_or_execute<TR>(b, w, side, price, vol, ref, true, false);
-  else if (type == LOBSIM_MSG_MARKET) submit_or_execute<TR>(b, w, side, 0, vol, ref, false, false);
-  else remove_order<TR>(b, w, side, price, vol, true, ref, false);
+  if (type == LOBSIM_MSG_LIMIT || type == LOBSIM_MSG_MARKET) submit_or_execute<TR>(b, w, side, price, vol, ref, type == LOBSIM_MSG_LIMIT, is_agent);
+  else remove_order<TR>(b, w, side, price, vol, true, ref, is_agent);
 }
 
 // ---- Orderbook properties, rl4mm/orderbook/models.py:72-101 -------------------------------------------------------

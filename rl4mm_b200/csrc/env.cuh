@@ -47,7 +47,7 @@ __device__ __forceinline__ bool near_exiting(const Book& b, const WarpState& w, 
 // ---- OrderbookSimulator.update_outer_levels, OrderbookSimulator.py:105-135 ---------------------------------------
 // scratch: per-warp shared int2[2*NA] for the agent orders that are cancelled and re-queued behind the aggregates.
 template <bool TR>
-__device__ __forceinline__ void update_outer_levels(const Book& b, WarpState& w, const lobsim_cfg_t& c, const int32_t* __restrict__ row, int2* scratch) {
+__device__ __forceinline__ void update_outer_levels_impl(const Book& b, WarpState& w, const lobsim_cfg_t& c, const int32_t* __restrict__ row, int2* scratch) {
   BookHdr* h = b.hdr();
   const int L = c.n_levels;
   const int min_buy = h->min_buy, max_sell = h->max_sell;
@@ -92,6 +92,13 @@ __device__ __forceinline__ void update_outer_levels(const Book& b, WarpState& w,
     if (w.nlv1 && b.lvp(1)[0] > h->max_sell) h->max_sell = b.lvp(1)[0];
   }
   __syncwarp();
+}
+
+// cold wrapper: a real function call keeps the second copy of the book routines out of the kernel's hot code
+template <bool TR>
+__device__ __noinline__ WarpState update_outer_levels(const Book b, WarpState w, const lobsim_cfg_t* c, const int32_t* row, int2* scratch) {
+  update_outer_levels_impl<TR>(b, w, *c, row, scratch);
+  return w;
 }
 
 // ---- OrderbookSimulator.reset_episode, OrderbookSimulator.py:55-68,156-188 + Exchange.py:172-178 ---------------
@@ -143,6 +150,11 @@ __device__ __forceinline__ void init_book_from_snapshot(const Book& b, WarpState
   __syncwarp();
 }
 
+__device__ __noinline__ WarpState init_book_cold(const Book b, WarpState w, const lobsim_cfg_t* c, const lobsim_stream_t* st, int stream_id, int start_step) {
+  init_book_from_snapshot(b, w, *c, *st, stream_id, start_step);
+  return w;
+}
+
 // ---- BetaOrderDistributor, rl4mm/gym/action_interpretation/OrderDistributors.py:23-56 ----------------------------
 // lane k < Q returns the lot size of quote level k.  The sum follows numpy's pairwise summation order.
 __device__ __forceinline__ int beta_ladder_lane(double a, double bpar, int Q, int active_volume, int lane) {
@@ -175,11 +187,32 @@ __device__ __forceinline__ int beta_ladder_lane(double a, double bpar, int Q, in
   return lane < Q ? (int)rint(e / s * (double)active_volume) : 0;
 }
 
-// ---- HistoricalOrderbookEnvironment.convert_action_to_orders (HOE.py:206-258) fused with the processing of the
-//      resulting agent orders by Exchange.process_order (OrderbookSimulator.py:76-84: agent orders go first) -------
-__device__ __forceinline__ void agent_orders(const Book& b, WarpState& w, const EnvConst& ec, const double* action /* uniform regs */) {
+// ---- HistoricalOrderbookEnvironment.convert_action_to_orders (HOE.py:206-258) as a GENERATOR -----------------------
+// agent_prepare() computes the desired ladders and the per-level volume differences (one quote level per lane);
+// agent_next() then yields the agent's orders one at a time, in the reference's order -- per side: ladder level
+// k = 0..Q-1 (one limit order, or cancellations from the back of the agent's queue at that price, :231-249), then
+// the off-ladder ("wide") orders cancelled in full (:250-257); finally the inventory-clearing market order
+// (:213-215,260-266).  The kernel feeds them through the same process_order call site as the historical messages
+// (agent orders first: OrderbookSimulator.py:76-77).  Cancellations are resolved against the agent table when
+// they are yielded; this equals the reference's up-front list because orders yielded earlier in the same batch never
+// touch the agent's orders at other prices of the same side.
+struct AgentGen {
+  int side, k, need, wide_i;   // cursor: side 0/1 (2 = market order stage, 3 = done)
+  int diff0, diff1, price0, price1; // this lane's quote level
+  int Q, clearing, clear_vol, clear_side;
+  uint32_t pending_id;         // last wide cancel yielded (forces progress if it could not be applied)
+  uint32_t err_out; int dead_out; // error bits raised while preparing
+};
+
+// Cold (noinline, everything by value): the fp64 ladder math must not inflate the register budget of the hot loop.
+__device__ __noinline__ AgentGen agent_prepare(const Book b, int nlv0, int nlv1, int nag0, int nag1, long long inventory, const EnvConst* ecp,
+                                               double a0, double a1, double a2, double a3, double a4) {
+  const EnvConst& ec = *ecp;
   const lobsim_cfg_t& c = ec.cfg;
-  if (w.dead) return;
+  const double action[5] = {a0, a1, a2, a3, a4};
+  AgentGen g;
+  g.side = 3; g.err_out = 0; g.dead_out = 0;
+  g.k = g.need = g.wide_i = g.diff0 = g.diff1 = g.price0 = g.price1 = g.Q = g.clearing = g.clear_vol = g.clear_side = 0; g.pending_id = 0;
   const int Q = c.max_quote_level - c.min_quote_level;
   const double EPS = 0.000001;
   double ab, bbp, as, bsp;
@@ -188,65 +221,82 @@ __device__ __forceinline__ void agent_orders(const Book& b, WarpState& w, const 
   } else { ab = action[0] + EPS; bbp = action[1] + EPS; as = action[2] + EPS; bsp = action[3] + EPS; }
   int desired0 = beta_ladder_lane(ab, bbp, Q, c.active_volume, b.lane);
   int desired1 = beta_ladder_lane(as, bsp, Q, c.active_volume, b.lane);
-  long long absinv = w.inventory < 0 ? -w.inventory : w.inventory;
-  bool clearing = c.market_order_clearing && (double)absinv > pick5(action, ec.action_dim - 1);
+  long long absinv = inventory < 0 ? -inventory : inventory;
+  const bool clearing = c.market_order_clearing && (double)absinv > pick5(action, ec.action_dim - 1);
   if (clearing) desired0 = desired1 = 0;
-  if (w.nlv0 == 0 || w.nlv1 == 0) { w.err |= LOBSIM_ERR_EMPTY_BOOK; w.dead = 1; return; }
-  int bb = b.lvp(0)[w.nlv0 - 1], bs = b.lvp(1)[w.nlv1 - 1];
+  if (nlv0 == 0 || nlv1 == 0) { g.err_out = LOBSIM_ERR_EMPTY_BOOK; g.dead_out = 1; return g; }
+  int bb = b.lvp(0)[nlv0 - 1], bs = b.lvp(1)[nlv1 - 1];
   const int tick = c.tick_size;
   if (c.enter_spread) { // _get_best_prices :298-309
     double mid = (double)(bs + bb) / 2.0;
     bb = (int)(floor(mid / (double)tick) * (double)tick);
     bs = (int)(ceil(mid / (double)tick) * (double)tick);
   }
-  const int price0 = bb - (c.min_quote_level + b.lane) * tick; // ladder price of this lane's quote level
-  const int price1 = bs + (c.min_quote_level + b.lane) * tick;
-  int diff0 = 0, diff1 = 0;
+  g.price0 = bb - (c.min_quote_level + b.lane) * tick; // ladder price of this lane's quote level
+  g.price1 = bs + (c.min_quote_level + b.lane) * tick;
   if (b.lane < Q) { // _get_current_internal_order_volumes :291-296
     int cur0 = 0, cur1 = 0;
-    for (int i = 0; i < w.nag0; i++) cur0 += b.aprice(0)[i] == price0 ? b.avol(0)[i] : 0;
-    for (int i = 0; i < w.nag1; i++) cur1 += b.aprice(1)[i] == price1 ? b.avol(1)[i] : 0;
-    diff0 = desired0 - cur0; diff1 = desired1 - cur1;
+    for (int i = 0; i < nag0; i++) cur0 += b.aprice(0)[i] == g.price0 ? b.avol(0)[i] : 0;
+    for (int i = 0; i < nag1; i++) cur1 += b.aprice(1)[i] == g.price1 ? b.avol(1)[i] : 0;
+    g.diff0 = desired0 - cur0; g.diff1 = desired1 - cur1;
   }
   __syncwarp();
-  for (int side = 0; side < 2 && !w.dead; side++) { // _volume_diff_to_orders :227-258
-    const int myprice = side ? price1 : price0;
-    for (int k = 0; k < Q && !w.dead; k++) {
-      int d = __shfl_sync(FULL_MASK, side ? diff1 : diff0, k);
-      int p = __shfl_sync(FULL_MASK, myprice, k);
-      if (d > 0) submit_or_execute<true>(b, w, side, p, d, 0, true, true);
-      int need = -d;
-      while (need > 0) { // cancel from the back of the agent's queue at this price, :239-249
-        int nag = NAG(w, side), hit = -1;
-        for (int base = (nag - 1) & ~31; base >= 0; base -= 32) {
-          int i = base + b.lane;
-          unsigned m = __ballot_sync(FULL_MASK, i < nag && b.aprice(side)[i] == p);
-          if (m) { hit = base + 31 - __clz(m); break; }
-        }
-        if (hit < 0) break;
-        int av = b.avol(side)[hit];
-        uint32_t id = b.aid(side)[hit];
-        __syncwarp();
-        int v = av < need ? av : need;
-        remove_order<true>(b, w, side, p, v, true, LOBSIM_REF_AGENT | id, true);
-        need -= v;
+  g.side = 0; g.Q = Q;
+  g.clearing = clearing;
+  g.clear_vol = clearing ? (int)rint((double)absinv * c.market_order_fraction_of_inventory) : 0;
+  g.clear_side = inventory < 0 ? 0 : 1;
+  return g;
+}
+
+// yields the next agent order; false when the batch is exhausted
+__device__ __forceinline__ bool agent_next(const Book& b, WarpState& w, AgentGen& g, int& type, int& side, int& price, int& vol, uint32_t& ref) {
+  for (;;) {
+    if (w.dead || g.side >= 3) return false;
+    if (g.side == 2) { // _get_inventory_clearing_market_order :260-266
+      g.side = 3;
+      if (!g.clearing) return false;
+      if (g.clear_vol <= 0) { w.err |= LOBSIM_ERR_BAD_VOLUME; return false; } // assert volume > 0, Exchange.py:59-60
+      type = LOBSIM_MSG_MARKET; side = g.clear_side; price = 0; vol = g.clear_vol; ref = 0;
+      return true;
+    }
+    const int s = g.side;
+    const int myprice = s ? g.price1 : g.price0;
+    if (g.k < g.Q) {
+      const int p = __shfl_sync(FULL_MASK, myprice, g.k);
+      if (g.need == 0) {
+        const int d = __shfl_sync(FULL_MASK, s ? g.diff1 : g.diff0, g.k);
+        if (d > 0) { type = LOBSIM_MSG_LIMIT; side = s; price = p; vol = d; ref = 0; g.k++; return true; }
+        if (d == 0) { g.k++; continue; }
+        g.need = -d;
       }
+      // cancel from the back of the agent's queue at this price, :239-249
+      const int nag = NAG(w, s);
+      int hit = -1;
+      for (int base = (nag - 1) & ~31; base >= 0; base -= 32) {
+        const int i = base + b.lane;
+        const unsigned m = __ballot_sync(FULL_MASK, i < nag && b.aprice(s)[i] == p);
+        if (m) { hit = base + 31 - __clz(m); break; }
+      }
+      if (hit < 0) { g.need = 0; g.k++; continue; }
+      const int av = b.avol(s)[hit];
+      const uint32_t id = b.aid(s)[hit];
+      const int v = av < g.need ? av : g.need;
+      g.need -= v;
+      if (g.need == 0) g.k++;
+      type = LOBSIM_MSG_CANCEL; side = s; price = p; vol = v; ref = LOBSIM_REF_AGENT | id;
+      return true;
     }
-    for (int i = 0; i < NAG(w, side) && !w.dead;) { // agent orders off the ladder are cancelled in full, :250-257
-      int ap = b.aprice(side)[i], av = b.avol(side)[i];
-      uint32_t id = b.aid(side)[i];
-      __syncwarp();
-      bool on_ladder = __ballot_sync(FULL_MASK, b.lane < Q && myprice == ap) != 0;
-      if (on_ladder) { i++; continue; }
-      int before = NAG(w, side);
-      remove_order<true>(b, w, side, ap, av, true, LOBSIM_REF_AGENT | id, true);
-      if (NAG(w, side) == before) agent_remove_at(b, w, side, i);
-    }
-  }
-  if (clearing && !w.dead) { // _get_inventory_clearing_market_order :260-266
-    int vol = (int)rint((double)absinv * c.market_order_fraction_of_inventory);
-    if (vol <= 0) w.err |= LOBSIM_ERR_BAD_VOLUME;
-    else submit_or_execute<true>(b, w, w.inventory < 0 ? 0 : 1, 0, vol, 0, false, true);
+    // agent orders off the ladder are cancelled in full, :250-257
+    if (g.wide_i >= NAG(w, s)) { g.side = s + 1; g.k = 0; g.need = 0; g.wide_i = 0; g.pending_id = 0; continue; }
+    const int ap = b.aprice(s)[g.wide_i], av = b.avol(s)[g.wide_i];
+    const uint32_t id = b.aid(s)[g.wide_i];
+    __syncwarp();
+    if (id == g.pending_id) { agent_remove_at(b, w, s, g.wide_i); g.pending_id = 0; continue; } // keep books consistent
+    const bool on_ladder = __ballot_sync(FULL_MASK, b.lane < g.Q && myprice == ap) != 0;
+    if (on_ladder) { g.wide_i++; continue; }
+    g.pending_id = id;
+    type = LOBSIM_MSG_CANCEL; side = s; price = ap; vol = av; ref = LOBSIM_REF_AGENT | id;
+    return true;
   }
 }
 
@@ -397,4 +447,30 @@ __device__ __forceinline__ void feature_update(const lobsim_feature_t& fc, FeatS
   if ((v.now_us % 60000000LL) % fc.update_us != 0) return;
   feature_update_raw(fc, f, ring, v);
   f.cur = fmax(fmin(f.cur, fc.max_value), fc.min_value);
+}
+
+// Cold per-step feature phase: lane f < F loads its feature state from HBM, resets (mode 1) or updates (mode 0) it,
+// stores it back and returns Feature.current_value.  Keeping this out of line keeps the fp64 / 64-bit-division heavy
+// code (and its registers) away from the order-processing loop.
+__device__ __noinline__ double features_step(const EnvConst* ecp, FeatState* fstate_env, double* rings_env, int lane, const StepView v, long long episode_start_us, int mode) {
+  const EnvConst& ec = *ecp;
+  double cur = 0.0;
+  if (lane < ec.cfg.n_features) {
+    const lobsim_feature_t fc = ec.cfg.features[lane];
+    FeatState fs = fstate_env[lane];
+    double* ring = rings_env + ec.ring_off[lane];
+    if (mode == 1) feature_reset(fc, fs, ring, v);
+    else feature_update(fc, fs, ring, v, episode_start_us);
+    fstate_env[lane] = fs;
+    cur = fs.cur;
+  }
+  return cur;
+}
+
+// Agent.get_action for the fused rollout (cold)
+__device__ __noinline__ void agent_action_cold(const lobsim_agent_t* ag, double inventory_obs, double* out5_smem) {
+  double a[5] = {0, 0, 0, 0, 0};
+  agent_action(*ag, inventory_obs, a);
+#pragma unroll
+  for (int i = 0; i < 5; i++) out5_smem[i] = a[i];
 }

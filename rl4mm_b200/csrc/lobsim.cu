@@ -67,6 +67,12 @@ __device__ __forceinline__ void tma_store_wait() { asm volatile("cp.async.bulk.w
 // ====================================================================================================================
 //  kernel parameters
 // ====================================================================================================================
+#ifndef LOBSIM_WS_IN_SMEM
+#define LOBSIM_WS_IN_SMEM 0
+#endif
+#ifndef LOBSIM_ENV_MIN_BLOCKS
+#define LOBSIM_ENV_MIN_BLOCKS 3
+#endif
 #define MSG_TILE 32                      // records per TMA tile
 #define MSG_TILE_BYTES (MSG_TILE * 16)
 
@@ -104,7 +110,7 @@ __device__ __forceinline__ unsigned char* warp_smem_base(unsigned char* smem, in
 // kEnv: agent + features + rewards (HistoricalOrderbookEnvironment.step); kTrack: fills / flows / agent orders are
 // tracked (always with kEnv; the pure replay fast path <false,false> is used when no agent order can be resting).
 template <bool kEnv, bool kTrack>
-__global__ void __launch_bounds__(128, kEnv ? 3 : 4) k_advance(const __grid_constant__ AdvParams p, const __grid_constant__ EnvConst ec) {
+__global__ void __launch_bounds__(128, kEnv ? LOBSIM_ENV_MIN_BLOCKS : 4) k_advance(const __grid_constant__ AdvParams p, const __grid_constant__ EnvConst ec) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int sel = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -129,14 +135,18 @@ __global__ void __launch_bounds__(128, kEnv ? 3 : 4) k_advance(const __grid_cons
   __syncwarp();
   mbar_wait(&bars[2], 0);
 
+#if LOBSIM_WS_IN_SMEM
+  // the uniform per-warp state lives in shared memory (not registers): every lane stores identical values, so plain
+  // accesses are race-free; it trades a few broadcast LDS for ~35 registers per thread => more resident books per SM
+  WarpState& w = *reinterpret_cast<WarpState*>(reinterpret_cast<unsigned char*>(bars) + 32);
+#else
   WarpState w;
+#endif
   load_state<kTrack>(b, w);
   w.fill_log = p.fill_log ? p.fill_log + (size_t)env * p.fill_cap : nullptr;
   w.fill_cap = p.fill_cap; w.n_fills = 0;
   const long long inventory_in = w.inventory; const double cash_in = w.cash;
   BookHdr* h = b.hdr();
-  FeatState fs; double* ring = nullptr;
-  lobsim_feature_t fc;
   const int F = c.n_features;
 
   // ---- reset prologue ----------------------------------------------------------------------------------------------
@@ -145,7 +155,7 @@ __global__ void __launch_bounds__(128, kEnv ? 3 : 4) k_advance(const __grid_cons
     stream_id = p.reset_stream_ids[sel];
     int start = p.reset_steps[sel] - (p.reset_mode == 2 ? c.warmup_steps : 0);
     if (stream_id < 0 || stream_id >= p.n_streams) { stream_id = 0; start = -1; }
-    init_book_from_snapshot(b, w, c, p.streams[stream_id], stream_id, start);
+    w = init_book_cold(b, w, &ec.cfg, &p.streams[stream_id], stream_id, start);
     if (p.reset_mode == 2 && lane == 0) {
       h->episode_start_step = p.reset_steps[sel];
       if (!c.portfolio_carryover || !h->has_reset) { h->inventory = c.initial_inventory; h->cash = c.initial_cash; }
@@ -161,13 +171,10 @@ __global__ void __launch_bounds__(128, kEnv ? 3 : 4) k_advance(const __grid_cons
   int now_step = h->now_step;
   const long long episode_start_us = st_t0_us + (long long)h->episode_start_step * c.step_us;
 
-  if (kEnv) {
-    if (lane < F) {
-      fc = c.features[lane];
-      ring = p.rings + (size_t)env * ec.ring_stride + ec.ring_off[lane];
-      fs = p.fstate[(size_t)env * LOBSIM_MAX_FEATURES + lane];
-    }
-  }
+  FeatState* fstate_env = p.fstate + (size_t)env * LOBSIM_MAX_FEATURES;
+  double* rings_env = p.rings + (size_t)env * ec.ring_stride;
+  double feat_cur = 0.0; // Feature.current_value of this lane's feature
+  if (kEnv && lane < F) feat_cur = fstate_env[lane].cur;
 
   // price / tops of the current book
   auto tops = [&](StepView& v) {
@@ -185,7 +192,7 @@ __global__ void __launch_bounds__(128, kEnv ? 3 : 4) k_advance(const __grid_cons
     v.inventory = w.inventory; v.now_us = st_t0_us + (long long)now_step * c.step_us;
     v.n_ext0 = v.n_ext1 = v.vol_ext0 = v.vol_ext1 = v.n_int0 = v.n_int1 = v.vol_int0 = v.vol_int1 = 0;
     price = v.price;
-    if (lane < F) feature_reset(fc, fs, ring, v);
+    feat_cur = features_step(&ec, fstate_env, rings_env, lane, v, episode_start_us, 1);
   }
 
   // ---- message pipeline ----------------------------------------------------------------------------------------------
@@ -217,44 +224,55 @@ __global__ void __launch_bounds__(128, kEnv ? 3 : 4) k_advance(const __grid_cons
   if (g < g_end_all) { issue_tile(); issue_tile(); }
   __syncwarp();
 
-  double action[5] = {0, 0, 0, 0, 0};
+  AgentGen gen; gen.side = 3;
+  bool agent_phase = false;
+#pragma unroll 1
   for (int t = 0; t < T; t++) {
     // ---- agent: obs -> action -> orders (processed before the step's history, OrderbookSimulator.py:76-77) -------
     double cash0 = w.cash, p0 = price; long long inv0 = w.inventory;
     if (kEnv) {
       reset_flow(w);
       if (p.agent_kind != LOBSIM_AGENT_NONE) {
+        double* act_sm = reinterpret_cast<double*>(scratch); // 5 doubles of per-warp scratch
         if (p.agent_kind == LOBSIM_AGENT_EXTERNAL) {
           const double* a = p.actions_in + ((size_t)t * p.n_sel + sel) * ec.action_dim;
-#pragma unroll
-          for (int i = 0; i < 5; i++) if (i < ec.action_dim) action[i] = __ldg(&a[i]);
+          if (lane < 5) act_sm[lane] = lane < ec.action_dim ? __ldg(&a[lane]) : 0.0;
         } else {
-          double inv_obs = __shfl_sync(FULL_MASK, fs.cur, p.agent.inventory_index & 31);
-          agent_action(p.agent, inv_obs, action);
+          const double inv_obs = __shfl_sync(FULL_MASK, feat_cur, p.agent.inventory_index & 31);
+          if (lane == 0) agent_action_cold(&p.agent, inv_obs, act_sm);
         }
-        if (p.act && p.agent_kind != LOBSIM_AGENT_EXTERNAL && lane < ec.action_dim) p.act[((size_t)t * p.n_sel + sel) * ec.action_dim + lane] = pick5(action, lane);
-        agent_orders(b, w, ec, action);
+        __syncwarp();
+        const double a0 = act_sm[0], a1 = act_sm[1], a2 = act_sm[2], a3 = act_sm[3], a4 = act_sm[4];
+        const double mine = lane < 5 ? act_sm[lane] : 0.0;
+        __syncwarp();
+        if (p.act && p.agent_kind != LOBSIM_AGENT_EXTERNAL && lane < ec.action_dim) p.act[((size_t)t * p.n_sel + sel) * ec.action_dim + lane] = mine;
+        if (p.obs && !p.out_final_obs_only && c.inc_prev_action_in_obs && lane < ec.action_dim)
+          p.obs[((size_t)t * p.n_sel + sel) * ec.obs_dim + F + lane] = mine; // get_observation(action), HOE.py:171
+        gen = agent_prepare(b, w.nlv0, w.nlv1, w.nag0, w.nag1, w.inventory, &ec, a0, a1, a2, a3, a4);
+        w.err |= gen.err_out; if (gen.dead_out) w.dead = 1;
+        agent_phase = true;
       }
     }
-    // ---- historical messages of (now, now + step] ------------------------------------------------------------------
-    if (!w.dead) {
-      const unsigned g_step_end = __ldg(&st_step_off[now_step + 1]);
-      while (g < g_step_end) {
-        const unsigned tile = g / MSG_TILE - tile0;
-        if (tile == next_wait) wait_tile();
-        const unsigned tile_end = (g / MSG_TILE + 1) * MSG_TILE;
-        const unsigned lim = g_step_end < tile_end ? g_step_end : tile_end;
-        const uint4* buf = reinterpret_cast<const uint4*>(msgbuf + (tile & 1) * MSG_TILE_BYTES);
-        for (; g < lim; g++) {
-          const uint4 m = buf[g % MSG_TILE];
-          process_message<kTrack>(b, w, (int)m.x, (int)m.y, m.z, m.w);
-          if (w.dead) break;
+    // ---- the step's orders: the agent's first, then the historical messages of (now, now + step] ------------------
+    {
+      const unsigned g_step_end = w.dead ? g : __ldg(&st_step_off[now_step + 1]);
+#pragma unroll 1
+      for (;;) {
+        int type, side, price, vol; uint32_t ref; bool is_agent;
+        if (kEnv && agent_phase) {
+          if (!agent_next(b, w, gen, type, side, price, vol, ref)) { agent_phase = false; continue; }
+          is_agent = true;
+        } else {
+          if (w.dead || g >= g_step_end) break;
+          const unsigned tile = g / MSG_TILE - tile0;
+          if (tile == next_wait) wait_tile();
+          const uint4 m = *reinterpret_cast<const uint4*>(msgbuf + (tile & 1) * MSG_TILE_BYTES + (g % MSG_TILE) * 16);
+          price = (int)m.x; vol = (int)m.y; ref = m.z; type = (int)LOBSIM_META_TYPE(m.w); side = (int)LOBSIM_META_DIR(m.w);
+          is_agent = false;
+          g++;
+          if (g % MSG_TILE == 0) { __syncwarp(); issue_tile(); } // tile consumed: refill its buffer
         }
-        if (w.dead) break;
-        if (g == tile_end) { // tile consumed: refill its buffer with the tile after the next one
-          __syncwarp();
-          issue_tile();
-        }
+        process_order<kTrack>(b, w, type, side, price, vol, ref, is_agent);
       }
     }
     if (!w.dead) {
@@ -265,7 +283,7 @@ __global__ void __launch_bounds__(128, kEnv ? 3 : 4) k_advance(const __grid_cons
         if (rel % 1000000 == 0 && near_exiting(b, w, c)) {
           long long sec = rel / 1000000;
           if (sec <= (long long)stp->n_seconds && stp->snap_valid[sec]) {
-            update_outer_levels<kTrack>(b, w, c, stp->snapshots + (size_t)sec * 2 * c.n_levels * 2, scratch);
+            w = update_outer_levels<kTrack>(b, w, &ec.cfg, stp->snapshots + (size_t)sec * 2 * c.n_levels * 2, scratch);
                     }
         }
       }
@@ -278,14 +296,12 @@ __global__ void __launch_bounds__(128, kEnv ? 3 : 4) k_advance(const __grid_cons
       v.inventory = w.inventory; v.now_us = st_t0_us + (long long)now_step * c.step_us;
       v.n_ext0 = w.n_ext0; v.n_ext1 = w.n_ext1; v.vol_ext0 = w.vol_ext0; v.vol_ext1 = w.vol_ext1;
       v.n_int0 = w.n_int0; v.n_int1 = w.n_int1; v.vol_int0 = w.vol_int0; v.vol_int1 = w.vol_int1;
-      if (lane < F) feature_update(fc, fs, ring, v, episode_start_us);
+      feat_cur = features_step(&ec, fstate_env, rings_env, lane, v, episode_start_us, 0);
       const bool write_now = !p.out_final_obs_only || t == T - 1;
       if (p.obs && write_now) {
         double* o = p.obs + ((size_t)(p.out_final_obs_only ? 0 : t) * p.n_sel + sel) * ec.obs_dim;
-        if (lane < F) o[lane] = fs.cur;
-        if (c.inc_prev_action_in_obs && lane < ec.action_dim) {
-          o[F + lane] = p.agent_kind == LOBSIM_AGENT_NONE ? 0.0 : pick5(action, lane);
-        }
+        if (lane < F) o[lane] = feat_cur;
+        if (c.inc_prev_action_in_obs && lane < ec.action_dim && (p.agent_kind == LOBSIM_AGENT_NONE || p.out_final_obs_only)) o[F + lane] = 0.0;
       }
       if (p.agent_kind != LOBSIM_AGENT_NONE) {
         double r = reward_calc(c.step_reward, cash0, inv0, p0, w.cash, w.inventory, price);
@@ -300,7 +316,7 @@ __global__ void __launch_bounds__(128, kEnv ? 3 : 4) k_advance(const __grid_cons
   }
   if (kEnv && T == 0 && p.obs && p.reset_mode == 2) { // reset with no warm-up: obs straight after _reset_features
     double* o = p.obs + (size_t)sel * ec.obs_dim;
-    if (lane < F) o[lane] = fs.cur;
+    if (lane < F) o[lane] = feat_cur;
     if (c.inc_prev_action_in_obs && lane < ec.action_dim) o[F + lane] = 0.0;
   }
 
@@ -309,7 +325,6 @@ __global__ void __launch_bounds__(128, kEnv ? 3 : 4) k_advance(const __grid_cons
   // ---- write back ----------------------------------------------------------------------------------------------------
   // OrderbookSimulator.forward_step only returns the fills: the portfolio belongs to the env (HOE.py:280-289)
   if (!kEnv && !p.reset_mode) { w.inventory = inventory_in; w.cash = cash_in; }
-  if (kEnv && lane < F) p.fstate[(size_t)env * LOBSIM_MAX_FEATURES + lane] = fs;
   if (lane == 0) {
     h->now_step = now_step;
     h->price = price;
@@ -333,7 +348,7 @@ __device__ __noinline__ uint32_t fallback_resync(unsigned char* blob, const Layo
   __syncwarp();
   load_state<false>(b, w);
   w.err = errdead & 0x7fffffffu; w.dead = (int)(errdead >> 31); w.fill_log = nullptr; w.fill_cap = 0; w.n_fills = 0;
-  update_outer_levels<false>(b, w, *c, row, scratch);
+  update_outer_levels_impl<false>(b, w, *c, row, scratch);
   store_state<false>(b, w);
   return pack_errdead(w.err, w.dead);
 }
@@ -486,8 +501,8 @@ __global__ void __launch_bounds__(32) k_process_orders(const __grid_constant__ O
     const bool has_vol = !((o.type == LOBSIM_MSG_DELETE || o.type == LOBSIM_MSG_CANCEL) && o.volume <= 0);
     if (!w.dead) {
       if (has_vol && o.volume <= 0) w.err |= LOBSIM_ERR_BAD_VOLUME;
-      else if (o.type == LOBSIM_MSG_LIMIT) id = submit_or_execute<true>(b, w, o.direction, o.price, o.volume, is_agent ? 0u : o.ref, true, is_agent);
-      else if (o.type == LOBSIM_MSG_MARKET) id = submit_or_execute<true>(b, w, o.direction, 0, o.volume, is_agent ? 0u : o.ref, false, is_agent);
+      else if (o.type == LOBSIM_MSG_LIMIT || o.type == LOBSIM_MSG_MARKET)
+        id = submit_or_execute<true>(b, w, o.direction, o.price, o.volume, is_agent ? 0u : o.ref, o.type == LOBSIM_MSG_LIMIT, is_agent);
       else remove_order<true>(b, w, o.direction, o.price, o.volume, has_vol, is_agent ? (LOBSIM_REF_AGENT | (o.ref & 0x7fffffffu)) : o.ref, is_agent);
     }
     if (p.refs_out && lane == 0) p.refs_out[k] = id;
@@ -605,7 +620,7 @@ int64_t lobsim_state_bytes(const lobsim_cfg_t* c) {
   return make_layout(c->max_levels_per_side, c->max_orders_per_side, c->max_agent_orders).blob_bytes;
 }
 
-static int warp_smem_bytes(const Layout& L) { return (L.blob_bytes + 2 * MSG_TILE_BYTES + 2 * L.NA * 8 + 32 + 127) & ~127; }
+static int warp_smem_bytes(const Layout& L) { return (L.blob_bytes + 2 * MSG_TILE_BYTES + 2 * L.NA * 8 + 32 + 128 + 127) & ~127; }
 
 int lobsim_create(const lobsim_cfg_t* cfg, int device, lobsim_t** out) {
   if (!out) return fail(LOBSIM_E_INVALID, "out is null");
