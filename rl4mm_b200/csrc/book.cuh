@@ -40,7 +40,8 @@ struct __align__(16) BookHdr {
   double cash;
   double price;
   int32_t has_reset;
-  int32_t reserved[9];
+  int32_t flow[8];   // per-step fill flow: n_ext[2], vol_ext[2], n_int[2], vol_int[2] (by recorded direction)
+  int32_t n_fills;   // fills recorded during the current launch (tracked fast path)
 };
 static_assert(sizeof(BookHdr) == 128, "BookHdr must be 128 bytes");
 

@@ -1,4 +1,4 @@
-// book_fast.cuh -- the replay fast path (k_advance<false,false>): same semantics as process_message<false> in
+// book_fast.cuh -- the straight-line order path (k_replay_fast, k_env_fast): same semantics as process_order in
 // book.cuh, specialised for the overwhelmingly common shapes -- the touched level is among the 32 best, at most 32
 // (64 for removals) queue entries have to move, no capacity is exhausted -- as straight-line warp-wide code without
 // search / shift loops.  Anything else falls back, BEFORE mutating the book, to the general routines.
@@ -30,6 +30,9 @@ struct FastState {
   int best0, best1; // INT32_MIN / INT32_MAX when the side is empty
   uint32_t err;
   int dead;
+  // tracked mode only: optional fill log (global memory); the fill counter lives in the header
+  lobsim_fill_t* fill_log;
+  int fill_cap;
 };
 
 template <class LT>
@@ -48,25 +51,82 @@ struct FastBook {
 // the updated (err | dead << 31) word and the caller re-reads the best prices from shared memory.
 __device__ __forceinline__ uint32_t pack_errdead(uint32_t err, int dead) { return err | ((uint32_t)dead << 31); }
 
-__device__ __noinline__ uint32_t fallback_rest(unsigned char* blob, const Layout* L, int lane, int side, int price, int vol, uint32_t ref, uint32_t errdead) {
+template <bool TR>
+__device__ __noinline__ uint32_t fallback_rest(unsigned char* blob, const Layout* L, int lane, int side, int price, int vol, uint32_t ref, bool is_agent, uint32_t errdead) {
   Book b; b.blob = blob; b.L = *L; b.lane = lane;
   WarpState w;
   __syncwarp();
-  load_state<false>(b, w);
+  load_state<TR>(b, w);
   w.err = errdead & 0x7fffffffu; w.dead = (int)(errdead >> 31); w.fill_log = nullptr; w.fill_cap = 0; w.n_fills = 0;
-  rest_order<false>(b, w, side, price, vol, ref, false);
-  store_state<false>(b, w);
+  rest_order<TR>(b, w, side, price, vol, ref, is_agent);
+  store_state<TR>(b, w);
   return pack_errdead(w.err, w.dead);
 }
-__device__ __noinline__ uint32_t fallback_remove(unsigned char* blob, const Layout* L, int lane, int side, int price, int vol, uint32_t ref, uint32_t errdead) {
+// (no fills can result from a removal, so the general routine's WarpState flow counters stay zero)
+template <bool TR>
+__device__ __noinline__ uint32_t fallback_remove(unsigned char* blob, const Layout* L, int lane, int side, int price, int vol, uint32_t ref, bool is_agent, uint32_t errdead) {
   Book b; b.blob = blob; b.L = *L; b.lane = lane;
   WarpState w;
   __syncwarp();
-  load_state<false>(b, w);
+  load_state<TR>(b, w);
   w.err = errdead & 0x7fffffffu; w.dead = (int)(errdead >> 31); w.fill_log = nullptr; w.fill_cap = 0; w.n_fills = 0;
-  remove_order<false>(b, w, side, price, vol, true, ref, false);
-  store_state<false>(b, w);
+  remove_order<TR>(b, w, side, price, vol, true, ref, is_agent);
+  store_state<TR>(b, w);
   return pack_errdead(w.err, w.dead);
+}
+
+// ---- tracked mode: fills -> per-step flow, portfolio (HOE.py:280-289) and the optional fill log; all by lane 0 on the
+//      shared-memory header --------------------------------------------------------------------------------------------
+// (real functions with by-value arguments: one copy of each in the instruction cache, no address-taken locals)
+__device__ __noinline__ void fast_record_fn(unsigned char* blob, int lane, lobsim_fill_t* fill_log, int fill_cap, int list, int dir, int price, int vol, int is_market, uint32_t ref) {
+  if (lane == 0) {
+    BookHdr* h = reinterpret_cast<BookHdr*>(blob);
+    if (list == 0) { // FilledOrders.internal
+      const long long notional = (long long)vol * (long long)price;
+      if (dir == 1) { h->inventory -= vol; h->cash += (double)notional; } else { h->inventory += vol; h->cash -= (double)notional; }
+      h->flow[4 + dir] += 1; h->flow[6 + dir] += vol;
+    } else { h->flow[dir] += 1; h->flow[2 + dir] += vol; }
+    const int n = h->n_fills;
+    if (fill_log && n < fill_cap) {
+      lobsim_fill_t r; r.list = list; r.direction = dir; r.price = price; r.volume = vol; r.is_market = is_market; r.ref = ref;
+      fill_log[n] = r;
+    }
+    h->n_fills = n + 1;
+  }
+}
+template <class LT>
+__device__ __forceinline__ void fast_record(const FastBook<LT>& fb, FastState& f, int list, int dir, int price, int vol, int is_market, uint32_t ref) {
+  fast_record_fn(fb.blob, fb.lane, f.fill_log, f.fill_cap, list, dir, price, vol, is_market, ref);
+}
+
+// the agent's order `id` loses v (or everything): Exchange.internal_orderbook mirror.  NA <= 64.
+__device__ __noinline__ void fast_agent_reduce_fn(unsigned char* blob, int lane, int agent_off, int NA, int side, uint32_t id, int v, int full) {
+  BookHdr* h = reinterpret_cast<BookHdr*>(blob);
+  int32_t* ap = reinterpret_cast<int32_t*>(blob + agent_off + side * NA * 12);
+  int32_t* av = ap + NA;
+  uint32_t* ai = reinterpret_cast<uint32_t*>(ap + 2 * NA);
+  const int nag = h->nag[side];
+  const unsigned m0 = __ballot_sync(FULL_MASK, lane < nag && ai[lane] == id);
+  const unsigned m1 = __ballot_sync(FULL_MASK, lane + 32 < nag && ai[lane + 32] == id);
+  if (!(m0 | m1)) return;
+  const int i = m0 ? __ffs(m0) - 1 : 32 + __ffs(m1) - 1;
+  const int nv = full ? 0 : av[i] - v;
+  __syncwarp();
+  if (nv > 0) { if (lane == 0) av[i] = nv; __syncwarp(); return; }
+  const int tail = nag - i - 1; // <= 63 entries move down by one
+  int p0 = 0, p1 = 0, v0 = 0, v1 = 0; uint32_t i0 = 0, i1 = 0;
+  if (lane < tail) { p0 = ap[i + 1 + lane]; v0 = av[i + 1 + lane]; i0 = ai[i + 1 + lane]; }
+  if (lane + 32 < tail) { p1 = ap[i + 33 + lane]; v1 = av[i + 33 + lane]; i1 = ai[i + 33 + lane]; }
+  __syncwarp();
+  if (lane < tail) { ap[i + lane] = p0; av[i + lane] = v0; ai[i + lane] = i0; }
+  if (lane + 32 < tail) { ap[i + 32 + lane] = p1; av[i + 32 + lane] = v1; ai[i + 32 + lane] = i1; }
+  if (lane == 0) h->nag[side] = nag - 1;
+  __syncwarp();
+}
+template <class LT>
+__device__ __forceinline__ void fast_agent_reduce(const FastBook<LT>& fb, int side, uint32_t id, int v, bool full) {
+  static_assert(LT::NA <= 64, "the straight-line agent table code handles at most 64 agent orders per side");
+  fast_agent_reduce_fn(fb.blob, fb.lane, LT::agent_off, LT::NA, side, id, v, full ? 1 : 0);
 }
 
 template <class LT>
@@ -77,9 +137,10 @@ __device__ __forceinline__ void fast_refresh_best(const FastBook<LT>& fb, FastSt
   f.best1 = n1 ? fb.P(fb.side(1))[n1 - 1] : INT32_MAX;
 }
 
-template <class LT>
-__device__ __forceinline__ void fast_message(const FastBook<LT>& fb, FastState& f, const Layout* L, int price, int vol, uint32_t ref, uint32_t meta) {
-  const int type = (int)(meta & 7u), side = (int)((meta >> 3) & 1u);
+// TR: fills / flows / agent orders are tracked (env kernels); TR == false is the pure replay.
+template <class LT, bool TR>
+__device__ __forceinline__ void fast_order(const FastBook<LT>& fb, FastState& f, const Layout* L, int type, int side, int price, int vol, uint32_t ref, bool is_agent) {
+  if (!TR) is_agent = false;
   const int lane = fb.lane;
   if (vol <= 0) { f.err |= LOBSIM_ERR_BAD_VOLUME; return; }
   const bool crosses = side ? price <= f.best0 : price >= f.best1;
@@ -103,12 +164,24 @@ __device__ __forceinline__ void fast_message(const FastBook<LT>& fb, FastState& 
       uint2 e = make_uint2(0u, 0u);
       if (lane < len) e = fb.O(sb)[start + lane];           // first 32 entries of the best queue
       const int hv = (int)__shfl_sync(FULL_MASK, e.x, 0);
-      if (rem < hv) {                                        // partial fill of the head
-        if (lane == 0) fb.O(sb)[start].x = (unsigned)(hv - rem);
-        rem = 0;
-        break;
+      const uint32_t href = TR ? __shfl_sync(FULL_MASK, e.y, 0) : 0u;
+      const bool hagent = TR && (href & LOBSIM_REF_AGENT) != 0;
+      const bool self_match = TR && is_agent && hagent;      // cannot fill our own order => delete it, :91-94
+      if (!self_match) {
+        const int v = rem < hv ? rem : hv;
+        if (TR) {
+          if (hagent) { fast_record(fb, f, 0, opp, bp, v, 0, href); }
+          else fast_record(fb, f, 1, opp, bp, v, 0, href);
+          if (is_agent) fast_record(fb, f, 0, side, bp, v, 1, href);   // the synthetic MarketOrder fill, :111-115
+        }
+        if (rem < hv) {                                      // partial fill of the head
+          if (lane == 0) fb.O(sb)[start].x = (unsigned)(hv - rem);
+          if (TR && hagent) { __syncwarp(); fast_agent_reduce(fb, opp, href & 0x7fffffffu, rem, false); }
+          rem = 0;
+          break;
+        }
+        rem -= hv;                                           // the head is consumed
       }
-      rem -= hv;                                             // the head is consumed
       if (len > 33) { __syncwarp(); shift_down(fb.O(sb), start, 1, c.y, lane); }
       else {
         uint2 e32 = make_uint2(0u, 0u);
@@ -124,11 +197,12 @@ __device__ __forceinline__ void fast_message(const FastBook<LT>& fb, FastState& 
         if (opp) f.best1 = nb; else f.best0 = nb;
       } else if (lane == 0) fb.LE(sb)[j] = (uint16_t)c.y;
       __syncwarp();
+      if (TR && hagent) fast_agent_reduce(fb, opp, href & 0x7fffffffu, 0, true);   // the resting agent order is gone
     }
     if (lane == 0) *fb.cnt(opp) = c;
     __syncwarp();
     if (rem > 0 && type == LOBSIM_MSG_LIMIT && !f.dead) {    // the remainder rests (Exchange.py:116-119); rare
-      const uint32_t ed = fallback_rest(fb.blob, L, lane, side, price, rem, ref, pack_errdead(f.err, f.dead));
+      const uint32_t ed = fallback_rest<TR>(fb.blob, L, lane, side, price, rem, ref, is_agent, pack_errdead(f.err, f.dead));
       f.err = ed & 0x7fffffffu; f.dead = (int)(ed >> 31);
       fast_refresh_best(fb, f);
     }
@@ -148,8 +222,10 @@ __device__ __forceinline__ void fast_message(const FastBook<LT>& fb, FastState& 
   if (type == LOBSIM_MSG_LIMIT) {
     // ---- a non-crossing limit order rests (Exchange.py:74-83) -------------------------------------------------------
     const int cb = __popc(gt);
-    if ((!eq && (cb == 32 || nlv >= LT::NL)) || nord >= LT::NO) { // deep level or a capacity limit: general path
-      const uint32_t ed = fallback_rest(fb.blob, L, lane, side, price, vol, ref, pack_errdead(f.err, f.dead));
+    int nag = 0;
+    if (TR && is_agent) nag = reinterpret_cast<BookHdr*>(fb.blob)->nag[side];
+    if ((!eq && (cb == 32 || nlv >= LT::NL)) || nord >= LT::NO || (TR && is_agent && nag >= LT::NA)) { // deep level or a capacity limit
+      const uint32_t ed = fallback_rest<TR>(fb.blob, L, lane, side, price, vol, ref, is_agent, pack_errdead(f.err, f.dead));
       f.err = ed & 0x7fffffffu; f.dead = (int)(ed >> 31);
       fast_refresh_best(fb, f);
       return;
@@ -179,6 +255,17 @@ __device__ __forceinline__ void fast_message(const FastBook<LT>& fb, FastState& 
       __syncwarp();
       if (lane < above) fb.O(sb)[pos + lane + 1] = v;
     }
+    if (TR && is_agent) {   // OrderIdConvertor.add_internal_id_to_order_and_track + internal book append
+      BookHdr* h = reinterpret_cast<BookHdr*>(fb.blob);
+      const uint32_t id = h->next_agent_id;
+      ref = LOBSIM_REF_AGENT | id;
+      __syncwarp();
+      if (lane == 0) {
+        int32_t* ap = reinterpret_cast<int32_t*>(fb.blob + LT::agent_off + side * LT::NA * 12);
+        ap[nag] = price; ap[LT::NA + nag] = vol; reinterpret_cast<uint32_t*>(ap)[2 * LT::NA + nag] = id;
+        h->nag[side] = nag + 1; h->next_agent_id = id + 1;
+      }
+    }
     if (lane == 0) { fb.O(sb)[pos] = make_uint2((unsigned)vol, ref); *fb.cnt(side) = make_int2(nlv2, nord + 1); }
     { const int i = j + lane; if (i < nlv2) fb.LE(sb)[i] = (uint16_t)(fb.LE(sb)[i] + 1); }   // nlv2 - j <= 32
     __syncwarp();
@@ -187,7 +274,7 @@ __device__ __forceinline__ void fast_message(const FastBook<LT>& fb, FastState& 
   // ---- cancellation / deletion (Exchange.py:122-147) ------------------------------------------------------------------
   if (!eq) {
     if (__popc(gt) == 32) {                                  // the level may be deeper than the 32 best
-      const uint32_t ed = fallback_remove(fb.blob, L, lane, side, price, vol, ref, pack_errdead(f.err, f.dead));
+      const uint32_t ed = fallback_remove<TR>(fb.blob, L, lane, side, price, vol, ref, is_agent, pack_errdead(f.err, f.dead));
       f.err = ed & 0x7fffffffu; f.dead = (int)(ed >> 31);
       fast_refresh_best(fb, f);
     }
@@ -197,7 +284,7 @@ __device__ __forceinline__ void fast_message(const FastBook<LT>& fb, FastState& 
   const int start = j > 0 ? (int)fb.LE(sb)[j - 1] : 0, end = fb.LE(sb)[j];
   const int len = end - start;
   if (len > 32 || nord - start > 64) {                       // long queue / long shift: general path
-    const uint32_t ed = fallback_remove(fb.blob, L, lane, side, price, vol, ref, pack_errdead(f.err, f.dead));
+    const uint32_t ed = fallback_remove<TR>(fb.blob, L, lane, side, price, vol, ref, is_agent, pack_errdead(f.err, f.dead));
     f.err = ed & 0x7fffffffu; f.dead = (int)(ed >> 31);
     fast_refresh_best(fb, f);
     return;
@@ -206,16 +293,18 @@ __device__ __forceinline__ void fast_message(const FastBook<LT>& fb, FastState& 
   if (lane < len) e = fb.O(sb)[start + lane];
   const unsigned m = __ballot_sync(FULL_MASK, lane < len && e.y == ref);   // _find_queue_position :196-217
   int l;
+  bool aggregate = false;
   if (m) l = __ffs(m) - 1;
   else {
     if (__shfl_sync(FULL_MASK, e.y, 0) != LOBSIM_REF_AGGREGATE) return;    // already filled (:138-139)
-    l = 0;                                                                // hit the aggregate at the head (:133-137)
+    l = 0; aggregate = true;                                              // hit the aggregate at the head (:133-137)
   }
   const int cur = (int)__shfl_sync(FULL_MASK, e.x, l);
   const int pos = start + l;
   if (vol < cur) {                                           // partial: reduce in place
     if (lane == l) fb.O(sb)[pos].x = (unsigned)(cur - vol);
     __syncwarp();
+    if (TR && is_agent && !aggregate) fast_agent_reduce(fb, side, ref & 0x7fffffffu, vol, false);
     return;
   }
   // full removal (over-size requests remove the resting volume, :142-146): entries (pos, nord) move down by one
@@ -242,4 +331,11 @@ __device__ __forceinline__ void fast_message(const FastBook<LT>& fb, FastState& 
     if (lane == 0) *fb.cnt(side) = make_int2(nlv, nord - 1);
   }
   __syncwarp();
+  if (TR && is_agent && !aggregate) fast_agent_reduce(fb, side, ref & 0x7fffffffu, cur, true);
+}
+
+// the replay form: a packed historical message
+template <class LT>
+__device__ __forceinline__ void fast_message(const FastBook<LT>& fb, FastState& f, const Layout* L, int price, int vol, uint32_t ref, uint32_t meta) {
+  fast_order<LT, false>(fb, f, L, (int)(meta & 7u), (int)((meta >> 3) & 1u), price, vol, ref, false);
 }

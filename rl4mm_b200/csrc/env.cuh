@@ -5,6 +5,7 @@
 #include <math.h>
 
 #include "book.cuh"
+#include "book_fast.cuh"
 
 struct __align__(16) FeatState {
   double cur;        // Feature.current_value
@@ -157,7 +158,7 @@ __device__ __noinline__ WarpState init_book_cold(const Book b, WarpState w, cons
 
 // ---- BetaOrderDistributor, rl4mm/gym/action_interpretation/OrderDistributors.py:23-56 ----------------------------
 // lane k < Q returns the lot size of quote level k.  The sum follows numpy's pairwise summation order.
-__device__ __forceinline__ int beta_ladder_lane(double a, double bpar, int Q, int active_volume, int lane) {
+__device__ __noinline__ int beta_ladder_lane(double a, double bpar, int Q, int active_volume, int lane) {
   double x = 1.0 / (double)Q * ((double)lane + 0.5);
   double A = -INFINITY;
   if (lane < Q) {
@@ -473,4 +474,58 @@ __device__ __noinline__ void agent_action_cold(const lobsim_agent_t* ag, double 
   agent_action(*ag, inventory_obs, a);
 #pragma unroll
   for (int i = 0; i < 5; i++) out5_smem[i] = a[i];
+}
+
+// agent_next for the straight-line path: the agent table counters live in the shared-memory header
+template <class LT>
+__device__ __forceinline__ bool agent_next_fast(const FastBook<LT>& fb, FastState& f, AgentGen& g, int& type, int& side, int& price, int& vol, uint32_t& ref) {
+  BookHdr* h = reinterpret_cast<BookHdr*>(fb.blob);
+  for (;;) {
+    if (f.dead || g.side >= 3) return false;
+    if (g.side == 2) { // _get_inventory_clearing_market_order :260-266
+      g.side = 3;
+      if (!g.clearing) return false;
+      if (g.clear_vol <= 0) { f.err |= LOBSIM_ERR_BAD_VOLUME; return false; }
+      type = LOBSIM_MSG_MARKET; side = g.clear_side; price = 0; vol = g.clear_vol; ref = 0;
+      return true;
+    }
+    const int s = g.side;
+    const int myprice = s ? g.price1 : g.price0;
+    const int32_t* ap = reinterpret_cast<const int32_t*>(fb.blob + LT::agent_off + s * LT::NA * 12);
+    const int32_t* av = ap + LT::NA;
+    const uint32_t* ai = reinterpret_cast<const uint32_t*>(ap + 2 * LT::NA);
+    const int nag = h->nag[s];
+    if (g.k < g.Q) {
+      const int p = __shfl_sync(FULL_MASK, myprice, g.k);
+      if (g.need == 0) {
+        const int d = __shfl_sync(FULL_MASK, s ? g.diff1 : g.diff0, g.k);
+        if (d > 0) { type = LOBSIM_MSG_LIMIT; side = s; price = p; vol = d; ref = 0; g.k++; return true; }
+        if (d == 0) { g.k++; continue; }
+        g.need = -d;
+      }
+      // cancel from the back of the agent's queue at this price, :239-249 (NA <= 64)
+      const unsigned m1 = __ballot_sync(FULL_MASK, fb.lane + 32 < nag && ap[fb.lane + 32] == p);
+      const unsigned m0 = __ballot_sync(FULL_MASK, fb.lane < nag && ap[fb.lane] == p);
+      if (!(m0 | m1)) { g.need = 0; g.k++; continue; }
+      const int hit = m1 ? 63 - __clz(m1) : 31 - __clz(m0);
+      const int a = av[hit];
+      const uint32_t id = ai[hit];
+      const int v = a < g.need ? a : g.need;
+      g.need -= v;
+      if (g.need == 0) g.k++;
+      type = LOBSIM_MSG_CANCEL; side = s; price = p; vol = v; ref = LOBSIM_REF_AGENT | id;
+      return true;
+    }
+    // agent orders off the ladder are cancelled in full, :250-257
+    if (g.wide_i >= nag) { g.side = s + 1; g.k = 0; g.need = 0; g.wide_i = 0; g.pending_id = 0; continue; }
+    const int wp = ap[g.wide_i], wv = av[g.wide_i];
+    const uint32_t id = ai[g.wide_i];
+    __syncwarp();
+    if (id == g.pending_id) { fast_agent_reduce(fb, s, id, 0, true); g.pending_id = 0; continue; } // keep books consistent
+    const bool on_ladder = __ballot_sync(FULL_MASK, fb.lane < g.Q && myprice == wp) != 0;
+    if (on_ladder) { g.wide_i++; continue; }
+    g.pending_id = id;
+    type = LOBSIM_MSG_CANCEL; side = s; price = wp; vol = wv; ref = LOBSIM_REF_AGENT | id;
+    return true;
+  }
 }

@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -21,7 +22,6 @@
 #include <string>
 #include <vector>
 
-#include "book_fast.cuh"
 #include "env.cuh"
 #include "lobsim.h"
 
@@ -457,8 +457,269 @@ __global__ void __launch_bounds__(128, 7) k_replay_fast(const __grid_constant__ 
   __syncwarp();
 }
 
+// ====================================================================================================================
+//  the env fast kernel: k_advance<true,true> with the straight-line tracked order path (book_fast.cuh fast_order<LT,true>)
+//  and all per-env scalars (counters, portfolio, per-step flow) in the shared-memory header instead of registers.
+// ====================================================================================================================
+__device__ __noinline__ uint32_t fallback_resync_tracked(unsigned char* blob, const Layout* L, int lane, const lobsim_cfg_t* c, const int32_t* row, int2* scratch, uint32_t errdead) {
+  Book b; b.blob = blob; b.L = *L; b.lane = lane;
+  WarpState w;
+  __syncwarp();
+  load_state<true>(b, w);
+  w.err = errdead & 0x7fffffffu; w.dead = (int)(errdead >> 31); w.fill_log = nullptr; w.fill_cap = 0; w.n_fills = 0;
+  update_outer_levels_impl<true>(b, w, *c, row, scratch);
+  store_state<true>(b, w);
+  return pack_errdead(w.err, w.dead);
+}
+__device__ __noinline__ uint32_t reset_book_cold(unsigned char* blob, const Layout* L, int lane, const lobsim_cfg_t* c, const lobsim_stream_t* st, int stream_id, int start_step) {
+  Book b; b.blob = blob; b.L = *L; b.lane = lane;
+  WarpState w;
+  __syncwarp();
+  load_state<true>(b, w);
+  w.fill_log = nullptr; w.fill_cap = 0; w.n_fills = 0;
+  init_book_from_snapshot(b, w, *c, *st, stream_id, start_step);
+  store_state<true>(b, w);
+  return pack_errdead(w.err, w.dead);
+}
+
+#ifndef LOBSIM_ENVFAST_WARPS
+#define LOBSIM_ENVFAST_WARPS 8    // warps per CTA of the env fast kernel (two CTAs per SM at 128 registers)
+#endif
+#ifndef LOBSIM_PHASE_SYNC
+#define LOBSIM_PHASE_SYNC 1
+#endif
+#if LOBSIM_PHASE_SYNC
+#define PHASE_SYNC() __syncthreads()
+#else
+#define PHASE_SYNC() ((void)0)
+#endif
+template <class LT>
+__global__ void __launch_bounds__(32 * LOBSIM_ENVFAST_WARPS, 16 / LOBSIM_ENVFAST_WARPS) k_env_fast(const __grid_constant__ AdvParams p, const __grid_constant__ EnvConst ec) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sel = blockIdx.x * (blockDim.x >> 5) + warp;
+  // All warps of an SM form ONE CTA and move through the phases of a step together (PHASE_SYNC = __syncthreads):
+  // the instruction working set at any moment is a single phase, which is what keeps the 32 KB L1.5 I-cache warm
+  // (profiles/r01_envstep_*: "no instruction" was the top stall with free-running warps).
+  if (sel >= p.n_sel) { // idle warp of the last CTA: only keeps the barrier counts matched
+    PHASE_SYNC();
+    for (int t = 0; t < p.T; t++) { PHASE_SYNC(); PHASE_SYNC(); PHASE_SYNC(); }
+    return;
+  }
+  const int env = p.env_ids ? p.env_ids[sel] : sel;
+  const lobsim_cfg_t& c = ec.cfg;
+  unsigned char* base = warp_smem_base(smem, warp, p.warp_smem);
+  unsigned char* msgbuf = base + LT::blob_bytes;
+  int2* scratch = reinterpret_cast<int2*>(msgbuf + 2 * MSG_TILE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(scratch) + 2 * LT::NA * 8);
+  unsigned char* gblob = p.blobs + (size_t)env * LT::blob_bytes;
+  if (lane == 0) {
+    mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
+    fence_mbar_init();
+    mbar_expect_tx(&bars[2], (uint32_t)LT::blob_bytes);
+    tma_load(base, gblob, (uint32_t)LT::blob_bytes, &bars[2]);
+  }
+  __syncwarp();
+  mbar_wait(&bars[2], 0);
+
+  FastBook<LT> fb; fb.blob = base; fb.lane = lane;
+  Book b; b.blob = base; b.L = p.L; b.lane = lane;
+  BookHdr* h = reinterpret_cast<BookHdr*>(base);
+  FastState f; f.err = h->err; f.dead = h->dead;
+  f.fill_log = p.fill_log ? p.fill_log + (size_t)env * p.fill_cap : nullptr; f.fill_cap = p.fill_cap;
+  if (lane == 0) h->n_fills = 0;
+  const int F = c.n_features;
+
+  // ---- reset prologue ----------------------------------------------------------------------------------------------
+  int stream_id = h->stream_id;
+  if (p.reset_mode) {
+    stream_id = p.reset_stream_ids[sel];
+    int start = p.reset_steps[sel] - (p.reset_mode == 2 ? c.warmup_steps : 0);
+    if (stream_id < 0 || stream_id >= p.n_streams) { stream_id = 0; start = -1; }
+    const uint32_t ed = reset_book_cold(base, &p.L, lane, &ec.cfg, &p.streams[stream_id], stream_id, start);
+    f.err = ed & 0x7fffffffu; f.dead = (int)(ed >> 31);
+    if (p.reset_mode == 2 && lane == 0) {
+      h->episode_start_step = p.reset_steps[sel];
+      if (!c.portfolio_carryover || !h->has_reset) { h->inventory = c.initial_inventory; h->cash = c.initial_cash; }
+      h->has_reset = 1;
+    }
+    __syncwarp();
+  }
+  fast_refresh_best(fb, f);
+  const lobsim_stream_t* stp = &p.streams[stream_id];
+  const lobsim_msg_t* __restrict__ st_msgs = stp->msgs;
+  const uint32_t* __restrict__ st_step_off = stp->step_off;
+  const long long st_t0_us = stp->t0_us;
+  int now_step = h->now_step;
+  const long long episode_start_us = st_t0_us + (long long)h->episode_start_step * c.step_us;
+  FeatState* fstate_env = p.fstate + (size_t)env * LOBSIM_MAX_FEATURES;
+  double* rings_env = p.rings + (size_t)env * ec.ring_stride;
+  double feat_cur = 0.0;
+  if (lane < F) feat_cur = fstate_env[lane].cur;
+
+  auto tops = [&](StepView& v) { // Orderbook.best_* / microprice, models.py:72-101
+    const int n0 = h->cnt[0][0], n1 = h->cnt[1][0];
+    v.have_tops = n0 > 0 && n1 > 0;
+    if (v.have_tops) {
+      v.bb = f.best0; v.bs = f.best1;
+      v.bv = best_level_volume(b, 0, n0); v.sv = best_level_volume(b, 1, n1);
+      double imb; v.price = microprice(v.bb, v.bs, v.bv, v.sv, imb);
+    } else { v.bb = v.bs = v.bv = v.sv = 0; v.price = NAN; }
+  };
+  double price = h->price;
+  if (p.reset_mode == 2) { // State(...) + _reset_features, HOE.py:152-154,218-221
+    StepView v; tops(v);
+    v.inventory = h->inventory; v.now_us = st_t0_us + (long long)now_step * c.step_us;
+    v.n_ext0 = v.n_ext1 = v.vol_ext0 = v.vol_ext1 = v.n_int0 = v.n_int1 = v.vol_int0 = v.vol_int1 = 0;
+    price = v.price;
+    feat_cur = features_step(&ec, fstate_env, rings_env, lane, v, episode_start_us, 1);
+  }
+
+  // ---- message pipeline ----------------------------------------------------------------------------------------------
+  const int T = p.T;
+  if (!(now_step >= 0 && (long long)now_step + T <= (long long)stp->n_grid_steps) && !f.dead && T > 0) { f.err |= LOBSIM_ERR_END_OF_STREAM; f.dead = 1; }
+  unsigned g = 0, g_end_all = 0;
+  if (!f.dead && T > 0) { g = __ldg(&st_step_off[now_step]); g_end_all = __ldg(&st_step_off[now_step + T]); }
+  const unsigned tile0 = g / MSG_TILE;
+  unsigned next_issue = 0, next_wait = 0;
+  auto issue_tile = [&]() {
+    const unsigned first = (tile0 + next_issue) * MSG_TILE;
+    if (first >= g_end_all) return;
+    if (lane == 0) {
+      const unsigned n_total = (unsigned)stp->n_msgs;
+      const unsigned cnt = n_total - first < MSG_TILE ? n_total - first : MSG_TILE;
+      uint64_t* bar = &bars[next_issue & 1];
+      mbar_expect_tx(bar, cnt * 16);
+      tma_load(msgbuf + (next_issue & 1) * MSG_TILE_BYTES, st_msgs + first, cnt * 16, bar);
+    }
+    next_issue++;
+  };
+  auto wait_tile = [&]() { mbar_wait(&bars[next_wait & 1], (next_wait >> 1) & 1); next_wait++; };
+  if (g < g_end_all) { issue_tile(); issue_tile(); }
+  __syncwarp();
+  PHASE_SYNC();
+  const int steps_per_sec = (int)(1000000 / c.step_us);
+  int sub = now_step >= 0 ? now_step % steps_per_sec : 0;
+
+  AgentGen gen; gen.side = 3;
+  bool agent_phase = false;
+#pragma unroll 1
+  for (int t = 0; t < T; t++) {
+    PHASE_SYNC(); // ---- phase A: action -> ladders (fp64) --------------------------------------------------------
+    const double cash0 = h->cash, p0 = price; const long long inv0 = h->inventory; // deepcopy(self.state), HOE.py:166
+    if (lane < 8) h->flow[lane] = 0;
+    __syncwarp();
+    if (p.agent_kind != LOBSIM_AGENT_NONE) {
+      double* act_sm = reinterpret_cast<double*>(scratch);
+      if (p.agent_kind == LOBSIM_AGENT_EXTERNAL) {
+        const double* a = p.actions_in + ((size_t)t * p.n_sel + sel) * ec.action_dim;
+        if (lane < 5) act_sm[lane] = lane < ec.action_dim ? __ldg(&a[lane]) : 0.0;
+      } else {
+        const double inv_obs = __shfl_sync(FULL_MASK, feat_cur, p.agent.inventory_index & 31);
+        if (lane == 0) agent_action_cold(&p.agent, inv_obs, act_sm);
+      }
+      __syncwarp();
+      const double a0 = act_sm[0], a1 = act_sm[1], a2 = act_sm[2], a3 = act_sm[3], a4 = act_sm[4];
+      const double mine = lane < 5 ? act_sm[lane] : 0.0;
+      __syncwarp();
+      if (p.act && p.agent_kind != LOBSIM_AGENT_EXTERNAL && lane < ec.action_dim) p.act[((size_t)t * p.n_sel + sel) * ec.action_dim + lane] = mine;
+      if (p.obs && !p.out_final_obs_only && c.inc_prev_action_in_obs && lane < ec.action_dim)
+        p.obs[((size_t)t * p.n_sel + sel) * ec.obs_dim + F + lane] = mine;
+      if (!f.dead) {
+        gen = agent_prepare(b, h->cnt[0][0], h->cnt[1][0], h->nag[0], h->nag[1], h->inventory, &ec, a0, a1, a2, a3, a4);
+        f.err |= gen.err_out; if (gen.dead_out) f.dead = 1;
+        agent_phase = true;
+      }
+    }
+    PHASE_SYNC(); // ---- phase B: the step's orders: the agent's first, then the historical messages of (now, now + step]
+    {
+      const unsigned g_step_end = f.dead ? g : __ldg(&st_step_off[now_step + 1]);
+#pragma unroll 1
+      for (;;) {
+        int type, side, oprice, vol; uint32_t ref; bool is_agent;
+        if (agent_phase) {
+          if (!agent_next_fast(fb, f, gen, type, side, oprice, vol, ref)) { agent_phase = false; continue; }
+          is_agent = true;
+        } else {
+          if (f.dead || g >= g_step_end) break;
+          const unsigned tile = g / MSG_TILE - tile0;
+          if (tile == next_wait) wait_tile();
+          const uint4 m = *reinterpret_cast<const uint4*>(msgbuf + (tile & 1) * MSG_TILE_BYTES + (g % MSG_TILE) * 16);
+          oprice = (int)m.x; vol = (int)m.y; ref = m.z; type = (int)(m.w & 7u); side = (int)((m.w >> 3) & 1u);
+          is_agent = false;
+          g++;
+          if (g % MSG_TILE == 0) { __syncwarp(); issue_tile(); }
+        }
+        if (!f.dead) fast_order<LT, true>(fb, f, &p.L, type, side, oprice, vol, ref, is_agent);
+      }
+    }
+    if (!f.dead) {
+      now_step++;
+      if (++sub == steps_per_sec) {                          // whole second: outer-level resync, OrderbookSimulator.py:86-87
+        sub = 0;
+        if (c.resync && (!p.resync_last_only || t == T - 1)) {
+          const double prop = (double)c.outer_levels / (double)c.n_levels;
+          const double bbd = f.best0 == INT32_MIN ? 0.0 : (double)f.best0;
+          const double bsd = f.best1 == INT32_MAX ? (double)INFINITY : (double)f.best1;
+          if (bbd < (double)h->min_buy + prop * (double)h->init_buy_range || bsd > (double)h->max_sell - prop * (double)h->init_sell_range) {
+            const long long sec = (long long)now_step / steps_per_sec;
+            if (sec <= (long long)stp->n_seconds && stp->snap_valid[sec]) {
+              const int32_t* row = stp->snapshots + (size_t)sec * 2 * c.n_levels * 2;
+              const uint32_t ed = fallback_resync_tracked(base, &p.L, lane, &ec.cfg, row, scratch, pack_errdead(f.err, f.dead));
+              f.err = ed & 0x7fffffffu; f.dead = (int)(ed >> 31);
+              fast_refresh_best(fb, f);
+            }
+          }
+        }
+      }
+    }
+    PHASE_SYNC(); // ---- phase C: update_internal_state + _update_features + reward, HOE.py:163-178,199-204 -------------
+    StepView v; tops(v);
+    if (!v.have_tops) f.err |= LOBSIM_ERR_EMPTY_BOOK;
+    price = v.price;
+    v.inventory = h->inventory; v.now_us = st_t0_us + (long long)now_step * c.step_us;
+    v.n_ext0 = h->flow[0]; v.n_ext1 = h->flow[1]; v.vol_ext0 = h->flow[2]; v.vol_ext1 = h->flow[3];
+    v.n_int0 = h->flow[4]; v.n_int1 = h->flow[5]; v.vol_int0 = h->flow[6]; v.vol_int1 = h->flow[7];
+    feat_cur = features_step(&ec, fstate_env, rings_env, lane, v, episode_start_us, 0);
+    const bool write_now = !p.out_final_obs_only || t == T - 1;
+    if (p.obs && write_now) {
+      double* o = p.obs + ((size_t)(p.out_final_obs_only ? 0 : t) * p.n_sel + sel) * ec.obs_dim;
+      if (lane < F) o[lane] = feat_cur;
+      if (c.inc_prev_action_in_obs && lane < ec.action_dim && (p.agent_kind == LOBSIM_AGENT_NONE || p.out_final_obs_only)) o[F + lane] = 0.0;
+    }
+    if (p.agent_kind != LOBSIM_AGENT_NONE) {
+      const double cash1 = h->cash; const long long inv1 = h->inventory;
+      double r = reward_calc(c.step_reward, cash0, inv0, p0, cash1, inv1, price);
+      const bool d = now_step >= h->episode_start_step + c.episode_steps; // terminal_time - now < step/2, HOE.py:172
+      if (d) r = reward_calc(c.terminal_reward, cash0, inv0, p0, cash1, inv1, price);
+      if (lane == 0) {
+        if (p.rew) p.rew[(size_t)t * p.n_sel + sel] = r;
+        if (p.done) p.done[(size_t)t * p.n_sel + sel] = d ? 1 : 0;
+      }
+    }
+  }
+  if (T == 0 && p.obs && p.reset_mode == 2) { // reset with no warm-up: obs straight after _reset_features
+    double* o = p.obs + (size_t)sel * ec.obs_dim;
+    if (lane < F) o[lane] = feat_cur;
+    if (c.inc_prev_action_in_obs && lane < ec.action_dim) o[F + lane] = 0.0;
+  }
+  while (next_wait < next_issue) wait_tile();
+  __syncwarp();
+  if (lane == 0) {
+    if (f.fill_log && h->n_fills > f.fill_cap) f.err |= LOBSIM_ERR_FILL_LOG_FULL;
+    h->now_step = now_step; h->price = price; h->err = f.err; h->dead = f.dead;
+    if (p.fill_count) p.fill_count[env] = h->n_fills;
+  }
+  __syncwarp();
+  fence_proxy_async();
+  __syncwarp();
+  if (lane == 0) { tma_store(gblob, base, (uint32_t)LT::blob_bytes); tma_store_wait(); }
+  __syncwarp();
+}
+
 typedef StaticLayout<64, 256, 32> FastLayoutA;   // BASELINE config 2 (10-level books)
 typedef StaticLayout<128, 512, 64> FastLayoutB;  // the default capacities (50-level books)
+typedef StaticLayout<64, 256, 64> FastLayoutC;   // 10-level books with a 64-order agent table
 
 // ====================================================================================================================
 //  Exchange.process_order for a list of orders (drop-in / test entry point; one warp, sequential)
@@ -566,6 +827,7 @@ struct lobsim {
   Layout L;
   int device;
   int warps_per_cta;
+  int env_warps_per_cta;
   int warp_smem;
   unsigned char* blobs = nullptr;
   FeatState* fstate = nullptr;
@@ -580,6 +842,7 @@ struct lobsim {
   lobsim_env_state_t* st_state = nullptr;
   lobsim_msg_t* st_msgs = nullptr; uint64_t st_msgs_cap = 0;
   bool has_reset = false;
+  bool force_general = false;         // LOBSIM_FORCE_GENERAL=1: always use the runtime-layout kernels (testing)
   bool agent_orders_possible = false; // an agent order may rest in some book (disables the replay fast path)
   int64_t launches = 0;
 };
@@ -633,6 +896,7 @@ int lobsim_create(const lobsim_cfg_t* cfg, int device, lobsim_t** out) {
   lobsim* h = new (std::nothrow) lobsim();
   if (!h) return fail(LOBSIM_E_NOMEM, "out of host memory");
   h->cfg = *cfg; h->device = device;
+  { const char* e = getenv("LOBSIM_FORCE_GENERAL"); h->force_general = e && e[0] == '1'; }
   h->L = make_layout(cfg->max_levels_per_side, cfg->max_orders_per_side, cfg->max_agent_orders);
   h->warp_smem = warp_smem_bytes(h->L);
   int max_smem = 0;
@@ -640,14 +904,22 @@ int lobsim_create(const lobsim_cfg_t* cfg, int device, lobsim_t** out) {
   if (h->warp_smem > max_smem) { delete h; return fail(LOBSIM_E_INVALID, "book capacities exceed the shared memory of one SM"); }
   h->warps_per_cta = 4;
   while (h->warps_per_cta > 1 && h->warps_per_cta * h->warp_smem > max_smem) h->warps_per_cta >>= 1;
+  h->env_warps_per_cta = LOBSIM_ENVFAST_WARPS;
+  while (h->env_warps_per_cta > 1 && h->env_warps_per_cta * h->warp_smem > max_smem - 1024) h->env_warps_per_cta >>= 1;
   CUDA_TRY((cudaFuncSetAttribute(k_advance<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->warps_per_cta * h->warp_smem)));
   CUDA_TRY((cudaFuncSetAttribute(k_advance<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->warps_per_cta * h->warp_smem)));
-  CUDA_TRY((cudaFuncSetAttribute(k_replay_fast<FastLayoutA>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->warps_per_cta * h->warp_smem)));
-  CUDA_TRY((cudaFuncSetAttribute(k_replay_fast<FastLayoutB>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->warps_per_cta * h->warp_smem)));
+  {
+    const void* fast_kernels[] = {(const void*)k_replay_fast<FastLayoutA>, (const void*)k_replay_fast<FastLayoutB>, (const void*)k_replay_fast<FastLayoutC>,
+                                  (const void*)k_env_fast<FastLayoutA>, (const void*)k_env_fast<FastLayoutB>, (const void*)k_env_fast<FastLayoutC>};
+    for (int i = 0; i < 6; i++) {
+      const void* k = fast_kernels[i];
+      const int dyn = (i < 3 ? h->warps_per_cta : h->env_warps_per_cta) * h->warp_smem;
+      CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+      CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    }
+  }
   CUDA_TRY((cudaFuncSetAttribute(k_advance<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)));
   CUDA_TRY((cudaFuncSetAttribute(k_advance<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)));
-  CUDA_TRY((cudaFuncSetAttribute(k_replay_fast<FastLayoutA>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)));
-  CUDA_TRY((cudaFuncSetAttribute(k_replay_fast<FastLayoutB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)));
   CUDA_TRY(cudaFuncSetAttribute(k_process_orders, cudaFuncAttributeMaxDynamicSharedMemorySize, h->L.blob_bytes));
   // feature rings
   memset(&h->ec, 0, sizeof h->ec);
@@ -732,12 +1004,33 @@ static int launch_advance(lobsim* h, const AdvParams& p, cudaStream_t stream) {
 
 static int launch_replay_fast(lobsim* h, const AdvParams& p, cudaStream_t stream) {
   if (h->streams.empty()) return fail(LOBSIM_E_STATE, "no stream loaded");
-  const bool a = FastLayoutA::matches(h->L), b = FastLayoutB::matches(h->L);
-  if (!a && !b) return 1;
+  const bool a = FastLayoutA::matches(h->L), b = FastLayoutB::matches(h->L), cc = FastLayoutC::matches(h->L);
+  if (!a && !b && !cc) return 1;
   CUDA_TRY(cudaSetDevice(h->device));
   const int wpc = h->warps_per_cta, grid = (p.n_sel + wpc - 1) / wpc;
-  if (a) k_replay_fast<FastLayoutA><<<grid, wpc * 32, (size_t)wpc * h->warp_smem, stream>>>(p, h->ec);
-  else k_replay_fast<FastLayoutB><<<grid, wpc * 32, (size_t)wpc * h->warp_smem, stream>>>(p, h->ec);
+  if (grid <= 0) return LOBSIM_OK;
+  const size_t dyn = (size_t)wpc * h->warp_smem;
+  if (a) k_replay_fast<FastLayoutA><<<grid, wpc * 32, dyn, stream>>>(p, h->ec);
+  else if (b) k_replay_fast<FastLayoutB><<<grid, wpc * 32, dyn, stream>>>(p, h->ec);
+  else k_replay_fast<FastLayoutC><<<grid, wpc * 32, dyn, stream>>>(p, h->ec);
+  CUDA_TRY(cudaGetLastError());
+  h->launches++;
+  return LOBSIM_OK;
+}
+
+// env launches (reset / step / rollout): the straight-line kernel when a compiled StaticLayout matches the capacities,
+// the general runtime-layout kernel otherwise
+static int launch_env(lobsim* h, const AdvParams& p, cudaStream_t stream) {
+  if (h->streams.empty()) return fail(LOBSIM_E_STATE, "no stream loaded");
+  const bool a = FastLayoutA::matches(h->L), b = FastLayoutB::matches(h->L), cc = FastLayoutC::matches(h->L);
+  if ((!a && !b && !cc) || h->force_general) return launch_advance<true, true>(h, p, stream);
+  CUDA_TRY(cudaSetDevice(h->device));
+  const int wpc = h->env_warps_per_cta, grid = (p.n_sel + wpc - 1) / wpc;
+  if (grid <= 0) return LOBSIM_OK;
+  const size_t dyn = (size_t)wpc * h->warp_smem;
+  if (a) k_env_fast<FastLayoutA><<<grid, wpc * 32, dyn, stream>>>(p, h->ec);
+  else if (b) k_env_fast<FastLayoutB><<<grid, wpc * 32, dyn, stream>>>(p, h->ec);
+  else k_env_fast<FastLayoutC><<<grid, wpc * 32, dyn, stream>>>(p, h->ec);
   CUDA_TRY(cudaGetLastError());
   h->launches++;
   return LOBSIM_OK;
@@ -761,7 +1054,7 @@ int lobsim_reset(lobsim_t* h, const int32_t* env_ids, int32_t n, const int32_t* 
   p.T = h->cfg.warmup_steps; p.reset_mode = 2; p.reset_stream_ids = stream_ids; p.reset_steps = episode_start_steps;
   p.agent_kind = LOBSIM_AGENT_NONE; p.obs = obs_out; p.out_final_obs_only = 1;
   h->has_reset = true;
-  return launch_advance<true, true>(h, p, (cudaStream_t)stream);
+  return launch_env(h, p, (cudaStream_t)stream);
 }
 
 int lobsim_step(lobsim_t* h, const double* actions, double* obs_out, double* reward_out, uint8_t* done_out, void* stream) {
@@ -770,7 +1063,7 @@ int lobsim_step(lobsim_t* h, const double* actions, double* obs_out, double* rew
   AdvParams p; base_params(h, p);
   p.T = 1; p.agent_kind = LOBSIM_AGENT_EXTERNAL; p.actions_in = actions; p.obs = obs_out; p.rew = reward_out; p.done = done_out;
   h->agent_orders_possible = true;
-  return launch_advance<true, true>(h, p, (cudaStream_t)stream);
+  return launch_env(h, p, (cudaStream_t)stream);
 }
 
 static int ensure_staging(lobsim* h) {
@@ -809,7 +1102,7 @@ int lobsim_rollout(lobsim_t* h, int32_t T, const lobsim_agent_t* agent, double* 
   p.T = T; p.agent_kind = agent->kind; p.agent = *agent; p.obs = obs; p.rew = rew; p.done = done;
   if (agent->kind == LOBSIM_AGENT_EXTERNAL) p.actions_in = act; else p.act = act;
   if (agent->kind != LOBSIM_AGENT_NONE) h->agent_orders_possible = true;
-  return launch_advance<true, true>(h, p, (cudaStream_t)stream);
+  return launch_env(h, p, (cudaStream_t)stream);
 }
 
 int lobsim_replay(lobsim_t* h, int32_t n_steps, void* stream) {
@@ -817,7 +1110,7 @@ int lobsim_replay(lobsim_t* h, int32_t n_steps, void* stream) {
   AdvParams p; base_params(h, p);
   p.T = n_steps; p.agent_kind = LOBSIM_AGENT_NONE;
   // fast path: no fill log requested and no agent order can be resting in any book
-  if (!h->fill_log && !h->agent_orders_possible) {
+  if (!h->fill_log && !h->agent_orders_possible && !h->force_general) {
     int rc = launch_replay_fast(h, p, (cudaStream_t)stream);
     if (rc != 1) return rc; // 1: no compiled StaticLayout matches these capacities
   }

@@ -2,7 +2,7 @@
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
 cp rl4mm_b200/_native/liblobsim.so /tmp/orig.so
-for v in nb3s0 nb4s0 nb4s1 nb5s1; do
+for v in w16p1 w16p0 w8p1 w4p0; do
   cp rl4mm_b200/_native/liblobsim_$v.so rl4mm_b200/_native/liblobsim.so
   timeout 600 python bench.py --workload rollout --envs-per-gpu 65536 --steps 3 --warmup 3 > gpurun_out/bench_rollout_$v.log 2>&1
   echo "$v: $(tail -1 gpurun_out/bench_rollout_$v.log | cut -c1-110)"
