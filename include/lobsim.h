@@ -47,6 +47,7 @@ extern "C" {
 #define LOBSIM_ERR_NO_SNAPSHOT 32u      /* "There is no data before the episode start time", OrderbookSimulator.py:92 */
 #define LOBSIM_ERR_END_OF_STREAM 64u    /* stepped past the loaded message grid                                  */
 #define LOBSIM_ERR_FILL_LOG_FULL 128u   /* fill log capacity exceeded (log truncated, simulation unaffected)     */
+#define LOBSIM_ERR_AUM_NONPOSITIVE 256u  /* "AUM has gone non_positive", rl4mm/rewards/RewardFunctions.py:12-13      */
 
 /* ---- packed message record (16 B) -- device-resident replacement of the `messages` table ---------------------
  * rl4mm/database/models.py:10-22 + rl4mm/simulation/HistoricalOrderGenerator.py:77-90.
@@ -88,7 +89,8 @@ enum {
   LOBSIM_FEAT_TRADE_VOL_IMBALANCE = 7,/* :410 */
   LOBSIM_FEAT_INVENTORY = 8,          /* :474 */
   LOBSIM_FEAT_EPISODE_PROPORTION = 9, /* :493 */
-  LOBSIM_FEAT_TIME_OF_DAY = 10        /* :515 */
+  LOBSIM_FEAT_TIME_OF_DAY = 10,       /* :515 */
+  LOBSIM_FEAT_AMIHUD_LAMBDA = 11      /* :245 (lookback = (true_lookback + 1) * slowing_factor, iparam = slowing_factor) */
 };
 
 typedef struct {
@@ -97,20 +99,22 @@ typedef struct {
   int64_t update_us; /* update_frequency in microseconds (<= 60 s, Features.py:53)           */
   double min_value;  /* clamp, Features.py:83,99                                             */
   double max_value;
-  int32_t iparam;    /* TIME_OF_DAY: n_buckets; TRADE_*_IMBALANCE: track_internal            */
+  int32_t iparam;    /* TIME_OF_DAY: n_buckets; TRADE_*_IMBALANCE: track_internal; AMIHUD: slowing_factor */
   int32_t reserved;
   double dparam;     /* EPISODE_PROPORTION: update_frequency / episode_length                */
 } lobsim_feature_t;
 
 /* ---- rewards: rl4mm/rewards/RewardFunctions.py -------------------------------------------------------------- */
 enum {
-  LOBSIM_REWARD_PNL = 0,          /* RewardFunctions.py:97-101  */
-  LOBSIM_REWARD_INV_ADJ_PNL = 1   /* RewardFunctions.py:107-118 */
+  LOBSIM_REWARD_PNL = 0,            /* RewardFunctions.py:97-101  */
+  LOBSIM_REWARD_INV_ADJ_PNL = 1,    /* RewardFunctions.py:107-118 */
+  LOBSIM_REWARD_ROLLING_SHARPE = 2  /* RewardFunctions.py:38-94   */
 };
+#define LOBSIM_MAX_SHARPE_WINDOW 256
 typedef struct {
   int32_t kind;
-  int32_t asymmetric; /* asymmetrically_dampened */
-  double inventory_aversion;
+  int32_t asymmetric;        /* INV_ADJ_PNL: asymmetrically_dampened; ROLLING_SHARPE: max_window_size | min_window_size << 16 */
+  double inventory_aversion; /* INV_ADJ_PNL */
 } lobsim_reward_t;
 
 /* ---- built-in agents for the fused rollout: rl4mm/agents/baseline_agents.py --------------------------------- */

@@ -132,6 +132,9 @@ def feature_specs():
          dict(kind="PRICE_MOVE", lookback=1, update_us=1000000, min=-10000, max=10000)),
         (lambda: F.PriceRange(lookback_periods=1),
          dict(kind="PRICE_RANGE", lookback=1, update_us=1000000, min=0, max=10000)),
+        # index 14: AmihudLambda, window (4 + 1) * 2 * 0.1 s = 1 s
+        (lambda: F.AmihudLambda(update_frequency=td(seconds=0.1), lookback_periods=4, slowing_factor=2, max_value=1e-3),
+         dict(kind="AMIHUD_LAMBDA", lookback=10, update_us=100000, min=0, max=1e-3, iparam=2)),
     ]
 
 
@@ -142,8 +145,12 @@ def run_env_case(name, actions, env_kwargs, reward_step, reward_term, features=N
     from rl4mm.rewards.RewardFunctions import InventoryAdjustedPnL, PnL
 
     def reward(spec):
+        from rl4mm.rewards.RewardFunctions import RollingSharpe
+
         if spec[0] == "PnL":
             return PnL()
+        if spec[0] == "RS":
+            return RollingSharpe(max_window_size=spec[1], min_window_size=spec[2])
         return InventoryAdjustedPnL(inventory_aversion=spec[1], asymmetrically_dampened=spec[2])
 
     specs = feature_specs() if features is None else [feature_specs()[i] for i in features]
@@ -210,6 +217,10 @@ def golden_env_episodes():
         run_env_case("float_cash", rand4[40:], {}, ("PnL",), ("PnL",), portfolio=(25, 1e12)),
         run_env_case("reference_test_features", [[1, 2, 1, 2]], {}, ("IA", 1e-4, False), ("IA", 0.1, False),
                      features=[9, 0, 12, 13], episode_seconds=1.0, start_seconds=36001.0),
+        run_env_case("amihud_rolling_sharpe", rand4[50:], {}, ("RS", 6, 3), ("RS", 4, 2), features=[14, 9, 0, 7],
+                     n_episodes=3, episode_seconds=1.0, start_seconds=36001.0, portfolio=(0, 10**10)),
+        run_env_case("amihud_full", rand4[10:], {}, ("RS", 12, 5), ("PnL",), features=list(range(12)) + [14],
+                     portfolio=(0, 10**10)),
     ]
     save("env_episodes.json.gz", cases)
 

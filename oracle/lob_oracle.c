@@ -149,7 +149,13 @@ typedef struct {
   int64_t* iring[2];        /* deques of ints (trades / volumes), [buy, sell] */
   int len;                  /* current deque length */
   int64_t total, diff;      /* total_trades / trade_diff, total_volume / volume_imbalance */
+  double partial_price_sum; /* AmihudLambda */
+  int64_t partial_dollar_volume;
+  int steps_until_update, dv_len;
 } o_feat;
+
+/* RollingSharpe.aum_array / n_filled -- rl4mm/rewards/RewardFunctions.py:50-59 (never reset by the env) */
+typedef struct { double aum[LOBSIM_MAX_SHARPE_WINDOW]; int n_filled; } o_sharpe;
 
 struct lo {
   lobsim_cfg_t cfg;
@@ -169,6 +175,7 @@ struct lo {
   uint32_t err;
   int dead;
   o_feat feat[LOBSIM_MAX_FEATURES];
+  o_sharpe sharpe[2];       /* [per-step reward, terminal reward] */
   /* fills of the current step */
   lobsim_fill_t* fills;
   int n_fills, cap_fills;
@@ -583,6 +590,47 @@ static void feature_update_raw(lo_t* o, int fi) {
       }
       break;
     }
+    case LOBSIM_FEAT_AMIHUD_LAMBDA: { /* :285-324; ring = prices (oldest first), iring[0] = dollar volumes */
+      const int sf = fc->iparam, kk = fc->lookback / sf - 1; /* true_lookback_periods */
+      if (f->steps_until_update > 0) {
+        f->steps_until_update -= 1;
+        f->partial_price_sum += o->price;
+        o_flow fl = step_flow(o);
+        f->partial_dollar_volume += fl.vol_ext[0] + fl.vol_ext[1];
+      } else {
+        f->steps_until_update = sf - 1;
+        const double new_price = f->partial_price_sum / (double)sf;
+        const int64_t new_dv = f->partial_dollar_volume;
+        if (f->len < kk) {
+          f->ring[f->len++] = new_price;
+          if (f->dv_len < kk) f->iring[0][f->dv_len++] = new_dv; else { memmove(&f->iring[0][0], &f->iring[0][1], (size_t)(kk - 1) * sizeof(int64_t)); f->iring[0][kk - 1] = new_dv; }
+          f->cur = 0.0;
+        } else if (f->len == kk) {
+          f->ring[f->len++] = new_price;
+          if (f->dv_len < kk) f->iring[0][f->dv_len++] = new_dv; else { memmove(&f->iring[0][0], &f->iring[0][1], (size_t)(kk - 1) * sizeof(int64_t)); f->iring[0][kk - 1] = new_dv; }
+          double sacc = 0.0;
+          for (int i = 0; i < kk; i++) {
+            double r = (f->ring[i + 1] - f->ring[i]) / f->ring[0];
+            if (f->iring[0][i] > 0) sacc += fabs(r) / (double)f->iring[0][i];
+          }
+          f->cur = sacc / (double)kk;
+        } else {
+          double oldest = f->ring[0];
+          memmove(&f->ring[0], &f->ring[1], (size_t)kk * sizeof(double));
+          double oldest_ret = (f->ring[0] - oldest) / oldest;
+          int64_t oldest_dv = f->iring[0][0];
+          memmove(&f->iring[0][0], &f->iring[0][1], (size_t)(kk - 1) * sizeof(int64_t));
+          double new_ret = (new_price - f->ring[kk - 1]) / f->ring[kk - 1];
+          f->ring[kk] = new_price; f->iring[0][kk - 1] = new_dv;
+          double new_ratio = new_dv > 0 ? fabs(new_ret) / (double)new_dv : 0.0;
+          double old_ratio = oldest_dv > 0 ? fabs(oldest_ret) / (double)oldest_dv : 0.0;
+          double sum_of_ratio = f->cur * (double)kk + new_ratio - old_ratio;
+          f->cur = sum_of_ratio / (double)kk;
+        }
+        f->partial_price_sum = 0.0; f->partial_dollar_volume = 0;
+      }
+      break;
+    }
     default: break;
   }
 }
@@ -593,6 +641,9 @@ static void feature_reset(lo_t* o, int fi, int64_t first_usage_us) {
   o_feat* f = &o->feat[fi];
   f->first_usage_us = first_usage_us;
   f->len = 0; f->total = 0; f->diff = 0;
+  if (fc->kind == LOBSIM_FEAT_AMIHUD_LAMBDA) { /* AmihudLambda.reset :278-283 */
+    f->dv_len = 0; f->partial_price_sum = 0.0; f->partial_dollar_volume = 0; f->steps_until_update = fc->iparam - 1;
+  }
   feature_update_raw(o, fi);
   if (fc->kind == LOBSIM_FEAT_EPISODE_PROPORTION) f->cur = 0.0; /* :507-509 */
 }
@@ -761,6 +812,45 @@ static void get_observation(const lo_t* o, const double* prev_action, double* ob
   }
 }
 
+/* numpy's pairwise summation (np.add.reduce on a contiguous double array) */
+static double np_pairwise_sum(const double* a, int n) {
+  if (n < 8) { double r = 0.0; for (int i = 0; i < n; i++) r += a[i]; return r; }
+  if (n <= 128) {
+    double r[8]; int i;
+    for (i = 0; i < 8; i++) r[i] = a[i];
+    for (i = 8; i < n - (n % 8); i += 8) for (int j = 0; j < 8; j++) r[j] += a[i + j];
+    double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    for (; i < n; i++) res += a[i];
+    return res;
+  }
+  int n2 = n / 2; n2 -= n2 % 8;
+  return np_pairwise_sum(a, n2) + np_pairwise_sum(a + n2, n - n2);
+}
+
+/* get_sharpe -- rl4mm/rewards/RewardFunctions.py:10-22 */
+static double get_sharpe(lo_t* o, const double* aum, int n) {
+  double simple[LOBSIM_MAX_SHARPE_WINDOW];
+  for (int i = 0; i < n; i++) if (aum[i] <= 0) { o->err |= LOBSIM_ERR_AUM_NONPOSITIVE; return NAN; } /* raise Exception */
+  for (int i = 0; i + 1 < n; i++) simple[i] = exp(log(aum[i + 1]) - log(aum[i])) - 1.0;
+  int m = n - 1;
+  double mean = np_pairwise_sum(simple, m) / (double)m;
+  double sq[LOBSIM_MAX_SHARPE_WINDOW];
+  for (int i = 0; i < m; i++) { double d = simple[i] - mean; sq[i] = d * d; }
+  double sd = sqrt(np_pairwise_sum(sq, m) / (double)(m - 1));
+  return mean / (sd + 2.2250738585072014e-308);
+}
+
+/* RollingSharpe.calculate -- RewardFunctions.py:64-94 */
+static double rolling_sharpe_calc(lo_t* o, const lobsim_reward_t* r, o_sharpe* st, double cash1, int64_t inv1, double p1) {
+  const int maxw = r->asymmetric & 0xffff, minw = (r->asymmetric >> 16) & 0xffff;
+  double new_aum = cash1 + p1 * (double)inv1; /* calculate_aum :61-62 */
+  memmove(&st->aum[0], &st->aum[1], (size_t)(maxw - 1) * sizeof(double)); /* overwrite oldest + roll */
+  st->aum[maxw - 1] = new_aum;
+  st->n_filled = st->n_filled + 1 < maxw ? st->n_filled + 1 : maxw;
+  if (st->n_filled < minw) return 0.0;
+  return get_sharpe(o, &st->aum[maxw - st->n_filled], st->n_filled);
+}
+
 /* RewardFunctions.py:97-118 */
 static double reward_calc(const lobsim_reward_t* r, double cash0, int64_t inv0, double p0, double cash1, int64_t inv1, double p1) {
   double cur = cash0 + (double)inv0 * p0;
@@ -809,11 +899,15 @@ int lo_step(lo_t* o, const double* action, double* obs, double* reward, uint8_t*
   env_forward(o, orders.v, orders.n);
   free(orders.v);
   for (int i = 0; i < o->cfg.n_features; i++) feature_update(o, i);
-  double r = reward_calc(&o->cfg.step_reward, cash0, inv0, p0, o->cash, o->inventory, o->price);
+  double r = o->cfg.step_reward.kind == LOBSIM_REWARD_ROLLING_SHARPE
+                 ? rolling_sharpe_calc(o, &o->cfg.step_reward, &o->sharpe[0], o->cash, o->inventory, o->price)
+                 : reward_calc(&o->cfg.step_reward, cash0, inv0, p0, o->cash, o->inventory, o->price);
   int d = 0;
   /* terminal_time - now < step/2  <=>  now_step >= episode_start + episode_steps (integers) */
   if (o->now_step >= o->episode_start_step + o->cfg.episode_steps) {
-    r = reward_calc(&o->cfg.terminal_reward, cash0, inv0, p0, o->cash, o->inventory, o->price);
+    r = o->cfg.terminal_reward.kind == LOBSIM_REWARD_ROLLING_SHARPE
+            ? rolling_sharpe_calc(o, &o->cfg.terminal_reward, &o->sharpe[1], o->cash, o->inventory, o->price)
+            : reward_calc(&o->cfg.terminal_reward, cash0, inv0, p0, o->cash, o->inventory, o->price);
     d = 1;
   }
   if (obs) get_observation(o, action, obs);

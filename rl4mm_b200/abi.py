@@ -23,10 +23,11 @@ ERR_BAD_VOLUME = 16
 ERR_NO_SNAPSHOT = 32
 ERR_END_OF_STREAM = 64
 ERR_FILL_LOG_FULL = 128
+ERR_AUM_NONPOSITIVE = 256
 ERR_NAMES = {
     ERR_EMPTY_BOOK: "EMPTY_BOOK", ERR_LEVEL_OVERFLOW: "LEVEL_OVERFLOW", ERR_ORDER_OVERFLOW: "ORDER_OVERFLOW",
     ERR_AGENT_OVERFLOW: "AGENT_OVERFLOW", ERR_BAD_VOLUME: "BAD_VOLUME", ERR_NO_SNAPSHOT: "NO_SNAPSHOT",
-    ERR_END_OF_STREAM: "END_OF_STREAM", ERR_FILL_LOG_FULL: "FILL_LOG_FULL",
+    ERR_END_OF_STREAM: "END_OF_STREAM", ERR_FILL_LOG_FULL: "FILL_LOG_FULL", ERR_AUM_NONPOSITIVE: "AUM_NONPOSITIVE",
 }
 
 MSG_LIMIT, MSG_CANCEL, MSG_DELETE, MSG_MARKET = 1, 2, 3, 4
@@ -39,7 +40,9 @@ FEAT_SPREAD, FEAT_BOOK_IMBALANCE, FEAT_PRICE_MOVE, FEAT_PRICE_RANGE, FEAT_VOLATI
 FEAT_TRADE_DIR_IMBALANCE, FEAT_TRADE_VOL_IMBALANCE, FEAT_INVENTORY, FEAT_EPISODE_PROPORTION, FEAT_TIME_OF_DAY = range(
     6, 11
 )
-REWARD_PNL, REWARD_INV_ADJ_PNL = 0, 1
+REWARD_PNL, REWARD_INV_ADJ_PNL, REWARD_ROLLING_SHARPE = 0, 1, 2
+MAX_SHARPE_WINDOW = 256
+FEAT_AMIHUD_LAMBDA = 11
 AGENT_NONE, AGENT_FIXED, AGENT_TERADACTYL, AGENT_EXTERNAL = 0, 1, 2, 3
 
 MSG_DTYPE = np.dtype([("price", "<i4"), ("volume", "<i4"), ("ref", "<u4"), ("meta", "<u4")])
@@ -160,6 +163,15 @@ def set_features(cfg: Cfg, feats) -> None:
 
 def feature(kind, lookback=0, update_us=100_000, min_value=0.0, max_value=0.0, iparam=0, dparam=0.0) -> Feature:
     return Feature(kind, lookback, update_us, float(min_value), float(max_value), iparam, 0, float(dparam))
+
+
+def rolling_sharpe(max_window_size: int = 120, min_window_size: int = 60) -> Reward:
+    assert 2 <= min_window_size <= max_window_size <= MAX_SHARPE_WINDOW
+    return Reward(REWARD_ROLLING_SHARPE, max_window_size | (min_window_size << 16), 0.0)
+
+
+def amihud(true_lookback: int = 10, slowing_factor: int = 10, update_us: int = 100_000, min_value=0.0, max_value=1.0) -> Feature:
+    return feature(FEAT_AMIHUD_LAMBDA, (true_lookback + 1) * slowing_factor, update_us, min_value, max_value, iparam=slowing_factor)
 
 
 def action_dim(cfg: Cfg) -> int:

@@ -430,6 +430,51 @@ __device__ __forceinline__ void feature_update_raw(const lobsim_feature_t& fc, F
       }
       break;
     }
+    case LOBSIM_FEAT_AMIHUD_LAMBDA: { // Features.py:285-324; ring[0..kk] prices (oldest first), ring[kk+1..2kk] dollar volumes
+      const int sf = fc.iparam, kk = fc.lookback / sf - 1;
+      int plen = f.len & 0xffff, until = (f.len >> 16) & 0x3fff, dvlen = f.head;
+      long long* dv = reinterpret_cast<long long*>(ring + kk + 1);
+      if (until > 0) {
+        until -= 1;
+        f.diff = __double_as_longlong(__longlong_as_double(f.diff) + v.price);   // partial_price_sum
+        f.total += (long long)v.vol_ext0 + v.vol_ext1;                            // partial_dollar_volume
+      } else {
+        until = sf - 1;
+        const double new_price = __longlong_as_double(f.diff) / (double)sf;
+        const long long new_dv = f.total;
+        if (plen <= kk) { // prices deque not full yet: both deques append (the full dollar-volume deque drops its oldest)
+          ring[plen] = new_price;
+          if (dvlen < kk) dv[dvlen++] = new_dv; else { for (int i = 0; i + 1 < kk; i++) dv[i] = dv[i + 1]; dv[kk - 1] = new_dv; }
+          plen += 1;
+          if (plen <= kk) f.cur = 0.0;
+          else {
+            double sacc = 0.0; const double first = ring[0];
+            for (int i = 0; i < kk; i++) {
+              const double r = (ring[i + 1] - ring[i]) / first;
+              const long long d = dv[i];
+              if (d > 0) sacc += fabs(r) / (double)d;
+            }
+            f.cur = sacc / (double)kk;
+          }
+        } else {
+          const double oldest = ring[0];
+          for (int i = 0; i < kk; i++) ring[i] = ring[i + 1];
+          const double oldest_ret = (ring[0] - oldest) / oldest;
+          const long long oldest_dv = dv[0];
+          for (int i = 0; i + 1 < kk; i++) dv[i] = dv[i + 1];
+          const double last = ring[kk - 1];
+          const double new_ret = (new_price - last) / last;
+          ring[kk] = new_price; dv[kk - 1] = new_dv;
+          const double new_ratio = new_dv > 0 ? fabs(new_ret) / (double)new_dv : 0.0;
+          const double old_ratio = oldest_dv > 0 ? fabs(oldest_ret) / (double)oldest_dv : 0.0;
+          const double sum_of_ratio = f.cur * (double)kk + new_ratio - old_ratio;
+          f.cur = sum_of_ratio / (double)kk;
+        }
+        f.diff = __double_as_longlong(0.0); f.total = 0;
+      }
+      f.len = plen | (until << 16); f.head = dvlen;
+      break;
+    }
     default: break;
   }
 }
@@ -437,6 +482,7 @@ __device__ __forceinline__ void feature_update_raw(const lobsim_feature_t& fc, F
 // Feature.reset/_reset, Features.py:92-96
 __device__ __forceinline__ void feature_reset(const lobsim_feature_t& fc, FeatState& f, double* ring, const StepView& v) {
   f.len = 0; f.head = 0; f.total = 0; f.diff = 0;
+  if (fc.kind == LOBSIM_FEAT_AMIHUD_LAMBDA) { f.len = (fc.iparam - 1) << 16; f.diff = __double_as_longlong(0.0); } // AmihudLambda.reset :278-283
   feature_update_raw(fc, f, ring, v);
   if (fc.kind == LOBSIM_FEAT_EPISODE_PROPORTION) f.cur = 0.0;
 }
@@ -528,4 +574,42 @@ __device__ __forceinline__ bool agent_next_fast(const FastBook<LT>& fb, FastStat
     type = LOBSIM_MSG_CANCEL; side = s; price = wp; vol = wv; ref = LOBSIM_REF_AGENT | id;
     return true;
   }
+}
+
+// ---- RollingSharpe.calculate, rl4mm/rewards/RewardFunctions.py:10-22,64-94 (cold; warp-collective) -------------------
+// ring: maxw doubles (circular, logical order oldest -> newest), state[0] = n_filled, state[1] = head (next write).
+// Returns the reward; *err_out gets LOBSIM_ERR_AUM_NONPOSITIVE when an AUM in the window is <= 0 (the reference raises).
+struct SharpeOut { double reward; uint32_t err; };
+__device__ __noinline__ SharpeOut rolling_sharpe_step(double* ring, int* state, int packed_windows, double new_aum, int lane) {
+  const int maxw = packed_windows & 0xffff, minw = (packed_windows >> 16) & 0xffff;
+  int n = state[0], head = state[1];
+  __syncwarp();
+  if (lane == 0) { ring[head] = new_aum; state[0] = n + 1 < maxw ? n + 1 : maxw; state[1] = head + 1 == maxw ? 0 : head + 1; }
+  __syncwarp();
+  n = n + 1 < maxw ? n + 1 : maxw; head = head + 1 == maxw ? 0 : head + 1;
+  SharpeOut out; out.reward = 0.0; out.err = 0;
+  if (n < minw) return out;
+  const int first = n < maxw ? 0 : head;     // physical index of the oldest entry (the ring starts at 0 after create)
+  const int m = n - 1;                       // number of returns
+  double s1 = 0.0; int bad = 0;
+  for (int i = lane; i < n; i += 32) { int k = first + i; if (k >= maxw) k -= maxw; if (ring[k] <= 0.0) bad = 1; }
+  if (__any_sync(FULL_MASK, bad)) { out.reward = NAN; out.err = LOBSIM_ERR_AUM_NONPOSITIVE; return out; }
+  for (int i = lane; i < m; i += 32) {
+    int k0 = first + i; if (k0 >= maxw) k0 -= maxw;
+    int k1 = k0 + 1 == maxw ? 0 : k0 + 1;
+    s1 += exp(log(ring[k1]) - log(ring[k0])) - 1.0;
+  }
+  for (int d = 16; d; d >>= 1) s1 += __shfl_xor_sync(FULL_MASK, s1, d);
+  const double mean = s1 / (double)m;
+  double s2 = 0.0;
+  for (int i = lane; i < m; i += 32) {
+    int k0 = first + i; if (k0 >= maxw) k0 -= maxw;
+    int k1 = k0 + 1 == maxw ? 0 : k0 + 1;
+    const double dlt = (exp(log(ring[k1]) - log(ring[k0])) - 1.0) - mean;
+    s2 += dlt * dlt;
+  }
+  for (int d = 16; d; d >>= 1) s2 += __shfl_xor_sync(FULL_MASK, s2, d);
+  const double sd = sqrt(s2 / (double)(m - 1));
+  out.reward = mean / (sd + 2.2250738585072014e-308);
+  return out;
 }

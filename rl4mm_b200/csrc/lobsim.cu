@@ -80,6 +80,8 @@ struct AdvParams {
   unsigned char* blobs;             // [n_envs][blob_bytes]
   FeatState* fstate;                // [n_envs][LOBSIM_MAX_FEATURES]
   double* rings;                    // [n_envs][ring_stride]
+  double* rs_ring;                  // RollingSharpe windows [n_envs][2][LOBSIM_MAX_SHARPE_WINDOW] or null
+  int32_t* rs_state;                // [n_envs][2][2] = {n_filled, head}
   const lobsim_stream_t* streams;   // device array [n_streams]
   int32_t n_streams;
   lobsim_fill_t* fill_log;          // [n_envs][fill_cap] or null
@@ -101,6 +103,23 @@ struct AdvParams {
   Layout L;
   int32_t warp_smem;                // bytes of shared memory per warp
 };
+
+// per_step / terminal reward of one env step (HOE.py:170-174); RollingSharpe keeps one AUM window per reward function
+__device__ __forceinline__ double step_reward(const AdvParams& p, const lobsim_cfg_t& c, int env, int lane, bool done, double cash0, long long inv0, double p0,
+                                              double cash1, long long inv1, double p1, uint32_t& err) {
+  double r;
+  if (c.step_reward.kind == LOBSIM_REWARD_ROLLING_SHARPE) {
+    SharpeOut o = rolling_sharpe_step(p.rs_ring + ((size_t)env * 2 + 0) * LOBSIM_MAX_SHARPE_WINDOW, p.rs_state + ((size_t)env * 2 + 0) * 2, c.step_reward.asymmetric, cash1 + p1 * (double)inv1, lane);
+    r = o.reward; err |= o.err;
+  } else r = reward_calc(c.step_reward, cash0, inv0, p0, cash1, inv1, p1);
+  if (done) {
+    if (c.terminal_reward.kind == LOBSIM_REWARD_ROLLING_SHARPE) {
+      SharpeOut o = rolling_sharpe_step(p.rs_ring + ((size_t)env * 2 + 1) * LOBSIM_MAX_SHARPE_WINDOW, p.rs_state + ((size_t)env * 2 + 1) * 2, c.terminal_reward.asymmetric, cash1 + p1 * (double)inv1, lane);
+      r = o.reward; err |= o.err;
+    } else r = reward_calc(c.terminal_reward, cash0, inv0, p0, cash1, inv1, p1);
+  }
+  return r;
+}
 
 __device__ __forceinline__ unsigned char* warp_smem_base(unsigned char* smem, int warp, int warp_smem) { return smem + (size_t)warp * warp_smem; }
 
@@ -304,9 +323,8 @@ __global__ void __launch_bounds__(128, kEnv ? LOBSIM_ENV_MIN_BLOCKS : 4) k_advan
         if (c.inc_prev_action_in_obs && lane < ec.action_dim && (p.agent_kind == LOBSIM_AGENT_NONE || p.out_final_obs_only)) o[F + lane] = 0.0;
       }
       if (p.agent_kind != LOBSIM_AGENT_NONE) {
-        double r = reward_calc(c.step_reward, cash0, inv0, p0, w.cash, w.inventory, price);
-        bool d = now_step >= h->episode_start_step + c.episode_steps; // terminal_time - now < step/2, HOE.py:172
-        if (d) r = reward_calc(c.terminal_reward, cash0, inv0, p0, w.cash, w.inventory, price);
+        const bool d = now_step >= h->episode_start_step + c.episode_steps; // terminal_time - now < step/2, HOE.py:172
+        const double r = step_reward(p, c, env, lane, d, cash0, inv0, p0, w.cash, w.inventory, price, w.err);
         if (lane == 0) {
           if (p.rew) p.rew[(size_t)t * p.n_sel + sel] = r;
           if (p.done) p.done[(size_t)t * p.n_sel + sel] = d ? 1 : 0;
@@ -689,9 +707,8 @@ __global__ void __launch_bounds__(32 * LOBSIM_ENVFAST_WARPS, 16 / LOBSIM_ENVFAST
     }
     if (p.agent_kind != LOBSIM_AGENT_NONE) {
       const double cash1 = h->cash; const long long inv1 = h->inventory;
-      double r = reward_calc(c.step_reward, cash0, inv0, p0, cash1, inv1, price);
       const bool d = now_step >= h->episode_start_step + c.episode_steps; // terminal_time - now < step/2, HOE.py:172
-      if (d) r = reward_calc(c.terminal_reward, cash0, inv0, p0, cash1, inv1, price);
+      const double r = step_reward(p, c, env, lane, d, cash0, inv0, p0, cash1, inv1, price, f.err);
       if (lane == 0) {
         if (p.rew) p.rew[(size_t)t * p.n_sel + sel] = r;
         if (p.done) p.done[(size_t)t * p.n_sel + sel] = d ? 1 : 0;
@@ -832,6 +849,8 @@ struct lobsim {
   unsigned char* blobs = nullptr;
   FeatState* fstate = nullptr;
   double* rings = nullptr;
+  double* rs_ring = nullptr;
+  int32_t* rs_state = nullptr;
   lobsim_fill_t* fill_log = nullptr;
   int32_t* fill_count = nullptr;
   std::vector<lobsim_stream_t> streams;
@@ -867,9 +886,19 @@ static int validate_cfg(const lobsim_cfg_t* c) {
   if (c->max_agent_orders < 1 || c->max_agent_orders > 1024) return fail(LOBSIM_E_INVALID, "max_agent_orders must be in [1, 1024]");
   if (c->n_levels > c->max_levels_per_side) return fail(LOBSIM_E_INVALID, "n_levels exceeds max_levels_per_side");
   if (c->warmup_steps < 0 || c->episode_steps <= 0) return fail(LOBSIM_E_INVALID, "bad episode_steps / warmup_steps");
+  const lobsim_reward_t* rw[2] = {&c->step_reward, &c->terminal_reward};
+  for (int i = 0; i < 2; i++) {
+    if (rw[i]->kind < 0 || rw[i]->kind > LOBSIM_REWARD_ROLLING_SHARPE) return fail(LOBSIM_E_INVALID, "unknown reward kind");
+    if (rw[i]->kind == LOBSIM_REWARD_ROLLING_SHARPE) {
+      const int maxw = rw[i]->asymmetric & 0xffff, minw = (rw[i]->asymmetric >> 16) & 0xffff;
+      if (minw < 2 || minw > maxw || maxw > LOBSIM_MAX_SHARPE_WINDOW) return fail(LOBSIM_E_INVALID, "ROLLING_SHARPE: need 2 <= min_window <= max_window <= 256");
+    }
+  }
   for (int i = 0; i < c->n_features; i++) {
     const lobsim_feature_t& f = c->features[i];
-    if (f.kind < 0 || f.kind > LOBSIM_FEAT_TIME_OF_DAY) return fail(LOBSIM_E_INVALID, "unknown feature kind");
+    if (f.kind < 0 || f.kind > LOBSIM_FEAT_AMIHUD_LAMBDA) return fail(LOBSIM_E_INVALID, "unknown feature kind");
+    if (f.kind == LOBSIM_FEAT_AMIHUD_LAMBDA && (f.iparam < 1 || f.iparam > 16383 || f.lookback % f.iparam || f.lookback / f.iparam < 2 || f.lookback / f.iparam > 65535))
+      return fail(LOBSIM_E_INVALID, "AMIHUD_LAMBDA: lookback must be (true_lookback + 1) * slowing_factor with true_lookback >= 1");
     if (f.update_us <= 0 || f.update_us > 60000000 || f.lookback < 0) return fail(LOBSIM_E_INVALID, "bad feature update_us / lookback");
     if (f.kind == LOBSIM_FEAT_TIME_OF_DAY && f.iparam <= 0) return fail(LOBSIM_E_INVALID, "TIME_OF_DAY needs n_buckets > 0");
     if ((f.kind == LOBSIM_FEAT_VOLATILITY || f.kind == LOBSIM_FEAT_TRADE_DIR_IMBALANCE || f.kind == LOBSIM_FEAT_TRADE_VOL_IMBALANCE) && f.lookback < 1)
@@ -925,7 +954,12 @@ int lobsim_create(const lobsim_cfg_t* cfg, int device, lobsim_t** out) {
   memset(&h->ec, 0, sizeof h->ec);
   h->ec.cfg = *cfg;
   int slots = 0;
-  for (int i = 0; i < cfg->n_features; i++) { h->ec.ring_off[i] = slots; slots += cfg->features[i].lookback + 2; }
+  for (int i = 0; i < cfg->n_features; i++) {
+    const lobsim_feature_t& ft = cfg->features[i];
+    int need = ft.lookback + 2;
+    if (ft.kind == LOBSIM_FEAT_AMIHUD_LAMBDA) { const int kk = ft.lookback / ft.iparam - 1; if (2 * kk + 2 > need) need = 2 * kk + 2; }
+    h->ec.ring_off[i] = slots; slots += need;
+  }
   h->ec.ring_stride = (slots + 1) & ~1;
   h->ec.action_dim = lobsim_action_dim(cfg); h->ec.obs_dim = lobsim_obs_dim(cfg);
   const size_t n = (size_t)cfg->n_envs;
@@ -934,6 +968,11 @@ int lobsim_create(const lobsim_cfg_t* cfg, int device, lobsim_t** out) {
   CUDA_TRY(cudaMemset(h->fstate, 0, n * LOBSIM_MAX_FEATURES * sizeof(FeatState)));
   CUDA_TRY(cudaMalloc(&h->rings, n * (size_t)(h->ec.ring_stride > 0 ? h->ec.ring_stride : 2) * sizeof(double)));
   CUDA_TRY(cudaMemset(h->blobs, 0, n * h->L.blob_bytes));
+  if (cfg->step_reward.kind == LOBSIM_REWARD_ROLLING_SHARPE || cfg->terminal_reward.kind == LOBSIM_REWARD_ROLLING_SHARPE) {
+    CUDA_TRY(cudaMalloc(&h->rs_ring, n * 2 * LOBSIM_MAX_SHARPE_WINDOW * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&h->rs_state, n * 4 * sizeof(int32_t)));
+    CUDA_TRY(cudaMemset(h->rs_state, 0, n * 4 * sizeof(int32_t)));
+  }
   if (cfg->fill_log_capacity > 0) {
     CUDA_TRY(cudaMalloc(&h->fill_log, n * (size_t)cfg->fill_log_capacity * sizeof(lobsim_fill_t)));
     CUDA_TRY(cudaMalloc(&h->fill_count, n * sizeof(int32_t)));
@@ -950,7 +989,7 @@ int lobsim_create(const lobsim_cfg_t* cfg, int device, lobsim_t** out) {
 int lobsim_destroy(lobsim_t* h) {
   if (!h) return LOBSIM_OK;
   cudaSetDevice(h->device);
-  cudaFree(h->blobs); cudaFree(h->fstate); cudaFree(h->rings); cudaFree(h->fill_log); cudaFree(h->fill_count);
+  cudaFree(h->blobs); cudaFree(h->fstate); cudaFree(h->rings); cudaFree(h->rs_ring); cudaFree(h->rs_state); cudaFree(h->fill_log); cudaFree(h->fill_count);
   cudaFree(h->streams_dev); cudaFree(h->st_actions); cudaFree(h->st_obs); cudaFree(h->st_rew); cudaFree(h->st_done);
   cudaFree(h->st_state); cudaFree(h->st_msgs);
   delete h;
@@ -982,7 +1021,7 @@ int lobsim_load_stream(lobsim_t* h, int stream_id, const lobsim_stream_t* s) {
 
 static void base_params(lobsim* h, AdvParams& p) {
   memset(&p, 0, sizeof p);
-  p.blobs = h->blobs; p.fstate = h->fstate; p.rings = h->rings; p.streams = h->streams_dev; p.n_streams = (int)h->streams.size();
+  p.blobs = h->blobs; p.fstate = h->fstate; p.rings = h->rings; p.rs_ring = h->rs_ring; p.rs_state = h->rs_state; p.streams = h->streams_dev; p.n_streams = (int)h->streams.size();
   p.fill_log = h->fill_log; p.fill_count = h->fill_count; p.fill_cap = h->cfg.fill_log_capacity;
   p.n_envs = h->cfg.n_envs; p.n_sel = h->cfg.n_envs; p.L = h->L; p.warp_smem = h->warp_smem;
 }

@@ -156,5 +156,14 @@ class TimeOfDay(Feature):
 
 
 class AmihudLambda(Feature):
-    def __init__(self, *a, **k):
-        raise NotImplementedError("AmihudLambda (Features.py:245-324) is not on the device path yet (SURVEY.md 8f.4)")
+    kind = abi.FEAT_AMIHUD_LAMBDA
+
+    def __init__(self, name="AmihudLambda", min_value=0, max_value=1.0, update_frequency=timedelta(seconds=0.1),
+                 lookback_periods=10, slowing_factor=10, normalisation_on=False, max_norm_len=100_000):
+        super().__init__(name, min_value, max_value, update_frequency, (lookback_periods + 1) * slowing_factor,
+                         normalisation_on, max_norm_len)
+        self.true_lookback_periods = lookback_periods
+        self.slowing_factor = slowing_factor
+
+    def _params(self):
+        return dict(iparam=self.slowing_factor)

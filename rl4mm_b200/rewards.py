@@ -48,11 +48,15 @@ class InventoryAdjustedPnL(RewardFunction):
 
 
 class RollingSharpe(RewardFunction):
-    def __init__(self, *a, **k):
-        raise NotImplementedError("RollingSharpe (RewardFunctions.py:38-94) is not on the device path yet (SURVEY.md 8f.4)")
+    """RewardFunctions.py:38-94.  On the device the AUM window lives in HBM per env and, as in the reference, is never
+    reset by the environment."""
 
-    def calculate(self, current_state, next_state):  # pragma: no cover
-        raise NotImplementedError
+    def __init__(self, max_window_size: int = 120, min_window_size: int = 60):
+        assert max_window_size >= min_window_size, "Error with window sizes"
+        self.max_window_size, self.min_window_size = max_window_size, min_window_size
 
-    def to_abi(self):  # pragma: no cover
-        raise NotImplementedError
+    def calculate(self, current_state, next_state):
+        raise NotImplementedError("RollingSharpe is stateful: it is evaluated by the kernel (csrc/env.cuh rolling_sharpe_step)")
+
+    def to_abi(self):
+        return abi.rolling_sharpe(self.max_window_size, self.min_window_size)

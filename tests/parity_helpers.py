@@ -33,7 +33,7 @@ _KINDS = {
     "PRICE_RANGE": abi.FEAT_PRICE_RANGE, "VOLATILITY": abi.FEAT_VOLATILITY, "PRICE": abi.FEAT_PRICE,
     "TRADE_DIR_IMBALANCE": abi.FEAT_TRADE_DIR_IMBALANCE, "TRADE_VOL_IMBALANCE": abi.FEAT_TRADE_VOL_IMBALANCE,
     "INVENTORY": abi.FEAT_INVENTORY, "EPISODE_PROPORTION": abi.FEAT_EPISODE_PROPORTION,
-    "TIME_OF_DAY": abi.FEAT_TIME_OF_DAY,
+    "TIME_OF_DAY": abi.FEAT_TIME_OF_DAY, "AMIHUD_LAMBDA": abi.FEAT_AMIHUD_LAMBDA,
 }
 
 
@@ -45,6 +45,8 @@ def features_from_golden(specs):
 def reward_from_golden(spec) -> abi.Reward:
     if spec[0] == "PnL":
         return abi.Reward(abi.REWARD_PNL, 0, 0.0)
+    if spec[0] == "RS":
+        return abi.rolling_sharpe(spec[1], spec[2])
     return abi.Reward(abi.REWARD_INV_ADJ_PNL, int(spec[2]), float(spec[1]))
 
 

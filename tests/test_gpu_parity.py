@@ -105,7 +105,7 @@ def test_fixture_replay_in_one_launch(torch_cuda):
         assert H.canon_book(sim.dump_book(2, side), s.ext_ids) == case["steps"][27]["book"][side]
 
 
-@pytest.mark.parametrize("case_idx", range(10))
+@pytest.mark.parametrize("case_idx", range(12))
 def test_env_episodes(case_idx, torch_cuda):
     torch = torch_cuda
     case = H.load_golden("env_episodes.json.gz")[case_idx]
@@ -137,7 +137,9 @@ def test_env_episodes(case_idx, torch_cuda):
             H.assert_close_vec(obs[env], step["obs"], f"{case['name']} step {k} obs")
             assert H.close(rew[env], step["reward"]), (case["name"], k, rew[env], step["reward"])
             assert bool(done[env]) == step["done"]
-            assert np.all(obs == obs[0]) and np.all(rew == rew[0])  # identical replicas stay identical
+            # identical replicas stay identical (RollingSharpe over a single return is NaN in the reference too)
+            assert np.array_equal(obs, np.broadcast_to(obs[0], obs.shape), equal_nan=True)
+            assert np.array_equal(rew, np.full_like(rew, rew[0]), equal_nan=True)
 
 
 @pytest.mark.parametrize("case_idx", range(40))
