@@ -100,7 +100,7 @@ typedef struct {
   double min_value;  /* clamp, Features.py:83,99                                             */
   double max_value;
   int32_t iparam;    /* TIME_OF_DAY: n_buckets; TRADE_*_IMBALANCE: track_internal; AMIHUD: slowing_factor */
-  int32_t reserved;
+  int32_t norm_len;  /* normalisation_on ? max_norm_len : 0  (rolling z-score over the clamped values, Features.py:67-74) */
   double dparam;     /* EPISODE_PROPORTION: update_frequency / episode_length                */
 } lobsim_feature_t;
 

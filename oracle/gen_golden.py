@@ -135,6 +135,17 @@ def feature_specs():
         # index 14: AmihudLambda, window (4 + 1) * 2 * 0.1 s = 1 s
         (lambda: F.AmihudLambda(update_frequency=td(seconds=0.1), lookback_periods=4, slowing_factor=2, max_value=1e-3),
          dict(kind="AMIHUD_LAMBDA", lookback=10, update_us=100000, min=0, max=1e-3, iparam=2)),
+        # indices 15-19: rolling z-score normalisation (Features.py:67-74), short histories so that eviction happens
+        (lambda: F.Spread(normalisation_on=True, max_norm_len=6),
+         dict(kind="SPREAD", lookback=0, update_us=100000, min=0, max=5000, norm_len=6)),
+        (lambda: F.PriceMove(name="pmn", update_frequency=td(seconds=0.1), lookback_periods=2, normalisation_on=True, max_norm_len=5),
+         dict(kind="PRICE_MOVE", lookback=2, update_us=100000, min=-10000, max=10000, norm_len=5)),
+        (lambda: F.Volatility(name="vn", update_frequency=td(seconds=0.1), lookback_periods=3, normalisation_on=True, max_norm_len=100),
+         dict(kind="VOLATILITY", lookback=3, update_us=100000, min=0, max=1.0, norm_len=100)),
+        (lambda: F.Inventory(normalisation_on=True, max_norm_len=7),
+         dict(kind="INVENTORY", lookback=0, update_us=100000, min=-1000000, max=1000000, norm_len=7)),
+        (lambda: F.TradeVolumeImbalance(update_frequency=td(seconds=0.1), lookback_periods=10, normalisation_on=True, max_norm_len=1000),
+         dict(kind="TRADE_VOL_IMBALANCE", lookback=10, update_us=100000, min=-1, max=1, iparam=0, norm_len=1000)),
     ]
 
 
@@ -153,7 +164,7 @@ def run_env_case(name, actions, env_kwargs, reward_step, reward_term, features=N
             return RollingSharpe(max_window_size=spec[1], min_window_size=spec[2])
         return InventoryAdjustedPnL(inventory_aversion=spec[1], asymmetrically_dampened=spec[2])
 
-    specs = feature_specs() if features is None else [feature_specs()[i] for i in features]
+    specs = feature_specs()[:14] if features is None else [feature_specs()[i] for i in features]
     feats = [mk() for mk, _ in specs]
     max_window = max(f.window_size for f in feats)
     episode_length = timedelta(seconds=episode_seconds)
@@ -221,6 +232,8 @@ def golden_env_episodes():
                      n_episodes=3, episode_seconds=1.0, start_seconds=36001.0, portfolio=(0, 10**10)),
         run_env_case("amihud_full", rand4[10:], {}, ("RS", 12, 5), ("PnL",), features=list(range(12)) + [14],
                      portfolio=(0, 10**10)),
+        run_env_case("normalised_features", rand4[25:], {}, ("PnL",), ("PnL",), features=[15, 16, 17, 18, 19, 9],
+                     n_episodes=2, episode_seconds=1.5, start_seconds=36001.0),
     ]
     save("env_episodes.json.gz", cases)
 

@@ -152,6 +152,8 @@ typedef struct {
   double partial_price_sum; /* AmihudLambda */
   int64_t partial_dollar_volume;
   int steps_until_update, dv_len;
+  double* hist;             /* Feature.history (deque(maxlen=max_norm_len)) */
+  int hist_len;
 } o_feat;
 
 /* RollingSharpe.aum_array / n_filled -- rl4mm/rewards/RewardFunctions.py:50-59 (never reset by the env) */
@@ -641,11 +643,28 @@ static void feature_reset(lo_t* o, int fi, int64_t first_usage_us) {
   o_feat* f = &o->feat[fi];
   f->first_usage_us = first_usage_us;
   f->len = 0; f->total = 0; f->diff = 0;
+  f->hist_len = 0; /* history.clear() :94-95 */
   if (fc->kind == LOBSIM_FEAT_AMIHUD_LAMBDA) { /* AmihudLambda.reset :278-283 */
     f->dv_len = 0; f->partial_price_sum = 0.0; f->partial_dollar_volume = 0; f->steps_until_update = fc->iparam - 1;
   }
   feature_update_raw(o, fi);
   if (fc->kind == LOBSIM_FEAT_EPISODE_PROPORTION) f->cur = 0.0; /* :507-509 */
+}
+
+/* Feature.normalise -- Features.py:67-74: scipy.stats.zscore(history)[-1] = (value - mean) / std (ddof 0), numpy's
+ * pairwise mean and two-pass variance */
+static double np_pairwise_sum(const double* a, int n);
+static double feature_normalise(o_feat* f, int maxlen, double value) {
+  if (f->hist_len == 0) f->hist[f->hist_len++] = value + 1e-06;
+  if (f->hist_len == maxlen) { memmove(&f->hist[0], &f->hist[1], (size_t)(maxlen - 1) * sizeof(double)); f->hist_len--; }
+  f->hist[f->hist_len++] = value;
+  const int n = f->hist_len;
+  double mean = np_pairwise_sum(f->hist, n) / (double)n;
+  double* sq = (double*)malloc((size_t)n * sizeof(double));
+  for (int i = 0; i < n; i++) { double d = f->hist[i] - mean; sq[i] = d * d; }
+  double sd = sqrt(np_pairwise_sum(sq, n) / (double)n);
+  free(sq);
+  return (value - mean) / sd;
 }
 
 /* Feature.update -- Features.py:80-86, _now_is_multiple_of_update_freq :102-105 */
@@ -657,6 +676,7 @@ static void feature_update(lo_t* o, int fi) {
   if ((t % 60000000LL) % fc->update_us != 0) return;
   feature_update_raw(o, fi);
   f->cur = clampd(f->cur, fc->min_value, fc->max_value);
+  if (fc->norm_len > 0) f->cur = feature_normalise(f, fc->norm_len, f->cur);
 }
 
 /* ------------------------------------------------------------------------------------------------------------ */
@@ -981,6 +1001,7 @@ lo_t* lo_create(const lobsim_cfg_t* cfg) {
     o->feat[i].ring = (double*)calloc((size_t)k, sizeof(double));
     o->feat[i].iring[0] = (int64_t*)calloc((size_t)k, sizeof(int64_t));
     o->feat[i].iring[1] = (int64_t*)calloc((size_t)k, sizeof(int64_t));
+    o->feat[i].hist = (double*)calloc((size_t)(cfg->features[i].norm_len > 0 ? cfg->features[i].norm_len : 1), sizeof(double));
   }
   o->inventory = cfg->initial_inventory; o->cash = cfg->initial_cash;
   return o;
@@ -989,7 +1010,7 @@ lo_t* lo_create(const lobsim_cfg_t* cfg) {
 void lo_destroy(lo_t* o) {
   if (!o) return;
   book_free(&o->central); book_free(&o->internal); map_free(&o->ext2int);
-  for (int i = 0; i < o->cfg.n_features; i++) { free(o->feat[i].ring); free(o->feat[i].iring[0]); free(o->feat[i].iring[1]); }
+  for (int i = 0; i < o->cfg.n_features; i++) { free(o->feat[i].ring); free(o->feat[i].iring[0]); free(o->feat[i].iring[1]); free(o->feat[i].hist); }
   free(o->fills); free(o);
 }
 

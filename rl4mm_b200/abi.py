@@ -56,7 +56,7 @@ def meta(msg_type, direction):
 class Feature(C.Structure):
     _fields_ = [
         ("kind", C.c_int32), ("lookback", C.c_int32), ("update_us", C.c_int64), ("min_value", C.c_double),
-        ("max_value", C.c_double), ("iparam", C.c_int32), ("reserved", C.c_int32), ("dparam", C.c_double),
+        ("max_value", C.c_double), ("iparam", C.c_int32), ("norm_len", C.c_int32), ("dparam", C.c_double),
     ]
 
 
@@ -161,8 +161,9 @@ def set_features(cfg: Cfg, feats) -> None:
         cfg.features[i] = f
 
 
-def feature(kind, lookback=0, update_us=100_000, min_value=0.0, max_value=0.0, iparam=0, dparam=0.0) -> Feature:
-    return Feature(kind, lookback, update_us, float(min_value), float(max_value), iparam, 0, float(dparam))
+def feature(kind, lookback=0, update_us=100_000, min_value=0.0, max_value=0.0, iparam=0, dparam=0.0, norm_len=0) -> Feature:
+    """norm_len > 0 switches on the rolling z-score (normalisation_on=True with max_norm_len=norm_len)."""
+    return Feature(kind, lookback, update_us, float(min_value), float(max_value), iparam, int(norm_len), float(dparam))
 
 
 def rolling_sharpe(max_window_size: int = 120, min_window_size: int = 60) -> Reward:

@@ -13,13 +13,19 @@ struct __align__(16) FeatState {
   long long diff;    // trade_diff / volume_imbalance
   int32_t len;       // deque length (bit 30: running sums valid)
   int32_t head;      // circular write position
+  // rolling z-score (Feature.normalise): shifted running sums over the history ring
+  double nK, nS1, nS2; // shift K (first history value), sum (x-K), sum (x-K)^2
+  int32_t nlen, nhead; // history length, next write position (= oldest entry once full)
+  int32_t nrun;        // number of equal trailing history values (an all-equal window is a 0/0 in the reference)
+  int32_t pad;
 };
-static_assert(sizeof(FeatState) == 32, "FeatState must be 32 bytes");
+static_assert(sizeof(FeatState) == 72 || sizeof(FeatState) == 80, "FeatState layout");
 #define FEAT_SUMS_VALID (1 << 30)
 
 struct EnvConst { // what the device needs of lobsim_cfg_t, by value in the kernel parameters
   lobsim_cfg_t cfg;
   int32_t ring_off[LOBSIM_MAX_FEATURES]; // slot offset of each feature's ring inside an env's ring block
+  int32_t hist_off[LOBSIM_MAX_FEATURES]; // slot offset of each feature's normalisation history (norm_len slots)
   int32_t ring_stride;                   // slots per env
   int32_t action_dim, obs_dim;
 };
@@ -479,21 +485,57 @@ __device__ __forceinline__ void feature_update_raw(const lobsim_feature_t& fc, F
   }
 }
 
+// Feature.normalise, Features.py:67-74: scipy.stats.zscore(history)[-1] = (value - mean) / std (ddof 0) over a
+// deque(maxlen) of the clamped values.  The reference recomputes mean and std from scratch every step (O(history));
+// here shifted running sums over a ring in HBM give the same number to ~1e-12 (documented in DESIGN.md section 4).
+__device__ __forceinline__ double feature_normalise(FeatState& f, double* hist, int maxlen, double value) {
+  int n = f.nlen;
+  int head = f.nhead;
+  double last = NAN;
+  if (n == 0) { // "to prevent a NaN value from being returned if the queue is empty" :68-72
+    const double x0 = value + 1e-06;
+    f.nK = x0; f.nS1 = 0.0; f.nS2 = 0.0; f.nrun = 1;
+    hist[0] = x0; n = 1; head = maxlen > 1 ? 1 : 0; last = x0;
+  } else last = hist[head == 0 ? maxlen - 1 : head - 1];
+  if (n == maxlen) { const double old = hist[head] - f.nK; f.nS1 -= old; f.nS2 -= old * old; n -= 1; }
+  hist[head] = value;
+  head = head + 1 == maxlen ? 0 : head + 1;
+  const double d = value - f.nK;
+  n += 1;
+  f.nrun = value == last ? (f.nrun < 0x7fffffff ? f.nrun + 1 : f.nrun) : 1;
+  f.nlen = n; f.nhead = head;
+  if (f.nrun >= n) {
+    // the whole window holds one value: the sums are exactly n*d and n*d^2 (this also sheds accumulated rounding), and
+    // scipy's zscore is (v - mean) / 0 = 0/0 = NaN whenever n*v is exact (integer-valued features: spread, inventory,
+    // flow counts, 0.0 volatility ...).  For other values numpy's mean may be off by an ulp and the reference returns
+    // +-1 instead; that rounding artefact is not reproduced.
+    f.nS1 = (double)n * d; f.nS2 = (double)n * d * d;
+    return NAN;
+  }
+  f.nS1 += d; f.nS2 += d * d;
+  const double m1 = f.nS1 / (double)n;
+  double var = f.nS2 / (double)n - m1 * m1;
+  if (var < 0.0) var = 0.0;
+  return (d - m1) / sqrt(var);
+}
+
 // Feature.reset/_reset, Features.py:92-96
 __device__ __forceinline__ void feature_reset(const lobsim_feature_t& fc, FeatState& f, double* ring, const StepView& v) {
   f.len = 0; f.head = 0; f.total = 0; f.diff = 0;
+  f.nlen = 0; f.nhead = 0; f.nrun = 0; // history.clear()
   if (fc.kind == LOBSIM_FEAT_AMIHUD_LAMBDA) { f.len = (fc.iparam - 1) << 16; f.diff = __double_as_longlong(0.0); } // AmihudLambda.reset :278-283
   feature_update_raw(fc, f, ring, v);
   if (fc.kind == LOBSIM_FEAT_EPISODE_PROPORTION) f.cur = 0.0;
 }
 
 // Feature.update, Features.py:80-86,102-105
-__device__ __forceinline__ void feature_update(const lobsim_feature_t& fc, FeatState& f, double* ring, const StepView& v, long long episode_start_us) {
+__device__ __forceinline__ void feature_update(const lobsim_feature_t& fc, FeatState& f, double* ring, double* hist, const StepView& v, long long episode_start_us) {
   long long first_usage = episode_start_us - (long long)fc.lookback * fc.update_us;
   if (v.now_us < first_usage) return;
   if ((v.now_us % 60000000LL) % fc.update_us != 0) return;
   feature_update_raw(fc, f, ring, v);
   f.cur = fmax(fmin(f.cur, fc.max_value), fc.min_value);
+  if (fc.norm_len > 0) f.cur = feature_normalise(f, hist, fc.norm_len, f.cur);
 }
 
 // Cold per-step feature phase: lane f < F loads its feature state from HBM, resets (mode 1) or updates (mode 0) it,
@@ -507,7 +549,7 @@ __device__ __noinline__ double features_step(const EnvConst* ecp, FeatState* fst
     FeatState fs = fstate_env[lane];
     double* ring = rings_env + ec.ring_off[lane];
     if (mode == 1) feature_reset(fc, fs, ring, v);
-    else feature_update(fc, fs, ring, v, episode_start_us);
+    else feature_update(fc, fs, ring, rings_env + ec.hist_off[lane], v, episode_start_us);
     fstate_env[lane] = fs;
     cur = fs.cur;
   }

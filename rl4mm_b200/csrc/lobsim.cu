@@ -900,6 +900,7 @@ static int validate_cfg(const lobsim_cfg_t* c) {
     if (f.kind == LOBSIM_FEAT_AMIHUD_LAMBDA && (f.iparam < 1 || f.iparam > 16383 || f.lookback % f.iparam || f.lookback / f.iparam < 2 || f.lookback / f.iparam > 65535))
       return fail(LOBSIM_E_INVALID, "AMIHUD_LAMBDA: lookback must be (true_lookback + 1) * slowing_factor with true_lookback >= 1");
     if (f.update_us <= 0 || f.update_us > 60000000 || f.lookback < 0) return fail(LOBSIM_E_INVALID, "bad feature update_us / lookback");
+    if (f.norm_len < 0 || f.norm_len > 10000000) return fail(LOBSIM_E_INVALID, "bad feature norm_len");
     if (f.kind == LOBSIM_FEAT_TIME_OF_DAY && f.iparam <= 0) return fail(LOBSIM_E_INVALID, "TIME_OF_DAY needs n_buckets > 0");
     if ((f.kind == LOBSIM_FEAT_VOLATILITY || f.kind == LOBSIM_FEAT_TRADE_DIR_IMBALANCE || f.kind == LOBSIM_FEAT_TRADE_VOL_IMBALANCE) && f.lookback < 1)
       return fail(LOBSIM_E_INVALID, "windowed feature needs lookback >= 1");
@@ -959,6 +960,7 @@ int lobsim_create(const lobsim_cfg_t* cfg, int device, lobsim_t** out) {
     int need = ft.lookback + 2;
     if (ft.kind == LOBSIM_FEAT_AMIHUD_LAMBDA) { const int kk = ft.lookback / ft.iparam - 1; if (2 * kk + 2 > need) need = 2 * kk + 2; }
     h->ec.ring_off[i] = slots; slots += need;
+    h->ec.hist_off[i] = slots; slots += ft.norm_len > 0 ? ft.norm_len : 0;
   }
   h->ec.ring_stride = (slots + 1) & ~1;
   h->ec.action_dim = lobsim_action_dim(cfg); h->ec.obs_dim = lobsim_obs_dim(cfg);
@@ -966,7 +968,13 @@ int lobsim_create(const lobsim_cfg_t* cfg, int device, lobsim_t** out) {
   CUDA_TRY(cudaMalloc(&h->blobs, n * h->L.blob_bytes));
   CUDA_TRY(cudaMalloc(&h->fstate, n * LOBSIM_MAX_FEATURES * sizeof(FeatState)));
   CUDA_TRY(cudaMemset(h->fstate, 0, n * LOBSIM_MAX_FEATURES * sizeof(FeatState)));
-  CUDA_TRY(cudaMalloc(&h->rings, n * (size_t)(h->ec.ring_stride > 0 ? h->ec.ring_stride : 2) * sizeof(double)));
+  {
+    size_t free_b = 0, total_b = 0;
+    CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+    const size_t ring_bytes = n * (size_t)(h->ec.ring_stride > 0 ? h->ec.ring_stride : 2) * sizeof(double);
+    if (ring_bytes > free_b) { lobsim_destroy(h); return fail(LOBSIM_E_NOMEM, "feature windows / normalisation histories (n_envs x sum(lookback + max_norm_len) x 8 B) exceed the free HBM"); }
+    CUDA_TRY(cudaMalloc(&h->rings, ring_bytes));
+  }
   CUDA_TRY(cudaMemset(h->blobs, 0, n * h->L.blob_bytes));
   if (cfg->step_reward.kind == LOBSIM_REWARD_ROLLING_SHARPE || cfg->terminal_reward.kind == LOBSIM_REWARD_ROLLING_SHARPE) {
     CUDA_TRY(cudaMalloc(&h->rs_ring, n * 2 * LOBSIM_MAX_SHARPE_WINDOW * sizeof(double)));

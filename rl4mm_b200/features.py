@@ -35,8 +35,6 @@ class Feature:
     def __init__(self, name: str, min_value: float, max_value: float, update_frequency: timedelta,
                  lookback_periods: int, normalisation_on: bool = False, max_norm_len: int = 10000):
         assert update_frequency <= timedelta(minutes=1), "HFT update frequency must be less than 1 minute."
-        if normalisation_on:
-            raise NotImplementedError("z-score normalisation (Features.py:67-74) is not on the device path yet")
         self.name, self.min_value, self.max_value = name, min_value, max_value
         self.update_frequency, self.lookback_periods = update_frequency, lookback_periods
         self.normalisation_on, self.max_norm_len = normalisation_on, max_norm_len
@@ -51,7 +49,7 @@ class Feature:
 
     def to_abi(self) -> abi.Feature:
         return abi.feature(self.kind, self.lookback_periods, _us(self.update_frequency), self.min_value, self.max_value,
-                           **self._params())
+                           norm_len=self.max_norm_len if self.normalisation_on else 0, **self._params())
 
 
 class Spread(Feature):

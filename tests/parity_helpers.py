@@ -39,7 +39,7 @@ _KINDS = {
 
 def features_from_golden(specs):
     return [abi.feature(_KINDS[d["kind"]], d["lookback"], d["update_us"], d["min"], d["max"], d.get("iparam", 0),
-                        d.get("dparam", 0.0)) for d in specs]
+                        d.get("dparam", 0.0), d.get("norm_len", 0)) for d in specs]
 
 
 def reward_from_golden(spec) -> abi.Reward:
