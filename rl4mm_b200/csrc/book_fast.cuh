@@ -199,6 +199,7 @@ __device__ __forceinline__ void fast_order(const FastBook<LT>& fb, FastState& f,
       __syncwarp();
       if (TR && hagent) fast_agent_reduce(fb, opp, href & 0x7fffffffu, 0, true);   // the resting agent order is gone
     }
+    __syncwarp();   // every lane has read the counters (WAR) before lane 0 rewrites them
     if (lane == 0) *fb.cnt(opp) = c;
     __syncwarp();
     if (rem > 0 && type == LOBSIM_MSG_LIMIT && !f.dead) {    // the remainder rests (Exchange.py:116-119); rare
@@ -266,6 +267,7 @@ __device__ __forceinline__ void fast_order(const FastBook<LT>& fb, FastState& f,
         h->nag[side] = nag + 1; h->next_agent_id = id + 1;
       }
     }
+    __syncwarp();   // every lane has read the counters / level ends (WAR) before they are rewritten
     if (lane == 0) { fb.O(sb)[pos] = make_uint2((unsigned)vol, ref); *fb.cnt(side) = make_int2(nlv2, nord + 1); }
     { const int i = j + lane; if (i < nlv2) fb.LE(sb)[i] = (uint16_t)(fb.LE(sb)[i] + 1); }   // nlv2 - j <= 32
     __syncwarp();

@@ -89,6 +89,7 @@ struct AdvParams {
   int32_t fill_cap;
   int32_t n_envs;                   // total envs of the handle
   int32_t n_sel;                    // number of envs this launch works on
+  int32_t sel_offset;               // first selection index handled by this launch (tail launches)
   const int32_t* env_ids;           // [n_sel] or null (identity)
   int32_t T;                        // simulation steps to run
   int32_t reset_mode;               // 0 none, 1 book reset only, 2 full env reset (+ warm-up of T steps)
@@ -511,19 +512,17 @@ __device__ __noinline__ uint32_t reset_book_cold(unsigned char* blob, const Layo
 #else
 #define PHASE_SYNC() ((void)0)
 #endif
-template <class LT>
+// SYNC: the launch consists of full CTAs only, whose warps move through the phases of a step together
+// (launch_env puts the n_sel % warps-per-CTA tail into a second, free-running launch).
+template <class LT, bool SYNC>
 __global__ void __launch_bounds__(32 * LOBSIM_ENVFAST_WARPS, 16 / LOBSIM_ENVFAST_WARPS) k_env_fast(const __grid_constant__ AdvParams p, const __grid_constant__ EnvConst ec) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int sel = blockIdx.x * (blockDim.x >> 5) + warp;
-  // All warps of an SM form ONE CTA and move through the phases of a step together (PHASE_SYNC = __syncthreads):
-  // the instruction working set at any moment is a single phase, which is what keeps the 32 KB L1.5 I-cache warm
+  const int sel = p.sel_offset + blockIdx.x * (blockDim.x >> 5) + warp;
+  // The warps of a CTA move through the phases of a step together (PHASE_SYNC = __syncthreads): the instruction
+  // working set at any moment is a single phase, which is what keeps the 32 KB L1.5 I-cache warm
   // (profiles/r01_envstep_*: "no instruction" was the top stall with free-running warps).
-  if (sel >= p.n_sel) { // idle warp of the last CTA: only keeps the barrier counts matched
-    PHASE_SYNC();
-    for (int t = 0; t < p.T; t++) { PHASE_SYNC(); PHASE_SYNC(); PHASE_SYNC(); }
-    return;
-  }
+  if (sel >= p.n_sel) return; // only in SYNC == false launches
   const int env = p.env_ids ? p.env_ids[sel] : sel;
   const lobsim_cfg_t& c = ec.cfg;
   unsigned char* base = warp_smem_base(smem, warp, p.warp_smem);
@@ -615,7 +614,7 @@ __global__ void __launch_bounds__(32 * LOBSIM_ENVFAST_WARPS, 16 / LOBSIM_ENVFAST
   auto wait_tile = [&]() { mbar_wait(&bars[next_wait & 1], (next_wait >> 1) & 1); next_wait++; };
   if (g < g_end_all) { issue_tile(); issue_tile(); }
   __syncwarp();
-  PHASE_SYNC();
+  if (SYNC) PHASE_SYNC();
   const int steps_per_sec = (int)(1000000 / c.step_us);
   int sub = now_step >= 0 ? now_step % steps_per_sec : 0;
 
@@ -623,8 +622,9 @@ __global__ void __launch_bounds__(32 * LOBSIM_ENVFAST_WARPS, 16 / LOBSIM_ENVFAST
   bool agent_phase = false;
 #pragma unroll 1
   for (int t = 0; t < T; t++) {
-    PHASE_SYNC(); // ---- phase A: action -> ladders (fp64) --------------------------------------------------------
+    if (SYNC) PHASE_SYNC(); // ---- phase A: action -> ladders (fp64) --------------------------------------------------------
     const double cash0 = h->cash, p0 = price; const long long inv0 = h->inventory; // deepcopy(self.state), HOE.py:166
+    __syncwarp();
     if (lane < 8) h->flow[lane] = 0;
     __syncwarp();
     if (p.agent_kind != LOBSIM_AGENT_NONE) {
@@ -649,7 +649,7 @@ __global__ void __launch_bounds__(32 * LOBSIM_ENVFAST_WARPS, 16 / LOBSIM_ENVFAST
         agent_phase = true;
       }
     }
-    PHASE_SYNC(); // ---- phase B: the step's orders: the agent's first, then the historical messages of (now, now + step]
+    if (SYNC) PHASE_SYNC(); // ---- phase B: the step's orders: the agent's first, then the historical messages of (now, now + step]
     {
       const unsigned g_step_end = f.dead ? g : __ldg(&st_step_off[now_step + 1]);
 #pragma unroll 1
@@ -691,7 +691,7 @@ __global__ void __launch_bounds__(32 * LOBSIM_ENVFAST_WARPS, 16 / LOBSIM_ENVFAST
         }
       }
     }
-    PHASE_SYNC(); // ---- phase C: update_internal_state + _update_features + reward, HOE.py:163-178,199-204 -------------
+    if (SYNC) PHASE_SYNC(); // ---- phase C: update_internal_state + _update_features + reward, HOE.py:163-178,199-204 -------------
     StepView v; tops(v);
     if (!v.have_tops) f.err |= LOBSIM_ERR_EMPTY_BOOK;
     price = v.price;
@@ -940,8 +940,9 @@ int lobsim_create(const lobsim_cfg_t* cfg, int device, lobsim_t** out) {
   CUDA_TRY((cudaFuncSetAttribute(k_advance<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->warps_per_cta * h->warp_smem)));
   {
     const void* fast_kernels[] = {(const void*)k_replay_fast<FastLayoutA>, (const void*)k_replay_fast<FastLayoutB>, (const void*)k_replay_fast<FastLayoutC>,
-                                  (const void*)k_env_fast<FastLayoutA>, (const void*)k_env_fast<FastLayoutB>, (const void*)k_env_fast<FastLayoutC>};
-    for (int i = 0; i < 6; i++) {
+                                  (const void*)k_env_fast<FastLayoutA, true>, (const void*)k_env_fast<FastLayoutB, true>, (const void*)k_env_fast<FastLayoutC, true>,
+                                  (const void*)k_env_fast<FastLayoutA, false>, (const void*)k_env_fast<FastLayoutB, false>, (const void*)k_env_fast<FastLayoutC, false>};
+    for (int i = 0; i < 9; i++) {
       const void* k = fast_kernels[i];
       const int dyn = (i < 3 ? h->warps_per_cta : h->env_warps_per_cta) * h->warp_smem;
       CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
@@ -1072,14 +1073,25 @@ static int launch_env(lobsim* h, const AdvParams& p, cudaStream_t stream) {
   const bool a = FastLayoutA::matches(h->L), b = FastLayoutB::matches(h->L), cc = FastLayoutC::matches(h->L);
   if ((!a && !b && !cc) || h->force_general) return launch_advance<true, true>(h, p, stream);
   CUDA_TRY(cudaSetDevice(h->device));
-  const int wpc = h->env_warps_per_cta, grid = (p.n_sel + wpc - 1) / wpc;
-  if (grid <= 0) return LOBSIM_OK;
+  const int wpc = h->env_warps_per_cta;
   const size_t dyn = (size_t)wpc * h->warp_smem;
-  if (a) k_env_fast<FastLayoutA><<<grid, wpc * 32, dyn, stream>>>(p, h->ec);
-  else if (b) k_env_fast<FastLayoutB><<<grid, wpc * 32, dyn, stream>>>(p, h->ec);
-  else k_env_fast<FastLayoutC><<<grid, wpc * 32, dyn, stream>>>(p, h->ec);
-  CUDA_TRY(cudaGetLastError());
-  h->launches++;
+  const int full = p.n_sel / wpc, tail = p.n_sel % wpc;
+  if (full > 0) { // full CTAs: phase-synchronous
+    if (a) k_env_fast<FastLayoutA, true><<<full, wpc * 32, dyn, stream>>>(p, h->ec);
+    else if (b) k_env_fast<FastLayoutB, true><<<full, wpc * 32, dyn, stream>>>(p, h->ec);
+    else k_env_fast<FastLayoutC, true><<<full, wpc * 32, dyn, stream>>>(p, h->ec);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+  }
+  if (tail > 0) { // the remaining n_sel % wpc envs: one partially filled CTA without block-level barriers
+    AdvParams pt = p;
+    pt.sel_offset = full * wpc;
+    if (a) k_env_fast<FastLayoutA, false><<<1, wpc * 32, dyn, stream>>>(pt, h->ec);
+    else if (b) k_env_fast<FastLayoutB, false><<<1, wpc * 32, dyn, stream>>>(pt, h->ec);
+    else k_env_fast<FastLayoutC, false><<<1, wpc * 32, dyn, stream>>>(pt, h->ec);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+  }
   return LOBSIM_OK;
 }
 
