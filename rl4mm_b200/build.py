@@ -2,6 +2,7 @@
 
 * ``rl4mm_b200/_native/liblobsim.so``  -- CUDA kernels + C ABI (include/lobsim.h), nvcc, sm_100a only
 * ``rl4mm_b200/_native/libsynth.so``   -- synthetic LOBSTER stream generator (host C++)
+* ``rl4mm_b200/_native/libingest.so``  -- LOBSTER CSV reader for the packer (host C++)
 """
 from __future__ import annotations
 
@@ -41,6 +42,15 @@ def build_synth(force: bool = False) -> Path:
     return out
 
 
+def build_ingest(force: bool = False) -> Path:
+    OUT.mkdir(exist_ok=True)
+    out = OUT / "libingest.so"
+    srcs = [CSRC / "lobster_ingest.cpp"]
+    if force or _newer(srcs, out):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", str(out), str(srcs[0])], check=True)
+    return out
+
+
 def build_lobsim(force: bool = False, verbose: bool = False) -> Path:
     OUT.mkdir(exist_ok=True)
     out = OUT / "liblobsim.so"
@@ -58,6 +68,7 @@ def build_lobsim(force: bool = False, verbose: bool = False) -> Path:
 
 def build_all(force: bool = False, verbose: bool = False) -> None:
     build_synth(force)
+    build_ingest(force)
     build_lobsim(force, verbose)
 
 

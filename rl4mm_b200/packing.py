@@ -105,7 +105,7 @@ def pack_arrays(
     size: np.ndarray,
     price: np.ndarray,
     direction: np.ndarray,
-    book_rows: np.ndarray,
+    book_rows,
     n_levels: int,
     step_us: int = 100_000,
     t0_us: Optional[int] = None,
@@ -115,12 +115,13 @@ def pack_arrays(
     date: str = "",
 ) -> PackedStream:
     """Pack raw LOBSTER columns.  ``book_rows`` is the orderbook file as int64 [n_rows, 4*n_levels] (one row per
-    message row, columns ask price, ask size, bid price, bid size per level -- rl4mm/orderbook/helpers.py:52-55)."""
+    message row, columns ask price, ask size, bid price, bid size per level -- rl4mm/orderbook/helpers.py:52-55), or a
+    callable ``rows(idx) -> int64 [len(idx), 4*n_levels]`` that loads just the requested (ascending) row indices."""
     time_ns = np.asarray(time_ns, np.int64)
     msg_type = np.asarray(msg_type, np.int64)
     n = len(time_ns)
     assert np.all(np.diff(time_ns) >= 0), "LOBSTER messages must be time ordered"
-    assert book_rows.shape == (n, 4 * n_levels)
+    assert callable(book_rows) or book_rows.shape == (n, 4 * n_levels)
     if 1_000_000 % step_us:
         raise ValueError("step_us must divide one second")
     ts_us = time_ns // 1000
@@ -176,7 +177,9 @@ def pack_arrays(
     sec_ns = (t0_us + np.arange(n_seconds + 1, dtype=np.int64) * 1_000_000) * 1000
     idx = np.searchsorted(time_ns, sec_ns, side="right") - 1
     snap_valid = (idx >= 0).astype(np.uint8)
-    rows = np.asarray(book_rows, np.int64)[np.maximum(idx, 0)].reshape(n_seconds + 1, n_levels, 4)
+    need = np.maximum(idx, 0)
+    rows = book_rows(need) if callable(book_rows) else np.asarray(book_rows, np.int64)[need]
+    rows = np.asarray(rows, np.int64).reshape(n_seconds + 1, n_levels, 4)
     snapshots = np.zeros((n_seconds + 1, 2, n_levels, 2), np.int32)
     for s, (pc, vc) in ((abi.SELL, (0, 1)), (abi.BUY, (2, 3))):
         p, v = rows[:, :, pc], rows[:, :, vc]
@@ -189,8 +192,68 @@ def pack_arrays(
     return out
 
 
-def pack_lobster(message_csv, orderbook_csv, n_levels: int, max_rows: Optional[int] = None, **kw) -> PackedStream:
-    """Pack a LOBSTER ``*_message_L.csv`` / ``*_orderbook_L.csv`` pair (populate_database.py:71-78 column layout)."""
+_INGEST = None
+
+
+def _ingest_lib():
+    global _INGEST
+    if _INGEST is None:
+        import ctypes as C
+
+        from .build import build_ingest
+
+        L = C.CDLL(str(build_ingest()))
+        L.lobingest_count_lines.restype = C.c_int64
+        L.lobingest_count_lines.argtypes = [C.c_char_p]
+        L.lobingest_parse_messages.argtypes = [C.c_char_p, C.c_int64] + [C.c_void_p] * 6 + [C.POINTER(C.c_int64)]
+        L.lobingest_parse_book_rows.argtypes = [C.c_char_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
+        _INGEST = L
+    return _INGEST
+
+
+def read_lobster_messages(message_csv, max_rows: Optional[int] = None):
+    """Columns of a LOBSTER message file through csrc/lobster_ingest.cpp: (time_ns, type, order_id, size, price,
+    direction) as numpy arrays; the time is parsed exactly from the decimal text."""
+    import ctypes as C
+
+    L = _ingest_lib()
+    path = str(message_csv).encode()
+    n = L.lobingest_count_lines(path)
+    if n < 0:
+        raise FileNotFoundError(message_csv)
+    if max_rows is not None:
+        n = min(n, max_rows)
+    t, oid, sz, pr = (np.zeros(n, np.int64) for _ in range(4))
+    ty, di = np.zeros(n, np.int32), np.zeros(n, np.int32)
+    got = C.c_int64(0)
+    rc = L.lobingest_parse_messages(path, n, t.ctypes.data, ty.ctypes.data, oid.ctypes.data, sz.ctypes.data,
+                                    pr.ctypes.data, di.ctypes.data, C.byref(got))
+    if rc != 0:
+        raise ValueError(f"malformed LOBSTER message file {message_csv} (rc {rc})")
+    k = got.value
+    return t[:k], ty[:k], oid[:k], sz[:k], pr[:k], di[:k]
+
+
+def read_lobster_book_rows(orderbook_csv, row_idx: np.ndarray, n_levels: int) -> np.ndarray:
+    """Only the requested rows (ascending indices) of a LOBSTER orderbook file."""
+    L = _ingest_lib()
+    idx = np.ascontiguousarray(row_idx, np.int64)
+    assert np.all(np.diff(idx) >= 0)
+    out = np.zeros((len(idx), 4 * n_levels), np.int64)
+    rc = L.lobingest_parse_book_rows(str(orderbook_csv).encode(), idx.ctypes.data, len(idx), 4 * n_levels, out.ctypes.data)
+    if rc != 0:
+        raise ValueError(f"could not read the requested rows of {orderbook_csv} (rc {rc})")
+    return out
+
+
+def pack_lobster(message_csv, orderbook_csv, n_levels: int, max_rows: Optional[int] = None, fast: bool = True, **kw) -> PackedStream:
+    """Pack a LOBSTER ``*_message_L.csv`` / ``*_orderbook_L.csv`` pair (populate_database.py:71-78 column layout).
+    ``fast=True`` reads the files with the C++ reader (and only the orderbook rows the snapshots need); ``fast=False``
+    is the pure-Python path (kept as the cross-check in the tests)."""
+    if fast:
+        t, ty, oid, sz, pr, di = read_lobster_messages(message_csv, max_rows)
+        return pack_arrays(t, ty, oid, sz, pr, di, lambda idx: read_lobster_book_rows(orderbook_csv, idx, n_levels),
+                           n_levels, **kw)
     t, ty, oid, sz, pr, di = [], [], [], [], [], []
     with open(message_csv) as f:
         for i, line in enumerate(f):

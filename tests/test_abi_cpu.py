@@ -176,3 +176,47 @@ def test_host_beta_distributor_matches_reference_lots():
             assert list(out["buy"][i]) == c["buy"] and list(out["sell"][i]) == c["sell"], (grp["quote_levels"], c["action"])
             n += 1
     assert n > 900
+
+
+def test_fast_lobster_reader_matches_python_packer(tmp_path):
+    """csrc/lobster_ingest.cpp (mmap CSV reader, only the needed orderbook rows) == the pure-Python path, on a
+    generated LOBSTER-format file pair with odd rows: sub-microsecond digits, no fraction, hidden executions, dummy
+    levels, duplicate timestamps."""
+    from rl4mm_b200.packing import pack_lobster, read_lobster_book_rows, read_lobster_messages
+
+    rng = np.random.default_rng(5)
+    n, L = 600, 3
+    t = np.sort(rng.integers(34_200_000_000_000, 34_206_000_000_000, size=n))
+    t[100:104] = t[100]            # duplicate timestamps
+    t[200] = t[200] // 10**9 * 10**9  # no fractional part
+    ty = rng.choice([1, 2, 3, 4, 5], size=n, p=[0.45, 0.1, 0.3, 0.1, 0.05])
+    oid = rng.integers(1, 10**9, size=n)
+    sz = rng.integers(1, 5000, size=n)
+    pr = rng.integers(3_000_000, 3_100_000, size=n) // 100 * 100
+    di = rng.choice([-1, 1], size=n)
+    msg = tmp_path / "X_2020-01-02_34200000_57600000_message_3.csv"
+    book = tmp_path / "X_2020-01-02_34200000_57600000_orderbook_3.csv"
+    with open(msg, "w") as f:
+        for i in range(n):
+            sec, ns = divmod(int(t[i]), 10**9)
+            ts = f"{sec}" if (i == 200) else f"{sec}.{ns:09d}"
+            f.write(f"{ts},{ty[i]},{oid[i]},{sz[i]},{pr[i]},{di[i]}\n")
+    rows = np.zeros((n, 4 * L), np.int64)
+    for i in range(n):
+        for lv in range(L):
+            dummy = lv == 2 and i % 7 == 0
+            rows[i, 4 * lv: 4 * lv + 4] = (9999999999, 0, -9999999999, 0) if dummy else \
+                (3_050_100 + 100 * lv, 10 + i + lv, 3_050_000 - 100 * lv, 20 + i + lv)
+    np.savetxt(book, rows, fmt="%d", delimiter=",")
+    rt, rty, roid, rsz, rpr, rdi = read_lobster_messages(msg)
+    assert np.array_equal(rt, t) and np.array_equal(rty, ty) and np.array_equal(roid, oid)
+    assert np.array_equal(rsz, sz) and np.array_equal(rpr, pr) and np.array_equal(rdi, di)
+    idx = np.array([0, 0, 5, 17, 17, 599])
+    assert np.array_equal(read_lobster_book_rows(book, idx, L), rows[idx])
+    for tie in ("reference", "file"):
+        a = pack_lobster(msg, book, L, fast=True, tie_order=tie)
+        b = pack_lobster(msg, book, L, fast=False, tie_order=tie)
+        for f_ in ("msgs", "step_off", "snapshots", "snap_valid", "ext_ids"):
+            assert np.array_equal(getattr(a, f_), getattr(b, f_)), (tie, f_)
+        assert a.t0_us == b.t0_us == 34_200_000_000
+    assert np.array_equal(read_lobster_messages(msg, max_rows=10)[0], t[:10])
