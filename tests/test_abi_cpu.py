@@ -186,9 +186,10 @@ def test_fast_lobster_reader_matches_python_packer(tmp_path):
 
     rng = np.random.default_rng(5)
     n, L = 600, 3
-    t = np.sort(rng.integers(34_200_000_000_000, 34_206_000_000_000, size=n))
+    t = rng.integers(34_200_000_000_000, 34_206_000_000_000, size=n)
+    t[0] = 34_203_000_000_000      # a whole second: written without a fractional part
+    t = np.sort(t)
     t[100:104] = t[100]            # duplicate timestamps
-    t[200] = t[200] // 10**9 * 10**9  # no fractional part
     ty = rng.choice([1, 2, 3, 4, 5], size=n, p=[0.45, 0.1, 0.3, 0.1, 0.05])
     oid = rng.integers(1, 10**9, size=n)
     sz = rng.integers(1, 5000, size=n)
@@ -199,7 +200,7 @@ def test_fast_lobster_reader_matches_python_packer(tmp_path):
     with open(msg, "w") as f:
         for i in range(n):
             sec, ns = divmod(int(t[i]), 10**9)
-            ts = f"{sec}" if (i == 200) else f"{sec}.{ns:09d}"
+            ts = f"{sec}" if ns == 0 else f"{sec}.{ns:09d}"
             f.write(f"{ts},{ty[i]},{oid[i]},{sz[i]},{pr[i]},{di[i]}\n")
     rows = np.zeros((n, 4 * L), np.int64)
     for i in range(n):
