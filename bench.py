@@ -139,6 +139,38 @@ def cpu_oracle_throughput(stream, sample_steps: int, threads: int, reps: int = 1
     return threads * reps * msgs / dt, threads * reps * sample_steps / dt, dt, msgs
 
 
+def cpu_oracle_env_throughput(stream, cfg, threads: int, n_steps: int):
+    """Env steps/s of the oracle (C port of the reference env step) on `threads` host threads: one env per thread,
+    default full_state features, random Beta actions."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from oracle.oracle import Oracle
+    from rl4mm_b200 import abi
+
+    import ctypes as C
+
+    c1 = abi.Cfg.from_buffer_copy(bytes(cfg))
+    c1.n_envs = 1
+    oracles = [Oracle(c1, stream) for _ in range(threads)]
+    sps = stream.steps_per_second
+    starts = [(1800 + 60 * i) * sps for i in range(threads)]
+    for o, st in zip(oracles, starts):
+        o.reset(st)
+    agent = abi.Agent(kind=abi.AGENT_EXTERNAL)
+    acts = np.random.default_rng(0).uniform(0.0, 10.0, size=(n_steps, abi.action_dim(c1)))
+
+    def work(o):
+        o.rollout(n_steps, agent, acts)
+        return int(o.state()["err"])
+
+    with ThreadPoolExecutor(threads) as ex:
+        t0 = time.perf_counter()
+        errs = list(ex.map(work, oracles))
+        dt = time.perf_counter() - t0
+    assert not any(errs), errs
+    return threads * n_steps / dt, dt
+
+
 def run_reference(args):
     """--impl reference: the reference's algorithm on the host cores (the reference itself is pure Python and cannot
     be compiled; oracle/lob_oracle.c is its C restatement, pinned against the reference by tests/golden/)."""
@@ -284,6 +316,12 @@ def run_rollout(args):
                      "peak_source": peak_src, "kernel": "k_env_fast<StaticLayout<64,256,64>> (one launch per env step; `achieved` includes the torch policy time)",
                      "algorithmic_bytes_per_launch": algo},
     }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        v, dt = cpu_oracle_env_throughput(stream, cfg, threads, 2000)
+        line["cpu_baseline"] = {"value": v, "unit": "env steps/s", "cores": threads, "kind": "port",
+                                "sample": f"{threads} envs x 2000 env steps (random Beta actions, same features / reward) on "
+                                          f"{threads} host threads after the 3000-step warm-up, {dt:.2f} s wall"}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

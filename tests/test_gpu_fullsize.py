@@ -133,3 +133,15 @@ def test_config3_rollout_65536_envs():
     total = rew.sum(0).cpu().numpy()
     mtm = st["cash"] + st["inventory"] * st["price"]
     assert np.allclose(total, mtm - 1000.0, rtol=1e-9, atol=1e-3)
+
+
+def test_config4_collect_rollouts_example_single_gpu():
+    """examples/collect_rollouts.py (sharding + fused Teradactyl rollout + episode-stat gather) on one GPU."""
+    import importlib.util
+    from pathlib import Path
+
+    spec = importlib.util.spec_from_file_location("collect_rollouts", Path(__file__).resolve().parent.parent / "examples" / "collect_rollouts.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    out = mod.main(["--envs", "4096", "--T", "32", "--rollouts", "2", "--n-msgs", "300000", "--duration-s", "700"])
+    assert out["errors"] == 0 and out["gathered_shape"] == [4096, 8] and np.isfinite(out["mean_return"])
