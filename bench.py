@@ -33,6 +33,7 @@ ALGO_BYTES_PER_MSG = 16          # packed record
 ALGO_BYTES_PER_STEP_REPLAY = 4   # CSR step offset
 ALGO_BYTES_PER_STEP_ENV = 65     # action 4x4 B + obs 10x4 B + reward 4 B + done 1 B + CSR offset 4 B
 S_STATE_L10 = 1216               # SURVEY.md section 8d book-state size for L=10 (round trip per launch)
+CPU_SAMPLE_SECONDS = 10.0        # bounded cpu_baseline sample (the contract asks for about 10-30 s of CPU work)
 
 
 def parse_args():
@@ -112,6 +113,27 @@ def make_stream(args):
     return synthetic.generate(synthetic.spy_day(seed=0, n_msgs=args.n_msgs, duration_s=23_400))
 
 
+def _pinned_pool(threads: int):
+    """Thread pool with worker i pinned to host CPU i: freshly created threads otherwise start on their parent's CPU
+    and this VM's scheduler takes about a second to spread them, which made 8 threads measure like 1."""
+    import itertools
+    import threading
+    from concurrent.futures import ThreadPoolExecutor
+
+    cpus = sorted(os.sched_getaffinity(0))
+    counter, lock = itertools.count(), threading.Lock()
+
+    def pin():
+        with lock:
+            i = next(counter)
+        try:
+            os.sched_setaffinity(0, {cpus[i % len(cpus)]})       # pid 0 = the calling thread
+        except OSError:
+            pass
+
+    return ThreadPoolExecutor(threads, initializer=pin)
+
+
 def cpu_oracle_throughput(stream, sample_steps: int, threads: int, reps: int = 1):
     """The oracle (C port of the reference algorithm) on the host cores: `threads` books replay the first
     `sample_steps` grid steps of the stream concurrently (ctypes releases the GIL)."""
@@ -130,7 +152,7 @@ def cpu_oracle_throughput(stream, sample_steps: int, threads: int, reps: int = 1
             o.replay(sample_steps)
         return int(o.state()["err"])
 
-    with ThreadPoolExecutor(threads) as ex:
+    with _pinned_pool(threads) as ex:
         list(ex.map(work, oracles[:1]))  # warm the caches / page in
         t0 = time.perf_counter()
         errs = list(ex.map(work, oracles))
@@ -140,35 +162,41 @@ def cpu_oracle_throughput(stream, sample_steps: int, threads: int, reps: int = 1
 
 
 def cpu_oracle_env_throughput(stream, cfg, threads: int, n_steps: int):
-    """Env steps/s of the oracle (C port of the reference env step) on `threads` host threads: one env per thread,
-    default full_state features, random Beta actions."""
+    """Env steps/s of the oracle (C port of the reference env step) on `threads` host threads: one env per task,
+    same features / rewards as the GPU run, random Beta actions; enough tasks for about CPU_SAMPLE_SECONDS of work."""
     from concurrent.futures import ThreadPoolExecutor
 
     from oracle.oracle import Oracle
     from rl4mm_b200 import abi
 
-    import ctypes as C
-
     c1 = abi.Cfg.from_buffer_copy(bytes(cfg))
     c1.n_envs = 1
-    oracles = [Oracle(c1, stream) for _ in range(threads)]
     sps = stream.steps_per_second
-    starts = [(1800 + 60 * i) * sps for i in range(threads)]
-    for o, st in zip(oracles, starts):
-        o.reset(st)
     agent = abi.Agent(kind=abi.AGENT_EXTERNAL)
     acts = np.random.default_rng(0).uniform(0.0, 10.0, size=(n_steps, abi.action_dim(c1)))
+    last = stream.n_seconds - (n_steps + c1.warmup_steps) // sps - 60
+
+    def make(i):
+        o = Oracle(c1, stream)
+        o.reset(int((600 + (i * 97) % max(last - 600, 1)) * sps))
+        return o
 
     def work(o):
         o.rollout(n_steps, agent, acts)
         return int(o.state()["err"])
 
-    with ThreadPoolExecutor(threads) as ex:
+    with _pinned_pool(threads) as ex:
+        oracles = list(ex.map(make, range(threads)))
         t0 = time.perf_counter()
-        errs = list(ex.map(work, oracles))
+        errs = list(ex.map(work, oracles))                                          # calibrate (and warm the caches)
+        dt1 = time.perf_counter() - t0
+        k = int(min(max(round(CPU_SAMPLE_SECONDS / dt1), 1), 256))
+        oracles = list(ex.map(make, range(threads, threads * (k + 1))))
+        t0 = time.perf_counter()
+        errs += list(ex.map(work, oracles))
         dt = time.perf_counter() - t0
     assert not any(errs), errs
-    return threads * n_steps / dt, dt
+    return len(oracles) * n_steps / dt, dt, len(oracles)
 
 
 def run_reference(args):
@@ -180,14 +208,17 @@ def run_reference(args):
     stream = make_stream(args)
     threads = os.cpu_count() or 1
     sample_steps = min(stream.n_grid_steps, args.segment_steps * 20)
+    _, _, dt1, _ = cpu_oracle_throughput(stream, sample_steps, threads)                     # calibrate: ~4 s per step
+    reps = int(min(max(round(4.0 / max(dt1, 1e-3)), 1), 200))
     for _ in range(max(args.warmup, 1)):
-        cpu_oracle_throughput(stream, sample_steps, threads)
+        cpu_oracle_throughput(stream, sample_steps, threads, reps=max(reps // 4, 1))
     vals, steps_s, t_all = [], [], 0.0
     for _ in range(args.steps):
-        v, s, dt, msgs = cpu_oracle_throughput(stream, sample_steps, threads)
+        v, s, dt, msgs = cpu_oracle_throughput(stream, sample_steps, threads, reps=reps)
         vals.append(v); steps_s.append(s); t_all += dt
     value = float(np.mean(vals))
-    sample = f"{threads} books x first {sample_steps} grid steps ({msgs} messages each) per step, C port of the reference algorithm"
+    sample = (f"{threads} books x {reps} replays of the first {sample_steps} grid steps ({msgs} messages each) per step, "
+              f"C port of the reference algorithm on {threads} host threads")
     line = {
         "impl": "reference", "metric": "lob_messages_per_sec", "value": value, "unit": "messages/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_all / args.steps,
@@ -318,10 +349,10 @@ def run_rollout(args):
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        v, dt = cpu_oracle_env_throughput(stream, cfg, threads, 2000)
+        v, dt, n_cpu = cpu_oracle_env_throughput(stream, cfg, threads, 8000)
         line["cpu_baseline"] = {"value": v, "unit": "env steps/s", "cores": threads, "kind": "port",
-                                "sample": f"{threads} envs x 2000 env steps (random Beta actions, same features / reward) on "
-                                          f"{threads} host threads after the 3000-step warm-up, {dt:.2f} s wall"}
+                                "sample": f"{n_cpu} envs x 8000 env steps (random Beta actions, same features / reward) on "
+                                          f"{threads} host threads after the feature warm-up, {dt:.2f} s wall"}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
@@ -454,9 +485,11 @@ def main():
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         threads = os.cpu_count() or 1
         sample_steps = min(stream.n_grid_steps, seg * 20)
-        v, s, dt, m = cpu_oracle_throughput(stream, sample_steps, threads, reps=2)
+        _, _, dt1, _ = cpu_oracle_throughput(stream, sample_steps, threads, reps=1)       # calibrate
+        reps = int(min(max(round(CPU_SAMPLE_SECONDS / max(dt1, 1e-3)), 2), 400))
+        v, s, dt, m = cpu_oracle_throughput(stream, sample_steps, threads, reps=reps)
         line["cpu_baseline"] = {"value": v, "unit": "messages/s", "cores": threads, "kind": "port",
-                                "sample": f"{threads} books x 2 replays of the first {sample_steps} grid steps "
+                                "sample": f"{threads} books x {reps} replays of the first {sample_steps} grid steps "
                                           f"({m} messages) on {threads} host threads, {dt:.2f} s wall"}
     if rank == 0:
         print(json.dumps(line))
