@@ -270,6 +270,23 @@ int lobsim_step_host(lobsim_t* h, const double* actions_host, double* obs_out_ho
 int lobsim_rollout(lobsim_t* h, int32_t T, const lobsim_agent_t* agent, double* obs_dev, double* act_dev,
                    double* rew_dev, uint8_t* done_dev, void* stream);
 
+/* lobsim_rollout plus the per-step info series the reference's evaluation path is built from
+ * (SimpleInfoCalculator.calculate, rl4mm/gym/order_tracking/InfoCalculators.py:31-59, collected by generate_trajectory,
+ * rl4mm/gym/utils.py:100-117, and reduced by append_to_episode_summary_dict :146-190): info [T, n_envs,
+ * LOBSIM_INFO_DIM] f64, the state at the END of each env step (after fills, portfolio and price update).
+ * The action-derived entries of the info dict (agent spreads / midprice offsets) are functions of `act` alone.     */
+#define LOBSIM_INFO_ASSET_PRICE 0   /* microprice of the central book (State.price, HOE.py:203)                 */
+#define LOBSIM_INFO_INVENTORY 1
+#define LOBSIM_INFO_CASH 2
+#define LOBSIM_INFO_AUM 3           /* cash + asset_price * inventory                                           */
+#define LOBSIM_INFO_MARKET_SPREAD 4 /* best_sell - best_buy of the central book (NaN when a side is empty)      */
+#define LOBSIM_INFO_BEST_BUY 5
+#define LOBSIM_INFO_BEST_SELL 6
+#define LOBSIM_INFO_ERR 7           /* the env's sticky error bits so far, as a double                          */
+#define LOBSIM_INFO_DIM 8
+int lobsim_rollout_info(lobsim_t* h, int32_t T, const lobsim_agent_t* agent, double* obs_dev, double* act_dev,
+                        double* rew_dev, uint8_t* done_dev, double* info_dev, void* stream);
+
 /* OrderbookSimulator.forward_step (OrderbookSimulator.py:70-88) with internal_orders=None, n_steps times, for
  * every env: pure replay of the stream through the book (no features / rewards).                               */
 int lobsim_replay(lobsim_t* h, int32_t n_steps, void* stream);

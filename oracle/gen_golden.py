@@ -366,6 +366,55 @@ def golden_packed_fixture():
     np.savez_compressed(GOLDEN / "msft_fixture_packed.npz", **arrays)
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+def golden_episode_summary():
+    """G6: the evaluation path -- generate_trajectory + append_to_episode_summary_dict + get_sharpe of the unmodified
+    reference (rl4mm/gym/utils.py:100-190, RewardFunctions.py:10-22) on the MSFT fixture, FixedActionAgent and Teradactyl."""
+    import contextlib
+    import io
+
+    from rl4mm.agents.baseline_agents import FixedActionAgent, Teradactyl
+    from rl4mm.features.Features import Inventory, Spread, Portfolio
+    from rl4mm.gym.HistoricalOrderbookEnvironment import HistoricalOrderbookEnvironment
+    from rl4mm.gym.order_tracking.InfoCalculators import SimpleInfoCalculator
+    from rl4mm.rewards.RewardFunctions import PnL
+
+    utils = refshim.import_eval_utils()
+    cases = []
+    specs = [
+        ("fixed_1212", lambda: FixedActionAgent(np.array([1.0, 2.0, 1.0, 2.0])), dict(kind="fixed", action=[1, 2, 1, 2]), 2),
+        ("teradactyl", lambda: Teradactyl(max_inventory=300, default_kappa=8.0, default_omega=0.4, max_kappa=12.0,
+                                          exponent=1.5, inventory_index=1),
+         dict(kind="teradactyl", max_inventory=300, default_kappa=8.0, default_omega=0.4, max_kappa=12.0, exponent=1.5,
+              inventory_index=1), 3),
+    ]
+    for name, mk_agent, agent_desc, n_iter in specs:
+        episode_length = timedelta(seconds=1.5)
+        feats = [Spread(), Inventory(max_value=100000)]
+        db = make_db("S", "reference")
+        sim = make_sim(db, 20, preload=True, episode_length=episode_length, warm_up=max(f.window_size for f in feats))
+        start_td = timedelta(seconds=36001.0)
+        env = HistoricalOrderbookEnvironment(
+            features=feats, ticker="MSFT", step_size=timedelta(seconds=0.1), episode_length=episode_length,
+            initial_portfolio=Portfolio(inventory=0, cash=10**7), min_date=DAY, max_date=DAY, min_start_timedelta=start_td,
+            max_end_timedelta=start_td + episode_length, simulator=sim, per_step_reward_function=PnL(),
+            terminal_reward_function=PnL(), n_levels=50, info_calculator=SimpleInfoCalculator(),
+        )
+        esd = utils.init_episode_summary_dict()
+        sharpes = []
+        agent = mk_agent()
+        for _ in range(n_iter):                # get_episode_summary_dict_NONPARALLEL, utils.py:193-201 (portfolio carries over)
+            with contextlib.redirect_stdout(io.StringIO()):
+                d = utils.generate_trajectory(agent=agent, env=env)
+                esd = utils.append_to_episode_summary_dict(esd, d)
+            sharpes.append(float(utils.get_sharpe(esd["equity_curves"][-1])))
+        cases.append(dict(name=name, agent=agent_desc, n_iterations=n_iter, start_seconds=36001.0, episode_steps=15,
+                          initial_cash=10**7, sharpe=sharpes,
+                          esd=json.loads(json.dumps(esd, cls=utils.NumpyEncoder))))
+    save("episode_summary.json.gz", cases)
+
+
+
 def main():
     refshim.install()
     golden_packed_fixture()
@@ -381,6 +430,7 @@ def main():
         golden_env_episodes()
         golden_beta_ladders()
         golden_exchange_fuzz()
+        golden_episode_summary()
     for p in sorted(GOLDEN.glob("*.gz")):
         print(p.name, p.stat().st_size)
 

@@ -961,7 +961,24 @@ void lo_agent_action(const lobsim_agent_t* ag, const double* obs, double* action
 }
 
 /* generate_trajectory -- rl4mm/gym/utils.py:100-117 (without the reset; obs_t is the observation after step t) */
+/* one row of the info series: what SimpleInfoCalculator.calculate (InfoCalculators.py:31-43) reads from the state at
+ * the end of HistoricalOrderbookEnvironment.step (HOE.py:175-177) */
+static void info_row(const lo_t* o, double* row) {
+  const o_side* b = &o->central.s[0]; const o_side* s = &o->central.s[1];
+  int tops = b->n > 0 && s->n > 0;
+  row[LOBSIM_INFO_ASSET_PRICE] = o->price; row[LOBSIM_INFO_INVENTORY] = (double)o->inventory; row[LOBSIM_INFO_CASH] = o->cash;
+  row[LOBSIM_INFO_AUM] = o->cash + o->price * (double)o->inventory;
+  row[LOBSIM_INFO_BEST_BUY] = tops ? (double)b->lv[b->n - 1].price : NAN;
+  row[LOBSIM_INFO_BEST_SELL] = tops ? (double)s->lv[0].price : NAN;
+  row[LOBSIM_INFO_MARKET_SPREAD] = tops ? (double)(s->lv[0].price - b->lv[b->n - 1].price) : NAN;
+  row[LOBSIM_INFO_ERR] = (double)o->err;
+}
+
 int lo_rollout(lo_t* o, int T, const lobsim_agent_t* ag, double* obs, double* act, double* rew, uint8_t* done) {
+  return lo_rollout_info(o, T, ag, obs, act, rew, done, NULL);
+}
+
+int lo_rollout_info(lo_t* o, int T, const lobsim_agent_t* ag, double* obs, double* act, double* rew, uint8_t* done, double* info) {
   int od = lo_obs_dim(&o->cfg), ad = lo_action_dim(&o->cfg);
   double cur_obs[LOBSIM_MAX_FEATURES + 8], a[8];
   get_observation(o, o->prev_action, cur_obs);
@@ -981,6 +998,7 @@ int lo_rollout(lo_t* o, int T, const lobsim_agent_t* ag, double* obs, double* ac
     if (act && ag->kind != LOBSIM_AGENT_EXTERNAL) memcpy(act + (size_t)t * ad, a, sizeof(double) * (size_t)ad);
     if (rew) rew[t] = r;
     if (done) done[t] = d;
+    if (info) info_row(o, info + (size_t)t * LOBSIM_INFO_DIM);
   }
   return LOBSIM_OK;
 }

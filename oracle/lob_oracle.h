@@ -14,6 +14,7 @@ int lo_reset(lo_t* o, int episode_start_step, double* obs_out);
 int lo_step(lo_t* o, const double* action, double* obs, double* reward, uint8_t* done);
 int lo_replay(lo_t* o, int n_steps);
 int lo_rollout(lo_t* o, int T, const lobsim_agent_t* agent, double* obs, double* act, double* rew, uint8_t* done);
+int lo_rollout_info(lo_t* o, int T, const lobsim_agent_t* agent, double* obs, double* act, double* rew, uint8_t* done, double* info);
 void lo_agent_action(const lobsim_agent_t* agent, const double* obs, double* action);
 void lo_action_to_ladders(const lo_t* o, const double* action, int64_t* buy, int64_t* sell);
 int lo_process_order(lo_t* o, const lobsim_order_t* order, uint32_t* ref_out);

@@ -40,6 +40,8 @@ def lib():
         L.lo_replay.argtypes = [C.c_void_p, C.c_int]
         L.lo_rollout.argtypes = [C.c_void_p, C.c_int, C.POINTER(abi.Agent), C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p]
+        L.lo_rollout_info.argtypes = [C.c_void_p, C.c_int, C.POINTER(abi.Agent), C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p]
         L.lo_agent_action.argtypes = [C.POINTER(abi.Agent), C.c_void_p, C.c_void_p]
         L.lo_action_to_ladders.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.lo_process_order.argtypes = [C.c_void_p, C.POINTER(abi.Order), C.POINTER(C.c_uint32)]
@@ -104,11 +106,15 @@ class Oracle:
     def replay(self, n_steps: int):
         self._check(lib().lo_replay(self._h, int(n_steps)))
 
-    def rollout(self, T: int, agent: abi.Agent, actions=None):
+    def rollout(self, T: int, agent: abi.Agent, actions=None, want_info=False):
         obs = np.zeros((T, self.obs_dim))
         act = np.zeros((T, self.action_dim)) if actions is None else np.ascontiguousarray(actions, np.float64)
         rew = np.zeros(T)
         done = np.zeros(T, np.uint8)
+        if want_info:
+            info = np.zeros((T, abi.INFO_DIM))
+            self._check(lib().lo_rollout_info(self._h, T, C.byref(agent), _ptr(obs), _ptr(act), _ptr(rew), _ptr(done), _ptr(info)))
+            return obs, act, rew, done, info
         self._check(lib().lo_rollout(self._h, T, C.byref(agent), _ptr(obs), _ptr(act), _ptr(rew), _ptr(done)))
         return obs, act, rew, done
 

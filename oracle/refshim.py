@@ -100,6 +100,17 @@ def install() -> None:
     gym.utils.seeding_mod = gym.utils.seeding
     gym.envs = _module("gym.envs")
     gym.envs.registration = _module("gym.envs.registration", EnvSpec=lambda **k: types.SimpleNamespace(**k))
+    # plotting / JSON helpers imported at module level by rl4mm/gym/utils.py:8-15 (evaluation path); never called here
+    mpl = _module("matplotlib")
+    mpl.pyplot = _module("matplotlib.pyplot")
+    _module("seaborn")
+    import json as _json
+
+    class _NumpyEncoder(_json.JSONEncoder):
+        def default(self, o):
+            return o.tolist() if isinstance(o, (np.ndarray, np.generic)) else super().default(o)
+
+    _module("numpyencoder", NumpyEncoder=_NumpyEncoder)
     sys.path.insert(0, str(REFERENCE_ROOT))
     import rl4mm.gym.HistoricalOrderbookEnvironment as hoe  # noqa: E402
 
@@ -231,3 +242,19 @@ class InMemoryDatabase:
     def get_next_snapshot(self, timestamp, ticker):
         i = int(np.searchsorted(self._snap_key, self._us(timestamp), side="left"))
         return pd.DataFrame() if i >= len(self._snap_key) else self._series(i)
+
+
+def import_eval_utils():
+    """Import rl4mm/gym/utils.py (generate_trajectory, episode summary dict).  Its module-level default argument
+    `database=HistoricalDatabase()` (utils.py:42) opens a Postgres engine at import time; neutralise the constructor
+    for the duration of the import only."""
+    install()
+    import rl4mm.database.HistoricalDatabase as hd
+
+    orig = hd.HistoricalDatabase.__init__
+    hd.HistoricalDatabase.__init__ = lambda self, *a, **k: None
+    try:
+        import rl4mm.gym.utils as utils
+    finally:
+        hd.HistoricalDatabase.__init__ = orig
+    return utils

@@ -43,6 +43,8 @@ FEAT_TRADE_DIR_IMBALANCE, FEAT_TRADE_VOL_IMBALANCE, FEAT_INVENTORY, FEAT_EPISODE
 REWARD_PNL, REWARD_INV_ADJ_PNL, REWARD_ROLLING_SHARPE = 0, 1, 2
 MAX_SHARPE_WINDOW = 256
 FEAT_AMIHUD_LAMBDA = 11
+INFO_FIELDS = ("asset_price", "inventory", "cash", "aum", "market_spread", "best_buy", "best_sell", "err")
+INFO_DIM = len(INFO_FIELDS)
 AGENT_NONE, AGENT_FIXED, AGENT_TERADACTYL, AGENT_EXTERNAL = 0, 1, 2, 3
 
 MSG_DTYPE = np.dtype([("price", "<i4"), ("volume", "<i4"), ("ref", "<u4"), ("meta", "<u4")])

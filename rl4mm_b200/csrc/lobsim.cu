@@ -100,10 +100,25 @@ struct AdvParams {
   int32_t resync_last_only;         // forward_step over several grid steps: resync check only at the end
   const double* actions_in;         // EXTERNAL: [T][n_sel][action_dim]
   double* obs; double* act; double* rew; uint8_t* done; // [T][n_sel][...] (any may be null)
+  double* info;                     // [T][n_sel][LOBSIM_INFO_DIM] per-step info series (SimpleInfoCalculator source) or null
   lobsim_agent_t agent;
   Layout L;
   int32_t warp_smem;                // bytes of shared memory per warp
 };
+
+// one row of the per-step info series (InfoCalculators.py:31-59: asset_price, inventory, cash, aum, market_spread) --
+// the state the reference's info_calculator sees at the end of HistoricalOrderbookEnvironment.step (HOE.py:175-177)
+__device__ __forceinline__ void write_info(double* row, int lane, const StepView& v, double cash, long long inv, uint32_t err) {
+  double x = v.price;
+  if (lane == LOBSIM_INFO_INVENTORY) x = (double)inv;
+  else if (lane == LOBSIM_INFO_CASH) x = cash;
+  else if (lane == LOBSIM_INFO_AUM) x = cash + v.price * (double)inv;
+  else if (lane == LOBSIM_INFO_MARKET_SPREAD) x = v.have_tops ? (double)(v.bs - v.bb) : NAN;
+  else if (lane == LOBSIM_INFO_BEST_BUY) x = v.have_tops ? (double)v.bb : NAN;
+  else if (lane == LOBSIM_INFO_BEST_SELL) x = v.have_tops ? (double)v.bs : NAN;
+  else if (lane == LOBSIM_INFO_ERR) x = (double)err;
+  if (lane < LOBSIM_INFO_DIM) row[lane] = x;
+}
 
 // per_step / terminal reward of one env step (HOE.py:170-174); RollingSharpe keeps one AUM window per reward function
 __device__ __forceinline__ double step_reward(const AdvParams& p, const lobsim_cfg_t& c, int env, int lane, bool done, double cash0, long long inv0, double p0,
@@ -330,6 +345,7 @@ __global__ void __launch_bounds__(128, kEnv ? LOBSIM_ENV_MIN_BLOCKS : 4) k_advan
           if (p.rew) p.rew[(size_t)t * p.n_sel + sel] = r;
           if (p.done) p.done[(size_t)t * p.n_sel + sel] = d ? 1 : 0;
         }
+        if (p.info) write_info(p.info + ((size_t)t * p.n_sel + sel) * LOBSIM_INFO_DIM, lane, v, w.cash, w.inventory, w.err);
       }
     }
   }
@@ -698,6 +714,7 @@ __global__ void __launch_bounds__(32 * LOBSIM_ENVFAST_WARPS, 16 / LOBSIM_ENVFAST
     v.inventory = h->inventory; v.now_us = st_t0_us + (long long)now_step * c.step_us;
     v.n_ext0 = h->flow[0]; v.n_ext1 = h->flow[1]; v.vol_ext0 = h->flow[2]; v.vol_ext1 = h->flow[3];
     v.n_int0 = h->flow[4]; v.n_int1 = h->flow[5]; v.vol_int0 = h->flow[6]; v.vol_int1 = h->flow[7];
+    __syncwarp(); // every lane has read this step's flow counters before lanes 0-7 zero them for the next step
     feat_cur = features_step(&ec, fstate_env, rings_env, lane, v, episode_start_us, 0);
     const bool write_now = !p.out_final_obs_only || t == T - 1;
     if (p.obs && write_now) {
@@ -713,6 +730,7 @@ __global__ void __launch_bounds__(32 * LOBSIM_ENVFAST_WARPS, 16 / LOBSIM_ENVFAST
         if (p.rew) p.rew[(size_t)t * p.n_sel + sel] = r;
         if (p.done) p.done[(size_t)t * p.n_sel + sel] = d ? 1 : 0;
       }
+      if (p.info) write_info(p.info + ((size_t)t * p.n_sel + sel) * LOBSIM_INFO_DIM, lane, v, cash1, inv1, f.err);
     }
   }
   if (T == 0 && p.obs && p.reset_mode == 2) { // reset with no warm-up: obs straight after _reset_features
@@ -1153,12 +1171,16 @@ int lobsim_step_host(lobsim_t* h, const double* actions, double* obs_out, double
 }
 
 int lobsim_rollout(lobsim_t* h, int32_t T, const lobsim_agent_t* agent, double* obs, double* act, double* rew, uint8_t* done, void* stream) {
+  return lobsim_rollout_info(h, T, agent, obs, act, rew, done, nullptr, stream);
+}
+
+int lobsim_rollout_info(lobsim_t* h, int32_t T, const lobsim_agent_t* agent, double* obs, double* act, double* rew, uint8_t* done, double* info, void* stream) {
   if (!h || !agent || T < 0) return fail(LOBSIM_E_INVALID, "bad argument");
   if (!h->has_reset) return fail(LOBSIM_E_STATE, "rollout before reset");
   if (agent->kind == LOBSIM_AGENT_EXTERNAL && !act) return fail(LOBSIM_E_INVALID, "EXTERNAL agent needs the act tensor as input");
   if (agent->kind == LOBSIM_AGENT_TERADACTYL && (agent->inventory_index < 0 || agent->inventory_index >= h->cfg.n_features)) return fail(LOBSIM_E_INVALID, "bad inventory_index");
   AdvParams p; base_params(h, p);
-  p.T = T; p.agent_kind = agent->kind; p.agent = *agent; p.obs = obs; p.rew = rew; p.done = done;
+  p.T = T; p.agent_kind = agent->kind; p.agent = *agent; p.obs = obs; p.rew = rew; p.done = done; p.info = info;
   if (agent->kind == LOBSIM_AGENT_EXTERNAL) p.actions_in = act; else p.act = act;
   if (agent->kind != LOBSIM_AGENT_NONE) h->agent_orders_possible = true;
   return launch_env(h, p, (cudaStream_t)stream);

@@ -112,7 +112,9 @@ class LobSim:
         assert actions.dtype == np.float64 and actions.shape == (self.n_envs, self.action_dim)
         check(lib().lobsim_step_host(self._h, np_ptr(actions), np_ptr(obs), np_ptr(rew), np_ptr(done)))
 
-    def rollout(self, T: int, agent: abi.Agent, actions: Optional[torch.Tensor] = None, want_obs=True, stream=None):
+    def rollout(self, T: int, agent: abi.Agent, actions: Optional[torch.Tensor] = None, want_obs=True, stream=None,
+                want_info=False):
+        """Fused T-step rollout; with ``want_info`` a fifth tensor info [T, N, abi.INFO_DIM] is returned as well."""
         N = self.n_envs
         obs = torch.empty((T, N, self.obs_dim), dtype=torch.float64, device=self.device) if want_obs else None
         if agent.kind == abi.AGENT_EXTERNAL:
@@ -122,6 +124,11 @@ class LobSim:
             act = torch.zeros((T, N, self.action_dim), dtype=torch.float64, device=self.device)
         rew = torch.zeros((T, N), dtype=torch.float64, device=self.device)
         done = torch.zeros((T, N), dtype=torch.uint8, device=self.device)
+        if want_info:
+            info = torch.empty((T, N, abi.INFO_DIM), dtype=torch.float64, device=self.device)
+            check(lib().lobsim_rollout_info(self._h, T, C.byref(agent), _dptr(obs), _dptr(act), _dptr(rew), _dptr(done),
+                                            _dptr(info), self._stream_arg(stream)))
+            return obs, act, rew, done, info
         check(lib().lobsim_rollout(self._h, T, C.byref(agent), _dptr(obs), _dptr(act), _dptr(rew), _dptr(done),
                                    self._stream_arg(stream)))
         return obs, act, rew, done

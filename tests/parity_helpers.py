@@ -113,3 +113,33 @@ def snapshot_stream(levels, n_levels: int = 50, step_us: int = 100_000) -> Packe
                      step_us, n_levels)
     s.validate()
     return s
+
+
+# ---- evaluation path (tests/golden/episode_summary.json.gz) -----------------------------------------------------------
+def summary_case_cfg(case, n_envs: int = 1) -> abi.Cfg:
+    """The env of oracle/gen_golden.py::golden_episode_summary: features [Spread, Inventory], PnL rewards, L=50."""
+    feats = [abi.feature(abi.FEAT_SPREAD, 0, 100_000, 0, 100 * 100), abi.feature(abi.FEAT_INVENTORY, 0, 100_000, -100000, 100000)]
+    return abi.default_cfg(n_envs=n_envs, n_levels=50, episode_steps=case["episode_steps"], warmup_steps=0, features=feats,
+                           step_reward=abi.Reward(abi.REWARD_PNL, 0, 0.0), terminal_reward=abi.Reward(abi.REWARD_PNL, 0, 0.0),
+                           initial_cash=float(case["initial_cash"]), initial_inventory=0, portfolio_carryover=1)
+
+
+def summary_case_agent(case) -> abi.Agent:
+    import ctypes
+
+    a = case["agent"]
+    if a["kind"] == "fixed":
+        return abi.Agent(kind=abi.AGENT_FIXED, fixed_action=(ctypes.c_double * 5)(*(list(map(float, a["action"])) + [0.0])))
+    return abi.Agent(kind=abi.AGENT_TERADACTYL, inventory_index=a["inventory_index"], max_inventory=float(a["max_inventory"]),
+                     default_kappa=a["default_kappa"], default_omega=a["default_omega"], max_kappa=a["max_kappa"],
+                     exponent=a["exponent"], market_clearing=0)
+
+
+def assert_summary_matches(esd, case, sharpes):
+    exp = case["esd"]
+    assert set(esd) == set(exp)
+    for key in exp:
+        assert len(esd[key]) == len(exp[key]) == case["n_iterations"], key
+        for e, (got, want) in enumerate(zip(esd[key], exp[key])):
+            assert_close_vec(np.atleast_1d(np.asarray(got, dtype=float)), np.atleast_1d(np.asarray(want, dtype=float)), f"{case['name']} {key}[{e}]")
+    assert_close_vec(np.asarray(sharpes, dtype=float), np.asarray(case["sharpe"], dtype=float), "sharpe")

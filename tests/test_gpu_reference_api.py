@@ -395,3 +395,39 @@ def test_teradactyl_matches_reference_formula(m):
     # inventory 0 => omega_bid = omega_ask = default_omega, kappa = default_kappa
     assert np.allclose(a[2], [0.4 * 6 + 1, 0.6 * 6 + 1, 0.4 * 6 + 1, 0.6 * 6 + 1])
     assert a[0, 0] > a[0, 2] and a[1, 0] < a[1, 2]  # long => skew bids away; short => the opposite
+
+
+# ---- rl4mm/gym/utils.py evaluation path ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("case_idx", range(2))
+def test_episode_summary_dict_matches_reference(m, case_idx, tmp_path):
+    """get_episode_summary_dict (utils.py:120-201) through the façade: fused device rollout + info series vs the summary
+    dict the unmodified reference produced (tests/golden/episode_summary.json.gz), then the JSON round trip (:417-420)."""
+    import json
+
+    from rl4mm_b200 import evaluation
+    from rl4mm_b200.agents import FixedActionAgent, Teradactyl
+    from rl4mm_b200.features import Inventory, Portfolio, Spread
+    from rl4mm_b200.rewards import PnL
+
+    case = H.load_golden("episode_summary.json.gz")[case_idx]
+    a = case["agent"]
+    agent = (FixedActionAgent(np.array(a["action"], dtype=float)) if a["kind"] == "fixed" else
+             Teradactyl(max_inventory=a["max_inventory"], default_kappa=a["default_kappa"], default_omega=a["default_omega"],
+                        max_kappa=a["max_kappa"], exponent=a["exponent"], inventory_index=a["inventory_index"]))
+    kw = dict(features=[Spread(), Inventory(max_value=100000)], episode_length=timedelta(seconds=1.5),
+              min_start_timedelta=timedelta(hours=10, seconds=1), max_end_timedelta=timedelta(hours=10, seconds=2.5),
+              initial_portfolio=Portfolio(inventory=0, cash=case["initial_cash"]), per_step_reward_function=PnL(),
+              terminal_reward_function=PnL(), n_levels=50, fill_log_capacity=0)
+    env = make_env(**kw)
+    esd = evaluation.get_episode_summary_dict(agent, env, case["n_iterations"])          # n_envs = 1: carry-over chain
+    H.assert_summary_matches(esd, case, [float(evaluation.get_sharpe(c)) for c in esd["equity_curves"]])
+    evaluation.save_episode_summary_json(esd, tmp_path / "esd.json")
+    back = json.loads((tmp_path / "esd.json").read_text())
+    assert set(back) == set(case["esd"]) and back["inventories"] == case["esd"]["inventories"]
+    env3 = make_env(n_envs=3, **kw)                                                      # batch: every env = iteration 0
+    esd3 = evaluation.get_episode_summary_dict(agent, env3)
+    for key in esd3:
+        for e in range(3):
+            H.assert_close_vec(np.atleast_1d(np.asarray(esd3[key][e], float)), np.atleast_1d(np.asarray(case["esd"][key][0], float)), key)
+    sh = evaluation.get_sharpe(np.stack(esd3["equity_curves"]))
+    assert sh.shape == (3,) and H.close(sh[0], case["sharpe"][0])
