@@ -1,0 +1,197 @@
+"""Policy-update loop around the device env (replaces the RLlib PPO trainer of the reference's
+main.py:48-58 / rl4mm/utils/utils.py get_ray_config).  Plumbing only: torch modules + torch.distributed (DDP over NCCL),
+the env step is the CUDA path (``LobSim.step`` on device tensors, no host round trip).
+
+* policy: MLP (2 x 64 tanh, RLlib's default fcnet) -> per-action-dimension Beta(a, b) on (0, 1), scaled to the env's
+  action box (0, max_distribution_param]; value head on a separate MLP;
+* rollouts: all envs of a rank step in lock-step for T steps (fixed episode length => every env finishes together and
+  the batch is reset at once, i.e. the reference's env.reset() per worker);
+* update: GAE(lambda) + clipped surrogate + value loss + entropy bonus, minibatch Adam; with world_size > 1 the
+  modules are wrapped in DistributedDataParallel so gradients are all-reduced over NVLink.
+"""
+from __future__ import annotations
+
+import time
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import torch
+import torch.nn as nn
+
+
+@dataclass
+class PPOConfig:
+    rollout_steps: int = 128
+    epochs: int = 4
+    minibatches: int = 4
+    gamma: float = 0.99
+    lam: float = 0.95
+    clip: float = 0.2
+    vf_coef: float = 0.5
+    ent_coef: float = 0.0
+    lr: float = 3e-4
+    max_grad_norm: float = 0.5
+    hidden: int = 64
+    reward_scale: float = 1.0
+
+
+class BetaPolicy(nn.Module):
+    def __init__(self, obs_dim: int, action_dim: int, action_low: torch.Tensor, action_high: torch.Tensor, hidden: int = 64):
+        super().__init__()
+        mlp = lambda out: nn.Sequential(nn.Linear(obs_dim, hidden), nn.Tanh(), nn.Linear(hidden, hidden), nn.Tanh(), nn.Linear(hidden, out))  # noqa: E731
+        self.pi, self.vf = mlp(2 * action_dim), mlp(1)
+        self.register_buffer("low", action_low.float())
+        self.register_buffer("span", (action_high - action_low).float())
+
+    def dist(self, obs: torch.Tensor) -> torch.distributions.Beta:
+        a, b = (nn.functional.softplus(self.pi(obs)) + 1.0).chunk(2, dim=-1)      # unimodal: a, b > 1
+        return torch.distributions.Beta(a, b)
+
+    def forward(self, obs: torch.Tensor):
+        return self.dist(obs), self.vf(obs).squeeze(-1)
+
+    def to_env(self, x: torch.Tensor) -> torch.Tensor:
+        """(0,1)^A sample -> env action (Beta-ladder parameters in the env's action box, open at 0)."""
+        return self.low + self.span * x.clamp(1e-6, 1.0)
+
+
+class RunningNorm:
+    """Running mean / variance of the observations (Welford, batched); synchronised over ranks when distributed."""
+
+    def __init__(self, dim: int, device):
+        self.n = torch.zeros((), dtype=torch.float64, device=device)
+        self.mean = torch.zeros(dim, dtype=torch.float64, device=device)
+        self.m2 = torch.zeros(dim, dtype=torch.float64, device=device)
+
+    def update(self, x: torch.Tensor) -> None:
+        x = x.reshape(-1, x.shape[-1]).double()
+        x = torch.nan_to_num(x, nan=0.0, posinf=0.0, neginf=0.0)
+        stats = torch.cat([torch.tensor([x.shape[0]], dtype=torch.float64, device=x.device), x.sum(0), (x * x).sum(0)])
+        if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
+            torch.distributed.all_reduce(stats)
+        d = x.shape[1]
+        nb, sb, qb = stats[0], stats[1:1 + d], stats[1 + d:]
+        mb = sb / nb
+        m2b = qb - nb * mb * mb
+        delta = mb - self.mean
+        tot = self.n + nb
+        self.mean = self.mean + delta * nb / tot
+        self.m2 = self.m2 + m2b + delta * delta * self.n * nb / tot
+        self.n = tot
+
+    def __call__(self, x: torch.Tensor) -> torch.Tensor:
+        std = torch.sqrt(self.m2 / torch.clamp(self.n, min=1.0)).clamp(min=1e-8)
+        z = (torch.nan_to_num(x.double(), nan=0.0, posinf=0.0, neginf=0.0) - self.mean) / std
+        return z.clamp(-10.0, 10.0).float()
+
+
+def gae(rew: torch.Tensor, val: torch.Tensor, last_val: torch.Tensor, done: torch.Tensor, gamma: float, lam: float):
+    """Generalised advantage estimation over [T, N] tensors; `done[t]` ends the episode AFTER step t."""
+    T = rew.shape[0]
+    adv = torch.zeros_like(rew)
+    nxt, run = last_val, torch.zeros_like(last_val)
+    for t in range(T - 1, -1, -1):
+        nd = 1.0 - done[t].float()
+        delta = rew[t] + gamma * nxt * nd - val[t]
+        run = delta + gamma * lam * nd * run
+        adv[t], nxt = run, val[t]
+    return adv, adv + val
+
+
+class PPOTrainer:
+    def __init__(self, env, cfg: PPOConfig = PPOConfig(), seed: int = 0):
+        """`env`: rl4mm_b200.gym.HistoricalOrderbookEnvironment (batched).  One trainer per rank / GPU."""
+        self.env, self.cfg = env, cfg
+        self.device = env.sim.device
+        torch.manual_seed(seed)
+        low = torch.as_tensor(env.action_space.low, device=self.device)
+        high = torch.as_tensor(env.action_space.high, device=self.device)
+        self.policy = BetaPolicy(env.sim.obs_dim, env.sim.action_dim, low, high, cfg.hidden).to(self.device)
+        self.module = self.policy
+        if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
+            self.module = nn.parallel.DistributedDataParallel(self.policy, device_ids=[self.device.index])
+        self.opt = torch.optim.Adam(self.policy.parameters(), lr=cfg.lr, eps=1e-5)
+        self.norm = RunningNorm(env.sim.obs_dim, self.device)
+        self.obs: Optional[torch.Tensor] = None
+        self.steps_left = 0
+        self.episode_return = torch.zeros(env.n_envs, dtype=torch.float64, device=self.device)
+        self.finished_returns = []
+
+    def _reset(self):
+        self.obs = torch.as_tensor(self.env.reset(), device=self.device).reshape(self.env.n_envs, -1)
+        self.steps_left = self.env.n_steps
+        self.episode_return.zero_()
+
+    @torch.no_grad()
+    def collect(self) -> Dict[str, torch.Tensor]:
+        T, N, cfg = self.cfg.rollout_steps, self.env.n_envs, self.cfg
+        if self.obs is None:
+            self._reset()
+        obs_b = torch.empty((T, N, self.env.sim.obs_dim), dtype=torch.float64, device=self.device)
+        x_b = torch.empty((T, N, self.env.sim.action_dim), device=self.device)
+        logp_b, val_b, rew_b = (torch.empty((T, N), device=self.device) for _ in range(3))
+        done_b = torch.zeros((T, N), dtype=torch.bool, device=self.device)
+        if float(self.norm.n) == 0:                     # first rollout: seed the statistics with the reset observations
+            self.norm.update(self.obs)
+        for t in range(T):
+            obs_b[t] = self.obs
+            dist, val = self.policy(self.norm(self.obs))
+            x = dist.sample()
+            obs, rew, done = self.env.step_torch(self.policy.to_env(x).double())
+            x_b[t], logp_b[t], val_b[t] = x, dist.log_prob(x.clamp(1e-6, 1 - 1e-6)).sum(-1), val
+            rew_b[t], done_b[t] = (rew * cfg.reward_scale).float(), done.bool()
+            self.episode_return += rew
+            self.obs = obs
+            self.steps_left -= 1
+            if self.steps_left == 0:                    # every env ends together: batch reset (env.reset per worker)
+                self.finished_returns.append(float(self.episode_return.mean()))
+                self._reset()
+        self.norm.update(obs_b)
+        last_val = self.policy(self.norm(self.obs))[1]
+        adv, ret = gae(rew_b, val_b, last_val, done_b, cfg.gamma, cfg.lam)
+        return dict(obs=obs_b, x=x_b, logp=logp_b, adv=adv, ret=ret, rew=rew_b)
+
+    def update(self, batch: Dict[str, torch.Tensor]) -> Dict[str, float]:
+        cfg = self.cfg
+        obs = self.norm(batch["obs"]).flatten(0, 1)
+        x, logp0 = batch["x"].flatten(0, 1).clamp(1e-6, 1 - 1e-6), batch["logp"].flatten()
+        adv, ret = batch["adv"].flatten(), batch["ret"].flatten()
+        adv = (adv - adv.mean()) / (adv.std() + 1e-8)
+        n = obs.shape[0]
+        stats = {}
+        for _ in range(cfg.epochs):
+            perm = torch.randperm(n, device=self.device)
+            for idx in perm.chunk(cfg.minibatches):
+                dist, val = self.module(obs[idx])
+                logp = dist.log_prob(x[idx]).sum(-1)
+                ratio = torch.exp(logp - logp0[idx])
+                pg = -torch.min(ratio * adv[idx], ratio.clamp(1 - cfg.clip, 1 + cfg.clip) * adv[idx]).mean()
+                vf = 0.5 * (val - ret[idx]).pow(2).mean()
+                ent = dist.entropy().sum(-1).mean()
+                loss = pg + cfg.vf_coef * vf - cfg.ent_coef * ent
+                self.opt.zero_grad(set_to_none=True)
+                loss.backward()
+                nn.utils.clip_grad_norm_(self.policy.parameters(), cfg.max_grad_norm)
+                self.opt.step()
+                stats = dict(loss=float(loss), pg=float(pg), vf=float(vf), entropy=float(ent),
+                             kl=float((logp0[idx] - logp).mean()))
+        return stats
+
+    def train(self, iterations: int, log=None):
+        history = []
+        for it in range(iterations):
+            torch.cuda.synchronize(self.device)
+            t0 = time.perf_counter()
+            batch = self.collect()
+            torch.cuda.synchronize(self.device)
+            t1 = time.perf_counter()
+            stats = self.update(batch)
+            torch.cuda.synchronize(self.device)
+            t2 = time.perf_counter()
+            stats.update(iteration=it, mean_step_reward=float(batch["rew"].mean()),
+                         env_steps_per_sec=self.cfg.rollout_steps * self.env.n_envs / (t1 - t0), collect_s=t1 - t0, update_s=t2 - t1,
+                         episode_reward_mean=self.finished_returns[-1] if self.finished_returns else float("nan"))
+            history.append(stats)
+            if log:
+                log(stats)
+        return history

@@ -221,3 +221,43 @@ def test_fast_lobster_reader_matches_python_packer(tmp_path):
             assert np.array_equal(getattr(a, f_), getattr(b, f_)), (tie, f_)
         assert a.t0_us == b.t0_us == 34_200_000_000
     assert np.array_equal(read_lobster_messages(msg, max_rows=10)[0], t[:10])
+
+
+def test_gae_matches_naive_sum():
+    import torch
+
+    from rl4mm_b200.ppo import gae
+
+    torch.manual_seed(0)
+    T, N = 7, 3
+    rew, val, last = torch.randn(T, N), torch.randn(T, N), torch.randn(N)
+    done = torch.zeros(T, N, dtype=torch.bool)
+    done[3, 1] = True
+    adv, ret = gae(rew, val, last, done, 0.9, 0.8)
+    for n in range(N):
+        for t in range(T):
+            a, coef = 0.0, 1.0
+            for k in range(t, T):
+                nv = last[n] if k == T - 1 else val[k + 1, n]
+                a += coef * (rew[k, n] + 0.9 * nv * (0.0 if done[k, n] else 1.0) - val[k, n])
+                if done[k, n]:
+                    break
+                coef *= 0.9 * 0.8
+            assert abs(float(a) - float(adv[t, n])) < 1e-5
+    assert torch.allclose(ret, adv + val)
+
+
+def test_get_sharpe_matches_reference_formula():
+    """rl4mm/rewards/RewardFunctions.py:10-22 (ddof=1, + float_min), batched over the leading axis."""
+    import sys
+
+    from rl4mm_b200.evaluation import get_sharpe
+
+    rng = np.random.default_rng(0)
+    aum = 1000.0 + np.cumsum(rng.normal(0, 1, size=(4, 50)), axis=1)
+    got = get_sharpe(aum)
+    for i in range(4):
+        r = np.exp(np.diff(np.log(aum[i]))) - 1
+        assert abs(got[i] - np.mean(r) / (np.std(r, ddof=1) + sys.float_info.min)) < 1e-12
+    with pytest.raises(Exception):
+        get_sharpe(np.array([1.0, 0.0, 2.0]))
