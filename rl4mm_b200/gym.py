@@ -259,10 +259,21 @@ class HistoricalOrderbookEnvironment:
     def reset(self, env_ids=None):
         n = self.n_envs if env_ids is None else len(env_ids)
         sids, starts = np.zeros(n, np.int32), np.zeros(n, np.int32)
-        for i in range(n):
-            start = self._get_random_start_time()
-            sids[i] = self.database.stream_id(self.ticker, start)
-            starts[i] = self.database.step_of(sids[i], start)
+        if n > 64 and self.min_date == self.max_date:          # one trading day: draw all the offsets at once
+            day = self._get_random_trading_day()
+            sid = self.database.stream_id(self.ticker, day)
+            step_us = self.step_size // timedelta(microseconds=1)
+            max_offset_steps = int((self.max_end_timedelta - self.episode_length - self.min_start_timedelta) / self.step_size)
+            off = self.np_random.integers(0, max_offset_steps, size=n) if max_offset_steps > 0 else np.zeros(n, np.int64)
+            us = self.min_start_timedelta // timedelta(microseconds=1) + off.astype(np.int64) * step_us
+            us -= us % 1_000_000                                  # start episode on the second, HOE.py:342
+            sids[:] = sid
+            starts[:] = self.database.step_of(sid, day) + us // step_us
+        else:
+            for i in range(n):
+                start = self._get_random_start_time()
+                sids[i] = self.database.stream_id(self.ticker, start)
+                starts[i] = self.database.step_of(sids[i], start)
         idx = slice(None) if env_ids is None else np.asarray(env_ids)
         self.stream_ids[idx], self.episode_start_steps[idx] = sids, starts
         obs = self.sim.reset(sids, starts, env_ids=env_ids).cpu().numpy()

@@ -173,8 +173,8 @@ class PPOTrainer:
                 loss.backward()
                 nn.utils.clip_grad_norm_(self.policy.parameters(), cfg.max_grad_norm)
                 self.opt.step()
-                stats = dict(loss=float(loss), pg=float(pg), vf=float(vf), entropy=float(ent),
-                             kl=float((logp0[idx] - logp).mean()))
+                stats = dict(loss=loss.item(), pg=pg.item(), vf=vf.item(), entropy=ent.item(),
+                             kl=(logp0[idx] - logp).mean().item())
         return stats
 
     def train(self, iterations: int, log=None):
