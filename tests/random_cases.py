@@ -1,0 +1,78 @@
+"""Seeded random (stream, env config, action) cases for the differential tests: every knob of lobsim_cfg_t that changes
+behaviour is drawn at random, so that the CUDA path and the oracle are compared off the beaten track of the goldens."""
+import numpy as np
+
+from rl4mm_b200 import abi, synthetic
+
+
+def random_features(rng, step_us=100_000):
+    kinds = [
+        lambda: abi.feature(abi.FEAT_SPREAD, 0, step_us, 0, 5000),
+        lambda: abi.feature(abi.FEAT_BOOK_IMBALANCE, 0, step_us, -1, 1),
+        lambda: abi.feature(abi.FEAT_PRICE_MOVE, int(rng.integers(1, 12)), step_us * int(rng.choice([1, 2, 10])), -1e4, 1e4),
+        lambda: abi.feature(abi.FEAT_PRICE_RANGE, int(rng.integers(1, 8)), step_us * int(rng.choice([1, 5])), 0, 1e4),
+        lambda: abi.feature(abi.FEAT_VOLATILITY, int(rng.integers(2, 40)), step_us, 0, float(rng.choice([1.0, 1e-9]))),
+        lambda: abi.feature(abi.FEAT_PRICE, 0, step_us * int(rng.choice([1, 10])), 0, 1e8),
+        lambda: abi.feature(abi.FEAT_TRADE_DIR_IMBALANCE, int(rng.integers(1, 30)), step_us, -1, 1, iparam=int(rng.integers(0, 2))),
+        lambda: abi.feature(abi.FEAT_TRADE_VOL_IMBALANCE, int(rng.integers(1, 30)), step_us, -1, 1, iparam=int(rng.integers(0, 2))),
+        lambda: abi.feature(abi.FEAT_INVENTORY, 0, step_us, -float(rng.choice([50, 1e6])), float(rng.choice([50, 1e6]))),
+        lambda: abi.feature(abi.FEAT_EPISODE_PROPORTION, 0, step_us, 0, 1, dparam=1.0 / 77),
+        lambda: abi.feature(abi.FEAT_TIME_OF_DAY, 0, step_us * 10, 0, 9, iparam=10),
+        lambda: abi.amihud(int(rng.integers(2, 6)), int(rng.integers(1, 4)), step_us, 0, 1e-3),
+    ]
+    n = int(rng.integers(3, 13))
+    feats = [kinds[i]() for i in rng.permutation(len(kinds))[:n]]
+    for f in feats:                                   # rolling z-score on a few of them, short histories => eviction
+        if rng.random() < 0.25 and f.kind not in (abi.FEAT_EPISODE_PROPORTION,):
+            f.norm_len = int(rng.integers(3, 40))
+    return feats
+
+
+def random_reward(rng):
+    k = int(rng.integers(0, 4))
+    if k == 0:
+        return abi.Reward(abi.REWARD_PNL, 0, 0.0)
+    if k == 3:
+        mx = int(rng.integers(4, 30))
+        return abi.rolling_sharpe(mx, int(rng.integers(2, mx + 1)))
+    return abi.Reward(abi.REWARD_INV_ADJ_PNL, int(k == 2), float(rng.choice([1e-4, 0.01, 0.5])))
+
+
+def random_case(seed: int):
+    rng = np.random.default_rng(1000 + seed)
+    n_levels = int(rng.choice([5, 10, 50]))
+    thin = rng.random() < 0.3
+    sc = synthetic.SynthConfig(
+        seed=seed, n_msgs=int(rng.integers(40_000, 90_000)), duration_s=int(rng.integers(120, 260)), n_levels=n_levels,
+        mid0=int(rng.choice([300_000, 1_000_000, 4_000_000])), p_limit=0.44, p_cancel=float(rng.choice([0.02, 0.2])),
+        p_delete=0.0, p_exec=float(rng.choice([0.05, 0.12, 0.2])), geom_p=float(rng.choice([0.12, 0.35, 0.6])),
+        init_levels=int(rng.integers(n_levels + 2, 60)), mean_queue=int(rng.choice([1, 4, 10])),
+        target_orders=int(rng.choice([12, 25]) if thin else rng.choice([50, 200, 500])), max_offset_ticks=int(rng.choice([8, 40, 70])),
+        size_sigma=float(rng.choice([0.3, 0.8, 1.4])), p_sweep=float(rng.choice([0.0005, 0.01, 0.03])))
+    sc.p_delete = 1.0 - sc.p_limit - sc.p_cancel - sc.p_exec
+    feats = random_features(rng)
+    warm = max(int(f.lookback * (f.update_us // 100_000)) for f in feats)
+    warm = (warm + 9) // 10 * 10 + 10 * int(rng.integers(0, 2))       # the book reset (start - warm-up) must fall on a whole second
+    conc = float(rng.choice([-1.0, 12.0]))
+    minq = int(rng.choice([0, 0, 2]))
+    maxq = minq + int(rng.choice([3, 5, 10]))
+    clearing = int(rng.random() < 0.4)
+    cfg_kw = dict(
+        n_levels=n_levels, episode_steps=int(rng.integers(20, 120)), warmup_steps=warm, min_quote_level=minq, max_quote_level=maxq,
+        outer_levels=int(rng.choice([2, 20])) * n_levels // 50 if n_levels == 50 else int(rng.integers(1, n_levels)),
+        resync=int(rng.random() < 0.8), active_volume=int(rng.choice([10, 100, 1000])), market_order_clearing=clearing,
+        market_order_fraction_of_inventory=float(rng.choice([0.25, 1.0])) if clearing else 0.0,
+        enter_spread=int(rng.random() < 0.4), inc_prev_action_in_obs=int(rng.random() < 0.4),
+        portfolio_carryover=int(rng.random() < 0.6), concentration=conc, initial_cash=float(rng.choice([1e9, 1e12])),
+        initial_inventory=int(rng.choice([0, 0, 40, -300])), features=feats, step_reward=random_reward(rng),
+        terminal_reward=random_reward(rng), max_levels_per_side=128, max_orders_per_side=1024, max_agent_orders=64,
+        fill_log_capacity=int(rng.choice([0, 4096])))
+    n_envs = int(rng.integers(2, 6))
+    last = sc.duration_s * 10 - 2 * cfg_kw["episode_steps"] - 20
+    starts = np.sort(((warm + 10) // 10 + 1 + rng.integers(0, max(last // 10 - (warm + 10) // 10 - 1, 1), size=n_envs)) * 10).astype(np.int32)
+    ad = (2 if conc >= 0 else 4) + clearing
+    hi = np.array(([12.0] * 2 if conc >= 0 else [10.0] * 4) + ([200.0] if clearing else []))
+    T = 2 * cfg_kw["episode_steps"]                   # two episodes: reset in between (portfolio carry-over or not)
+    acts = rng.uniform(0.0, 1.0, size=(T, n_envs, ad)) * hi
+    acts[rng.random(acts.shape) < 0.03] = 0.0        # the reference's a + 1e-6 corner
+    return dict(synth=sc, cfg_kw=cfg_kw, n_envs=n_envs, starts=starts, actions=acts, T=T)
