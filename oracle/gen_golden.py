@@ -146,6 +146,14 @@ def feature_specs():
          dict(kind="INVENTORY", lookback=0, update_us=100000, min=-1000000, max=1000000, norm_len=7)),
         (lambda: F.TradeVolumeImbalance(update_frequency=td(seconds=0.1), lookback_periods=10, normalisation_on=True, max_norm_len=1000),
          dict(kind="TRADE_VOL_IMBALANCE", lookback=10, update_us=100000, min=-1, max=1, iparam=0, norm_len=1000)),
+        # indices 20-22: windows that stay (nearly) constant at a large, non-integer magnitude -- scipy's "std <= |eps * mean|
+        # -> NaN" rule and numpy's rounding in the noise-dominated window [p + 1e-06, p, p, ...]
+        (lambda: F.Price(name="pn4", update_frequency=td(seconds=0.1), normalisation_on=True, max_norm_len=4),
+         dict(kind="PRICE", lookback=0, update_us=100000, min=0, max=100000000, norm_len=4)),
+        (lambda: F.Price(name="pn300", update_frequency=td(seconds=0.1), normalisation_on=True, max_norm_len=300),
+         dict(kind="PRICE", lookback=0, update_us=100000, min=0, max=100000000, norm_len=300)),
+        (lambda: F.PriceRange(name="prn", update_frequency=td(seconds=0.1), lookback_periods=10, normalisation_on=True, max_norm_len=9),
+         dict(kind="PRICE_RANGE", lookback=10, update_us=100000, min=0, max=10000, norm_len=9)),
     ]
 
 
@@ -234,6 +242,8 @@ def golden_env_episodes():
                      portfolio=(0, 10**10)),
         run_env_case("normalised_features", rand4[25:], {}, ("PnL",), ("PnL",), features=[15, 16, 17, 18, 19, 9],
                      n_episodes=2, episode_seconds=1.5, start_seconds=36001.0),
+        run_env_case("normalised_constant_windows", [[1, 2, 1, 2]], {}, ("PnL",), ("PnL",), features=[20, 21, 22, 0],
+                     n_episodes=2, episode_seconds=2.0, start_seconds=36000.0 + 1.0),
     ]
     save("env_episodes.json.gz", cases)
 

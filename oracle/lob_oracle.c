@@ -652,7 +652,7 @@ static void feature_reset(lo_t* o, int fi, int64_t first_usage_us) {
 }
 
 /* Feature.normalise -- Features.py:67-74: scipy.stats.zscore(history)[-1] = (value - mean) / std (ddof 0), numpy's
- * pairwise mean and two-pass variance */
+ * pairwise mean and two-pass variance (np.mean of the squared deviations), NaN when std <= |eps * mean| */
 static double np_pairwise_sum(const double* a, int n);
 static double feature_normalise(o_feat* f, int maxlen, double value) {
   if (f->hist_len == 0) f->hist[f->hist_len++] = value + 1e-06;
@@ -664,6 +664,9 @@ static double feature_normalise(o_feat* f, int maxlen, double value) {
   for (int i = 0; i < n; i++) { double d = f->hist[i] - mean; sq[i] = d * d; }
   double sd = sqrt(np_pairwise_sum(sq, n) / (double)n);
   free(sq);
+  /* scipy.stats.zmap (scipy 1.18.1, the version installed where the goldens were generated; _stats_py.py):
+   * "zero = std <= xp.abs(eps * mn); z[zero] = nan" -- (nearly) constant windows give NaN, not +-1 */
+  if (sd <= fabs(2.220446049250313e-16 * mean)) return NAN;
   return (value - mean) / sd;
 }
 
@@ -834,7 +837,7 @@ static void get_observation(const lo_t* o, const double* prev_action, double* ob
 
 /* numpy's pairwise summation (np.add.reduce on a contiguous double array) */
 static double np_pairwise_sum(const double* a, int n) {
-  if (n < 8) { double r = 0.0; for (int i = 0; i < n; i++) r += a[i]; return r; }
+  if (n < 8) { double r = -0.0; for (int i = 0; i < n; i++) r += a[i]; return r; }
   if (n <= 128) {
     double r[8]; int i;
     for (i = 0; i < 8; i++) r[i] = a[i];

@@ -16,10 +16,11 @@ struct __align__(16) FeatState {
   // rolling z-score (Feature.normalise): shifted running sums over the history ring
   double nK, nS1, nS2; // shift K (first history value), sum (x-K), sum (x-K)^2
   int32_t nlen, nhead; // history length, next write position (= oldest entry once full)
-  int32_t nrun;        // number of equal trailing history values (an all-equal window is a 0/0 in the reference)
+  int32_t nrun;        // number of equal trailing history values (constant window)
   int32_t pad;
+  double nS2max;       // largest nS2 since the sums were last recomputed exactly (bounds their accumulated rounding error)
 };
-static_assert(sizeof(FeatState) == 72 || sizeof(FeatState) == 80, "FeatState layout");
+static_assert(sizeof(FeatState) == 80, "FeatState layout");
 #define FEAT_SUMS_VALID (1 << 30)
 
 struct EnvConst { // what the device needs of lobsim_cfg_t, by value in the kernel parameters
@@ -485,38 +486,119 @@ __device__ __forceinline__ void feature_update_raw(const lobsim_feature_t& fc, F
   }
 }
 
-// Feature.normalise, Features.py:67-74: scipy.stats.zscore(history)[-1] = (value - mean) / std (ddof 0) over a
-// deque(maxlen) of the clamped values.  The reference recomputes mean and std from scratch every step (O(history));
-// here shifted running sums over a ring in HBM give the same number to ~1e-12 (documented in DESIGN.md section 4).
+// ---- Feature.normalise, Features.py:67-74: scipy.stats.zscore(history)[-1] over a deque(maxlen) of the clamped values ----
+// scipy (1.18.1, the version the goldens were generated with; zmap in scipy/stats/_stats_py.py):
+//   mean = np.mean(a); std = np.mean((a - mean) * (a - mean)) ** 0.5; z = (a - mean) / std; z = NaN where std <= |eps * mean|
+// with numpy's pairwise summation.  The reference recomputes this from scratch every step (O(history)).  Here:
+//   * normal regime (std > 1e-8 |mean|, numpy's own rounding error < 1e-7 relative): shifted running sums, O(1);
+//   * constant window: numpy's pairwise sum of n equal values is replayed without touching memory (the mean may be off
+//     by an ulp or more, which decides between NaN and +-1);
+//   * noise-dominated window (|std| <= 1e-8 |mean|, e.g. [p + 1e-06, p, p, ...] for a price p ~ 4e6): the numpy arithmetic
+//     is replayed over the ring, O(history) like the reference, because there the result IS the rounding error.
+// mode 0: x_i, mode 1: (x_i - mean)^2, mode 2: the constant cval (no memory access)
+__device__ __noinline__ double np_pairwise_sum_ring(const double* hist, int maxlen, int start, int n, int mode, double mean, double cval) {
+  auto el = [&](int i) -> double {
+    if (mode == 2) return cval;
+    int k = start + i; if (k >= maxlen) k -= maxlen;
+    const double x = hist[k];
+    if (mode == 1) { const double d = x - mean; return d * d; }
+    return x;
+  };
+  auto leaf = [&](int off, int m) -> double {        // numpy pairwise_sum_DOUBLE for n <= PW_BLOCKSIZE (128)
+    if (m < 8) { double r = -0.0; for (int i = 0; i < m; i++) r += el(off + i); return r; }
+    const int body = m - (m % 8);
+    double res;
+    if (mode == 2) {                                  // eight identical accumulators
+      double r = cval;
+      for (int i = 8; i < body; i += 8) r += cval;
+      const double r2 = r + r, r4 = r2 + r2;
+      res = r4 + r4;
+    } else {
+      double r0 = el(off), r1 = el(off + 1), r2 = el(off + 2), r3 = el(off + 3), r4 = el(off + 4), r5 = el(off + 5), r6 = el(off + 6), r7 = el(off + 7);
+      for (int i = 8; i < body; i += 8) {
+        r0 += el(off + i); r1 += el(off + i + 1); r2 += el(off + i + 2); r3 += el(off + i + 3);
+        r4 += el(off + i + 4); r5 += el(off + i + 5); r6 += el(off + i + 6); r7 += el(off + i + 7);
+      }
+      res = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
+    }
+    for (int i = body; i < m; i++) res += el(off + i);
+    return res;
+  };
+  if (n <= 128) return leaf(0, n);
+  int f_off[16], f_n[16], f_stage[16]; double f_left[16];   // explicit post-order stack: depth <= log2(n / 64) (n < 2^21)
+  int sp = 1; double ret = 0.0;
+  f_off[0] = 0; f_n[0] = n; f_stage[0] = 0; f_left[0] = 0.0;
+  while (sp > 0) {
+    const int t = sp - 1;
+    if (f_n[t] <= 128) { ret = leaf(f_off[t], f_n[t]); sp--; continue; }
+    int n2 = f_n[t] / 2; n2 -= n2 % 8;
+    if (f_stage[t] == 0) { f_stage[t] = 1; f_off[sp] = f_off[t]; f_n[sp] = n2; f_stage[sp] = 0; sp++; }
+    else if (f_stage[t] == 1) { f_left[t] = ret; f_stage[t] = 2; f_off[sp] = f_off[t] + n2; f_n[sp] = f_n[t] - n2; f_stage[sp] = 0; sp++; }
+    else { ret = f_left[t] + ret; sp--; }
+  }
+  return ret;
+}
+
+// scipy's zscore of the last element, replayed exactly; `start` = ring index of the oldest of the n window entries
+__device__ __noinline__ double zscore_exact(const double* hist, int maxlen, int start, int n, double value, int constant) {
+  const int m0 = constant ? 2 : 0;
+  const double mean = np_pairwise_sum_ring(hist, maxlen, start, n, m0, 0.0, value) / (double)n;
+  double var;
+  if (constant) { const double d = value - mean; var = np_pairwise_sum_ring(hist, maxlen, start, n, 2, 0.0, d * d) / (double)n; }
+  else var = np_pairwise_sum_ring(hist, maxlen, start, n, 1, mean, 0.0) / (double)n;
+  const double sd = sqrt(var);
+  if (sd <= fabs(2.220446049250313e-16 * mean)) return NAN;   // zmap: "zero = std <= abs(eps * mn)" -> NaN
+  return (value - mean) / sd;
+}
+
+// exact shifted sums of the window around a new centre (sheds accumulated rounding and cancellation)
+__device__ __noinline__ void zscore_recenter(FeatState& f, const double* hist, int maxlen, int start, int n, double centre) {
+  double s1 = 0.0, s2 = 0.0;
+  for (int i = 0; i < n; i++) {
+    int k = start + i; if (k >= maxlen) k -= maxlen;
+    const double d = hist[k] - centre;
+    s1 += d; s2 += d * d;
+  }
+  f.nK = centre; f.nS1 = s1; f.nS2 = s2; f.nS2max = s2;
+}
+
 __device__ __forceinline__ double feature_normalise(FeatState& f, double* hist, int maxlen, double value) {
   int n = f.nlen;
   int head = f.nhead;
   double last = NAN;
   if (n == 0) { // "to prevent a NaN value from being returned if the queue is empty" :68-72
     const double x0 = value + 1e-06;
-    f.nK = x0; f.nS1 = 0.0; f.nS2 = 0.0; f.nrun = 1;
+    f.nK = x0; f.nS1 = 0.0; f.nS2 = 0.0; f.nS2max = 0.0; f.nrun = 1;
     hist[0] = x0; n = 1; head = maxlen > 1 ? 1 : 0; last = x0;
   } else last = hist[head == 0 ? maxlen - 1 : head - 1];
   if (n == maxlen) { const double old = hist[head] - f.nK; f.nS1 -= old; f.nS2 -= old * old; n -= 1; }
   hist[head] = value;
   head = head + 1 == maxlen ? 0 : head + 1;
-  const double d = value - f.nK;
   n += 1;
   f.nrun = value == last ? (f.nrun < 0x7fffffff ? f.nrun + 1 : f.nrun) : 1;
   f.nlen = n; f.nhead = head;
-  if (f.nrun >= n) {
-    // the whole window holds one value: the sums are exactly n*d and n*d^2 (this also sheds accumulated rounding), and
-    // scipy's zscore is (v - mean) / 0 = 0/0 = NaN whenever n*v is exact (integer-valued features: spread, inventory,
-    // flow counts, 0.0 volatility ...).  For other values numpy's mean may be off by an ulp and the reference returns
-    // +-1 instead; that rounding artefact is not reproduced.
-    f.nS1 = (double)n * d; f.nS2 = (double)n * d * d;
-    return NAN;
+  int start = head - n; if (start < 0) start += maxlen;      // ring index of the oldest entry
+  if (f.nrun >= n) {                                          // the whole window holds one value
+    f.nK = value; f.nS1 = 0.0; f.nS2 = 0.0; f.nS2max = 0.0;   // exact sums around the value itself
+    return zscore_exact(hist, maxlen, start, n, value, 1);
   }
+  double d = value - f.nK;
   f.nS1 += d; f.nS2 += d * d;
-  const double m1 = f.nS1 / (double)n;
-  double var = f.nS2 / (double)n - m1 * m1;
-  if (var < 0.0) var = 0.0;
-  return (d - m1) / sqrt(var);
+  f.nS2max = fmax(f.nS2max, f.nS2);
+  double m1 = f.nS1 / (double)n, msq = f.nS2 / (double)n;
+  double var = msq - m1 * m1;
+  // the running sums carry an absolute error ~ eps * nS2max: recompute them exactly (around the current mean) when that is
+  // not negligible against n * var -- a dominant entry (e.g. the 1e-06 offset of the first one) left the window, or the mean
+  // drifted far from the centre -- when a NaN got in, and once per lap of the ring
+  if (!(var * (double)n > 1e-6 * f.nS2max) || (head == 0 && n == maxlen)) {
+    double centre = f.nK + m1;
+    if (!isfinite(centre)) centre = isfinite(value) ? value : 0.0;
+    zscore_recenter(f, hist, maxlen, start, n, centre);
+    d = value - f.nK; m1 = f.nS1 / (double)n; msq = f.nS2 / (double)n; var = msq - m1 * m1;
+  }
+  const double sd = sqrt(var);
+  if (!(sd > 1e-8 * fabs(f.nK + m1))) return zscore_exact(hist, maxlen, start, n, value, 0);   // noise-dominated (or NaN)
+  return (d - m1) / sd;
 }
 
 // Feature.reset/_reset, Features.py:92-96

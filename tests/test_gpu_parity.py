@@ -105,7 +105,7 @@ def test_fixture_replay_in_one_launch(torch_cuda):
         assert H.canon_book(sim.dump_book(2, side), s.ext_ids) == case["steps"][27]["book"][side]
 
 
-@pytest.mark.parametrize("case_idx", range(13))
+@pytest.mark.parametrize("case_idx", range(14))
 def test_env_episodes(case_idx, torch_cuda):
     torch = torch_cuda
     case = H.load_golden("env_episodes.json.gz")[case_idx]

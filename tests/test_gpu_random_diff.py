@@ -12,7 +12,7 @@ from rl4mm_b200 import abi
 
 pytestmark = pytest.mark.gpu
 
-N_CASES = 32
+N_CASES = 64
 
 
 @pytest.mark.parametrize("seed", range(N_CASES))
