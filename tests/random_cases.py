@@ -75,4 +75,43 @@ def random_case(seed: int):
     T = 2 * cfg_kw["episode_steps"]                   # two episodes: reset in between (portfolio carry-over or not)
     acts = rng.uniform(0.0, 1.0, size=(T, n_envs, ad)) * hi
     acts[rng.random(acts.shape) < 0.03] = 0.0        # the reference's a + 1e-6 corner
-    return dict(synth=sc, cfg_kw=cfg_kw, n_envs=n_envs, starts=starts, actions=acts, T=T)
+    # agent: separate generator so that the (stream, config, action) draws above do not depend on it
+    rng2 = np.random.default_rng(5000 + seed)
+    kind = str(rng2.choice(["external", "external", "fixed", "teradactyl"]))
+    if kind == "teradactyl" and conc >= 0:
+        kind = "fixed"                                # Teradactyl emits (alpha, beta) x 2: needs the 4(+1)-dimensional action
+    agent = abi.Agent(kind=abi.AGENT_EXTERNAL)
+    if kind == "fixed":
+        import ctypes
+
+        fa = list(rng2.uniform(0.0, 1.0, size=ad) * hi) + [0.0] * (5 - ad)
+        agent = abi.Agent(kind=abi.AGENT_FIXED, fixed_action=(ctypes.c_double * 5)(*fa))
+    elif kind == "teradactyl":
+        idx = [i for i, f in enumerate(feats) if f.kind == abi.FEAT_INVENTORY]
+        if not idx:
+            feats.append(abi.feature(abi.FEAT_INVENTORY, 0, 100_000, -1e6, 1e6))
+            idx = [len(feats) - 1]
+        agent = abi.Agent(kind=abi.AGENT_TERADACTYL, inventory_index=idx[0], max_inventory=float(rng2.choice([50.0, 300.0, 5000.0])),
+                          default_kappa=float(rng2.uniform(3.0, 10.0)), default_omega=float(rng2.uniform(0.2, 0.8)),
+                          max_kappa=float(rng2.uniform(10.0, 14.0)), exponent=float(rng2.choice([1.0, 1.5, 2.0])), market_clearing=clearing)
+    return dict(synth=sc, cfg_kw=cfg_kw, n_envs=n_envs, starts=starts, actions=acts, T=T, agent=agent, agent_kind=kind)
+
+
+def random_replay_case(seed: int):
+    """Replay-only case: a random stream shape (thin / deep books, many sweeps) and random resync settings."""
+    rng = np.random.default_rng(9000 + seed)
+    n_levels = int(rng.choice([5, 10, 50]))
+    sc = synthetic.SynthConfig(
+        seed=100 + seed, n_msgs=int(rng.integers(60_000, 150_000)), duration_s=int(rng.integers(100, 300)), n_levels=n_levels,
+        mid0=int(rng.choice([300_000, 2_000_000, 5_000_000])), p_limit=float(rng.choice([0.35, 0.48])), p_cancel=float(rng.choice([0.02, 0.25])),
+        p_delete=0.0, p_exec=float(rng.choice([0.05, 0.1, 0.2])), geom_p=float(rng.choice([0.1, 0.35, 0.6])),
+        init_levels=int(rng.integers(n_levels + 2, 60)), mean_queue=int(rng.choice([1, 4, 12])),
+        target_orders=int(rng.choice([10, 30, 100, 600])), max_offset_ticks=int(rng.choice([8, 40, 70])),
+        size_sigma=float(rng.choice([0.3, 0.8, 1.4])), p_sweep=float(rng.choice([0.0005, 0.01, 0.05])))
+    sc.p_delete = 1.0 - sc.p_limit - sc.p_cancel - sc.p_exec
+    cfg_kw = dict(n_levels=n_levels, outer_levels=int(rng.integers(1, n_levels)), resync=int(rng.random() < 0.8),
+                  max_levels_per_side=int(rng.choice([64, 128])), max_orders_per_side=int(rng.choice([256, 512, 1536])))
+    n_envs = int(rng.integers(3, 9))
+    starts = (np.sort(rng.integers(0, sc.duration_s - 60, size=n_envs)) * 10).astype(np.int32)
+    chunks = [int(x) for x in rng.choice([1, 3, 10, 57, 200], size=5)]
+    return dict(synth=sc, cfg_kw=cfg_kw, n_envs=n_envs, starts=starts, chunks=chunks)
