@@ -287,6 +287,13 @@ int lobsim_rollout(lobsim_t* h, int32_t T, const lobsim_agent_t* agent, double* 
 int lobsim_rollout_info(lobsim_t* h, int32_t T, const lobsim_agent_t* agent, double* obs_dev, double* act_dev,
                         double* rew_dev, uint8_t* done_dev, double* info_dev, void* stream);
 
+/* lobsim_rollout_info with ONE BUILT-IN AGENT PER ENV: agents_host [n_envs] (FIXED or TERADACTYL, copied to the device
+ * by the call).  This is the batched form of the reference's rule-based-agent tuning (tune_rule_based_agents.py:24-72 runs
+ * one Ray trial per Teradactyl parameter set, each trial stepping its own env): K parameter sets x M episodes are one
+ * launch.  act_dev is an output.                                                                                  */
+int lobsim_rollout_agents(lobsim_t* h, int32_t T, const lobsim_agent_t* agents_host, double* obs_dev, double* act_dev,
+                          double* rew_dev, uint8_t* done_dev, double* info_dev, void* stream);
+
 /* OrderbookSimulator.forward_step (OrderbookSimulator.py:70-88) with internal_orders=None, n_steps times, for
  * every env: pure replay of the stream through the book (no features / rewards).                               */
 int lobsim_replay(lobsim_t* h, int32_t n_steps, void* stream);

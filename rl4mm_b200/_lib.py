@@ -42,6 +42,7 @@ def lib():
         "lobsim_step_host": (C.c_int, [vp, vp, vp, vp, vp]),
         "lobsim_rollout": (C.c_int, [vp, i32, C.POINTER(abi.Agent), vp, vp, vp, vp, vp]),
         "lobsim_rollout_info": (C.c_int, [vp, i32, C.POINTER(abi.Agent), vp, vp, vp, vp, vp, vp]),
+        "lobsim_rollout_agents": (C.c_int, [vp, i32, vp, vp, vp, vp, vp, vp, vp]),
         "lobsim_replay": (C.c_int, [vp, i32, vp]),
         "lobsim_forward_step": (C.c_int, [vp, i32, vp]),
         "lobsim_set_book": (C.c_int, [vp, i32, vp, i32, vp, i32]),
@@ -69,7 +70,7 @@ def lib():
 
 EXPORTED_SYMBOLS = [
     "lobsim_last_error", "lobsim_abi_version", "lobsim_state_bytes", "lobsim_create", "lobsim_destroy",
-    "lobsim_load_stream", "lobsim_reset", "lobsim_step", "lobsim_step_host", "lobsim_rollout", "lobsim_rollout_info", "lobsim_replay",
+    "lobsim_load_stream", "lobsim_reset", "lobsim_step", "lobsim_step_host", "lobsim_rollout", "lobsim_rollout_info", "lobsim_rollout_agents", "lobsim_replay",
     "lobsim_replay_host", "lobsim_forward_step", "lobsim_set_book", "lobsim_reset_book", "lobsim_process_orders", "lobsim_dump_book",
     "lobsim_dump_agent_orders", "lobsim_get_state", "lobsim_get_state_dev", "lobsim_get_fills", "lobsim_errors",
     "lobsim_obs_dim", "lobsim_action_dim", "lobsim_launch_count",

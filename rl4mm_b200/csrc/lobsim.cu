@@ -102,6 +102,7 @@ struct AdvParams {
   double* obs; double* act; double* rew; uint8_t* done; // [T][n_sel][...] (any may be null)
   double* info;                     // [T][n_sel][LOBSIM_INFO_DIM] per-step info series (SimpleInfoCalculator source) or null
   lobsim_agent_t agent;
+  const lobsim_agent_t* agents;     // per-env built-in agents [n_sel] (parameter sweeps) or null: every env runs `agent`
   Layout L;
   int32_t warp_smem;                // bytes of shared memory per warp
 };
@@ -273,8 +274,9 @@ __global__ void __launch_bounds__(128, kEnv ? LOBSIM_ENV_MIN_BLOCKS : 4) k_advan
           const double* a = p.actions_in + ((size_t)t * p.n_sel + sel) * ec.action_dim;
           if (lane < 5) act_sm[lane] = lane < ec.action_dim ? __ldg(&a[lane]) : 0.0;
         } else {
-          const double inv_obs = __shfl_sync(FULL_MASK, feat_cur, p.agent.inventory_index & 31);
-          if (lane == 0) agent_action_cold(&p.agent, inv_obs, act_sm);
+          const lobsim_agent_t* agp = p.agents ? p.agents + sel : &p.agent;
+          const double inv_obs = __shfl_sync(FULL_MASK, feat_cur, agp->inventory_index & 31);
+          if (lane == 0) agent_action_cold(agp, inv_obs, act_sm);
         }
         __syncwarp();
         const double a0 = act_sm[0], a1 = act_sm[1], a2 = act_sm[2], a3 = act_sm[3], a4 = act_sm[4];
@@ -649,8 +651,9 @@ __global__ void __launch_bounds__(32 * LOBSIM_ENVFAST_WARPS, 16 / LOBSIM_ENVFAST
         const double* a = p.actions_in + ((size_t)t * p.n_sel + sel) * ec.action_dim;
         if (lane < 5) act_sm[lane] = lane < ec.action_dim ? __ldg(&a[lane]) : 0.0;
       } else {
-        const double inv_obs = __shfl_sync(FULL_MASK, feat_cur, p.agent.inventory_index & 31);
-        if (lane == 0) agent_action_cold(&p.agent, inv_obs, act_sm);
+        const lobsim_agent_t* agp = p.agents ? p.agents + sel : &p.agent;
+        const double inv_obs = __shfl_sync(FULL_MASK, feat_cur, agp->inventory_index & 31);
+        if (lane == 0) agent_action_cold(agp, inv_obs, act_sm);
       }
       __syncwarp();
       const double a0 = act_sm[0], a1 = act_sm[1], a2 = act_sm[2], a3 = act_sm[3], a4 = act_sm[4];
@@ -871,6 +874,7 @@ struct lobsim {
   int32_t* rs_state = nullptr;
   lobsim_fill_t* fill_log = nullptr;
   int32_t* fill_count = nullptr;
+  lobsim_agent_t* agents_dev = nullptr; // per-env agents of lobsim_rollout_agents (allocated on first use)
   std::vector<lobsim_stream_t> streams;
   lobsim_stream_t* streams_dev = nullptr;
   int streams_cap = 0;
@@ -1016,7 +1020,7 @@ int lobsim_create(const lobsim_cfg_t* cfg, int device, lobsim_t** out) {
 int lobsim_destroy(lobsim_t* h) {
   if (!h) return LOBSIM_OK;
   cudaSetDevice(h->device);
-  cudaFree(h->blobs); cudaFree(h->fstate); cudaFree(h->rings); cudaFree(h->rs_ring); cudaFree(h->rs_state); cudaFree(h->fill_log); cudaFree(h->fill_count);
+  cudaFree(h->blobs); cudaFree(h->fstate); cudaFree(h->rings); cudaFree(h->rs_ring); cudaFree(h->rs_state); cudaFree(h->fill_log); cudaFree(h->fill_count); cudaFree(h->agents_dev);
   cudaFree(h->streams_dev); cudaFree(h->st_actions); cudaFree(h->st_obs); cudaFree(h->st_rew); cudaFree(h->st_done);
   cudaFree(h->st_state); cudaFree(h->st_msgs);
   delete h;
@@ -1183,6 +1187,25 @@ int lobsim_rollout_info(lobsim_t* h, int32_t T, const lobsim_agent_t* agent, dou
   p.T = T; p.agent_kind = agent->kind; p.agent = *agent; p.obs = obs; p.rew = rew; p.done = done; p.info = info;
   if (agent->kind == LOBSIM_AGENT_EXTERNAL) p.actions_in = act; else p.act = act;
   if (agent->kind != LOBSIM_AGENT_NONE) h->agent_orders_possible = true;
+  return launch_env(h, p, (cudaStream_t)stream);
+}
+
+int lobsim_rollout_agents(lobsim_t* h, int32_t T, const lobsim_agent_t* agents_host, double* obs, double* act, double* rew, uint8_t* done, double* info, void* stream) {
+  if (!h || !agents_host || T < 0) return fail(LOBSIM_E_INVALID, "bad argument");
+  if (!h->has_reset) return fail(LOBSIM_E_STATE, "rollout before reset");
+  const int n = h->cfg.n_envs;
+  for (int i = 0; i < n; i++) {
+    const lobsim_agent_t& a = agents_host[i];
+    if (a.kind != LOBSIM_AGENT_FIXED && a.kind != LOBSIM_AGENT_TERADACTYL) return fail(LOBSIM_E_INVALID, "per-env agents must be FIXED or TERADACTYL");
+    if (a.kind == LOBSIM_AGENT_TERADACTYL && (a.inventory_index < 0 || a.inventory_index >= h->cfg.n_features)) return fail(LOBSIM_E_INVALID, "bad inventory_index");
+  }
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (!h->agents_dev) CUDA_TRY(cudaMalloc(&h->agents_dev, (size_t)n * sizeof(lobsim_agent_t)));
+  CUDA_TRY(cudaMemcpyAsync(h->agents_dev, agents_host, (size_t)n * sizeof(lobsim_agent_t), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  AdvParams p; base_params(h, p);
+  p.T = T; p.agent_kind = LOBSIM_AGENT_TERADACTYL; p.agent = agents_host[0]; p.agents = h->agents_dev;
+  p.obs = obs; p.act = act; p.rew = rew; p.done = done; p.info = info;
+  h->agent_orders_possible = true;
   return launch_env(h, p, (cudaStream_t)stream);
 }
 

@@ -114,8 +114,20 @@ class LobSim:
 
     def rollout(self, T: int, agent: abi.Agent, actions: Optional[torch.Tensor] = None, want_obs=True, stream=None,
                 want_info=False):
-        """Fused T-step rollout; with ``want_info`` a fifth tensor info [T, N, abi.INFO_DIM] is returned as well."""
+        """Fused T-step rollout; with ``want_info`` a fifth tensor info [T, N, abi.INFO_DIM] is returned as well.
+        ``agent`` may be a sequence of n_envs built-in agents (one per env: parameter sweeps)."""
         N = self.n_envs
+        if not isinstance(agent, abi.Agent):
+            agents = (abi.Agent * N)(*agent)
+            assert len(agent) == N, "one agent per env"
+            obs = torch.empty((T, N, self.obs_dim), dtype=torch.float64, device=self.device) if want_obs else None
+            act = torch.zeros((T, N, self.action_dim), dtype=torch.float64, device=self.device)
+            rew = torch.zeros((T, N), dtype=torch.float64, device=self.device)
+            done = torch.zeros((T, N), dtype=torch.uint8, device=self.device)
+            info = torch.empty((T, N, abi.INFO_DIM), dtype=torch.float64, device=self.device) if want_info else None
+            check(lib().lobsim_rollout_agents(self._h, T, C.cast(agents, C.c_void_p), _dptr(obs), _dptr(act), _dptr(rew), _dptr(done),
+                                              _dptr(info), self._stream_arg(stream)))
+            return (obs, act, rew, done, info) if want_info else (obs, act, rew, done)
         obs = torch.empty((T, N, self.obs_dim), dtype=torch.float64, device=self.device) if want_obs else None
         if agent.kind == abi.AGENT_EXTERNAL:
             act = actions.to(device=self.device, dtype=torch.float64).contiguous()

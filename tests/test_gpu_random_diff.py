@@ -102,3 +102,63 @@ def test_random_replay_case(seed, monkeypatch):
                     assert st[f][env] == os_[f], (what, f, st[f][env], os_[f])
                 compare_books(sim, env, o, what)
         sim.close()
+
+
+def test_per_env_agents_match_oracle_and_sweep_table():
+    """lobsim_rollout_agents: one built-in agent per env (parameter sweep) == the oracle run once per (env, agent); then the
+    sweep helper of rl4mm_b200/tuning.py on the façade."""
+    import ctypes
+    from datetime import datetime, timedelta
+
+    from oracle.oracle import Oracle
+    from rl4mm_b200 import synthetic, tuning
+    from rl4mm_b200.agents import FixedActionAgent, Teradactyl
+    from rl4mm_b200.features import Inventory, Portfolio, Spread
+    from rl4mm_b200.gym import HistoricalOrderbookEnvironment
+    from rl4mm_b200.rewards import PnL
+    from rl4mm_b200.simulation import DeviceDatabase
+    from test_gpu_parity import compare_books, make_sim
+
+    s = synthetic.generate(synthetic.spy_day(seed=21, n_msgs=150_000, duration_s=400))
+    feats = [abi.feature(abi.FEAT_SPREAD, 0, 100_000, 0, 5000), abi.feature(abi.FEAT_INVENTORY, 0, 100_000, -1e6, 1e6)]
+    kw = dict(n_levels=10, episode_steps=80, warmup_steps=10, features=feats, step_reward=abi.Reward(abi.REWARD_PNL, 0, 0.0),
+              terminal_reward=abi.Reward(abi.REWARD_PNL, 0, 0.0), initial_cash=1e7, max_levels_per_side=64, max_orders_per_side=256)
+    rng = np.random.default_rng(3)
+    agents = []
+    for i in range(11):
+        if i % 4 == 3:
+            agents.append(abi.Agent(kind=abi.AGENT_FIXED, fixed_action=(ctypes.c_double * 5)(*rng.uniform(0.5, 9, 4), 0.0)))
+        else:
+            agents.append(abi.Agent(kind=abi.AGENT_TERADACTYL, inventory_index=1, max_inventory=float(rng.choice([100, 1000])),
+                                    default_kappa=float(rng.uniform(3, 10)), default_omega=float(rng.uniform(0.2, 0.8)),
+                                    max_kappa=float(rng.uniform(10, 14)), exponent=float(rng.choice([1.0, 2.0]))))
+    starts = (rng.integers(2, 300, size=len(agents)) * 10).astype(np.int32)
+    sim = make_sim(abi.default_cfg(n_envs=len(agents), **kw), [s])
+    sim.reset(0, starts)
+    obs, act, rew, done, info = (x.cpu().numpy() for x in sim.rollout(80, agents, want_info=True))
+    for env, ag in enumerate(agents):
+        o = Oracle(abi.default_cfg(n_envs=1, **kw), s)
+        o.reset(int(starts[env]))
+        oo, oa, orw, od, oi = o.rollout(80, ag, want_info=True)
+        for t in range(80):
+            H.assert_close_vec(act[t, env], oa[t], f"env {env} t {t} action")
+            H.assert_close_vec(obs[t, env], oo[t], f"env {env} t {t} obs")
+            H.assert_close_vec(info[t, env], oi[t], f"env {env} t {t} info")
+            assert H.close(rew[t, env], orw[t]) and done[t, env] == od[t]
+        compare_books(sim, env, o, f"per-env agent {env}")
+    sim.close()
+
+    day = datetime(2019, 1, 2)
+    db = DeviceDatabase()
+    db.add_stream("SPY", day, s)
+    grid = tuning.teradactyl_grid(500, [4.0, 8.0], [0.3, 0.5], [12.0], inventory_index=1) + [FixedActionAgent(np.array([1.0, 2.0, 1.0, 2.0]))]
+    env = HistoricalOrderbookEnvironment(
+        features=[Spread(), Inventory()], ticker="SPY", episode_length=timedelta(seconds=8), min_date=day, max_date=day,
+        min_start_timedelta=timedelta(hours=9, minutes=30, seconds=5), max_end_timedelta=timedelta(hours=9, minutes=36),
+        initial_portfolio=Portfolio(inventory=0, cash=10**7), per_step_reward_function=PnL(), terminal_reward_function=PnL(),
+        n_levels=10, database=db, n_envs=len(grid) * 6, max_levels_per_side=64, max_orders_per_side=256, seed=5)
+    table = tuning.sweep_agents(env, grid)
+    assert len(table) == len(grid) and all(r["episodes"] == 6 and np.isfinite(r["episode_reward_mean"]) for r in table)
+    starts2 = env.episode_start_steps.reshape(len(grid), 6)
+    assert (starts2 == starts2[0]).all()                      # every agent saw the same six episodes
+    assert len({round(r["episode_reward_mean"], 6) for r in table}) > 1
