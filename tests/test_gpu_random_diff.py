@@ -12,7 +12,10 @@ from rl4mm_b200 import abi
 
 pytestmark = pytest.mark.gpu
 
-N_CASES = 64
+import os
+
+N_CASES = int(os.environ.get("LOBSIM_RANDOM_CASES", "64"))          # soak runs: LOBSIM_RANDOM_CASES=1000 pytest ...
+N_REPLAY_CASES = int(os.environ.get("LOBSIM_RANDOM_REPLAY_CASES", "24"))
 
 
 @pytest.mark.parametrize("seed", range(N_CASES))
@@ -69,7 +72,7 @@ def test_random_env_case(seed):
     sim.close()
 
 
-@pytest.mark.parametrize("seed", range(24))
+@pytest.mark.parametrize("seed", range(N_REPLAY_CASES))
 def test_random_replay_case(seed, monkeypatch):
     """Pure replay (both kernel families: the straight-line k_replay_fast and, forced, the general k_advance) vs the oracle."""
     from oracle.oracle import Oracle
