@@ -48,6 +48,8 @@ extern "C" {
 #define LOBSIM_ERR_END_OF_STREAM 64u    /* stepped past the loaded message grid                                  */
 #define LOBSIM_ERR_FILL_LOG_FULL 128u   /* fill log capacity exceeded (log truncated, simulation unaffected)     */
 #define LOBSIM_ERR_AUM_NONPOSITIVE 256u  /* "AUM has gone non_positive", rl4mm/rewards/RewardFunctions.py:12-13      */
+#define LOBSIM_ERR_BAD_ACTION 512u       /* non-finite Beta ladder (NaN action): np.round(nan).astype(int) is INT64_MIN in the
+                                            reference and _volume_diff_to_orders (HOE.py:227-258) then raises -> episode dead */
 
 /* ---- packed message record (16 B) -- device-resident replacement of the `messages` table ---------------------
  * rl4mm/database/models.py:10-22 + rl4mm/simulation/HistoricalOrderGenerator.py:77-90.

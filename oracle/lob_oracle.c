@@ -714,7 +714,10 @@ static void beta_ladder(const lo_t* o, double a, double b, int64_t* out) {
   } else if (Q == 8) {
     s = ((w[0] + w[1]) + (w[2] + w[3])) + ((w[4] + w[5]) + (w[6] + w[7]));
   }
-  for (int i = 0; i < Q; i++) out[i] = (int64_t)round_half_even(w[i] / s * (double)o->cfg.active_volume);
+  for (int i = 0; i < Q; i++) {
+    double lots = round_half_even(w[i] / s * (double)o->cfg.active_volume);
+    out[i] = isfinite(lots) ? (int64_t)lots : INT64_MIN; /* np.round(nan).astype(int) */
+  }
 }
 
 static void action_to_ladders(const lo_t* o, const double* action, int64_t* buy, int64_t* sell) {
@@ -752,6 +755,8 @@ static void convert_action_to_orders(lo_t* o, const double* action, o_msgs* out)
   int64_t absinv = o->inventory < 0 ? -o->inventory : o->inventory;
   int clearing = o->cfg.market_order_clearing && (double)absinv > action[ad - 1];
   if (clearing) { memset(desired, 0, sizeof desired); }
+  for (int i = 0; i < Q; i++) /* a NaN ladder is INT64_MIN lots: _volume_diff_to_orders raises (KeyError / pop from an empty deque) */
+    if (desired[0][i] == INT64_MIN || desired[1][i] == INT64_MIN) { o->err |= LOBSIM_ERR_BAD_ACTION; o->dead = 1; return; }
   int64_t bb, bs; int hb = best_buy(o, &bb), hs = best_sell(o, &bs);
   int64_t tick = o->cfg.tick_size;
   if (!hb || !hs) { o->err |= LOBSIM_ERR_EMPTY_BOOK; o->dead = 1; return; }

@@ -24,10 +24,12 @@ ERR_NO_SNAPSHOT = 32
 ERR_END_OF_STREAM = 64
 ERR_FILL_LOG_FULL = 128
 ERR_AUM_NONPOSITIVE = 256
+ERR_BAD_ACTION = 512
 ERR_NAMES = {
     ERR_EMPTY_BOOK: "EMPTY_BOOK", ERR_LEVEL_OVERFLOW: "LEVEL_OVERFLOW", ERR_ORDER_OVERFLOW: "ORDER_OVERFLOW",
     ERR_AGENT_OVERFLOW: "AGENT_OVERFLOW", ERR_BAD_VOLUME: "BAD_VOLUME", ERR_NO_SNAPSHOT: "NO_SNAPSHOT",
     ERR_END_OF_STREAM: "END_OF_STREAM", ERR_FILL_LOG_FULL: "FILL_LOG_FULL", ERR_AUM_NONPOSITIVE: "AUM_NONPOSITIVE",
+    ERR_BAD_ACTION: "BAD_ACTION",
 }
 
 MSG_LIMIT, MSG_CANCEL, MSG_DELETE, MSG_MARKET = 1, 2, 3, 4

@@ -192,7 +192,9 @@ __device__ __noinline__ int beta_ladder_lane(double a, double bpar, int Q, int a
     s = 0.0;
     for (int i = 0; i < Q; i++) s += __shfl_sync(FULL_MASK, e, i);
   }
-  return lane < Q ? (int)rint(e / s * (double)active_volume) : 0;
+  const double lots = rint(e / s * (double)active_volume);
+  if (lane >= Q) return 0;
+  return isfinite(lots) ? (int)lots : INT32_MIN;   // np.round(nan).astype(int): the reference then raises (agent_prepare)
 }
 
 // ---- HistoricalOrderbookEnvironment.convert_action_to_orders (HOE.py:206-258) as a GENERATOR -----------------------
@@ -232,6 +234,7 @@ __device__ __noinline__ AgentGen agent_prepare(const Book b, int nlv0, int nlv1,
   long long absinv = inventory < 0 ? -inventory : inventory;
   const bool clearing = c.market_order_clearing && (double)absinv > pick5(action, ec.action_dim - 1);
   if (clearing) desired0 = desired1 = 0;
+  if (__any_sync(FULL_MASK, desired0 == INT32_MIN || desired1 == INT32_MIN)) { g.err_out = LOBSIM_ERR_BAD_ACTION; g.dead_out = 1; return g; }
   if (nlv0 == 0 || nlv1 == 0) { g.err_out = LOBSIM_ERR_EMPTY_BOOK; g.dead_out = 1; return g; }
   int bb = b.lvp(0)[nlv0 - 1], bs = b.lvp(1)[nlv1 - 1];
   const int tick = c.tick_size;

@@ -315,6 +315,8 @@ class HistoricalOrderbookEnvironment:
             raise EmptyOrderbookError(f"empty book side in env(s) {np.flatnonzero(err & abi.ERR_EMPTY_BOOK)[:8]}")
         if np.any(err & abi.ERR_NO_SNAPSHOT):
             raise AssertionError("There is no data before the episode start time")
+        if np.any(err & abi.ERR_BAD_ACTION):
+            raise ValueError(f"non-finite action / Beta ladder in env(s) {np.flatnonzero(err & abi.ERR_BAD_ACTION)[:8]}")
         bad = err & (abi.ERR_LEVEL_OVERFLOW | abi.ERR_ORDER_OVERFLOW | abi.ERR_AGENT_OVERFLOW | abi.ERR_END_OF_STREAM)
         if np.any(bad):
             names = sorted({n for b, n in abi.ERR_NAMES.items() for e in np.unique(bad) if e & b})

@@ -15,6 +15,7 @@ pytestmark = pytest.mark.gpu
 import os
 
 N_CASES = int(os.environ.get("LOBSIM_RANDOM_CASES", "64"))          # soak runs: LOBSIM_RANDOM_CASES=1000 pytest ...
+CAPACITY_BITS = abi.ERR_LEVEL_OVERFLOW | abi.ERR_ORDER_OVERFLOW | abi.ERR_AGENT_OVERFLOW | abi.ERR_FILL_LOG_FULL
 N_REPLAY_CASES = int(os.environ.get("LOBSIM_RANDOM_REPLAY_CASES", "24"))
 
 
@@ -56,6 +57,8 @@ def test_random_env_case(seed):
             H.assert_close_vec(obs0[env], o.reset(int(starts[env])), what + " reset obs")
             oo, oa, orw, od, oi = o.rollout(ep, agent, acts[:, env] if external else None, want_info=True)
             os_ = o.state()
+            if int(st["err"][env]) & CAPACITY_BITS:   # fixed capacities are a device-side limit (the oracle is unbounded): flagged, not compared
+                continue
             assert int(st["err"][env]) == int(os_["err"]), (what, int(st["err"][env]), int(os_["err"]))
             for t in range(ep):
                 H.assert_close_vec(act[t, env], oa[t], f"{what} t {t} action")
