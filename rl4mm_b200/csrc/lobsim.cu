@@ -233,10 +233,11 @@ __global__ void __launch_bounds__(128, kEnv ? LOBSIM_ENV_MIN_BLOCKS : 4) k_advan
 
   // ---- message pipeline ----------------------------------------------------------------------------------------------
   const int T = p.T;
-  const bool in_grid = now_step >= 0 && (long long)now_step + T <= (long long)stp->n_grid_steps;
-  if (!in_grid && !w.dead && T > 0) { w.err |= LOBSIM_ERR_END_OF_STREAM; w.dead = 1; }
+  // steps beyond the end of the grid: the steps that exist are run, the first one past the end sets END_OF_STREAM
+  const int n_grid = (int)stp->n_grid_steps;
+  if ((now_step < 0 || now_step > n_grid) && !w.dead && T > 0) { w.err |= LOBSIM_ERR_END_OF_STREAM; w.dead = 1; }
   unsigned g = 0, g_end_all = 0;
-  if (!w.dead && T > 0) { g = __ldg(&st_step_off[now_step]); g_end_all = __ldg(&st_step_off[now_step + T]); }
+  if (!w.dead && T > 0) { g = __ldg(&st_step_off[now_step]); g_end_all = __ldg(&st_step_off[min((long long)now_step + T, (long long)n_grid)]); }
   // tiles are MSG_TILE-aligned in the global message index space; `rel` tile r lives in buffer r & 1 and completes
   // phase (r >> 1) & 1 of that buffer's mbarrier.  Tiles are issued and consumed strictly in order.
   const unsigned tile0 = g / MSG_TILE;
@@ -292,6 +293,7 @@ __global__ void __launch_bounds__(128, kEnv ? LOBSIM_ENV_MIN_BLOCKS : 4) k_advan
     }
     // ---- the step's orders: the agent's first, then the historical messages of (now, now + step] ------------------
     {
+      if (!w.dead && now_step >= n_grid) { w.err |= LOBSIM_ERR_END_OF_STREAM; w.dead = 1; }
       const unsigned g_step_end = w.dead ? g : __ldg(&st_step_off[now_step + 1]);
 #pragma unroll 1
       for (;;) {
@@ -420,9 +422,10 @@ __global__ void __launch_bounds__(128, 7) k_replay_fast(const __grid_constant__ 
   const uint32_t* __restrict__ st_step_off = stp->step_off;
   int now_step = h->now_step;
   const int T = p.T;
-  if (!(now_step >= 0 && (long long)now_step + T <= (long long)stp->n_grid_steps) && !f.dead && T > 0) { f.err |= LOBSIM_ERR_END_OF_STREAM; f.dead = 1; }
+  const int n_grid = (int)stp->n_grid_steps;   // steps beyond the end: the existing ones are run, the first one past the end sets END_OF_STREAM
+  if ((now_step < 0 || now_step > n_grid) && !f.dead && T > 0) { f.err |= LOBSIM_ERR_END_OF_STREAM; f.dead = 1; }
   unsigned g = 0, g_end_all = 0;
-  if (!f.dead && T > 0) { g = __ldg(&st_step_off[now_step]); g_end_all = __ldg(&st_step_off[now_step + T]); }
+  if (!f.dead && T > 0) { g = __ldg(&st_step_off[now_step]); g_end_all = __ldg(&st_step_off[min((long long)now_step + T, (long long)n_grid)]); }
   const unsigned tile0 = g / MSG_TILE;
   unsigned next_issue = 0, next_wait = 0;
   auto issue_tile = [&]() {
@@ -445,6 +448,7 @@ __global__ void __launch_bounds__(128, 7) k_replay_fast(const __grid_constant__ 
 
 #pragma unroll 1
   for (int t = 0; t < T && !f.dead; t++) {
+    if (now_step >= n_grid) { f.err |= LOBSIM_ERR_END_OF_STREAM; f.dead = 1; break; }
     const unsigned g_step_end = __ldg(&st_step_off[now_step + 1]);
 #pragma unroll 1
     while (g < g_step_end) {
@@ -612,9 +616,10 @@ __global__ void __launch_bounds__(32 * LOBSIM_ENVFAST_WARPS, 16 / LOBSIM_ENVFAST
 
   // ---- message pipeline ----------------------------------------------------------------------------------------------
   const int T = p.T;
-  if (!(now_step >= 0 && (long long)now_step + T <= (long long)stp->n_grid_steps) && !f.dead && T > 0) { f.err |= LOBSIM_ERR_END_OF_STREAM; f.dead = 1; }
+  const int n_grid = (int)stp->n_grid_steps;   // steps beyond the end: the existing ones are run, the first one past the end sets END_OF_STREAM
+  if ((now_step < 0 || now_step > n_grid) && !f.dead && T > 0) { f.err |= LOBSIM_ERR_END_OF_STREAM; f.dead = 1; }
   unsigned g = 0, g_end_all = 0;
-  if (!f.dead && T > 0) { g = __ldg(&st_step_off[now_step]); g_end_all = __ldg(&st_step_off[now_step + T]); }
+  if (!f.dead && T > 0) { g = __ldg(&st_step_off[now_step]); g_end_all = __ldg(&st_step_off[min((long long)now_step + T, (long long)n_grid)]); }
   const unsigned tile0 = g / MSG_TILE;
   unsigned next_issue = 0, next_wait = 0;
   auto issue_tile = [&]() {
@@ -670,6 +675,7 @@ __global__ void __launch_bounds__(32 * LOBSIM_ENVFAST_WARPS, 16 / LOBSIM_ENVFAST
     }
     if (SYNC) PHASE_SYNC(); // ---- phase B: the step's orders: the agent's first, then the historical messages of (now, now + step]
     {
+      if (!f.dead && now_step >= n_grid) { f.err |= LOBSIM_ERR_END_OF_STREAM; f.dead = 1; }
       const unsigned g_step_end = f.dead ? g : __ldg(&st_step_off[now_step + 1]);
 #pragma unroll 1
       for (;;) {

@@ -16,6 +16,7 @@ import os
 
 N_CASES = int(os.environ.get("LOBSIM_RANDOM_CASES", "64"))          # soak runs: LOBSIM_RANDOM_CASES=1000 pytest ...
 CAPACITY_BITS = abi.ERR_LEVEL_OVERFLOW | abi.ERR_ORDER_OVERFLOW | abi.ERR_AGENT_OVERFLOW | abi.ERR_FILL_LOG_FULL
+DEATH_BITS = abi.ERR_EMPTY_BOOK | abi.ERR_NO_SNAPSHOT | abi.ERR_END_OF_STREAM | abi.ERR_BAD_ACTION   # the reference raised: episode over
 N_REPLAY_CASES = int(os.environ.get("LOBSIM_RANDOM_REPLAY_CASES", "24"))
 
 
@@ -60,13 +61,18 @@ def test_random_env_case(seed):
             if int(st["err"][env]) & CAPACITY_BITS:   # fixed capacities are a device-side limit (the oracle is unbounded): flagged, not compared
                 continue
             assert int(st["err"][env]) == int(os_["err"]), (what, int(st["err"][env]), int(os_["err"]))
+            alive = [not (int(oi[t, abi.INFO_FIELDS.index("err")]) & DEATH_BITS) for t in range(ep)]   # outputs after the exception are undefined
             for t in range(ep):
+                if t >= k:
+                    assert int(info_b[t - k, env, abi.INFO_FIELDS.index("err")]) == int(oi[t, abi.INFO_FIELDS.index("err")]), (what, t)
+                if not alive[t]:
+                    break
                 H.assert_close_vec(act[t, env], oa[t], f"{what} t {t} action")
                 H.assert_close_vec(obs[t, env], oo[t], f"{what} t {t} obs")
                 assert H.close(rew[t, env], orw[t]), (what, t, rew[t, env], orw[t])
                 assert done[t, env] == od[t], (what, t)
-            for t in range(ep - k):
-                H.assert_close_vec(info_b[t, env], oi[k + t], f"{what} t {k + t} info")
+                if t >= k:
+                    H.assert_close_vec(info_b[t - k, env], oi[t], f"{what} t {t} info")
             compare_books(sim, env, o, what)
             assert st["inventory"][env] == os_["inventory"] and H.close(st["cash"][env], os_["cash"]), what
             assert H.close(st["price"][env], os_["price"]), what
