@@ -18,9 +18,10 @@ N_CASES = int(os.environ.get("LOBSIM_RANDOM_CASES", "64"))          # soak runs:
 CAPACITY_BITS = abi.ERR_LEVEL_OVERFLOW | abi.ERR_ORDER_OVERFLOW | abi.ERR_AGENT_OVERFLOW | abi.ERR_FILL_LOG_FULL
 DEATH_BITS = abi.ERR_EMPTY_BOOK | abi.ERR_NO_SNAPSHOT | abi.ERR_END_OF_STREAM | abi.ERR_BAD_ACTION   # the reference raised: episode over
 N_REPLAY_CASES = int(os.environ.get("LOBSIM_RANDOM_REPLAY_CASES", "24"))
+SEED0 = int(os.environ.get("LOBSIM_RANDOM_SEED0", "0"))
 
 
-@pytest.mark.parametrize("seed", range(N_CASES))
+@pytest.mark.parametrize("seed", range(SEED0, SEED0 + N_CASES))
 def test_random_env_case(seed):
     import torch
 
@@ -81,7 +82,7 @@ def test_random_env_case(seed):
     sim.close()
 
 
-@pytest.mark.parametrize("seed", range(N_REPLAY_CASES))
+@pytest.mark.parametrize("seed", range(SEED0, SEED0 + N_REPLAY_CASES))
 def test_random_replay_case(seed, monkeypatch):
     """Pure replay (both kernel families: the straight-line k_replay_fast and, forced, the general k_advance) vs the oracle."""
     from oracle.oracle import Oracle
