@@ -94,6 +94,11 @@ def random_case(seed: int):
         agent = abi.Agent(kind=abi.AGENT_TERADACTYL, inventory_index=idx[0], max_inventory=float(rng2.choice([50.0, 300.0, 5000.0])),
                           default_kappa=float(rng2.uniform(3.0, 10.0)), default_omega=float(rng2.uniform(0.2, 0.8)),
                           max_kappa=float(rng2.uniform(10.0, 14.0)), exponent=float(rng2.choice([1.0, 1.5, 2.0])), market_clearing=clearing)
+    # capacities: two of the three choices have a compiled StaticLayout (the straight-line k_env_fast), the third runs the
+    # general runtime-layout kernel; small capacities that overflow are flagged by the device and skipped by the test
+    rng3 = np.random.default_rng(7000 + seed)
+    caps = [(64, 256), (128, 512), (128, 1024)] if sc.target_orders <= 100 else [(128, 512), (128, 1024)]
+    cfg_kw["max_levels_per_side"], cfg_kw["max_orders_per_side"] = caps[int(rng3.integers(0, len(caps)))]
     return dict(synth=sc, cfg_kw=cfg_kw, n_envs=n_envs, starts=starts, actions=acts, T=T, agent=agent, agent_kind=kind)
 
 
