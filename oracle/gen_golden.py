@@ -280,7 +280,7 @@ def golden_exchange_fuzz():
     rng = np.random.default_rng(7)
     ts = datetime(2012, 6, 21, 12)
     cases = []
-    for case in range(40):
+    for case in range(120):
         ex = Exchange("MSFT")
         mid = 300000
         # snapshot aggregates on both sides (internal_id -1)

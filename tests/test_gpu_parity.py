@@ -142,7 +142,7 @@ def test_env_episodes(case_idx, torch_cuda):
             assert np.array_equal(rew, np.full_like(rew, rew[0]), equal_nan=True)
 
 
-@pytest.mark.parametrize("case_idx", range(40))
+@pytest.mark.parametrize("case_idx", range(120))
 def test_exchange_fuzz(case_idx, torch_cuda):
     from test_oracle_golden import replay_exchange_case
 
