@@ -248,6 +248,50 @@ def golden_env_episodes():
     save("env_episodes.json.gz", cases)
 
 
+def golden_env_random():
+    """G2b: the reference env on the MSFT fixture under RANDOM configurations (seeded): env kwargs, feature subsets, reward
+    kinds, portfolios and actions are drawn at random, so that the pins are not limited to hand-picked cases."""
+    rng = np.random.default_rng(2024)
+    n_specs = len(feature_specs())
+    cases = []
+    for k in range(16):
+        feats = sorted(set([int(rng.choice([12, 13, 14, 22]))] + [int(i) for i in rng.choice(n_specs, size=int(rng.integers(2, 9)), replace=False)]))
+        conc = bool(rng.random() < 0.25)
+        clearing = bool(rng.random() < 0.35)
+        kw = {}
+        if conc:
+            kw["concentration"] = 10.0
+        if clearing:
+            kw.update(market_order_clearing=True, market_order_fraction_of_inventory=float(rng.choice([0.3, 1.0])), max_inventory=60)
+        if rng.random() < 0.4:
+            kw["enter_spread"] = True
+        if rng.random() < 0.4:
+            kw["inc_prev_action_in_obs"] = True
+        if rng.random() < 0.5:
+            lo = int(rng.integers(0, 3))
+            kw.update(min_quote_level=lo, max_quote_level=lo + int(rng.choice([3, 5, 10])))
+        ad = (2 if conc else 4)
+        acts = rng.uniform(0.0, 10.0, size=(64, ad))
+        acts[rng.random(acts.shape) < 0.05] = 0.0
+        if clearing:
+            acts = np.c_[acts, rng.uniform(0, 80, size=64)]
+
+        def reward():
+            r = int(rng.integers(0, 4))
+            if r == 0:
+                return ("PnL",)
+            if r == 3:
+                mx = int(rng.integers(3, 9))
+                return ("RS", mx, int(rng.integers(2, mx + 1)))
+            return ("IA", float(rng.choice([1e-4, 0.01, 0.5])), bool(r == 2))
+
+        cases.append(run_env_case(
+            f"random_{k}", acts.tolist(), kw, reward(), reward(), features=feats, n_episodes=int(rng.integers(1, 4)),
+            episode_seconds=float(rng.choice([1.0, 1.5, 2.0])), start_seconds=36000.0 + 1.0,
+            outer_levels=int(rng.choice([20, 48])), portfolio=(int(rng.choice([0, 0, 25, -40])), int(rng.choice([10**8, 10**10])))))
+    save("env_random.json.gz", cases)
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 def golden_beta_ladders():
     """G3: BetaOrderDistributor lot sizes (scipy.stats.beta.pdf + np.round half-to-even)."""
@@ -438,6 +482,7 @@ def main():
         g1 = golden_fixture_replay
         g1()
         golden_env_episodes()
+        golden_env_random()
         golden_beta_ladders()
         golden_exchange_fuzz()
         golden_episode_summary()

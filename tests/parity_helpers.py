@@ -15,6 +15,10 @@ REL_TOL = 1e-6  # north_star: features and rewards within 1e-6 relative
 ABS_TOL = 1e-9
 
 
+# hand-picked env configurations + seeded random ones, both produced by the unmodified reference (oracle/gen_golden.py)
+ENV_GOLDEN_CASES = [("env_episodes.json.gz", i) for i in range(14)] + [("env_random.json.gz", i) for i in range(16)]
+
+
 def load_golden(name: str):
     with gzip.open(GOLDEN / name, "rb") as f:
         return json.loads(f.read().decode())

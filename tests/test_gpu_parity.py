@@ -105,10 +105,10 @@ def test_fixture_replay_in_one_launch(torch_cuda):
         assert H.canon_book(sim.dump_book(2, side), s.ext_ids) == case["steps"][27]["book"][side]
 
 
-@pytest.mark.parametrize("case_idx", range(14))
-def test_env_episodes(case_idx, torch_cuda):
+@pytest.mark.parametrize("golden,case_idx", H.ENV_GOLDEN_CASES)
+def test_env_episodes(golden, case_idx, torch_cuda):
     torch = torch_cuda
-    case = H.load_golden("env_episodes.json.gz")[case_idx]
+    case = H.load_golden(golden)[case_idx]
     s = H.load_fixture_stream("reference")
     n = 3
     sim = make_sim(H.cfg_from_env_case(case, n_envs=n), [s])
