@@ -565,7 +565,10 @@ __device__ __noinline__ void zscore_recenter(FeatState& f, const double* hist, i
   f.nK = centre; f.nS1 = s1; f.nS2 = s2; f.nS2max = s2;
 }
 
-__device__ __forceinline__ double feature_normalise(FeatState& f, double* hist, int maxlen, double value) {
+// Cold and out of line, working on the FeatState in global memory after features_step has stored it: nothing of the caller
+// stays live across the (rare) calls into the exact paths, so the per-step feature code keeps its registers.
+__device__ __noinline__ double feature_normalise(FeatState* fg, double* hist, int maxlen, double value) {
+  FeatState f = *fg;
   int n = f.nlen;
   int head = f.nhead;
   double last = NAN;
@@ -583,7 +586,9 @@ __device__ __forceinline__ double feature_normalise(FeatState& f, double* hist, 
   int start = head - n; if (start < 0) start += maxlen;      // ring index of the oldest entry
   if (f.nrun >= n) {                                          // the whole window holds one value
     f.nK = value; f.nS1 = 0.0; f.nS2 = 0.0; f.nS2max = 0.0;   // exact sums around the value itself
-    return zscore_exact(hist, maxlen, start, n, value, 1);
+    f.cur = zscore_exact(hist, maxlen, start, n, value, 1);
+    *fg = f;
+    return f.cur;
   }
   double d = value - f.nK;
   f.nS1 += d; f.nS2 += d * d;
@@ -600,8 +605,10 @@ __device__ __forceinline__ double feature_normalise(FeatState& f, double* hist, 
     d = value - f.nK; m1 = f.nS1 / (double)n; msq = f.nS2 / (double)n; var = msq - m1 * m1;
   }
   const double sd = sqrt(var);
-  if (!(sd > 1e-8 * fabs(f.nK + m1))) return zscore_exact(hist, maxlen, start, n, value, 0);   // noise-dominated (or NaN)
-  return (d - m1) / sd;
+  if (!(sd > 1e-8 * fabs(f.nK + m1))) f.cur = zscore_exact(hist, maxlen, start, n, value, 0);   // noise-dominated (or NaN)
+  else f.cur = (d - m1) / sd;
+  *fg = f;
+  return f.cur;
 }
 
 // Feature.reset/_reset, Features.py:92-96
@@ -614,18 +621,22 @@ __device__ __forceinline__ void feature_reset(const lobsim_feature_t& fc, FeatSt
 }
 
 // Feature.update, Features.py:80-86,102-105
-__device__ __forceinline__ void feature_update(const lobsim_feature_t& fc, FeatState& f, double* ring, double* hist, const StepView& v, long long episode_start_us) {
+// returns true when the (clamped) value still has to go through Feature.normalise (done by the caller, out of line)
+__device__ __forceinline__ bool feature_update(const lobsim_feature_t& fc, FeatState& f, double* ring, const StepView& v, long long episode_start_us) {
   long long first_usage = episode_start_us - (long long)fc.lookback * fc.update_us;
-  if (v.now_us < first_usage) return;
-  if ((v.now_us % 60000000LL) % fc.update_us != 0) return;
+  if (v.now_us < first_usage) return false;
+  if ((v.now_us % 60000000LL) % fc.update_us != 0) return false;
   feature_update_raw(fc, f, ring, v);
   f.cur = fmax(fmin(f.cur, fc.max_value), fc.min_value);
-  if (fc.norm_len > 0) f.cur = feature_normalise(f, hist, fc.norm_len, f.cur);
+  return fc.norm_len > 0;
 }
 
 // Cold per-step feature phase: lane f < F loads its feature state from HBM, resets (mode 1) or updates (mode 0) it,
 // stores it back and returns Feature.current_value.  Keeping this out of line keeps the fp64 / 64-bit-division heavy
 // code (and its registers) away from the order-processing loop.
+// NORM == false instantiations contain no call into the z-score code: a callee subtree that is never executed still costs
+// the calling kernel registers around the call and I-cache footprint (measured: 3.7 % of the env step).
+template <bool NORM>
 __device__ __noinline__ double features_step(const EnvConst* ecp, FeatState* fstate_env, double* rings_env, int lane, const StepView v, long long episode_start_us, int mode) {
   const EnvConst& ec = *ecp;
   double cur = 0.0;
@@ -633,10 +644,12 @@ __device__ __noinline__ double features_step(const EnvConst* ecp, FeatState* fst
     const lobsim_feature_t fc = ec.cfg.features[lane];
     FeatState fs = fstate_env[lane];
     double* ring = rings_env + ec.ring_off[lane];
+    bool norm = false;
     if (mode == 1) feature_reset(fc, fs, ring, v);
-    else feature_update(fc, fs, ring, rings_env + ec.hist_off[lane], v, episode_start_us);
+    else norm = feature_update(fc, fs, ring, v, episode_start_us);
     fstate_env[lane] = fs;
     cur = fs.cur;
+    if (NORM && norm) cur = feature_normalise(&fstate_env[lane], rings_env + ec.hist_off[lane], fc.norm_len, cur);
   }
   return cur;
 }

@@ -122,15 +122,16 @@ __device__ __forceinline__ void write_info(double* row, int lane, const StepView
 }
 
 // per_step / terminal reward of one env step (HOE.py:170-174); RollingSharpe keeps one AUM window per reward function
+template <bool RARE>
 __device__ __forceinline__ double step_reward(const AdvParams& p, const lobsim_cfg_t& c, int env, int lane, bool done, double cash0, long long inv0, double p0,
                                               double cash1, long long inv1, double p1, uint32_t& err) {
   double r;
-  if (c.step_reward.kind == LOBSIM_REWARD_ROLLING_SHARPE) {
+  if (RARE && c.step_reward.kind == LOBSIM_REWARD_ROLLING_SHARPE) {
     SharpeOut o = rolling_sharpe_step(p.rs_ring + ((size_t)env * 2 + 0) * LOBSIM_MAX_SHARPE_WINDOW, p.rs_state + ((size_t)env * 2 + 0) * 2, c.step_reward.asymmetric, cash1 + p1 * (double)inv1, lane);
     r = o.reward; err |= o.err;
   } else r = reward_calc(c.step_reward, cash0, inv0, p0, cash1, inv1, p1);
   if (done) {
-    if (c.terminal_reward.kind == LOBSIM_REWARD_ROLLING_SHARPE) {
+    if (RARE && c.terminal_reward.kind == LOBSIM_REWARD_ROLLING_SHARPE) {
       SharpeOut o = rolling_sharpe_step(p.rs_ring + ((size_t)env * 2 + 1) * LOBSIM_MAX_SHARPE_WINDOW, p.rs_state + ((size_t)env * 2 + 1) * 2, c.terminal_reward.asymmetric, cash1 + p1 * (double)inv1, lane);
       r = o.reward; err |= o.err;
     } else r = reward_calc(c.terminal_reward, cash0, inv0, p0, cash1, inv1, p1);
@@ -228,7 +229,7 @@ __global__ void __launch_bounds__(128, kEnv ? LOBSIM_ENV_MIN_BLOCKS : 4) k_advan
     v.inventory = w.inventory; v.now_us = st_t0_us + (long long)now_step * c.step_us;
     v.n_ext0 = v.n_ext1 = v.vol_ext0 = v.vol_ext1 = v.n_int0 = v.n_int1 = v.vol_int0 = v.vol_int1 = 0;
     price = v.price;
-    feat_cur = features_step(&ec, fstate_env, rings_env, lane, v, episode_start_us, 1);
+    feat_cur = features_step<true>(&ec, fstate_env, rings_env, lane, v, episode_start_us, 1);
   }
 
   // ---- message pipeline ----------------------------------------------------------------------------------------------
@@ -335,7 +336,7 @@ __global__ void __launch_bounds__(128, kEnv ? LOBSIM_ENV_MIN_BLOCKS : 4) k_advan
       v.inventory = w.inventory; v.now_us = st_t0_us + (long long)now_step * c.step_us;
       v.n_ext0 = w.n_ext0; v.n_ext1 = w.n_ext1; v.vol_ext0 = w.vol_ext0; v.vol_ext1 = w.vol_ext1;
       v.n_int0 = w.n_int0; v.n_int1 = w.n_int1; v.vol_int0 = w.vol_int0; v.vol_int1 = w.vol_int1;
-      feat_cur = features_step(&ec, fstate_env, rings_env, lane, v, episode_start_us, 0);
+      feat_cur = features_step<true>(&ec, fstate_env, rings_env, lane, v, episode_start_us, 0);
       const bool write_now = !p.out_final_obs_only || t == T - 1;
       if (p.obs && write_now) {
         double* o = p.obs + ((size_t)(p.out_final_obs_only ? 0 : t) * p.n_sel + sel) * ec.obs_dim;
@@ -344,7 +345,7 @@ __global__ void __launch_bounds__(128, kEnv ? LOBSIM_ENV_MIN_BLOCKS : 4) k_advan
       }
       if (p.agent_kind != LOBSIM_AGENT_NONE) {
         const bool d = now_step >= h->episode_start_step + c.episode_steps; // terminal_time - now < step/2, HOE.py:172
-        const double r = step_reward(p, c, env, lane, d, cash0, inv0, p0, w.cash, w.inventory, price, w.err);
+        const double r = step_reward<true>(p, c, env, lane, d, cash0, inv0, p0, w.cash, w.inventory, price, w.err);
         if (lane == 0) {
           if (p.rew) p.rew[(size_t)t * p.n_sel + sel] = r;
           if (p.done) p.done[(size_t)t * p.n_sel + sel] = d ? 1 : 0;
@@ -536,7 +537,11 @@ __device__ __noinline__ uint32_t reset_book_cold(unsigned char* blob, const Layo
 #endif
 // SYNC: the launch consists of full CTAs only, whose warps move through the phases of a step together
 // (launch_env puts the n_sel % warps-per-CTA tail into a second, free-running launch).
-template <class LT, bool SYNC>
+// Per-warp values that are only needed outside the order-processing phase (B) live in the spare shared memory behind the
+// mbarriers instead of in registers: the kernel is register-bound (128 at 2 CTAs x 8 warps) and phase B is where it spills.
+struct StepSave { double cash0, p0, price; long long inv0, episode_start_us, st_t0_us; };
+// RARE: the configuration uses z-score normalisation or a RollingSharpe reward (their code is compiled out otherwise).
+template <class LT, bool SYNC, bool RARE>
 __global__ void __launch_bounds__(32 * LOBSIM_ENVFAST_WARPS, 16 / LOBSIM_ENVFAST_WARPS) k_env_fast(const __grid_constant__ AdvParams p, const __grid_constant__ EnvConst ec) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -588,9 +593,10 @@ __global__ void __launch_bounds__(32 * LOBSIM_ENVFAST_WARPS, 16 / LOBSIM_ENVFAST
   const lobsim_stream_t* stp = &p.streams[stream_id];
   const lobsim_msg_t* __restrict__ st_msgs = stp->msgs;
   const uint32_t* __restrict__ st_step_off = stp->step_off;
-  const long long st_t0_us = stp->t0_us;
+  StepSave* sv = reinterpret_cast<StepSave*>(bars + 4);
   int now_step = h->now_step;
-  const long long episode_start_us = st_t0_us + (long long)h->episode_start_step * c.step_us;
+  if (lane == 0) { sv->st_t0_us = stp->t0_us; sv->episode_start_us = stp->t0_us + (long long)h->episode_start_step * c.step_us; sv->price = h->price; }
+  __syncwarp();
   FeatState* fstate_env = p.fstate + (size_t)env * LOBSIM_MAX_FEATURES;
   double* rings_env = p.rings + (size_t)env * ec.ring_stride;
   double feat_cur = 0.0;
@@ -605,13 +611,14 @@ __global__ void __launch_bounds__(32 * LOBSIM_ENVFAST_WARPS, 16 / LOBSIM_ENVFAST
       double imb; v.price = microprice(v.bb, v.bs, v.bv, v.sv, imb);
     } else { v.bb = v.bs = v.bv = v.sv = 0; v.price = NAN; }
   };
-  double price = h->price;
   if (p.reset_mode == 2) { // State(...) + _reset_features, HOE.py:152-154,218-221
     StepView v; tops(v);
-    v.inventory = h->inventory; v.now_us = st_t0_us + (long long)now_step * c.step_us;
+    v.inventory = h->inventory; v.now_us = sv->st_t0_us + (long long)now_step * c.step_us;
     v.n_ext0 = v.n_ext1 = v.vol_ext0 = v.vol_ext1 = v.n_int0 = v.n_int1 = v.vol_int0 = v.vol_int1 = 0;
-    price = v.price;
-    feat_cur = features_step(&ec, fstate_env, rings_env, lane, v, episode_start_us, 1);
+    __syncwarp();
+    if (lane == 0) sv->price = v.price;
+    feat_cur = features_step<RARE>(&ec, fstate_env, rings_env, lane, v, sv->episode_start_us, 1);
+    __syncwarp();
   }
 
   // ---- message pipeline ----------------------------------------------------------------------------------------------
@@ -646,8 +653,8 @@ __global__ void __launch_bounds__(32 * LOBSIM_ENVFAST_WARPS, 16 / LOBSIM_ENVFAST
 #pragma unroll 1
   for (int t = 0; t < T; t++) {
     if (SYNC) PHASE_SYNC(); // ---- phase A: action -> ladders (fp64) --------------------------------------------------------
-    const double cash0 = h->cash, p0 = price; const long long inv0 = h->inventory; // deepcopy(self.state), HOE.py:166
     __syncwarp();
+    if (lane == 0) { sv->cash0 = h->cash; sv->p0 = sv->price; sv->inv0 = h->inventory; } // deepcopy(self.state), HOE.py:166
     if (lane < 8) h->flow[lane] = 0;
     __syncwarp();
     if (p.agent_kind != LOBSIM_AGENT_NONE) {
@@ -656,7 +663,11 @@ __global__ void __launch_bounds__(32 * LOBSIM_ENVFAST_WARPS, 16 / LOBSIM_ENVFAST
         const double* a = p.actions_in + ((size_t)t * p.n_sel + sel) * ec.action_dim;
         if (lane < 5) act_sm[lane] = lane < ec.action_dim ? __ldg(&a[lane]) : 0.0;
       } else {
+#ifndef LOBSIM_EXPERIMENT_NO_AGENTS
         const lobsim_agent_t* agp = p.agents ? p.agents + sel : &p.agent;
+#else
+        const lobsim_agent_t* agp = &p.agent;
+#endif
         const double inv_obs = __shfl_sync(FULL_MASK, feat_cur, agp->inventory_index & 31);
         if (lane == 0) agent_action_cold(agp, inv_obs, act_sm);
       }
@@ -675,7 +686,7 @@ __global__ void __launch_bounds__(32 * LOBSIM_ENVFAST_WARPS, 16 / LOBSIM_ENVFAST
     }
     if (SYNC) PHASE_SYNC(); // ---- phase B: the step's orders: the agent's first, then the historical messages of (now, now + step]
     {
-      if (!f.dead && now_step >= n_grid) { f.err |= LOBSIM_ERR_END_OF_STREAM; f.dead = 1; }
+      if (!f.dead && now_step >= (int)stp->n_grid_steps) { f.err |= LOBSIM_ERR_END_OF_STREAM; f.dead = 1; } // re-read: keeps a register free
       const unsigned g_step_end = f.dead ? g : __ldg(&st_step_off[now_step + 1]);
 #pragma unroll 1
       for (;;) {
@@ -719,12 +730,13 @@ __global__ void __launch_bounds__(32 * LOBSIM_ENVFAST_WARPS, 16 / LOBSIM_ENVFAST
     if (SYNC) PHASE_SYNC(); // ---- phase C: update_internal_state + _update_features + reward, HOE.py:163-178,199-204 -------------
     StepView v; tops(v);
     if (!v.have_tops) f.err |= LOBSIM_ERR_EMPTY_BOOK;
-    price = v.price;
-    v.inventory = h->inventory; v.now_us = st_t0_us + (long long)now_step * c.step_us;
+    const double price = v.price;
+    if (lane == 0) sv->price = price;
+    v.inventory = h->inventory; v.now_us = sv->st_t0_us + (long long)now_step * c.step_us;
     v.n_ext0 = h->flow[0]; v.n_ext1 = h->flow[1]; v.vol_ext0 = h->flow[2]; v.vol_ext1 = h->flow[3];
     v.n_int0 = h->flow[4]; v.n_int1 = h->flow[5]; v.vol_int0 = h->flow[6]; v.vol_int1 = h->flow[7];
     __syncwarp(); // every lane has read this step's flow counters before lanes 0-7 zero them for the next step
-    feat_cur = features_step(&ec, fstate_env, rings_env, lane, v, episode_start_us, 0);
+    feat_cur = features_step<RARE>(&ec, fstate_env, rings_env, lane, v, sv->episode_start_us, 0);
     const bool write_now = !p.out_final_obs_only || t == T - 1;
     if (p.obs && write_now) {
       double* o = p.obs + ((size_t)(p.out_final_obs_only ? 0 : t) * p.n_sel + sel) * ec.obs_dim;
@@ -734,12 +746,14 @@ __global__ void __launch_bounds__(32 * LOBSIM_ENVFAST_WARPS, 16 / LOBSIM_ENVFAST
     if (p.agent_kind != LOBSIM_AGENT_NONE) {
       const double cash1 = h->cash; const long long inv1 = h->inventory;
       const bool d = now_step >= h->episode_start_step + c.episode_steps; // terminal_time - now < step/2, HOE.py:172
-      const double r = step_reward(p, c, env, lane, d, cash0, inv0, p0, cash1, inv1, price, f.err);
+      const double r = step_reward<RARE>(p, c, env, lane, d, sv->cash0, sv->inv0, sv->p0, cash1, inv1, price, f.err);
       if (lane == 0) {
         if (p.rew) p.rew[(size_t)t * p.n_sel + sel] = r;
         if (p.done) p.done[(size_t)t * p.n_sel + sel] = d ? 1 : 0;
       }
+#ifndef LOBSIM_EXPERIMENT_NO_INFO
       if (p.info) write_info(p.info + ((size_t)t * p.n_sel + sel) * LOBSIM_INFO_DIM, lane, v, cash1, inv1, f.err);
+#endif
     }
   }
   if (T == 0 && p.obs && p.reset_mode == 2) { // reset with no warm-up: obs straight after _reset_features
@@ -751,7 +765,7 @@ __global__ void __launch_bounds__(32 * LOBSIM_ENVFAST_WARPS, 16 / LOBSIM_ENVFAST
   __syncwarp();
   if (lane == 0) {
     if (f.fill_log && h->n_fills > f.fill_cap) f.err |= LOBSIM_ERR_FILL_LOG_FULL;
-    h->now_step = now_step; h->price = price; h->err = f.err; h->dead = f.dead;
+    h->now_step = now_step; h->price = sv->price; h->err = f.err; h->dead = f.dead;
     if (p.fill_count) p.fill_count[env] = h->n_fills;
   }
   __syncwarp();
@@ -881,6 +895,7 @@ struct lobsim {
   lobsim_fill_t* fill_log = nullptr;
   int32_t* fill_count = nullptr;
   lobsim_agent_t* agents_dev = nullptr; // per-env agents of lobsim_rollout_agents (allocated on first use)
+  bool rare_paths = false;              // z-score normalisation or a RollingSharpe reward configured: kernels with that code
   std::vector<lobsim_stream_t> streams;
   lobsim_stream_t* streams_dev = nullptr;
   int streams_cap = 0;
@@ -955,6 +970,8 @@ int lobsim_create(const lobsim_cfg_t* cfg, int device, lobsim_t** out) {
   if (!h) return fail(LOBSIM_E_NOMEM, "out of host memory");
   h->cfg = *cfg; h->device = device;
   { const char* e = getenv("LOBSIM_FORCE_GENERAL"); h->force_general = e && e[0] == '1'; }
+  h->rare_paths = cfg->step_reward.kind == LOBSIM_REWARD_ROLLING_SHARPE || cfg->terminal_reward.kind == LOBSIM_REWARD_ROLLING_SHARPE;
+  for (int i = 0; i < cfg->n_features; i++) h->rare_paths = h->rare_paths || cfg->features[i].norm_len > 0;
   h->L = make_layout(cfg->max_levels_per_side, cfg->max_orders_per_side, cfg->max_agent_orders);
   h->warp_smem = warp_smem_bytes(h->L);
   int max_smem = 0;
@@ -968,9 +985,11 @@ int lobsim_create(const lobsim_cfg_t* cfg, int device, lobsim_t** out) {
   CUDA_TRY((cudaFuncSetAttribute(k_advance<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->warps_per_cta * h->warp_smem)));
   {
     const void* fast_kernels[] = {(const void*)k_replay_fast<FastLayoutA>, (const void*)k_replay_fast<FastLayoutB>, (const void*)k_replay_fast<FastLayoutC>,
-                                  (const void*)k_env_fast<FastLayoutA, true>, (const void*)k_env_fast<FastLayoutB, true>, (const void*)k_env_fast<FastLayoutC, true>,
-                                  (const void*)k_env_fast<FastLayoutA, false>, (const void*)k_env_fast<FastLayoutB, false>, (const void*)k_env_fast<FastLayoutC, false>};
-    for (int i = 0; i < 9; i++) {
+                                  (const void*)k_env_fast<FastLayoutA, true, false>, (const void*)k_env_fast<FastLayoutB, true, false>, (const void*)k_env_fast<FastLayoutC, true, false>,
+                                  (const void*)k_env_fast<FastLayoutA, false, false>, (const void*)k_env_fast<FastLayoutB, false, false>, (const void*)k_env_fast<FastLayoutC, false, false>,
+                                  (const void*)k_env_fast<FastLayoutA, true, true>, (const void*)k_env_fast<FastLayoutB, true, true>, (const void*)k_env_fast<FastLayoutC, true, true>,
+                                  (const void*)k_env_fast<FastLayoutA, false, true>, (const void*)k_env_fast<FastLayoutB, false, true>, (const void*)k_env_fast<FastLayoutC, false, true>};
+    for (int i = 0; i < 15; i++) {
       const void* k = fast_kernels[i];
       const int dyn = (i < 3 ? h->warps_per_cta : h->env_warps_per_cta) * h->warp_smem;
       CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
@@ -1094,6 +1113,17 @@ static int launch_replay_fast(lobsim* h, const AdvParams& p, cudaStream_t stream
   return LOBSIM_OK;
 }
 
+template <bool SYNC, bool RARE>
+static void launch_env_fast_t(int layout, int grid, int block, size_t dyn, cudaStream_t stream, const AdvParams& p, const EnvConst& ec) {
+  if (layout == 0) k_env_fast<FastLayoutA, SYNC, RARE><<<grid, block, dyn, stream>>>(p, ec);
+  else if (layout == 1) k_env_fast<FastLayoutB, SYNC, RARE><<<grid, block, dyn, stream>>>(p, ec);
+  else k_env_fast<FastLayoutC, SYNC, RARE><<<grid, block, dyn, stream>>>(p, ec);
+}
+static void launch_env_fast(int layout, bool sync, bool rare, int grid, int block, size_t dyn, cudaStream_t stream, const AdvParams& p, const EnvConst& ec) {
+  if (sync) { if (rare) launch_env_fast_t<true, true>(layout, grid, block, dyn, stream, p, ec); else launch_env_fast_t<true, false>(layout, grid, block, dyn, stream, p, ec); }
+  else { if (rare) launch_env_fast_t<false, true>(layout, grid, block, dyn, stream, p, ec); else launch_env_fast_t<false, false>(layout, grid, block, dyn, stream, p, ec); }
+}
+
 // env launches (reset / step / rollout): the straight-line kernel when a compiled StaticLayout matches the capacities,
 // the general runtime-layout kernel otherwise
 static int launch_env(lobsim* h, const AdvParams& p, cudaStream_t stream) {
@@ -1104,19 +1134,16 @@ static int launch_env(lobsim* h, const AdvParams& p, cudaStream_t stream) {
   const int wpc = h->env_warps_per_cta;
   const size_t dyn = (size_t)wpc * h->warp_smem;
   const int full = p.n_sel / wpc, tail = p.n_sel % wpc;
+  const int layout = a ? 0 : (b ? 1 : 2);
   if (full > 0) { // full CTAs: phase-synchronous
-    if (a) k_env_fast<FastLayoutA, true><<<full, wpc * 32, dyn, stream>>>(p, h->ec);
-    else if (b) k_env_fast<FastLayoutB, true><<<full, wpc * 32, dyn, stream>>>(p, h->ec);
-    else k_env_fast<FastLayoutC, true><<<full, wpc * 32, dyn, stream>>>(p, h->ec);
+    launch_env_fast(layout, true, h->rare_paths, full, wpc * 32, dyn, stream, p, h->ec);
     CUDA_TRY(cudaGetLastError());
     h->launches++;
   }
   if (tail > 0) { // the remaining n_sel % wpc envs: one partially filled CTA without block-level barriers
     AdvParams pt = p;
     pt.sel_offset = full * wpc;
-    if (a) k_env_fast<FastLayoutA, false><<<1, wpc * 32, dyn, stream>>>(pt, h->ec);
-    else if (b) k_env_fast<FastLayoutB, false><<<1, wpc * 32, dyn, stream>>>(pt, h->ec);
-    else k_env_fast<FastLayoutC, false><<<1, wpc * 32, dyn, stream>>>(pt, h->ec);
+    launch_env_fast(layout, false, h->rare_paths, 1, wpc * 32, dyn, stream, pt, h->ec);
     CUDA_TRY(cudaGetLastError());
     h->launches++;
   }
