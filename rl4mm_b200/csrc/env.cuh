@@ -720,7 +720,10 @@ __device__ __forceinline__ bool agent_next_fast(const FastBook<LT>& fb, FastStat
 // ring: maxw doubles (circular, logical order oldest -> newest), state[0] = n_filled, state[1] = head (next write).
 // Returns the reward; *err_out gets LOBSIM_ERR_AUM_NONPOSITIVE when an AUM in the window is <= 0 (the reference raises).
 struct SharpeOut { double reward; uint32_t err; };
-__device__ __noinline__ SharpeOut rolling_sharpe_step(double* ring, int* state, int packed_windows, double new_aum, int lane) {
+// get_sharpe (RewardFunctions.py:10-22): np.mean and np.std(ddof=1) of the simple returns.  The returns are written to a scratch
+// row (`tmp`) by all lanes and then summed by lane 0 in numpy's pairwise order (np_pairwise_sum_ring) -- mean / std of tiny
+// returns amplifies any other summation order beyond the 1e-6 tolerance.
+__device__ __noinline__ SharpeOut rolling_sharpe_step(double* ring, int* state, int packed_windows, double new_aum, int lane, double* tmp) {
   const int maxw = packed_windows & 0xffff, minw = (packed_windows >> 16) & 0xffff;
   int n = state[0], head = state[1];
   __syncwarp();
@@ -731,25 +734,21 @@ __device__ __noinline__ SharpeOut rolling_sharpe_step(double* ring, int* state, 
   if (n < minw) return out;
   const int first = n < maxw ? 0 : head;     // physical index of the oldest entry (the ring starts at 0 after create)
   const int m = n - 1;                       // number of returns
-  double s1 = 0.0; int bad = 0;
+  int bad = 0;
   for (int i = lane; i < n; i += 32) { int k = first + i; if (k >= maxw) k -= maxw; if (ring[k] <= 0.0) bad = 1; }
   if (__any_sync(FULL_MASK, bad)) { out.reward = NAN; out.err = LOBSIM_ERR_AUM_NONPOSITIVE; return out; }
   for (int i = lane; i < m; i += 32) {
     int k0 = first + i; if (k0 >= maxw) k0 -= maxw;
     int k1 = k0 + 1 == maxw ? 0 : k0 + 1;
-    s1 += exp(log(ring[k1]) - log(ring[k0])) - 1.0;
+    tmp[i] = exp(log(ring[k1]) - log(ring[k0])) - 1.0;
   }
-  for (int d = 16; d; d >>= 1) s1 += __shfl_xor_sync(FULL_MASK, s1, d);
-  const double mean = s1 / (double)m;
-  double s2 = 0.0;
-  for (int i = lane; i < m; i += 32) {
-    int k0 = first + i; if (k0 >= maxw) k0 -= maxw;
-    int k1 = k0 + 1 == maxw ? 0 : k0 + 1;
-    const double dlt = (exp(log(ring[k1]) - log(ring[k0])) - 1.0) - mean;
-    s2 += dlt * dlt;
+  __syncwarp();
+  double r = 0.0;
+  if (lane == 0) {
+    const double mean = np_pairwise_sum_ring(tmp, m, 0, m, 0, 0.0, 0.0) / (double)m;
+    const double sd = sqrt(np_pairwise_sum_ring(tmp, m, 0, m, 1, mean, 0.0) / (double)(m - 1));
+    r = mean / (sd + 2.2250738585072014e-308);
   }
-  for (int d = 16; d; d >>= 1) s2 += __shfl_xor_sync(FULL_MASK, s2, d);
-  const double sd = sqrt(s2 / (double)(m - 1));
-  out.reward = mean / (sd + 2.2250738585072014e-308);
+  out.reward = __shfl_sync(FULL_MASK, r, 0);
   return out;
 }

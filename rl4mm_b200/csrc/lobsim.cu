@@ -80,7 +80,7 @@ struct AdvParams {
   unsigned char* blobs;             // [n_envs][blob_bytes]
   FeatState* fstate;                // [n_envs][LOBSIM_MAX_FEATURES]
   double* rings;                    // [n_envs][ring_stride]
-  double* rs_ring;                  // RollingSharpe windows [n_envs][2][LOBSIM_MAX_SHARPE_WINDOW] or null
+  double* rs_ring;                  // RollingSharpe [n_envs][3][LOBSIM_MAX_SHARPE_WINDOW]: two AUM windows + a scratch row of returns, or null
   int32_t* rs_state;                // [n_envs][2][2] = {n_filled, head}
   const lobsim_stream_t* streams;   // device array [n_streams]
   int32_t n_streams;
@@ -127,12 +127,12 @@ __device__ __forceinline__ double step_reward(const AdvParams& p, const lobsim_c
                                               double cash1, long long inv1, double p1, uint32_t& err) {
   double r;
   if (RARE && c.step_reward.kind == LOBSIM_REWARD_ROLLING_SHARPE) {
-    SharpeOut o = rolling_sharpe_step(p.rs_ring + ((size_t)env * 2 + 0) * LOBSIM_MAX_SHARPE_WINDOW, p.rs_state + ((size_t)env * 2 + 0) * 2, c.step_reward.asymmetric, cash1 + p1 * (double)inv1, lane);
+    SharpeOut o = rolling_sharpe_step(p.rs_ring + ((size_t)env * 3 + 0) * LOBSIM_MAX_SHARPE_WINDOW, p.rs_state + ((size_t)env * 2 + 0) * 2, c.step_reward.asymmetric, cash1 + p1 * (double)inv1, lane, p.rs_ring + ((size_t)env * 3 + 2) * LOBSIM_MAX_SHARPE_WINDOW);
     r = o.reward; err |= o.err;
   } else r = reward_calc(c.step_reward, cash0, inv0, p0, cash1, inv1, p1);
   if (done) {
     if (RARE && c.terminal_reward.kind == LOBSIM_REWARD_ROLLING_SHARPE) {
-      SharpeOut o = rolling_sharpe_step(p.rs_ring + ((size_t)env * 2 + 1) * LOBSIM_MAX_SHARPE_WINDOW, p.rs_state + ((size_t)env * 2 + 1) * 2, c.terminal_reward.asymmetric, cash1 + p1 * (double)inv1, lane);
+      SharpeOut o = rolling_sharpe_step(p.rs_ring + ((size_t)env * 3 + 1) * LOBSIM_MAX_SHARPE_WINDOW, p.rs_state + ((size_t)env * 2 + 1) * 2, c.terminal_reward.asymmetric, cash1 + p1 * (double)inv1, lane, p.rs_ring + ((size_t)env * 3 + 2) * LOBSIM_MAX_SHARPE_WINDOW);
       r = o.reward; err |= o.err;
     } else r = reward_calc(c.terminal_reward, cash0, inv0, p0, cash1, inv1, p1);
   }
@@ -1025,7 +1025,7 @@ int lobsim_create(const lobsim_cfg_t* cfg, int device, lobsim_t** out) {
   }
   CUDA_TRY(cudaMemset(h->blobs, 0, n * h->L.blob_bytes));
   if (cfg->step_reward.kind == LOBSIM_REWARD_ROLLING_SHARPE || cfg->terminal_reward.kind == LOBSIM_REWARD_ROLLING_SHARPE) {
-    CUDA_TRY(cudaMalloc(&h->rs_ring, n * 2 * LOBSIM_MAX_SHARPE_WINDOW * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&h->rs_ring, n * 3 * LOBSIM_MAX_SHARPE_WINDOW * sizeof(double)));
     CUDA_TRY(cudaMalloc(&h->rs_state, n * 4 * sizeof(int32_t)));
     CUDA_TRY(cudaMemset(h->rs_state, 0, n * 4 * sizeof(int32_t)));
   }

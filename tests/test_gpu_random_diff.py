@@ -35,6 +35,7 @@ def test_random_env_case(seed):
     sim = make_sim(abi.default_cfg(n_envs=n, **c["cfg_kw"]), [s])
     oracles = [Oracle(abi.default_cfg(n_envs=1, **c["cfg_kw"]), s) for _ in range(n)]
     agent, external = c["agent"], c["agent_kind"] == "external"
+    skipped = set()   # envs whose device book hit a fixed capacity (flagged): with portfolio carry-over they stay different
     for part in range(2):
         starts = (c["starts"] + part * 10).astype(np.int32)
         obs0 = sim.reset(0, starts).cpu().numpy()
@@ -56,11 +57,16 @@ def test_random_env_case(seed):
         st = sim.state()
         for env, o in enumerate(oracles):
             what = f"seed {seed} part {part} env {env}"
-            H.assert_close_vec(obs0[env], o.reset(int(starts[env])), what + " reset obs")
+            oobs0 = o.reset(int(starts[env]))
+            reset_err = int(o.state()["err"])
             oo, oa, orw, od, oi = o.rollout(ep, agent, acts[:, env] if external else None, want_info=True)
             os_ = o.state()
             if int(st["err"][env]) & CAPACITY_BITS:   # fixed capacities are a device-side limit (the oracle is unbounded): flagged, not compared
+                skipped.add(env)
+            if env in skipped:
                 continue
+            if not (reset_err & DEATH_BITS):          # (a reset onto an empty book side has no defined observation)
+                H.assert_close_vec(obs0[env], oobs0, what + " reset obs")
             assert int(st["err"][env]) == int(os_["err"]), (what, int(st["err"][env]), int(os_["err"]))
             alive = [not (int(oi[t, abi.INFO_FIELDS.index("err")]) & DEATH_BITS) for t in range(ep)]   # outputs after the exception are undefined
             for t in range(ep):
