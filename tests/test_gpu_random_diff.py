@@ -35,6 +35,11 @@ def test_random_env_case(seed):
     sim = make_sim(abi.default_cfg(n_envs=n, **c["cfg_kw"]), [s])
     oracles = [Oracle(abi.default_cfg(n_envs=1, **c["cfg_kw"]), s) for _ in range(n)]
     agent, external = c["agent"], c["agent_kind"] == "external"
+    # RollingSharpe takes exp(log(aum') - log(aum)) - 1 of AUMs around 1e9..1e12 against returns of 1e-10..1e-12: one ulp of log()
+    # (CUDA libm vs glibc vs numpy's SIMD loops) moves a return by up to 1e-3 relative, so the reward itself is only defined
+    # to ~1e-5 there; everything else keeps the 1e-6 tolerance
+    sharpe = abi.REWARD_ROLLING_SHARPE in (c["cfg_kw"]["step_reward"].kind, c["cfg_kw"]["terminal_reward"].kind)
+    rew_close = (lambda a, b: H.close(a, b, rel=1e-4)) if sharpe else H.close
     skipped = set()   # envs whose device book hit a fixed capacity (flagged): with portfolio carry-over they stay different
     for part in range(2):
         starts = (c["starts"] + part * 10).astype(np.int32)
@@ -76,7 +81,7 @@ def test_random_env_case(seed):
                     break
                 H.assert_close_vec(act[t, env], oa[t], f"{what} t {t} action")
                 H.assert_close_vec(obs[t, env], oo[t], f"{what} t {t} obs")
-                assert H.close(rew[t, env], orw[t]), (what, t, rew[t, env], orw[t])
+                assert rew_close(rew[t, env], orw[t]), (what, t, rew[t, env], orw[t])
                 assert done[t, env] == od[t], (what, t)
                 if t >= k:
                     H.assert_close_vec(info_b[t - k, env], oi[t], f"{what} t {t} info")
