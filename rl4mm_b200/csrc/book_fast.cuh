@@ -336,6 +336,106 @@ __device__ __forceinline__ void fast_order(const FastBook<LT>& fb, FastState& f,
   if (TR && is_agent && !aggregate) fast_agent_reduce(fb, side, ref & 0x7fffffffu, cur, true);
 }
 
+// ---- OrderbookSimulator.update_outer_levels (OrderbookSimulator.py:105-135) for books WITHOUT agent orders (pure replay) ----
+// One snapshot level beyond the tracked price range: central[side][price] = deque([aggregate]) -- the level's queue is replaced by
+// one aggregate order, or the level is inserted (anywhere, typically at the WORST end, i.e. the front of the arrays).  Static
+// layout, whole-side searches and shifts in 32-wide chunks, no call.
+template <class LT>
+__device__ __forceinline__ void fast_resync_level(const FastBook<LT>& fb, FastState& f, int side, int price, int vol) {
+  const int lane = fb.lane;
+  unsigned char* sb = fb.side(side);
+  const int2 c = *fb.cnt(side);
+  const int nlv = c.x, nord = c.y;
+  const int sm = -side;
+  const int tkey = (price ^ sm) - sm;                        // keys ascend from the worst to the best level on both sides
+  int j = 0, jeq = -1;
+#pragma unroll
+  for (int q = 0; q < LT::NL / 32; q++) {
+    const int i = q * 32 + lane;
+    int k = INT32_MAX;
+    if (i < nlv) k = (fb.P(sb)[i] ^ sm) - sm;
+    j += __popc(__ballot_sync(FULL_MASK, i < nlv && k < tkey));
+    const unsigned eq = __ballot_sync(FULL_MASK, i < nlv && k == tkey);
+    if (eq) jeq = q * 32 + __ffs(eq) - 1;
+  }
+  __syncwarp();
+  if (jeq >= 0) {                                            // the level exists: keep one entry, make it the aggregate
+    const int start = jeq > 0 ? (int)fb.LE(sb)[jeq - 1] : 0, end = fb.LE(sb)[jeq];
+    const int extra = end - start - 1;
+    __syncwarp();
+    if (extra > 0) {
+      for (int base = end; base < nord; base += 32) {       // entries behind the level move down by `extra`, ascending chunks
+        uint2 v = make_uint2(0u, 0u);
+        if (base + lane < nord) v = fb.O(sb)[base + lane];
+        __syncwarp();
+        if (base + lane < nord) fb.O(sb)[base + lane - extra] = v;
+        __syncwarp();
+      }
+#pragma unroll
+      for (int q = 0; q < LT::NL / 32; q++) {
+        const int i = q * 32 + lane;
+        if (i >= jeq && i < nlv) fb.LE(sb)[i] = (uint16_t)(fb.LE(sb)[i] - extra);
+      }
+    }
+    if (lane == 0) { fb.O(sb)[start] = make_uint2((unsigned)vol, LOBSIM_REF_AGGREGATE); *fb.cnt(side) = make_int2(nlv, nord - (extra > 0 ? extra : 0)); }
+    __syncwarp();
+    return;
+  }
+  if (nord >= LT::NO) { f.err |= LOBSIM_ERR_ORDER_OVERFLOW; return; }                       // same flags as the general routine
+  if (nlv >= LT::NL) { f.err |= LOBSIM_ERR_LEVEL_OVERFLOW | LOBSIM_ERR_ORDER_OVERFLOW; return; }
+  const int pos = j > 0 ? (int)fb.LE(sb)[j - 1] : 0;         // the new level's (one-entry) segment starts where level j-1 ends
+  __syncwarp();
+  for (int base = pos + ((nord - pos + 31) / 32 - 1) * 32; base >= pos; base -= 32) {   // entries [pos, nord) move up by one, descending chunks
+    uint2 v = make_uint2(0u, 0u);
+    if (base + lane < nord) v = fb.O(sb)[base + lane];
+    __syncwarp();
+    if (base + lane < nord) fb.O(sb)[base + lane + 1] = v;
+    __syncwarp();
+  }
+  for (int base = j + ((nlv - j + 31) / 32 - 1) * 32; base >= j; base -= 32) {          // levels [j, nlv) move up by one
+    int pv = 0; unsigned short ev = 0;
+    if (base + lane < nlv) { pv = fb.P(sb)[base + lane]; ev = fb.LE(sb)[base + lane]; }
+    __syncwarp();
+    if (base + lane < nlv) { fb.P(sb)[base + lane + 1] = pv; fb.LE(sb)[base + lane + 1] = (uint16_t)(ev + 1); }
+    __syncwarp();
+  }
+  if (lane == 0) {
+    fb.P(sb)[j] = price; fb.LE(sb)[j] = (uint16_t)(pos + 1);
+    fb.O(sb)[pos] = make_uint2((unsigned)vol, LOBSIM_REF_AGGREGATE);
+    *fb.cnt(side) = make_int2(nlv + 1, nord + 1);
+  }
+  __syncwarp();
+}
+
+// The whole update for a replay book: every snapshot level beyond [min_buy, max_sell] in the reference's order (buy side best ->
+// worst, then sell side), then the price-range trackers (:134-135).  `row` = the snapshot row of this second.
+template <class LT>
+__device__ __forceinline__ void fast_resync(const FastBook<LT>& fb, FastState& f, const int32_t* __restrict__ row, int L) {
+  const int lane = fb.lane;
+  BookHdr* h = reinterpret_cast<BookHdr*>(fb.blob);
+  const int min_buy = h->min_buy, max_sell = h->max_sell;   // the filter uses the range at entry (_initial_prices_filter_function)
+  for (int base = 0; base < 2 * L; base += 32) {
+    const int idx = base + lane;
+    int price = LOBSIM_NO_PRICE, vol = 0;
+    if (idx < 2 * L) { price = __ldg(&row[idx * 2]); vol = __ldg(&row[idx * 2 + 1]); }
+    unsigned hits = __ballot_sync(FULL_MASK, price != LOBSIM_NO_PRICE && (idx < L ? price < min_buy : price > max_sell));
+    while (hits) {
+      const int src = __ffs(hits) - 1;
+      hits &= hits - 1;
+      const int pr = __shfl_sync(FULL_MASK, price, src), vo = __shfl_sync(FULL_MASK, vol, src);
+      fast_resync_level(fb, f, base + src >= L ? 1 : 0, pr, vo);
+    }
+  }
+  __syncwarp();
+  if (lane == 0) {
+    const int n0 = fb.cnt(0)->x, n1 = fb.cnt(1)->x;
+    if (n0 && fb.P(fb.side(0))[0] < h->min_buy) h->min_buy = fb.P(fb.side(0))[0];
+    if (n1 && fb.P(fb.side(1))[0] > h->max_sell) h->max_sell = fb.P(fb.side(1))[0];
+  }
+  __syncwarp();
+  fast_refresh_best(fb, f);
+}
+
 // the replay form: a packed historical message
 template <class LT>
 __device__ __forceinline__ void fast_message(const FastBook<LT>& fb, FastState& f, const Layout* L, int price, int vol, uint32_t ref, uint32_t meta) {

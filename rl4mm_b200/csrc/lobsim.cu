@@ -481,9 +481,7 @@ __global__ void __launch_bounds__(128, 7) k_replay_fast(const __grid_constant__ 
           const long long sec = (long long)now_step / steps_per_sec;
           if (sec <= (long long)stp->n_seconds && stp->snap_valid[sec]) {
             const int32_t* row = stp->snapshots + (size_t)sec * 2 * c.n_levels * 2;
-            const uint32_t ed = fallback_resync(base, &p.L, lane, &ec.cfg, row, scratch, pack_errdead(f.err, f.dead));
-            f.err = ed & 0x7fffffffu; f.dead = (int)(ed >> 31);
-            fast_refresh_best(fb, f);
+            fast_resync(fb, f, row, c.n_levels);   // straight-line: a replay book holds no agent orders
           }
         }
       }
