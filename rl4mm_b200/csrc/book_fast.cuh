@@ -33,6 +33,10 @@ struct FastState {
   // tracked mode only: optional fill log (global memory); the fill counter lives in the header
   lobsim_fill_t* fill_log;
   int fill_cap;
+  // BAIL instantiations only (pure replay): instead of calling a general-routine fallback, fast_order leaves the rare order to
+  // its caller -- bail = 1: rest `bail_vol` (the whole order, or the unfilled remainder of a crossing limit order whose fills
+  // have been applied), bail = 2: cancel / delete; the caller runs the straight-line any-depth routines below
+  int bail, bail_vol;
 };
 
 template <class LT>
@@ -138,7 +142,7 @@ __device__ __forceinline__ void fast_refresh_best(const FastBook<LT>& fb, FastSt
 }
 
 // TR: fills / flows / agent orders are tracked (env kernels); TR == false is the pure replay.
-template <class LT, bool TR>
+template <class LT, bool TR, bool BAIL = false>
 __device__ __forceinline__ void fast_order(const FastBook<LT>& fb, FastState& f, const Layout* L, int type, int side, int price, int vol, uint32_t ref, bool is_agent) {
   if (!TR) is_agent = false;
   const int lane = fb.lane;
@@ -203,6 +207,7 @@ __device__ __forceinline__ void fast_order(const FastBook<LT>& fb, FastState& f,
     if (lane == 0) *fb.cnt(opp) = c;
     __syncwarp();
     if (rem > 0 && type == LOBSIM_MSG_LIMIT && !f.dead) {    // the remainder rests (Exchange.py:116-119); rare
+      if (BAIL) { f.bail = 1; f.bail_vol = rem; return; }
       const uint32_t ed = fallback_rest<TR>(fb.blob, L, lane, side, price, rem, ref, is_agent, pack_errdead(f.err, f.dead));
       f.err = ed & 0x7fffffffu; f.dead = (int)(ed >> 31);
       fast_refresh_best(fb, f);
@@ -226,6 +231,7 @@ __device__ __forceinline__ void fast_order(const FastBook<LT>& fb, FastState& f,
     int nag = 0;
     if (TR && is_agent) nag = reinterpret_cast<BookHdr*>(fb.blob)->nag[side];
     if ((!eq && (cb == 32 || nlv >= LT::NL)) || nord >= LT::NO || (TR && is_agent && nag >= LT::NA)) { // deep level or a capacity limit
+      if (BAIL) { f.bail = 1; f.bail_vol = vol; return; }
       const uint32_t ed = fallback_rest<TR>(fb.blob, L, lane, side, price, vol, ref, is_agent, pack_errdead(f.err, f.dead));
       f.err = ed & 0x7fffffffu; f.dead = (int)(ed >> 31);
       fast_refresh_best(fb, f);
@@ -276,6 +282,7 @@ __device__ __forceinline__ void fast_order(const FastBook<LT>& fb, FastState& f,
   // ---- cancellation / deletion (Exchange.py:122-147) ------------------------------------------------------------------
   if (!eq) {
     if (__popc(gt) == 32) {                                  // the level may be deeper than the 32 best
+      if (BAIL) { f.bail = 2; return; }
       const uint32_t ed = fallback_remove<TR>(fb.blob, L, lane, side, price, vol, ref, is_agent, pack_errdead(f.err, f.dead));
       f.err = ed & 0x7fffffffu; f.dead = (int)(ed >> 31);
       fast_refresh_best(fb, f);
@@ -286,6 +293,7 @@ __device__ __forceinline__ void fast_order(const FastBook<LT>& fb, FastState& f,
   const int start = j > 0 ? (int)fb.LE(sb)[j - 1] : 0, end = fb.LE(sb)[j];
   const int len = end - start;
   if (len > 32 || nord - start > 64) {                       // long queue / long shift: general path
+    if (BAIL) { f.bail = 2; return; }
     const uint32_t ed = fallback_remove<TR>(fb.blob, L, lane, side, price, vol, ref, is_agent, pack_errdead(f.err, f.dead));
     f.err = ed & 0x7fffffffu; f.dead = (int)(ed >> 31);
     fast_refresh_best(fb, f);
@@ -436,8 +444,129 @@ __device__ __forceinline__ void fast_resync(const FastBook<LT>& fb, FastState& f
   fast_refresh_best(fb, f);
 }
 
-// the replay form: a packed historical message
+// ---- the rare orders of a pure replay (no agent orders in the book), straight-line at any depth / queue length ----------------
+// whole-side level search: j = number of levels worse than `price` (insertion index), jeq = index of the level or -1
+template <class LT>
+__device__ __forceinline__ void fast_find_any(const FastBook<LT>& fb, unsigned char* sb, int side, int nlv, int price, int& j, int& jeq) {
+  const int sm = -side;
+  const int tkey = (price ^ sm) - sm;
+  j = 0; jeq = -1;
+#pragma unroll
+  for (int q = 0; q < LT::NL / 32; q++) {
+    const int i = q * 32 + fb.lane;
+    int k = INT32_MAX;
+    if (i < nlv) k = (fb.P(sb)[i] ^ sm) - sm;
+    j += __popc(__ballot_sync(FULL_MASK, i < nlv && k < tkey));
+    const unsigned eq = __ballot_sync(FULL_MASK, i < nlv && k == tkey);
+    if (eq) jeq = q * 32 + __ffs(eq) - 1;
+  }
+  __syncwarp();
+}
+// Exchange.submit_order, no-cross branch (Exchange.py:74-83) = book.cuh rest_order<false>: same result, same overflow flags
+template <class LT>
+__device__ __forceinline__ void fast_rest_any(const FastBook<LT>& fb, FastState& f, int side, int price, int vol, uint32_t ref) {
+  const int lane = fb.lane;
+  unsigned char* sb = fb.side(side);
+  const int2 c = *fb.cnt(side);
+  const int nlv = c.x, nord = c.y;
+  if (nord >= LT::NO) { f.err |= LOBSIM_ERR_ORDER_OVERFLOW; return; }
+  int j, jeq;
+  fast_find_any(fb, sb, side, nlv, price, j, jeq);
+  int nlv2 = nlv, pos;
+  if (jeq < 0) {
+    if (nlv >= LT::NL) { f.err |= LOBSIM_ERR_LEVEL_OVERFLOW; return; }
+    pos = j > 0 ? (int)fb.LE(sb)[j - 1] : 0;
+    __syncwarp();
+    for (int base = j + ((nlv - j + 31) / 32 - 1) * 32; base >= j; base -= 32) {   // levels [j, nlv) move up by one, descending chunks
+      int pv = 0; unsigned short ev = 0;
+      if (base + lane < nlv) { pv = fb.P(sb)[base + lane]; ev = fb.LE(sb)[base + lane]; }
+      __syncwarp();
+      if (base + lane < nlv) { fb.P(sb)[base + lane + 1] = pv; fb.LE(sb)[base + lane + 1] = ev; }
+      __syncwarp();
+    }
+    if (lane == 0) { fb.P(sb)[j] = price; fb.LE(sb)[j] = (uint16_t)pos; }
+    nlv2 = nlv + 1;
+    __syncwarp();
+  } else { j = jeq; pos = fb.LE(sb)[jeq]; __syncwarp(); }
+  for (int base = pos + ((nord - pos + 31) / 32 - 1) * 32; base >= pos; base -= 32) {   // entries [pos, nord) move up by one
+    uint2 v = make_uint2(0u, 0u);
+    if (base + lane < nord) v = fb.O(sb)[base + lane];
+    __syncwarp();
+    if (base + lane < nord) fb.O(sb)[base + lane + 1] = v;
+    __syncwarp();
+  }
+#pragma unroll
+  for (int q = 0; q < LT::NL / 32 + 1; q++) {               // (+1: nlv2 may be NL)
+    const int i = q * 32 + lane;
+    if (i >= j && i < nlv2) fb.LE(sb)[i] = (uint16_t)(fb.LE(sb)[i] + 1);
+  }
+  if (lane == 0) { fb.O(sb)[pos] = make_uint2((unsigned)vol, ref); *fb.cnt(side) = make_int2(nlv2, nord + 1); }
+  __syncwarp();
+  fast_refresh_best(fb, f);
+}
+// Exchange.remove_order (Exchange.py:122-147) = book.cuh remove_order<false> with a volume
+template <class LT>
+__device__ __forceinline__ void fast_remove_any(const FastBook<LT>& fb, FastState& f, int side, int price, int vol, uint32_t ref) {
+  const int lane = fb.lane;
+  unsigned char* sb = fb.side(side);
+  const int2 c = *fb.cnt(side);
+  const int nlv = c.x, nord = c.y;
+  int j, jeq;
+  fast_find_any(fb, sb, side, nlv, price, j, jeq);
+  if (jeq < 0) return;                                       // KeyError => continue, :129-132
+  const int start = jeq > 0 ? (int)fb.LE(sb)[jeq - 1] : 0, end = fb.LE(sb)[jeq];
+  int pos = -1;
+  for (int base = start; base < end; base += 32) {           // _find_queue_position :196-217
+    const int i = base + lane;
+    const unsigned m = __ballot_sync(FULL_MASK, i < end && fb.O(sb)[i < end ? i : start].y == ref);
+    if (m) { pos = base + __ffs(m) - 1; break; }
+  }
+  if (pos < 0) {
+    if (fb.O(sb)[start].y != LOBSIM_REF_AGGREGATE) return;   // already filled, :138-139
+    pos = start;                                             // initial orders remain in book, :133-137
+  }
+  const int cur = (int)fb.O(sb)[pos].x;
+  const int rv = vol < cur ? vol : cur;                      // over-size => the resting volume, :142-146
+  __syncwarp();
+  if (cur - rv > 0) { if (lane == 0) fb.O(sb)[pos].x = (unsigned)(cur - rv); __syncwarp(); return; }
+  for (int base = pos + 1; base < nord; base += 32) {       // entries behind it move down by one, ascending chunks
+    uint2 v = make_uint2(0u, 0u);
+    if (base + lane < nord) v = fb.O(sb)[base + lane];
+    __syncwarp();
+    if (base + lane < nord) fb.O(sb)[base + lane - 1] = v;
+    __syncwarp();
+  }
+  const bool level_gone = end - start == 1;
+  if (!level_gone) {
+#pragma unroll
+    for (int q = 0; q < LT::NL / 32; q++) {
+      const int i = q * 32 + lane;
+      if (i >= jeq && i < nlv) fb.LE(sb)[i] = (uint16_t)(fb.LE(sb)[i] - 1);
+    }
+    if (lane == 0) *fb.cnt(side) = make_int2(nlv, nord - 1);
+  } else {                                                   // the level disappears: levels above it move down by one
+    for (int base = jeq + 1; base < nlv; base += 32) {
+      int pv = 0; unsigned short ev = 0;
+      if (base + lane < nlv) { pv = fb.P(sb)[base + lane]; ev = fb.LE(sb)[base + lane]; }
+      __syncwarp();
+      if (base + lane < nlv) { fb.P(sb)[base + lane - 1] = pv; fb.LE(sb)[base + lane - 1] = (uint16_t)(ev - 1); }
+      __syncwarp();
+    }
+    if (lane == 0) *fb.cnt(side) = make_int2(nlv - 1, nord - 1);
+  }
+  __syncwarp();
+  fast_refresh_best(fb, f);
+}
+
+// the replay form: a packed historical message.  The common cases run in fast_order (BAIL form: no call); the rare ones (level
+// beyond the 32 best, queue longer than 32, shift longer than 64, remainder of a crossing limit order) in the any-depth routines.
 template <class LT>
 __device__ __forceinline__ void fast_message(const FastBook<LT>& fb, FastState& f, const Layout* L, int price, int vol, uint32_t ref, uint32_t meta) {
-  fast_order<LT, false>(fb, f, L, (int)(meta & 7u), (int)((meta >> 3) & 1u), price, vol, ref, false);
+  const int side = (int)((meta >> 3) & 1u);
+  fast_order<LT, false, true>(fb, f, L, (int)(meta & 7u), side, price, vol, ref, false);
+  if (f.bail) {
+    if (f.bail == 1) fast_rest_any(fb, f, side, price, f.bail_vol, ref);
+    else fast_remove_any(fb, f, side, price, vol, ref);
+    f.bail = 0;
+  }
 }

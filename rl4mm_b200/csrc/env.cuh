@@ -29,6 +29,8 @@ struct EnvConst { // what the device needs of lobsim_cfg_t, by value in the kern
   int32_t hist_off[LOBSIM_MAX_FEATURES]; // slot offset of each feature's normalisation history (norm_len slots)
   int32_t ring_stride;                   // slots per env
   int32_t action_dim, obs_dim;
+  int32_t steps_per_sec;                 // 1000000 / step_us        } precomputed on the host: 64-bit and fp64 divisions are
+  double outer_prop;                     // outer_levels / n_levels  } subroutine calls on the device, unwanted in the hot kernels
 };
 
 __device__ __forceinline__ long long now_us_of(const lobsim_stream_t& st, const lobsim_cfg_t& c, int now_step) {

@@ -416,7 +416,7 @@ __global__ void __launch_bounds__(128, 7) k_replay_fast(const __grid_constant__ 
 
   FastBook<LT> fb; fb.blob = base; fb.lane = lane;
   BookHdr* h = reinterpret_cast<BookHdr*>(base);
-  FastState f; f.err = h->err; f.dead = h->dead;
+  FastState f; f.err = h->err; f.dead = h->dead; f.bail = 0; f.bail_vol = 0;
   fast_refresh_best(fb, f);
   const lobsim_stream_t* stp = &p.streams[h->stream_id];
   const lobsim_msg_t* __restrict__ st_msgs = stp->msgs;
@@ -444,7 +444,7 @@ __global__ void __launch_bounds__(128, 7) k_replay_fast(const __grid_constant__ 
   auto wait_tile = [&]() { mbar_wait(&bars[next_wait & 1], (next_wait >> 1) & 1); next_wait++; };
   if (g < g_end_all) { issue_tile(); issue_tile(); }
   __syncwarp();
-  const int steps_per_sec = (int)(1000000 / c.step_us);
+  const int steps_per_sec = ec.steps_per_sec;
   int sub = now_step >= 0 ? now_step % steps_per_sec : 0;   // position inside the current second
 
 #pragma unroll 1
@@ -474,12 +474,12 @@ __global__ void __launch_bounds__(128, 7) k_replay_fast(const __grid_constant__ 
     if (++sub == steps_per_sec) {                            // whole second: outer-level resync, OrderbookSimulator.py:86-87
       sub = 0;
       if (c.resync && (!p.resync_last_only || t == T - 1)) {
-        const double prop = (double)c.outer_levels / (double)c.n_levels;
+        const double prop = ec.outer_prop;
         const double bb = f.best0 == INT32_MIN ? 0.0 : (double)f.best0;
         const double bs = f.best1 == INT32_MAX ? (double)INFINITY : (double)f.best1;
         if (bb < (double)h->min_buy + prop * (double)h->init_buy_range || bs > (double)h->max_sell - prop * (double)h->init_sell_range) {
-          const long long sec = (long long)now_step / steps_per_sec;
-          if (sec <= (long long)stp->n_seconds && stp->snap_valid[sec]) {
+          const int sec = now_step / steps_per_sec;
+          if (sec <= (int)stp->n_seconds && stp->snap_valid[sec]) {
             const int32_t* row = stp->snapshots + (size_t)sec * 2 * c.n_levels * 2;
             fast_resync(fb, f, row, c.n_levels);   // straight-line: a replay book holds no agent orders
           }
@@ -643,7 +643,7 @@ __global__ void __launch_bounds__(32 * LOBSIM_ENVFAST_WARPS, 16 / LOBSIM_ENVFAST
   if (g < g_end_all) { issue_tile(); issue_tile(); }
   __syncwarp();
   if (SYNC) PHASE_SYNC();
-  const int steps_per_sec = (int)(1000000 / c.step_us);
+  const int steps_per_sec = ec.steps_per_sec;
   int sub = now_step >= 0 ? now_step % steps_per_sec : 0;
 
   AgentGen gen; gen.side = 3;
@@ -710,12 +710,12 @@ __global__ void __launch_bounds__(32 * LOBSIM_ENVFAST_WARPS, 16 / LOBSIM_ENVFAST
       if (++sub == steps_per_sec) {                          // whole second: outer-level resync, OrderbookSimulator.py:86-87
         sub = 0;
         if (c.resync && (!p.resync_last_only || t == T - 1)) {
-          const double prop = (double)c.outer_levels / (double)c.n_levels;
+          const double prop = ec.outer_prop;
           const double bbd = f.best0 == INT32_MIN ? 0.0 : (double)f.best0;
           const double bsd = f.best1 == INT32_MAX ? (double)INFINITY : (double)f.best1;
           if (bbd < (double)h->min_buy + prop * (double)h->init_buy_range || bsd > (double)h->max_sell - prop * (double)h->init_sell_range) {
-            const long long sec = (long long)now_step / steps_per_sec;
-            if (sec <= (long long)stp->n_seconds && stp->snap_valid[sec]) {
+            const int sec = now_step / steps_per_sec;
+            if (sec <= (int)stp->n_seconds && stp->snap_valid[sec]) {
               const int32_t* row = stp->snapshots + (size_t)sec * 2 * c.n_levels * 2;
               const uint32_t ed = fallback_resync_tracked(base, &p.L, lane, &ec.cfg, row, scratch, pack_errdead(f.err, f.dead));
               f.err = ed & 0x7fffffffu; f.dead = (int)(ed >> 31);
@@ -1010,6 +1010,7 @@ int lobsim_create(const lobsim_cfg_t* cfg, int device, lobsim_t** out) {
   }
   h->ec.ring_stride = (slots + 1) & ~1;
   h->ec.action_dim = lobsim_action_dim(cfg); h->ec.obs_dim = lobsim_obs_dim(cfg);
+  h->ec.steps_per_sec = (int)(1000000 / cfg->step_us); h->ec.outer_prop = (double)cfg->outer_levels / (double)cfg->n_levels;
   const size_t n = (size_t)cfg->n_envs;
   CUDA_TRY(cudaMalloc(&h->blobs, n * h->L.blob_bytes));
   CUDA_TRY(cudaMalloc(&h->fstate, n * LOBSIM_MAX_FEATURES * sizeof(FeatState)));
