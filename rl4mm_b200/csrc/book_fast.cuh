@@ -1,7 +1,8 @@
 // book_fast.cuh -- the straight-line order path (k_replay_fast, k_env_fast): same semantics as process_order in
 // book.cuh, specialised for the overwhelmingly common shapes -- the touched level is among the 32 best, at most 32
 // (64 for removals) queue entries have to move, no capacity is exhausted -- as straight-line warp-wide code without
-// search / shift loops.  Anything else falls back, BEFORE mutating the book, to the general routines.
+// search / shift loops.  Anything else goes, BEFORE the book is mutated, to the any-depth routines at the end of this file
+// (chunked whole-side searches and shifts, still static layout, still no call): fast_order_full is the entry point.
 //
 // Differences from the general path, all for instruction count (the kernel is issue-bound):
 //   * the layout is a compile-time constant (StaticLayout<NL,NO,NA>), so every array access is base + immediate;
@@ -33,9 +34,8 @@ struct FastState {
   // tracked mode only: optional fill log (global memory); the fill counter lives in the header
   lobsim_fill_t* fill_log;
   int fill_cap;
-  // BAIL instantiations only (pure replay): instead of calling a general-routine fallback, fast_order leaves the rare order to
-  // its caller -- bail = 1: rest `bail_vol` (the whole order, or the unfilled remainder of a crossing limit order whose fills
-  // have been applied), bail = 2: cancel / delete; the caller runs the straight-line any-depth routines below
+  // fast_order handles the common cases and leaves the rare order to fast_order_full -- bail = 1: rest `bail_vol` (the whole
+  // order, or the unfilled remainder of a crossing limit order whose fills have been applied), bail = 2: cancel / delete
   int bail, bail_vol;
 };
 
@@ -50,34 +50,8 @@ struct FastBook {
   static __device__ __forceinline__ uint2* O(unsigned char* sb) { return reinterpret_cast<uint2*>(sb + LT::ord_off); }
 };
 
-// general-path fallbacks: run a book.cuh routine on a WarpState materialised from the header.  They are real
-// (noinline) functions taking everything BY VALUE, so that no hot-path variable has its address taken; they return
-// the updated (err | dead << 31) word and the caller re-reads the best prices from shared memory.
+// (err | dead << 31) word exchanged with the cold noinline routines of the kernels
 __device__ __forceinline__ uint32_t pack_errdead(uint32_t err, int dead) { return err | ((uint32_t)dead << 31); }
-
-template <bool TR>
-__device__ __noinline__ uint32_t fallback_rest(unsigned char* blob, const Layout* L, int lane, int side, int price, int vol, uint32_t ref, bool is_agent, uint32_t errdead) {
-  Book b; b.blob = blob; b.L = *L; b.lane = lane;
-  WarpState w;
-  __syncwarp();
-  load_state<TR>(b, w);
-  w.err = errdead & 0x7fffffffu; w.dead = (int)(errdead >> 31); w.fill_log = nullptr; w.fill_cap = 0; w.n_fills = 0;
-  rest_order<TR>(b, w, side, price, vol, ref, is_agent);
-  store_state<TR>(b, w);
-  return pack_errdead(w.err, w.dead);
-}
-// (no fills can result from a removal, so the general routine's WarpState flow counters stay zero)
-template <bool TR>
-__device__ __noinline__ uint32_t fallback_remove(unsigned char* blob, const Layout* L, int lane, int side, int price, int vol, uint32_t ref, bool is_agent, uint32_t errdead) {
-  Book b; b.blob = blob; b.L = *L; b.lane = lane;
-  WarpState w;
-  __syncwarp();
-  load_state<TR>(b, w);
-  w.err = errdead & 0x7fffffffu; w.dead = (int)(errdead >> 31); w.fill_log = nullptr; w.fill_cap = 0; w.n_fills = 0;
-  remove_order<TR>(b, w, side, price, vol, true, ref, is_agent);
-  store_state<TR>(b, w);
-  return pack_errdead(w.err, w.dead);
-}
 
 // ---- tracked mode: fills -> per-step flow, portfolio (HOE.py:280-289) and the optional fill log; all by lane 0 on the
 //      shared-memory header --------------------------------------------------------------------------------------------
@@ -142,8 +116,8 @@ __device__ __forceinline__ void fast_refresh_best(const FastBook<LT>& fb, FastSt
 }
 
 // TR: fills / flows / agent orders are tracked (env kernels); TR == false is the pure replay.
-template <class LT, bool TR, bool BAIL = false>
-__device__ __forceinline__ void fast_order(const FastBook<LT>& fb, FastState& f, const Layout* L, int type, int side, int price, int vol, uint32_t ref, bool is_agent) {
+template <class LT, bool TR>
+__device__ __forceinline__ void fast_order(const FastBook<LT>& fb, FastState& f, int type, int side, int price, int vol, uint32_t ref, bool is_agent) {
   if (!TR) is_agent = false;
   const int lane = fb.lane;
   if (vol <= 0) { f.err |= LOBSIM_ERR_BAD_VOLUME; return; }
@@ -207,10 +181,7 @@ __device__ __forceinline__ void fast_order(const FastBook<LT>& fb, FastState& f,
     if (lane == 0) *fb.cnt(opp) = c;
     __syncwarp();
     if (rem > 0 && type == LOBSIM_MSG_LIMIT && !f.dead) {    // the remainder rests (Exchange.py:116-119); rare
-      if (BAIL) { f.bail = 1; f.bail_vol = rem; return; }
-      const uint32_t ed = fallback_rest<TR>(fb.blob, L, lane, side, price, rem, ref, is_agent, pack_errdead(f.err, f.dead));
-      f.err = ed & 0x7fffffffu; f.dead = (int)(ed >> 31);
-      fast_refresh_best(fb, f);
+      f.bail = 1; f.bail_vol = rem;                        // -> fast_rest_any (fast_order_full)
     }
     return;
   }
@@ -231,10 +202,7 @@ __device__ __forceinline__ void fast_order(const FastBook<LT>& fb, FastState& f,
     int nag = 0;
     if (TR && is_agent) nag = reinterpret_cast<BookHdr*>(fb.blob)->nag[side];
     if ((!eq && (cb == 32 || nlv >= LT::NL)) || nord >= LT::NO || (TR && is_agent && nag >= LT::NA)) { // deep level or a capacity limit
-      if (BAIL) { f.bail = 1; f.bail_vol = vol; return; }
-      const uint32_t ed = fallback_rest<TR>(fb.blob, L, lane, side, price, vol, ref, is_agent, pack_errdead(f.err, f.dead));
-      f.err = ed & 0x7fffffffu; f.dead = (int)(ed >> 31);
-      fast_refresh_best(fb, f);
+      f.bail = 1; f.bail_vol = vol;                        // -> fast_rest_any (fast_order_full)
       return;
     }
     int j, pos;
@@ -282,10 +250,7 @@ __device__ __forceinline__ void fast_order(const FastBook<LT>& fb, FastState& f,
   // ---- cancellation / deletion (Exchange.py:122-147) ------------------------------------------------------------------
   if (!eq) {
     if (__popc(gt) == 32) {                                  // the level may be deeper than the 32 best
-      if (BAIL) { f.bail = 2; return; }
-      const uint32_t ed = fallback_remove<TR>(fb.blob, L, lane, side, price, vol, ref, is_agent, pack_errdead(f.err, f.dead));
-      f.err = ed & 0x7fffffffu; f.dead = (int)(ed >> 31);
-      fast_refresh_best(fb, f);
+      f.bail = 2;                                          // -> fast_remove_any (fast_order_full)
     }
     return;                                                  // level absent: nothing to do (:129-132)
   }
@@ -293,10 +258,7 @@ __device__ __forceinline__ void fast_order(const FastBook<LT>& fb, FastState& f,
   const int start = j > 0 ? (int)fb.LE(sb)[j - 1] : 0, end = fb.LE(sb)[j];
   const int len = end - start;
   if (len > 32 || nord - start > 64) {                       // long queue / long shift: general path
-    if (BAIL) { f.bail = 2; return; }
-    const uint32_t ed = fallback_remove<TR>(fb.blob, L, lane, side, price, vol, ref, is_agent, pack_errdead(f.err, f.dead));
-    f.err = ed & 0x7fffffffu; f.dead = (int)(ed >> 31);
-    fast_refresh_best(fb, f);
+    f.bail = 2;                                            // -> fast_remove_any (fast_order_full)
     return;
   }
   uint2 e = make_uint2(0u, 0xffffffffu);
@@ -463,12 +425,16 @@ __device__ __forceinline__ void fast_find_any(const FastBook<LT>& fb, unsigned c
   __syncwarp();
 }
 // Exchange.submit_order, no-cross branch (Exchange.py:74-83) = book.cuh rest_order<false>: same result, same overflow flags
-template <class LT>
-__device__ __forceinline__ void fast_rest_any(const FastBook<LT>& fb, FastState& f, int side, int price, int vol, uint32_t ref) {
+template <class LT, bool TR>
+__device__ __forceinline__ void fast_rest_any(const FastBook<LT>& fb, FastState& f, int side, int price, int vol, uint32_t ref, bool is_agent) {
+  if (!TR) is_agent = false;
   const int lane = fb.lane;
   unsigned char* sb = fb.side(side);
+  BookHdr* h = reinterpret_cast<BookHdr*>(fb.blob);
   const int2 c = *fb.cnt(side);
   const int nlv = c.x, nord = c.y;
+  int nag = 0;
+  if (TR && is_agent) { nag = h->nag[side]; if (nag >= LT::NA) { f.err |= LOBSIM_ERR_AGENT_OVERFLOW; return; } }
   if (nord >= LT::NO) { f.err |= LOBSIM_ERR_ORDER_OVERFLOW; return; }
   int j, jeq;
   fast_find_any(fb, sb, side, nlv, price, j, jeq);
@@ -488,6 +454,17 @@ __device__ __forceinline__ void fast_rest_any(const FastBook<LT>& fb, FastState&
     nlv2 = nlv + 1;
     __syncwarp();
   } else { j = jeq; pos = fb.LE(sb)[jeq]; __syncwarp(); }
+  if (TR && is_agent) {   // OrderIdConvertor.add_internal_id_to_order_and_track + internal book append (after the level exists)
+    const uint32_t id = h->next_agent_id;
+    ref = LOBSIM_REF_AGENT | id;
+    __syncwarp();
+    if (lane == 0) {
+      int32_t* ap = reinterpret_cast<int32_t*>(fb.blob + LT::agent_off + side * LT::NA * 12);
+      ap[nag] = price; ap[LT::NA + nag] = vol; reinterpret_cast<uint32_t*>(ap)[2 * LT::NA + nag] = id;
+      h->nag[side] = nag + 1; h->next_agent_id = id + 1;
+    }
+    __syncwarp();
+  }
   for (int base = pos + ((nord - pos + 31) / 32 - 1) * 32; base >= pos; base -= 32) {   // entries [pos, nord) move up by one
     uint2 v = make_uint2(0u, 0u);
     if (base + lane < nord) v = fb.O(sb)[base + lane];
@@ -505,8 +482,9 @@ __device__ __forceinline__ void fast_rest_any(const FastBook<LT>& fb, FastState&
   fast_refresh_best(fb, f);
 }
 // Exchange.remove_order (Exchange.py:122-147) = book.cuh remove_order<false> with a volume
-template <class LT>
-__device__ __forceinline__ void fast_remove_any(const FastBook<LT>& fb, FastState& f, int side, int price, int vol, uint32_t ref) {
+template <class LT, bool TR>
+__device__ __forceinline__ void fast_remove_any(const FastBook<LT>& fb, FastState& f, int side, int price, int vol, uint32_t ref, bool is_agent) {
+  if (!TR) is_agent = false;
   const int lane = fb.lane;
   unsigned char* sb = fb.side(side);
   const int2 c = *fb.cnt(side);
@@ -521,14 +499,20 @@ __device__ __forceinline__ void fast_remove_any(const FastBook<LT>& fb, FastStat
     const unsigned m = __ballot_sync(FULL_MASK, i < end && fb.O(sb)[i < end ? i : start].y == ref);
     if (m) { pos = base + __ffs(m) - 1; break; }
   }
+  bool aggregate = false;
   if (pos < 0) {
     if (fb.O(sb)[start].y != LOBSIM_REF_AGGREGATE) return;   // already filled, :138-139
-    pos = start;                                             // initial orders remain in book, :133-137
+    pos = start; aggregate = true;                           // initial orders remain in book, :133-137
   }
   const int cur = (int)fb.O(sb)[pos].x;
   const int rv = vol < cur ? vol : cur;                      // over-size => the resting volume, :142-146
   __syncwarp();
-  if (cur - rv > 0) { if (lane == 0) fb.O(sb)[pos].x = (unsigned)(cur - rv); __syncwarp(); return; }
+  if (cur - rv > 0) {
+    if (lane == 0) fb.O(sb)[pos].x = (unsigned)(cur - rv);
+    __syncwarp();
+    if (TR && is_agent && !aggregate) fast_agent_reduce(fb, side, ref & 0x7fffffffu, rv, false);
+    return;
+  }
   for (int base = pos + 1; base < nord; base += 32) {       // entries behind it move down by one, ascending chunks
     uint2 v = make_uint2(0u, 0u);
     if (base + lane < nord) v = fb.O(sb)[base + lane];
@@ -555,18 +539,26 @@ __device__ __forceinline__ void fast_remove_any(const FastBook<LT>& fb, FastStat
     if (lane == 0) *fb.cnt(side) = make_int2(nlv - 1, nord - 1);
   }
   __syncwarp();
+  if (TR && is_agent && !aggregate) fast_agent_reduce(fb, side, ref & 0x7fffffffu, rv, false);
   fast_refresh_best(fb, f);
 }
 
-// the replay form: a packed historical message.  The common cases run in fast_order (BAIL form: no call); the rare ones (level
-// beyond the 32 best, queue longer than 32, shift longer than 64, remainder of a crossing limit order) in the any-depth routines.
-template <class LT>
-__device__ __forceinline__ void fast_message(const FastBook<LT>& fb, FastState& f, const Layout* L, int price, int vol, uint32_t ref, uint32_t meta) {
-  const int side = (int)((meta >> 3) & 1u);
-  fast_order<LT, false, true>(fb, f, L, (int)(meta & 7u), side, price, vol, ref, false);
+// One order through the straight-line path: the common cases in fast_order (no call), the rare ones (level beyond the
+// 32 best, queue longer than 32, shift longer than 64, remainder of a crossing limit order, capacity limits) in the any-depth
+// routines above.  This is the only entry point the kernels use.
+template <class LT, bool TR>
+__device__ __forceinline__ void fast_order_full(const FastBook<LT>& fb, FastState& f, int type, int side, int price, int vol, uint32_t ref, bool is_agent) {
+  fast_order<LT, TR>(fb, f, type, side, price, vol, ref, is_agent);
   if (f.bail) {
-    if (f.bail == 1) fast_rest_any(fb, f, side, price, f.bail_vol, ref);
-    else fast_remove_any(fb, f, side, price, vol, ref);
+    if (f.bail == 1) fast_rest_any<LT, TR>(fb, f, side, price, f.bail_vol, ref, is_agent);
+    else fast_remove_any<LT, TR>(fb, f, side, price, vol, ref, is_agent);
     f.bail = 0;
   }
+}
+
+// the replay form: a packed historical message.  The common cases run in fast_order (no call); the rare ones (level
+// beyond the 32 best, queue longer than 32, shift longer than 64, remainder of a crossing limit order) in the any-depth routines.
+template <class LT>
+__device__ __forceinline__ void fast_message(const FastBook<LT>& fb, FastState& f, int price, int vol, uint32_t ref, uint32_t meta) {
+  fast_order_full<LT, false>(fb, f, (int)(meta & 7u), (int)((meta >> 3) & 1u), price, vol, ref, false);
 }

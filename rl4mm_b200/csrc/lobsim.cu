@@ -382,17 +382,6 @@ __global__ void __launch_bounds__(128, kEnv ? LOBSIM_ENV_MIN_BLOCKS : 4) k_advan
 //  Used by lobsim_replay when no fill log is requested, no agent order can be resting and the book capacities match
 //  one of the compiled StaticLayouts.  72 registers => 7 CTAs x 4 warps = 28 books resident per SM.
 // ====================================================================================================================
-__device__ __noinline__ uint32_t fallback_resync(unsigned char* blob, const Layout* L, int lane, const lobsim_cfg_t* c, const int32_t* row, int2* scratch, uint32_t errdead) {
-  Book b; b.blob = blob; b.L = *L; b.lane = lane;
-  WarpState w;
-  __syncwarp();
-  load_state<false>(b, w);
-  w.err = errdead & 0x7fffffffu; w.dead = (int)(errdead >> 31); w.fill_log = nullptr; w.fill_cap = 0; w.n_fills = 0;
-  update_outer_levels_impl<false>(b, w, *c, row, scratch);
-  store_state<false>(b, w);
-  return pack_errdead(w.err, w.dead);
-}
-
 template <class LT>
 __global__ void __launch_bounds__(128, 7) k_replay_fast(const __grid_constant__ AdvParams p, const __grid_constant__ EnvConst ec) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -462,7 +451,7 @@ __global__ void __launch_bounds__(128, 7) k_replay_fast(const __grid_constant__ 
 #pragma unroll 1
       for (unsigned i = 0; i < cnt; i++) {
         const uint4 m = mp[i];
-        fast_message(fb, f, &p.L, (int)m.x, (int)m.y, m.z, m.w);
+        fast_message(fb, f, (int)m.x, (int)m.y, m.z, m.w);
         if (f.dead) break;
       }
       if (f.dead) break;
@@ -567,7 +556,7 @@ __global__ void __launch_bounds__(32 * LOBSIM_ENVFAST_WARPS, 16 / LOBSIM_ENVFAST
   FastBook<LT> fb; fb.blob = base; fb.lane = lane;
   Book b; b.blob = base; b.L = p.L; b.lane = lane;
   BookHdr* h = reinterpret_cast<BookHdr*>(base);
-  FastState f; f.err = h->err; f.dead = h->dead;
+  FastState f; f.err = h->err; f.dead = h->dead; f.bail = 0; f.bail_vol = 0;
   f.fill_log = p.fill_log ? p.fill_log + (size_t)env * p.fill_cap : nullptr; f.fill_cap = p.fill_cap;
   if (lane == 0) h->n_fills = 0;
   const int F = c.n_features;
@@ -702,7 +691,7 @@ __global__ void __launch_bounds__(32 * LOBSIM_ENVFAST_WARPS, 16 / LOBSIM_ENVFAST
           g++;
           if (g % MSG_TILE == 0) { __syncwarp(); issue_tile(); }
         }
-        if (!f.dead) fast_order<LT, true>(fb, f, &p.L, type, side, oprice, vol, ref, is_agent);
+        if (!f.dead) fast_order_full<LT, true>(fb, f, type, side, oprice, vol, ref, is_agent);
       }
     }
     if (!f.dead) {
