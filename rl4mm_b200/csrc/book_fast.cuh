@@ -556,6 +556,62 @@ __device__ __forceinline__ void fast_order_full(const FastBook<LT>& fb, FastStat
   }
 }
 
+// update_outer_levels for a book WITH agent orders (env kernels), OrderbookSimulator.py:105-135: as fast_resync, plus -- the
+// agent's orders at an overwritten price are cancelled first (:116-129) and re-submitted, behind the new aggregate, after all
+// levels are done (:132-133, a normal limit order of the agent: it may cross).  scratch: per-warp int2[2*NA] = {price | side, vol}.
+template <class LT>
+__device__ __forceinline__ void fast_resync_tracked(const FastBook<LT>& fb, FastState& f, const int32_t* __restrict__ row, int L, int2* scratch) {
+  const int lane = fb.lane;
+  BookHdr* h = reinterpret_cast<BookHdr*>(fb.blob);
+  const int min_buy = h->min_buy, max_sell = h->max_sell;
+  int nrepl = 0, nrepl_buy = -1;
+  for (int base = 0; base < 2 * L; base += 32) {
+    const int idx = base + lane;
+    int price = LOBSIM_NO_PRICE, vol = 0;
+    if (idx < 2 * L) { price = __ldg(&row[idx * 2]); vol = __ldg(&row[idx * 2 + 1]); }
+    unsigned hits = __ballot_sync(FULL_MASK, price != LOBSIM_NO_PRICE && (idx < L ? price < min_buy : price > max_sell));
+    while (hits) {
+      const int src = __ffs(hits) - 1;
+      hits &= hits - 1;
+      const int pr = __shfl_sync(FULL_MASK, price, src), vo = __shfl_sync(FULL_MASK, vol, src);
+      const int side = base + src >= L ? 1 : 0;
+      if (side == 1 && nrepl_buy < 0) nrepl_buy = nrepl;       // everything saved so far belongs to the buy side
+      const int32_t* ap = reinterpret_cast<const int32_t*>(fb.blob + LT::agent_off + side * LT::NA * 12);
+      const int32_t* av = ap + LT::NA;
+      const uint32_t* ai = reinterpret_cast<const uint32_t*>(ap + 2 * LT::NA);
+      for (int i = 0; i < h->nag[side];) {
+        const int p_i = ap[i], v_i = av[i];
+        const uint32_t id = ai[i];
+        __syncwarp();
+        if (p_i != pr) { i++; continue; }
+        if (lane == 0) scratch[nrepl] = make_int2(pr, v_i);
+        nrepl++;
+        const int before = h->nag[side];
+        fast_order_full<LT, true>(fb, f, LOBSIM_MSG_CANCEL, side, pr, v_i, LOBSIM_REF_AGENT | id, true);
+        __syncwarp();
+        if (h->nag[side] == before) fast_agent_reduce(fb, side, id, 0, true);   // keep internal and central consistent
+        __syncwarp();
+      }
+      fast_resync_level(fb, f, side, pr, vo);
+    }
+  }
+  if (nrepl_buy < 0) nrepl_buy = nrepl;
+  __syncwarp();
+  for (int i = 0; i < nrepl; i++) {                          // :132-133
+    const int2 r = scratch[i];
+    __syncwarp();
+    fast_order_full<LT, true>(fb, f, LOBSIM_MSG_LIMIT, i < nrepl_buy ? 0 : 1, r.x, r.y, 0u, true);
+  }
+  __syncwarp();
+  if (lane == 0) {
+    const int n0 = fb.cnt(0)->x, n1 = fb.cnt(1)->x;
+    if (n0 && fb.P(fb.side(0))[0] < h->min_buy) h->min_buy = fb.P(fb.side(0))[0];
+    if (n1 && fb.P(fb.side(1))[0] > h->max_sell) h->max_sell = fb.P(fb.side(1))[0];
+  }
+  __syncwarp();
+  fast_refresh_best(fb, f);
+}
+
 // the replay form: a packed historical message.  The common cases run in fast_order (no call); the rare ones (level
 // beyond the 32 best, queue longer than 32, shift longer than 64, remainder of a crossing limit order) in the any-depth routines.
 template <class LT>

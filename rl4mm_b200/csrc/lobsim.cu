@@ -490,16 +490,6 @@ __global__ void __launch_bounds__(128, 7) k_replay_fast(const __grid_constant__ 
 //  the env fast kernel: k_advance<true,true> with the straight-line tracked order path (book_fast.cuh fast_order<LT,true>)
 //  and all per-env scalars (counters, portfolio, per-step flow) in the shared-memory header instead of registers.
 // ====================================================================================================================
-__device__ __noinline__ uint32_t fallback_resync_tracked(unsigned char* blob, const Layout* L, int lane, const lobsim_cfg_t* c, const int32_t* row, int2* scratch, uint32_t errdead) {
-  Book b; b.blob = blob; b.L = *L; b.lane = lane;
-  WarpState w;
-  __syncwarp();
-  load_state<true>(b, w);
-  w.err = errdead & 0x7fffffffu; w.dead = (int)(errdead >> 31); w.fill_log = nullptr; w.fill_cap = 0; w.n_fills = 0;
-  update_outer_levels_impl<true>(b, w, *c, row, scratch);
-  store_state<true>(b, w);
-  return pack_errdead(w.err, w.dead);
-}
 __device__ __noinline__ uint32_t reset_book_cold(unsigned char* blob, const Layout* L, int lane, const lobsim_cfg_t* c, const lobsim_stream_t* st, int stream_id, int start_step) {
   Book b; b.blob = blob; b.L = *L; b.lane = lane;
   WarpState w;
@@ -706,9 +696,7 @@ __global__ void __launch_bounds__(32 * LOBSIM_ENVFAST_WARPS, 16 / LOBSIM_ENVFAST
             const int sec = now_step / steps_per_sec;
             if (sec <= (int)stp->n_seconds && stp->snap_valid[sec]) {
               const int32_t* row = stp->snapshots + (size_t)sec * 2 * c.n_levels * 2;
-              const uint32_t ed = fallback_resync_tracked(base, &p.L, lane, &ec.cfg, row, scratch, pack_errdead(f.err, f.dead));
-              f.err = ed & 0x7fffffffu; f.dead = (int)(ed >> 31);
-              fast_refresh_best(fb, f);
+              fast_resync_tracked(fb, f, row, c.n_levels, scratch);
             }
           }
         }
