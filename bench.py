@@ -479,7 +479,7 @@ def main():
                      "note": "16 B per env-message + 4 B per env-step + 2 x 1216 B book state per book per launch; "
                              "all books of a GPU replay the same stream, so DRAM traffic (ncu) is far BELOW the "
                              "algorithmic bytes (L2 serves the other 4095 readers); per-book processing is serially "
-                             "dependent, so the kernel is instruction-issue bound (73% issue-slot utilisation, 112 "
+                             "dependent, so the kernel is instruction-issue bound (75% issue-slot utilisation, 110 "
                              "warp instructions per message), not HBM bound (see DESIGN.md section 3)"},
     }
     if rank == 0 and not args.no_cpu_baseline and world == 1:
