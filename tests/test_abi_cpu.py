@@ -261,3 +261,39 @@ def test_get_sharpe_matches_reference_formula():
         assert abs(got[i] - np.mean(r) / (np.std(r, ddof=1) + sys.float_info.min)) < 1e-12
     with pytest.raises(Exception):
         get_sharpe(np.array([1.0, 0.0, 2.0]))
+
+
+def test_weighted_midprice_offsets_match_info_calculator():
+    """evaluation.weighted_midprice_offsets (batched over [T, N, A]) == SimpleInfoCalculator's weighted_midprice_offset
+    (InfoCalculators.py:44-50) evaluated action by action."""
+    from rl4mm_b200 import evaluation
+    from rl4mm_b200.gym import BetaOrderDistributor, SimpleInfoCalculator
+
+    rng = np.random.default_rng(5)
+    acts = rng.uniform(0.0, 10.0, size=(6, 3, 4))
+    dist = BetaOrderDistributor(10)
+    got = evaluation.weighted_midprice_offsets(acts, dist)
+    st = np.zeros(3, dtype=abi.ENV_STATE_DTYPE)
+    st["best_buy"], st["best_sell"], st["price"], st["cash"] = 999900, 1000100, 1e6, 1e3
+    calc = SimpleInfoCalculator(order_distributor=dist)
+    for t in range(6):
+        info = calc.calculate(st, acts[t])
+        assert np.allclose(info["weighted_midprice_offset"], got[t], rtol=0, atol=1e-12)
+
+
+def test_episode_summary_shapes_and_reference_quirks():
+    """append_to_episode_summary_dict quirks (utils.py:146-190): mean action drops its LAST component, one entry per env."""
+    from rl4mm_b200 import evaluation
+    from rl4mm_b200.gym import BetaOrderDistributor
+
+    T, N = 5, 3
+    rng = np.random.default_rng(1)
+    act, rew = rng.uniform(0, 10, size=(T, N, 4)), rng.normal(size=(T, N))
+    info = np.zeros((T, N, abi.INFO_DIM))
+    info[..., abi.INFO_FIELDS.index("aum")] = 1000.0 + np.arange(T)[:, None]
+    info[..., abi.INFO_FIELDS.index("inventory")] = np.arange(N)[None, :]
+    esd = evaluation.episode_summary_from_rollout(act, rew, info, BetaOrderDistributor(10))
+    assert set(esd) == set(evaluation.SUMMARY_KEYS) and all(len(v) == N for v in esd.values())
+    assert esd["actions"][1].shape == (3,) and np.allclose(esd["actions"][1], act[:, 1, :].mean(axis=0)[:-1])
+    assert esd["inventory"][2] == 2.0 and np.allclose(esd["rewards"][0], rew[:, 0].mean())
+    assert np.isfinite(evaluation.get_sharpe(np.stack(esd["equity_curves"]))).all()
