@@ -640,11 +640,7 @@ __global__ void __launch_bounds__(32 * LOBSIM_ENVFAST_WARPS, 16 / LOBSIM_ENVFAST
         const double* a = p.actions_in + ((size_t)t * p.n_sel + sel) * ec.action_dim;
         if (lane < 5) act_sm[lane] = lane < ec.action_dim ? __ldg(&a[lane]) : 0.0;
       } else {
-#ifndef LOBSIM_EXPERIMENT_NO_AGENTS
         const lobsim_agent_t* agp = p.agents ? p.agents + sel : &p.agent;
-#else
-        const lobsim_agent_t* agp = &p.agent;
-#endif
         const double inv_obs = __shfl_sync(FULL_MASK, feat_cur, agp->inventory_index & 31);
         if (lane == 0) agent_action_cold(agp, inv_obs, act_sm);
       }
@@ -726,9 +722,7 @@ __global__ void __launch_bounds__(32 * LOBSIM_ENVFAST_WARPS, 16 / LOBSIM_ENVFAST
         if (p.rew) p.rew[(size_t)t * p.n_sel + sel] = r;
         if (p.done) p.done[(size_t)t * p.n_sel + sel] = d ? 1 : 0;
       }
-#ifndef LOBSIM_EXPERIMENT_NO_INFO
       if (p.info) write_info(p.info + ((size_t)t * p.n_sel + sel) * LOBSIM_INFO_DIM, lane, v, cash1, inv1, f.err);
-#endif
     }
   }
   if (T == 0 && p.obs && p.reset_mode == 2) { // reset with no warm-up: obs straight after _reset_features
