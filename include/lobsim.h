@@ -345,6 +345,18 @@ int lobsim_action_dim(const lobsim_cfg_t* cfg);
 /* number of kernel launches issued by this handle so far (bench.py reports it as gpu_launches) */
 int64_t lobsim_launch_count(lobsim_t* h);
 
+/* which kernel family serves this handle: the straight-line static-layout kernels exist for the capacity triples
+ * {max_levels_per_side, max_orders_per_side, max_agent_orders} listed in rl4mm_b200/csrc/layouts.h; every other triple
+ * (and LOBSIM_FORCE_GENERAL=1) runs on the general runtime-layout kernel -- identical results, about 2-3x the
+ * instructions per order.  lobsim_create prints one warning per process when it has to select the general kernel.   */
+#define LOBSIM_PATH_GENERAL 0
+#define LOBSIM_PATH_FAST 1
+int lobsim_kernel_path(lobsim_t* h);
+
+/* sha256 (hex) of the sources (rl4mm_b200/csrc/ and include/) this library was built from; rl4mm_b200/_lib.py compares
+ * it with the sources next to it, so a stale binary cannot be loaded silently.                                     */
+const char* lobsim_source_hash(void);
+
 #ifdef __cplusplus
 }
 #endif

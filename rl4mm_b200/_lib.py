@@ -58,12 +58,20 @@ def lib():
         "lobsim_obs_dim": (C.c_int, [C.POINTER(abi.Cfg)]),
         "lobsim_action_dim": (C.c_int, [C.POINTER(abi.Cfg)]),
         "lobsim_launch_count": (i64, [vp]),
+        "lobsim_kernel_path": (C.c_int, [vp]),
+        "lobsim_source_hash": (C.c_char_p, []),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
         fn.restype, fn.argtypes = res, args
     if L.lobsim_abi_version() != abi.ABI_VERSION:
         raise LobsimError("liblobsim.so ABI version mismatch: rebuild")
+    from .build import source_hash
+
+    built_from, here = L.lobsim_source_hash().decode(), source_hash()
+    if built_from != here:
+        raise LobsimError(f"{_NATIVE} was built from other sources (stamp {built_from[:12]}, tree {here[:12]}): rebuild "
+                          "(python -m rl4mm_b200.build, or __graft_entry__.build())")
     _LIB = L
     return L
 
@@ -73,7 +81,7 @@ EXPORTED_SYMBOLS = [
     "lobsim_load_stream", "lobsim_reset", "lobsim_step", "lobsim_step_host", "lobsim_rollout", "lobsim_rollout_info", "lobsim_rollout_agents", "lobsim_replay",
     "lobsim_replay_host", "lobsim_forward_step", "lobsim_set_book", "lobsim_reset_book", "lobsim_process_orders", "lobsim_dump_book",
     "lobsim_dump_agent_orders", "lobsim_get_state", "lobsim_get_state_dev", "lobsim_get_fills", "lobsim_errors",
-    "lobsim_obs_dim", "lobsim_action_dim", "lobsim_launch_count",
+    "lobsim_obs_dim", "lobsim_action_dim", "lobsim_launch_count", "lobsim_kernel_path", "lobsim_source_hash",
 ]
 
 

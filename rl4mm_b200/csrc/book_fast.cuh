@@ -56,7 +56,7 @@ __device__ __forceinline__ uint32_t pack_errdead(uint32_t err, int dead) { retur
 // ---- tracked mode: fills -> per-step flow, portfolio (HOE.py:280-289) and the optional fill log; all by lane 0 on the
 //      shared-memory header --------------------------------------------------------------------------------------------
 // (real functions with by-value arguments: one copy of each in the instruction cache, no address-taken locals)
-__device__ __noinline__ void fast_record_fn(unsigned char* blob, int lane, lobsim_fill_t* fill_log, int fill_cap, int list, int dir, int price, int vol, int is_market, uint32_t ref) {
+static __device__ __noinline__ void fast_record_fn(unsigned char* blob, int lane, lobsim_fill_t* fill_log, int fill_cap, int list, int dir, int price, int vol, int is_market, uint32_t ref) {
   if (lane == 0) {
     BookHdr* h = reinterpret_cast<BookHdr*>(blob);
     if (list == 0) { // FilledOrders.internal
@@ -78,7 +78,7 @@ __device__ __forceinline__ void fast_record(const FastBook<LT>& fb, FastState& f
 }
 
 // the agent's order `id` loses v (or everything): Exchange.internal_orderbook mirror.  NA <= 64.
-__device__ __noinline__ void fast_agent_reduce_fn(unsigned char* blob, int lane, int agent_off, int NA, int side, uint32_t id, int v, int full) {
+static __device__ __noinline__ void fast_agent_reduce_fn(unsigned char* blob, int lane, int agent_off, int NA, int side, uint32_t id, int v, int full) {
   BookHdr* h = reinterpret_cast<BookHdr*>(blob);
   int32_t* ap = reinterpret_cast<int32_t*>(blob + agent_off + side * NA * 12);
   int32_t* av = ap + NA;

@@ -106,7 +106,7 @@ __device__ __forceinline__ void update_outer_levels_impl(const Book& b, WarpStat
 
 // cold wrapper: a real function call keeps the second copy of the book routines out of the kernel's hot code
 template <bool TR>
-__device__ __noinline__ WarpState update_outer_levels(const Book b, WarpState w, const lobsim_cfg_t* c, const int32_t* row, int2* scratch) {
+static __device__ __noinline__ WarpState update_outer_levels(const Book b, WarpState w, const lobsim_cfg_t* c, const int32_t* row, int2* scratch) {
   update_outer_levels_impl<TR>(b, w, *c, row, scratch);
   return w;
 }
@@ -160,14 +160,14 @@ __device__ __forceinline__ void init_book_from_snapshot(const Book& b, WarpState
   __syncwarp();
 }
 
-__device__ __noinline__ WarpState init_book_cold(const Book b, WarpState w, const lobsim_cfg_t* c, const lobsim_stream_t* st, int stream_id, int start_step) {
+static __device__ __noinline__ WarpState init_book_cold(const Book b, WarpState w, const lobsim_cfg_t* c, const lobsim_stream_t* st, int stream_id, int start_step) {
   init_book_from_snapshot(b, w, *c, *st, stream_id, start_step);
   return w;
 }
 
 // ---- BetaOrderDistributor, rl4mm/gym/action_interpretation/OrderDistributors.py:23-56 ----------------------------
 // lane k < Q returns the lot size of quote level k.  The sum follows numpy's pairwise summation order.
-__device__ __noinline__ int beta_ladder_lane(double a, double bpar, int Q, int active_volume, int lane) {
+static __device__ __noinline__ int beta_ladder_lane(double a, double bpar, int Q, int active_volume, int lane) {
   double x = 1.0 / (double)Q * ((double)lane + 0.5);
   double A = -INFINITY;
   if (lane < Q) {
@@ -217,7 +217,7 @@ struct AgentGen {
 };
 
 // Cold (noinline, everything by value): the fp64 ladder math must not inflate the register budget of the hot loop.
-__device__ __noinline__ AgentGen agent_prepare(const Book b, int nlv0, int nlv1, int nag0, int nag1, long long inventory, const EnvConst* ecp,
+static __device__ __noinline__ AgentGen agent_prepare(const Book b, int nlv0, int nlv1, int nag0, int nag1, long long inventory, const EnvConst* ecp,
                                                double a0, double a1, double a2, double a3, double a4) {
   const EnvConst& ec = *ecp;
   const lobsim_cfg_t& c = ec.cfg;
@@ -501,7 +501,7 @@ __device__ __forceinline__ void feature_update_raw(const lobsim_feature_t& fc, F
 //   * noise-dominated window (|std| <= 1e-8 |mean|, e.g. [p + 1e-06, p, p, ...] for a price p ~ 4e6): the numpy arithmetic
 //     is replayed over the ring, O(history) like the reference, because there the result IS the rounding error.
 // mode 0: x_i, mode 1: (x_i - mean)^2, mode 2: the constant cval (no memory access)
-__device__ __noinline__ double np_pairwise_sum_ring(const double* hist, int maxlen, int start, int n, int mode, double mean, double cval) {
+static __device__ __noinline__ double np_pairwise_sum_ring(const double* hist, int maxlen, int start, int n, int mode, double mean, double cval) {
   auto el = [&](int i) -> double {
     if (mode == 2) return cval;
     int k = start + i; if (k >= maxlen) k -= maxlen;
@@ -545,7 +545,7 @@ __device__ __noinline__ double np_pairwise_sum_ring(const double* hist, int maxl
 }
 
 // scipy's zscore of the last element, replayed exactly; `start` = ring index of the oldest of the n window entries
-__device__ __noinline__ double zscore_exact(const double* hist, int maxlen, int start, int n, double value, int constant) {
+static __device__ __noinline__ double zscore_exact(const double* hist, int maxlen, int start, int n, double value, int constant) {
   const int m0 = constant ? 2 : 0;
   const double mean = np_pairwise_sum_ring(hist, maxlen, start, n, m0, 0.0, value) / (double)n;
   double var;
@@ -557,7 +557,7 @@ __device__ __noinline__ double zscore_exact(const double* hist, int maxlen, int 
 }
 
 // exact shifted sums of the window around a new centre (sheds accumulated rounding and cancellation)
-__device__ __noinline__ void zscore_recenter(FeatState& f, const double* hist, int maxlen, int start, int n, double centre) {
+static __device__ __noinline__ void zscore_recenter(FeatState& f, const double* hist, int maxlen, int start, int n, double centre) {
   double s1 = 0.0, s2 = 0.0;
   for (int i = 0; i < n; i++) {
     int k = start + i; if (k >= maxlen) k -= maxlen;
@@ -569,7 +569,7 @@ __device__ __noinline__ void zscore_recenter(FeatState& f, const double* hist, i
 
 // Cold and out of line, working on the FeatState in global memory after features_step has stored it: nothing of the caller
 // stays live across the (rare) calls into the exact paths, so the per-step feature code keeps its registers.
-__device__ __noinline__ double feature_normalise(FeatState* fg, double* hist, int maxlen, double value) {
+static __device__ __noinline__ double feature_normalise(FeatState* fg, double* hist, int maxlen, double value) {
   FeatState f = *fg;
   int n = f.nlen;
   int head = f.nhead;
@@ -639,7 +639,7 @@ __device__ __forceinline__ bool feature_update(const lobsim_feature_t& fc, FeatS
 // NORM == false instantiations contain no call into the z-score code: a callee subtree that is never executed still costs
 // the calling kernel registers around the call and I-cache footprint (measured: 3.7 % of the env step).
 template <bool NORM>
-__device__ __noinline__ double features_step(const EnvConst* ecp, FeatState* fstate_env, double* rings_env, int lane, const StepView v, long long episode_start_us, int mode) {
+static __device__ __noinline__ double features_step(const EnvConst* ecp, FeatState* fstate_env, double* rings_env, int lane, const StepView v, long long episode_start_us, int mode) {
   const EnvConst& ec = *ecp;
   double cur = 0.0;
   if (lane < ec.cfg.n_features) {
@@ -657,7 +657,7 @@ __device__ __noinline__ double features_step(const EnvConst* ecp, FeatState* fst
 }
 
 // Agent.get_action for the fused rollout (cold)
-__device__ __noinline__ void agent_action_cold(const lobsim_agent_t* ag, double inventory_obs, double* out5_smem) {
+static __device__ __noinline__ void agent_action_cold(const lobsim_agent_t* ag, double inventory_obs, double* out5_smem) {
   double a[5] = {0, 0, 0, 0, 0};
   agent_action(*ag, inventory_obs, a);
 #pragma unroll
@@ -725,7 +725,7 @@ struct SharpeOut { double reward; uint32_t err; };
 // get_sharpe (RewardFunctions.py:10-22): np.mean and np.std(ddof=1) of the simple returns.  The returns are written to a scratch
 // row (`tmp`) by all lanes and then summed by lane 0 in numpy's pairwise order (np_pairwise_sum_ring) -- mean / std of tiny
 // returns amplifies any other summation order beyond the 1e-6 tolerance.
-__device__ __noinline__ SharpeOut rolling_sharpe_step(double* ring, int* state, int packed_windows, double new_aum, int lane, double* tmp) {
+static __device__ __noinline__ SharpeOut rolling_sharpe_step(double* ring, int* state, int packed_windows, double new_aum, int lane, double* tmp) {
   const int maxw = packed_windows & 0xffff, minw = (packed_windows >> 16) & 0xffff;
   int n = state[0], head = state[1];
   __syncwarp();

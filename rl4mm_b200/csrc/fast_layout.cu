@@ -1,0 +1,53 @@
+// fast_layout.cu -- ONE compiled StaticLayout of the straight-line kernels (k_replay_fast / k_env_fast, kernels.cuh).
+// Compiled once per entry of layouts.h and per part (-DLOBSIM_LAYOUT_INDEX=i -DLOBSIM_TU_PART=p, build.py), in parallel:
+//   part 0: the replay kernel + the env kernels without the z-score / RollingSharpe code
+//   part 1: the env kernels with that code (RARE)
+// lobsim.cu calls the launchers below through the FastLayoutOps table.
+#include "kernels.cuh"
+#include "layouts.h"
+
+#if !defined(LOBSIM_LAYOUT_INDEX) || !defined(LOBSIM_TU_PART)
+#error "compile with -DLOBSIM_LAYOUT_INDEX=<entry of layouts.h> -DLOBSIM_TU_PART=<0|1>"
+#endif
+
+template <int I> struct LayoutAt;
+#define X(i, nl, no, na) template <> struct LayoutAt<i> { typedef StaticLayout<nl, no, na> type; };
+LOBSIM_FAST_LAYOUTS(X)
+#undef X
+typedef LayoutAt<LOBSIM_LAYOUT_INDEX>::type LT;
+
+#define LOBSIM_CAT3_(a, b, c) a##b##c
+#define LOBSIM_CAT3(a, b, c) LOBSIM_CAT3_(a, b, c)
+#define FN(name) LOBSIM_CAT3(lobsim_fast, LOBSIM_LAYOUT_INDEX, name)
+
+static cudaError_t set_attr(const void* k, int dyn) {
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+
+#if LOBSIM_TU_PART == 0
+cudaError_t FN(_attrs)(int dyn_replay, int dyn_env) {
+  cudaError_t e = set_attr((const void*)k_replay_fast<LT>, dyn_replay);
+  if (e == cudaSuccess) e = set_attr((const void*)k_env_fast<LT, true, false>, dyn_env);
+  if (e == cudaSuccess) e = set_attr((const void*)k_env_fast<LT, false, false>, dyn_env);
+  return e;
+}
+void FN(_replay)(int grid, int block, size_t dyn, cudaStream_t stream, const AdvParams& p, const EnvConst& ec) {
+  k_replay_fast<LT><<<grid, block, dyn, stream>>>(p, ec);
+}
+void FN(_env)(bool sync, int grid, int block, size_t dyn, cudaStream_t stream, const AdvParams& p, const EnvConst& ec) {
+  if (sync) k_env_fast<LT, true, false><<<grid, block, dyn, stream>>>(p, ec);
+  else k_env_fast<LT, false, false><<<grid, block, dyn, stream>>>(p, ec);
+}
+#else
+cudaError_t FN(_attrs_rare)(int dyn_env) {
+  cudaError_t e = set_attr((const void*)k_env_fast<LT, true, true>, dyn_env);
+  if (e == cudaSuccess) e = set_attr((const void*)k_env_fast<LT, false, true>, dyn_env);
+  return e;
+}
+void FN(_env_rare)(bool sync, int grid, int block, size_t dyn, cudaStream_t stream, const AdvParams& p, const EnvConst& ec) {
+  if (sync) k_env_fast<LT, true, true><<<grid, block, dyn, stream>>>(p, ec);
+  else k_env_fast<LT, false, true><<<grid, block, dyn, stream>>>(p, ec);
+}
+#endif

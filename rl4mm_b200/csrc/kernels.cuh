@@ -1,0 +1,736 @@
+// kernels.cuh -- the kernels of the B200-native LOB simulation step.
+//
+// Kernel design:
+//   * one warp per book; a CTA is `warps_per_cta` independent warps, no block-level synchronisation at all;
+//   * the book blob lives in shared memory for the whole launch: HBM -> smem by one TMA bulk copy
+//     (cp.async.bulk + mbarrier) at the start, smem -> HBM by one bulk store at the end;
+//   * historical messages are streamed by TMA bulk copies of 512-byte tiles (32 x 16 B records) into a per-warp
+//     double buffer, prefetched one tile ahead; all 32 lanes read a record with one broadcast LDS.128;
+//   * book operations are warp-collective (ballot / popc / ffs level and order search, <=32-entry shifts);
+//   * features run one per lane, the reward and the rollout tensors are written straight from the kernel.
+// fp64 everywhere the reference uses Python floats, compiled with --fmad=false (no FMA contraction).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "env.cuh"
+#include "lobsim.h"
+
+// ====================================================================================================================
+//  PTX helpers: mbarrier + TMA bulk copies (sm_90+; SASS: UBLKCP / SYNCS)
+// ====================================================================================================================
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ void tma_load(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tma_store(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+// ====================================================================================================================
+//  kernel parameters
+// ====================================================================================================================
+#ifndef LOBSIM_WS_IN_SMEM
+#define LOBSIM_WS_IN_SMEM 0
+#endif
+#ifndef LOBSIM_ENV_MIN_BLOCKS
+#define LOBSIM_ENV_MIN_BLOCKS 3
+#endif
+#define MSG_TILE 32                      // records per TMA tile
+#define MSG_TILE_BYTES (MSG_TILE * 16)
+
+struct AdvParams {
+  unsigned char* blobs;             // [n_envs][blob_bytes]
+  FeatState* fstate;                // [n_envs][LOBSIM_MAX_FEATURES]
+  double* rings;                    // [n_envs][ring_stride]
+  double* rs_ring;                  // RollingSharpe [n_envs][3][LOBSIM_MAX_SHARPE_WINDOW]: two AUM windows + a scratch row of returns, or null
+  int32_t* rs_state;                // [n_envs][2][2] = {n_filled, head}
+  const lobsim_stream_t* streams;   // device array [n_streams]
+  int32_t n_streams;
+  lobsim_fill_t* fill_log;          // [n_envs][fill_cap] or null
+  int32_t* fill_count;              // [n_envs]
+  int32_t fill_cap;
+  int32_t n_envs;                   // total envs of the handle
+  int32_t n_sel;                    // number of envs this launch works on
+  int32_t sel_offset;               // first selection index handled by this launch (tail launches)
+  const int32_t* env_ids;           // [n_sel] or null (identity)
+  int32_t T;                        // simulation steps to run
+  int32_t reset_mode;               // 0 none, 1 book reset only, 2 full env reset (+ warm-up of T steps)
+  const int32_t* reset_stream_ids;  // [n_sel]
+  const int32_t* reset_steps;       // [n_sel]: book reset: start step; env reset: episode start step
+  int32_t agent_kind;               // LOBSIM_AGENT_*
+  int32_t out_final_obs_only;       // reset: write obs once, after the warm-up
+  int32_t resync_last_only;         // forward_step over several grid steps: resync check only at the end
+  const double* actions_in;         // EXTERNAL: [T][n_sel][action_dim]
+  double* obs; double* act; double* rew; uint8_t* done; // [T][n_sel][...] (any may be null)
+  double* info;                     // [T][n_sel][LOBSIM_INFO_DIM] per-step info series (SimpleInfoCalculator source) or null
+  lobsim_agent_t agent;
+  const lobsim_agent_t* agents;     // per-env built-in agents [n_sel] (parameter sweeps) or null: every env runs `agent`
+  Layout L;
+  int32_t warp_smem;                // bytes of shared memory per warp
+};
+
+// one row of the per-step info series (InfoCalculators.py:31-59: asset_price, inventory, cash, aum, market_spread) --
+// the state the reference's info_calculator sees at the end of HistoricalOrderbookEnvironment.step (HOE.py:175-177)
+__device__ __forceinline__ void write_info(double* row, int lane, const StepView& v, double cash, long long inv, uint32_t err) {
+  double x = v.price;
+  if (lane == LOBSIM_INFO_INVENTORY) x = (double)inv;
+  else if (lane == LOBSIM_INFO_CASH) x = cash;
+  else if (lane == LOBSIM_INFO_AUM) x = cash + v.price * (double)inv;
+  else if (lane == LOBSIM_INFO_MARKET_SPREAD) x = v.have_tops ? (double)(v.bs - v.bb) : NAN;
+  else if (lane == LOBSIM_INFO_BEST_BUY) x = v.have_tops ? (double)v.bb : NAN;
+  else if (lane == LOBSIM_INFO_BEST_SELL) x = v.have_tops ? (double)v.bs : NAN;
+  else if (lane == LOBSIM_INFO_ERR) x = (double)err;
+  if (lane < LOBSIM_INFO_DIM) row[lane] = x;
+}
+
+// per_step / terminal reward of one env step (HOE.py:170-174); RollingSharpe keeps one AUM window per reward function
+template <bool RARE>
+__device__ __forceinline__ double step_reward(const AdvParams& p, const lobsim_cfg_t& c, int env, int lane, bool done, double cash0, long long inv0, double p0,
+                                              double cash1, long long inv1, double p1, uint32_t& err) {
+  double r;
+  if (RARE && c.step_reward.kind == LOBSIM_REWARD_ROLLING_SHARPE) {
+    SharpeOut o = rolling_sharpe_step(p.rs_ring + ((size_t)env * 3 + 0) * LOBSIM_MAX_SHARPE_WINDOW, p.rs_state + ((size_t)env * 2 + 0) * 2, c.step_reward.asymmetric, cash1 + p1 * (double)inv1, lane, p.rs_ring + ((size_t)env * 3 + 2) * LOBSIM_MAX_SHARPE_WINDOW);
+    r = o.reward; err |= o.err;
+  } else r = reward_calc(c.step_reward, cash0, inv0, p0, cash1, inv1, p1);
+  if (done) {
+    if (RARE && c.terminal_reward.kind == LOBSIM_REWARD_ROLLING_SHARPE) {
+      SharpeOut o = rolling_sharpe_step(p.rs_ring + ((size_t)env * 3 + 1) * LOBSIM_MAX_SHARPE_WINDOW, p.rs_state + ((size_t)env * 2 + 1) * 2, c.terminal_reward.asymmetric, cash1 + p1 * (double)inv1, lane, p.rs_ring + ((size_t)env * 3 + 2) * LOBSIM_MAX_SHARPE_WINDOW);
+      r = o.reward; err |= o.err;
+    } else r = reward_calc(c.terminal_reward, cash0, inv0, p0, cash1, inv1, p1);
+  }
+  return r;
+}
+
+__device__ __forceinline__ unsigned char* warp_smem_base(unsigned char* smem, int warp, int warp_smem) { return smem + (size_t)warp * warp_smem; }
+
+// ====================================================================================================================
+//  the advance kernel: [reset] + T x ([agent orders] + messages of the step + [resync] + [features, reward])
+// ====================================================================================================================
+// kEnv: agent + features + rewards (HistoricalOrderbookEnvironment.step); kTrack: fills / flows / agent orders are
+// tracked (always with kEnv; the pure replay fast path <false,false> is used when no agent order can be resting).
+template <bool kEnv, bool kTrack>
+__global__ void __launch_bounds__(128, kEnv ? LOBSIM_ENV_MIN_BLOCKS : 4) k_advance(const __grid_constant__ AdvParams p, const __grid_constant__ EnvConst ec) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sel = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (sel >= p.n_sel) return;
+  const int env = p.env_ids ? p.env_ids[sel] : sel;
+  const lobsim_cfg_t& c = ec.cfg;
+
+  unsigned char* base = warp_smem_base(smem, warp, p.warp_smem);
+  Book b; b.blob = base; b.L = p.L; b.lane = lane;
+  unsigned char* msgbuf = base + p.L.blob_bytes;                                   // 2 x 512 B
+  int2* scratch = reinterpret_cast<int2*>(msgbuf + 2 * MSG_TILE_BYTES);             // [2*NA]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(scratch) + 2 * p.L.NA * 8); // 3 barriers
+  unsigned char* gblob = p.blobs + (size_t)env * p.L.blob_bytes;
+
+  // ---- book blob: HBM -> shared memory ---------------------------------------------------------------------------
+  if (lane == 0) {
+    mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
+    fence_mbar_init();
+    mbar_expect_tx(&bars[2], (uint32_t)p.L.blob_bytes);
+    tma_load(base, gblob, (uint32_t)p.L.blob_bytes, &bars[2]);
+  }
+  __syncwarp();
+  mbar_wait(&bars[2], 0);
+
+#if LOBSIM_WS_IN_SMEM
+  // the uniform per-warp state lives in shared memory (not registers): every lane stores identical values, so plain
+  // accesses are race-free; it trades a few broadcast LDS for ~35 registers per thread => more resident books per SM
+  WarpState& w = *reinterpret_cast<WarpState*>(reinterpret_cast<unsigned char*>(bars) + 32);
+#else
+  WarpState w;
+#endif
+  load_state<kTrack>(b, w);
+  w.fill_log = p.fill_log ? p.fill_log + (size_t)env * p.fill_cap : nullptr;
+  w.fill_cap = p.fill_cap; w.n_fills = 0;
+  const long long inventory_in = w.inventory; const double cash_in = w.cash;
+  BookHdr* h = b.hdr();
+  const int F = c.n_features;
+
+  // ---- reset prologue ----------------------------------------------------------------------------------------------
+  int stream_id = h->stream_id;
+  if (kTrack && p.reset_mode) {
+    stream_id = p.reset_stream_ids[sel];
+    int start = p.reset_steps[sel] - (p.reset_mode == 2 ? c.warmup_steps : 0);
+    if (stream_id < 0 || stream_id >= p.n_streams) { stream_id = 0; start = -1; }
+    w = init_book_cold(b, w, &ec.cfg, &p.streams[stream_id], stream_id, start);
+    if (p.reset_mode == 2 && lane == 0) {
+      h->episode_start_step = p.reset_steps[sel];
+      if (!c.portfolio_carryover || !h->has_reset) { h->inventory = c.initial_inventory; h->cash = c.initial_cash; }
+      h->has_reset = 1;
+    }
+    __syncwarp();
+    w.inventory = h->inventory; w.cash = h->cash;
+  }
+  const lobsim_stream_t* stp = &p.streams[stream_id];
+  const lobsim_msg_t* __restrict__ st_msgs = stp->msgs;
+  const uint32_t* __restrict__ st_step_off = stp->step_off;
+  const long long st_t0_us = kEnv ? stp->t0_us : 0;
+  int now_step = h->now_step;
+  const long long episode_start_us = st_t0_us + (long long)h->episode_start_step * c.step_us;
+
+  FeatState* fstate_env = p.fstate + (size_t)env * LOBSIM_MAX_FEATURES;
+  double* rings_env = p.rings + (size_t)env * ec.ring_stride;
+  double feat_cur = 0.0; // Feature.current_value of this lane's feature
+  if (kEnv && lane < F) feat_cur = fstate_env[lane].cur;
+
+  // price / tops of the current book
+  auto tops = [&](StepView& v) {
+    v.have_tops = w.nlv0 > 0 && w.nlv1 > 0;
+    if (v.have_tops) {
+      v.bb = b.lvp(0)[w.nlv0 - 1]; v.bs = b.lvp(1)[w.nlv1 - 1];
+      v.bv = best_level_volume(b, 0, w.nlv0); v.sv = best_level_volume(b, 1, w.nlv1);
+      double imb; v.price = microprice(v.bb, v.bs, v.bv, v.sv, imb);
+    } else { v.bb = v.bs = v.bv = v.sv = 0; v.price = NAN; }
+  };
+
+  double price = h->price;
+  if (kEnv && p.reset_mode == 2) { // State(...) + _reset_features, HOE.py:152-154,218-221
+    StepView v; tops(v);
+    v.inventory = w.inventory; v.now_us = st_t0_us + (long long)now_step * c.step_us;
+    v.n_ext0 = v.n_ext1 = v.vol_ext0 = v.vol_ext1 = v.n_int0 = v.n_int1 = v.vol_int0 = v.vol_int1 = 0;
+    price = v.price;
+    feat_cur = features_step<true>(&ec, fstate_env, rings_env, lane, v, episode_start_us, 1);
+  }
+
+  // ---- message pipeline ----------------------------------------------------------------------------------------------
+  const int T = p.T;
+  // steps beyond the end of the grid: the steps that exist are run, the first one past the end sets END_OF_STREAM
+  const int n_grid = (int)stp->n_grid_steps;
+  if ((now_step < 0 || now_step > n_grid) && !w.dead && T > 0) { w.err |= LOBSIM_ERR_END_OF_STREAM; w.dead = 1; }
+  unsigned g = 0, g_end_all = 0;
+  if (!w.dead && T > 0) { g = __ldg(&st_step_off[now_step]); g_end_all = __ldg(&st_step_off[min((long long)now_step + T, (long long)n_grid)]); }
+  // tiles are MSG_TILE-aligned in the global message index space; `rel` tile r lives in buffer r & 1 and completes
+  // phase (r >> 1) & 1 of that buffer's mbarrier.  Tiles are issued and consumed strictly in order.
+  const unsigned tile0 = g / MSG_TILE;
+  unsigned next_issue = 0, next_wait = 0;
+  auto issue_tile = [&]() { // uniform; lane 0 talks to the TMA unit
+    const unsigned first = (tile0 + next_issue) * MSG_TILE;
+    if (first >= g_end_all) return;
+    if (lane == 0) {
+      const unsigned n_total = (unsigned)stp->n_msgs;
+      unsigned cnt = n_total - first < MSG_TILE ? n_total - first : MSG_TILE;
+      uint64_t* bar = &bars[next_issue & 1];
+      mbar_expect_tx(bar, cnt * 16);
+      tma_load(msgbuf + (next_issue & 1) * MSG_TILE_BYTES, st_msgs + first, cnt * 16, bar);
+    }
+    next_issue++;
+  };
+  auto wait_tile = [&]() { // wait for relative tile `next_wait`
+    mbar_wait(&bars[next_wait & 1], (next_wait >> 1) & 1);
+    next_wait++;
+  };
+  if (g < g_end_all) { issue_tile(); issue_tile(); }
+  __syncwarp();
+
+  AgentGen gen; gen.side = 3;
+  bool agent_phase = false;
+#pragma unroll 1
+  for (int t = 0; t < T; t++) {
+    // ---- agent: obs -> action -> orders (processed before the step's history, OrderbookSimulator.py:76-77) -------
+    double cash0 = w.cash, p0 = price; long long inv0 = w.inventory;
+    if (kEnv) {
+      reset_flow(w);
+      if (p.agent_kind != LOBSIM_AGENT_NONE) {
+        double* act_sm = reinterpret_cast<double*>(scratch); // 5 doubles of per-warp scratch
+        if (p.agent_kind == LOBSIM_AGENT_EXTERNAL) {
+          const double* a = p.actions_in + ((size_t)t * p.n_sel + sel) * ec.action_dim;
+          if (lane < 5) act_sm[lane] = lane < ec.action_dim ? __ldg(&a[lane]) : 0.0;
+        } else {
+          const lobsim_agent_t* agp = p.agents ? p.agents + sel : &p.agent;
+          const double inv_obs = __shfl_sync(FULL_MASK, feat_cur, agp->inventory_index & 31);
+          if (lane == 0) agent_action_cold(agp, inv_obs, act_sm);
+        }
+        __syncwarp();
+        const double a0 = act_sm[0], a1 = act_sm[1], a2 = act_sm[2], a3 = act_sm[3], a4 = act_sm[4];
+        const double mine = lane < 5 ? act_sm[lane] : 0.0;
+        __syncwarp();
+        if (p.act && p.agent_kind != LOBSIM_AGENT_EXTERNAL && lane < ec.action_dim) p.act[((size_t)t * p.n_sel + sel) * ec.action_dim + lane] = mine;
+        if (p.obs && !p.out_final_obs_only && c.inc_prev_action_in_obs && lane < ec.action_dim)
+          p.obs[((size_t)t * p.n_sel + sel) * ec.obs_dim + F + lane] = mine; // get_observation(action), HOE.py:171
+        gen = agent_prepare(b, w.nlv0, w.nlv1, w.nag0, w.nag1, w.inventory, &ec, a0, a1, a2, a3, a4);
+        w.err |= gen.err_out; if (gen.dead_out) w.dead = 1;
+        agent_phase = true;
+      }
+    }
+    // ---- the step's orders: the agent's first, then the historical messages of (now, now + step] ------------------
+    {
+      if (!w.dead && now_step >= n_grid) { w.err |= LOBSIM_ERR_END_OF_STREAM; w.dead = 1; }
+      const unsigned g_step_end = w.dead ? g : __ldg(&st_step_off[now_step + 1]);
+#pragma unroll 1
+      for (;;) {
+        int type, side, price, vol; uint32_t ref; bool is_agent;
+        if (kEnv && agent_phase) {
+          if (!agent_next(b, w, gen, type, side, price, vol, ref)) { agent_phase = false; continue; }
+          is_agent = true;
+        } else {
+          if (w.dead || g >= g_step_end) break;
+          const unsigned tile = g / MSG_TILE - tile0;
+          if (tile == next_wait) wait_tile();
+          const uint4 m = *reinterpret_cast<const uint4*>(msgbuf + (tile & 1) * MSG_TILE_BYTES + (g % MSG_TILE) * 16);
+          price = (int)m.x; vol = (int)m.y; ref = m.z; type = (int)LOBSIM_META_TYPE(m.w); side = (int)LOBSIM_META_DIR(m.w);
+          is_agent = false;
+          g++;
+          if (g % MSG_TILE == 0) { __syncwarp(); issue_tile(); } // tile consumed: refill its buffer
+        }
+        process_order<kTrack>(b, w, type, side, price, vol, ref, is_agent);
+      }
+    }
+    if (!w.dead) {
+      now_step++;
+      // ---- resync, OrderbookSimulator.py:86-87 ----------------------------------------------------------------------
+      if (c.resync && (!p.resync_last_only || t == T - 1)) {
+        long long rel = (long long)now_step * c.step_us;
+        if (rel % 1000000 == 0 && near_exiting(b, w, c)) {
+          long long sec = rel / 1000000;
+          if (sec <= (long long)stp->n_seconds && stp->snap_valid[sec]) {
+            w = update_outer_levels<kTrack>(b, w, &ec.cfg, stp->snapshots + (size_t)sec * 2 * c.n_levels * 2, scratch);
+                    }
+        }
+      }
+    }
+    if (kEnv) {
+      // ---- update_internal_state + _update_features + reward, HOE.py:163-178,199-204 -------------------------------
+      StepView v; tops(v);
+      if (!v.have_tops) w.err |= LOBSIM_ERR_EMPTY_BOOK;
+      price = v.price;
+      v.inventory = w.inventory; v.now_us = st_t0_us + (long long)now_step * c.step_us;
+      v.n_ext0 = w.n_ext0; v.n_ext1 = w.n_ext1; v.vol_ext0 = w.vol_ext0; v.vol_ext1 = w.vol_ext1;
+      v.n_int0 = w.n_int0; v.n_int1 = w.n_int1; v.vol_int0 = w.vol_int0; v.vol_int1 = w.vol_int1;
+      feat_cur = features_step<true>(&ec, fstate_env, rings_env, lane, v, episode_start_us, 0);
+      const bool write_now = !p.out_final_obs_only || t == T - 1;
+      if (p.obs && write_now) {
+        double* o = p.obs + ((size_t)(p.out_final_obs_only ? 0 : t) * p.n_sel + sel) * ec.obs_dim;
+        if (lane < F) o[lane] = feat_cur;
+        if (c.inc_prev_action_in_obs && lane < ec.action_dim && (p.agent_kind == LOBSIM_AGENT_NONE || p.out_final_obs_only)) o[F + lane] = 0.0;
+      }
+      if (p.agent_kind != LOBSIM_AGENT_NONE) {
+        const bool d = now_step >= h->episode_start_step + c.episode_steps; // terminal_time - now < step/2, HOE.py:172
+        const double r = step_reward<true>(p, c, env, lane, d, cash0, inv0, p0, w.cash, w.inventory, price, w.err);
+        if (lane == 0) {
+          if (p.rew) p.rew[(size_t)t * p.n_sel + sel] = r;
+          if (p.done) p.done[(size_t)t * p.n_sel + sel] = d ? 1 : 0;
+        }
+        if (p.info) write_info(p.info + ((size_t)t * p.n_sel + sel) * LOBSIM_INFO_DIM, lane, v, w.cash, w.inventory, w.err);
+      }
+    }
+  }
+  if (kEnv && T == 0 && p.obs && p.reset_mode == 2) { // reset with no warm-up: obs straight after _reset_features
+    double* o = p.obs + (size_t)sel * ec.obs_dim;
+    if (lane < F) o[lane] = feat_cur;
+    if (c.inc_prev_action_in_obs && lane < ec.action_dim) o[F + lane] = 0.0;
+  }
+
+  while (next_wait < next_issue) wait_tile(); // drain TMA loads still in flight (only after an aborted episode)
+
+  // ---- write back ----------------------------------------------------------------------------------------------------
+  // OrderbookSimulator.forward_step only returns the fills: the portfolio belongs to the env (HOE.py:280-289)
+  if (!kEnv && !p.reset_mode) { w.inventory = inventory_in; w.cash = cash_in; }
+  if (lane == 0) {
+    h->now_step = now_step;
+    h->price = price;
+    if (p.fill_count) p.fill_count[env] = w.n_fills;
+  }
+  store_state<kTrack>(b, w);
+  fence_proxy_async();
+  __syncwarp();
+  if (lane == 0) { tma_store(gblob, base, (uint32_t)p.L.blob_bytes); tma_store_wait(); }
+  __syncwarp();
+}
+
+// ====================================================================================================================
+//  the replay fast kernel: T x (messages of the step + [resync]) with the straight-line message path of book_fast.cuh.
+//  Used by lobsim_replay when no fill log is requested, no agent order can be resting and the book capacities match
+//  one of the compiled StaticLayouts.  72 registers => 7 CTAs x 4 warps = 28 books resident per SM.
+// ====================================================================================================================
+template <class LT>
+__global__ void __launch_bounds__(128, 7) k_replay_fast(const __grid_constant__ AdvParams p, const __grid_constant__ EnvConst ec) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int env = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (env >= p.n_sel) return;
+  const lobsim_cfg_t& c = ec.cfg;
+  unsigned char* base = warp_smem_base(smem, warp, p.warp_smem);
+  unsigned char* msgbuf = base + LT::blob_bytes;
+  int2* scratch = reinterpret_cast<int2*>(msgbuf + 2 * MSG_TILE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(scratch) + 2 * LT::NA * 8);
+  unsigned char* gblob = p.blobs + (size_t)env * LT::blob_bytes;
+  if (lane == 0) {
+    mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
+    fence_mbar_init();
+    mbar_expect_tx(&bars[2], (uint32_t)LT::blob_bytes);
+    tma_load(base, gblob, (uint32_t)LT::blob_bytes, &bars[2]);
+  }
+  __syncwarp();
+  mbar_wait(&bars[2], 0);
+
+  FastBook<LT> fb; fb.blob = base; fb.lane = lane;
+  BookHdr* h = reinterpret_cast<BookHdr*>(base);
+  FastState f; f.err = h->err; f.dead = h->dead; f.bail = 0; f.bail_vol = 0;
+  fast_refresh_best(fb, f);
+  const lobsim_stream_t* stp = &p.streams[h->stream_id];
+  const lobsim_msg_t* __restrict__ st_msgs = stp->msgs;
+  const uint32_t* __restrict__ st_step_off = stp->step_off;
+  int now_step = h->now_step;
+  const int T = p.T;
+  const int n_grid = (int)stp->n_grid_steps;   // steps beyond the end: the existing ones are run, the first one past the end sets END_OF_STREAM
+  if ((now_step < 0 || now_step > n_grid) && !f.dead && T > 0) { f.err |= LOBSIM_ERR_END_OF_STREAM; f.dead = 1; }
+  unsigned g = 0, g_end_all = 0;
+  if (!f.dead && T > 0) { g = __ldg(&st_step_off[now_step]); g_end_all = __ldg(&st_step_off[min((long long)now_step + T, (long long)n_grid)]); }
+  const unsigned tile0 = g / MSG_TILE;
+  unsigned next_issue = 0, next_wait = 0;
+  auto issue_tile = [&]() {
+    const unsigned first = (tile0 + next_issue) * MSG_TILE;
+    if (first >= g_end_all) return;
+    if (lane == 0) {
+      const unsigned n_total = (unsigned)stp->n_msgs;
+      const unsigned cnt = n_total - first < MSG_TILE ? n_total - first : MSG_TILE;
+      uint64_t* bar = &bars[next_issue & 1];
+      mbar_expect_tx(bar, cnt * 16);
+      tma_load(msgbuf + (next_issue & 1) * MSG_TILE_BYTES, st_msgs + first, cnt * 16, bar);
+    }
+    next_issue++;
+  };
+  auto wait_tile = [&]() { mbar_wait(&bars[next_wait & 1], (next_wait >> 1) & 1); next_wait++; };
+  if (g < g_end_all) { issue_tile(); issue_tile(); }
+  __syncwarp();
+  const int steps_per_sec = ec.steps_per_sec;
+  int sub = now_step >= 0 ? now_step % steps_per_sec : 0;   // position inside the current second
+
+#pragma unroll 1
+  for (int t = 0; t < T && !f.dead; t++) {
+    if (now_step >= n_grid) { f.err |= LOBSIM_ERR_END_OF_STREAM; f.dead = 1; break; }
+    const unsigned g_step_end = __ldg(&st_step_off[now_step + 1]);
+#pragma unroll 1
+    while (g < g_step_end) {
+      const unsigned tile = g / MSG_TILE - tile0;
+      if (tile == next_wait) wait_tile();
+      const unsigned tile_end = (g / MSG_TILE + 1) * MSG_TILE;
+      const unsigned lim = g_step_end < tile_end ? g_step_end : tile_end;
+      const uint4* mp = reinterpret_cast<const uint4*>(msgbuf + (tile & 1) * MSG_TILE_BYTES) + (g % MSG_TILE);
+      const unsigned cnt = lim - g;
+#pragma unroll 1
+      for (unsigned i = 0; i < cnt; i++) {
+        const uint4 m = mp[i];
+        fast_message(fb, f, (int)m.x, (int)m.y, m.z, m.w);
+        if (f.dead) break;
+      }
+      if (f.dead) break;
+      g = lim;
+      if (g == tile_end) { __syncwarp(); issue_tile(); }
+    }
+    if (f.dead) break;
+    now_step++;
+    if (++sub == steps_per_sec) {                            // whole second: outer-level resync, OrderbookSimulator.py:86-87
+      sub = 0;
+      if (c.resync && (!p.resync_last_only || t == T - 1)) {
+        const double prop = ec.outer_prop;
+        const double bb = f.best0 == INT32_MIN ? 0.0 : (double)f.best0;
+        const double bs = f.best1 == INT32_MAX ? (double)INFINITY : (double)f.best1;
+        if (bb < (double)h->min_buy + prop * (double)h->init_buy_range || bs > (double)h->max_sell - prop * (double)h->init_sell_range) {
+          const int sec = now_step / steps_per_sec;
+          if (sec <= (int)stp->n_seconds && stp->snap_valid[sec]) {
+            const int32_t* row = stp->snapshots + (size_t)sec * 2 * c.n_levels * 2;
+            fast_resync(fb, f, row, c.n_levels);   // straight-line: a replay book holds no agent orders
+          }
+        }
+      }
+    }
+  }
+  while (next_wait < next_issue) wait_tile();                // drain TMA loads still in flight (aborted episode)
+  __syncwarp();
+  if (lane == 0) { h->now_step = now_step; h->err = f.err; h->dead = f.dead; }
+  __syncwarp();
+  fence_proxy_async();
+  __syncwarp();
+  if (lane == 0) { tma_store(gblob, base, (uint32_t)LT::blob_bytes); tma_store_wait(); }
+  __syncwarp();
+}
+
+// ====================================================================================================================
+//  the env fast kernel: k_advance<true,true> with the straight-line tracked order path (book_fast.cuh fast_order<LT,true>)
+//  and all per-env scalars (counters, portfolio, per-step flow) in the shared-memory header instead of registers.
+// ====================================================================================================================
+static __device__ __noinline__ uint32_t reset_book_cold(unsigned char* blob, const Layout* L, int lane, const lobsim_cfg_t* c, const lobsim_stream_t* st, int stream_id, int start_step) {
+  Book b; b.blob = blob; b.L = *L; b.lane = lane;
+  WarpState w;
+  __syncwarp();
+  load_state<true>(b, w);
+  w.fill_log = nullptr; w.fill_cap = 0; w.n_fills = 0;
+  init_book_from_snapshot(b, w, *c, *st, stream_id, start_step);
+  store_state<true>(b, w);
+  return pack_errdead(w.err, w.dead);
+}
+
+#ifndef LOBSIM_ENVFAST_WARPS
+#define LOBSIM_ENVFAST_WARPS 4    // warps per CTA of the env fast kernel (four CTAs per SM at 128 registers; 8 measured 1.3 % slower)
+#endif
+#ifndef LOBSIM_PHASE_SYNC
+#define LOBSIM_PHASE_SYNC 1
+#endif
+#if LOBSIM_PHASE_SYNC
+#define PHASE_SYNC() __syncthreads()
+#else
+#define PHASE_SYNC() ((void)0)
+#endif
+// SYNC: the launch consists of full CTAs only, whose warps move through the phases of a step together
+// (launch_env puts the n_sel % warps-per-CTA tail into a second, free-running launch).
+// Per-warp values that are only needed outside the order-processing phase (B) live in the spare shared memory behind the
+// mbarriers instead of in registers: the kernel is register-bound (128 registers at 16 resident warps per SM) and phase B is where it spills.
+struct StepSave { double cash0, p0, price; long long inv0, episode_start_us, st_t0_us; };
+// RARE: the configuration uses z-score normalisation or a RollingSharpe reward (their code is compiled out otherwise).
+template <class LT, bool SYNC, bool RARE>
+__global__ void __launch_bounds__(32 * LOBSIM_ENVFAST_WARPS, 16 / LOBSIM_ENVFAST_WARPS) k_env_fast(const __grid_constant__ AdvParams p, const __grid_constant__ EnvConst ec) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sel = p.sel_offset + blockIdx.x * (blockDim.x >> 5) + warp;
+  // The warps of a CTA move through the phases of a step together (PHASE_SYNC = __syncthreads): the instruction
+  // working set at any moment is a single phase, which is what keeps the 32 KB L1.5 I-cache warm
+  // (profiles/r01_envstep_*: "no instruction" was the top stall with free-running warps).
+  if (sel >= p.n_sel) return; // only in SYNC == false launches
+  const int env = p.env_ids ? p.env_ids[sel] : sel;
+  const lobsim_cfg_t& c = ec.cfg;
+  unsigned char* base = warp_smem_base(smem, warp, p.warp_smem);
+  unsigned char* msgbuf = base + LT::blob_bytes;
+  int2* scratch = reinterpret_cast<int2*>(msgbuf + 2 * MSG_TILE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(scratch) + 2 * LT::NA * 8);
+  unsigned char* gblob = p.blobs + (size_t)env * LT::blob_bytes;
+  if (lane == 0) {
+    mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
+    fence_mbar_init();
+    mbar_expect_tx(&bars[2], (uint32_t)LT::blob_bytes);
+    tma_load(base, gblob, (uint32_t)LT::blob_bytes, &bars[2]);
+  }
+  __syncwarp();
+  mbar_wait(&bars[2], 0);
+
+  FastBook<LT> fb; fb.blob = base; fb.lane = lane;
+  Book b; b.blob = base; b.L = p.L; b.lane = lane;
+  BookHdr* h = reinterpret_cast<BookHdr*>(base);
+  FastState f; f.err = h->err; f.dead = h->dead; f.bail = 0; f.bail_vol = 0;
+  f.fill_log = p.fill_log ? p.fill_log + (size_t)env * p.fill_cap : nullptr; f.fill_cap = p.fill_cap;
+  if (lane == 0) h->n_fills = 0;
+  const int F = c.n_features;
+
+  // ---- reset prologue ----------------------------------------------------------------------------------------------
+  int stream_id = h->stream_id;
+  if (p.reset_mode) {
+    stream_id = p.reset_stream_ids[sel];
+    int start = p.reset_steps[sel] - (p.reset_mode == 2 ? c.warmup_steps : 0);
+    if (stream_id < 0 || stream_id >= p.n_streams) { stream_id = 0; start = -1; }
+    const uint32_t ed = reset_book_cold(base, &p.L, lane, &ec.cfg, &p.streams[stream_id], stream_id, start);
+    f.err = ed & 0x7fffffffu; f.dead = (int)(ed >> 31);
+    if (p.reset_mode == 2 && lane == 0) {
+      h->episode_start_step = p.reset_steps[sel];
+      if (!c.portfolio_carryover || !h->has_reset) { h->inventory = c.initial_inventory; h->cash = c.initial_cash; }
+      h->has_reset = 1;
+    }
+    __syncwarp();
+  }
+  fast_refresh_best(fb, f);
+  const lobsim_stream_t* stp = &p.streams[stream_id];
+  const lobsim_msg_t* __restrict__ st_msgs = stp->msgs;
+  const uint32_t* __restrict__ st_step_off = stp->step_off;
+  StepSave* sv = reinterpret_cast<StepSave*>(bars + 4);
+  int now_step = h->now_step;
+  if (lane == 0) { sv->st_t0_us = stp->t0_us; sv->episode_start_us = stp->t0_us + (long long)h->episode_start_step * c.step_us; sv->price = h->price; }
+  __syncwarp();
+  FeatState* fstate_env = p.fstate + (size_t)env * LOBSIM_MAX_FEATURES;
+  double* rings_env = p.rings + (size_t)env * ec.ring_stride;
+  double feat_cur = 0.0;
+  if (lane < F) feat_cur = fstate_env[lane].cur;
+
+  auto tops = [&](StepView& v) { // Orderbook.best_* / microprice, models.py:72-101
+    const int n0 = h->cnt[0][0], n1 = h->cnt[1][0];
+    v.have_tops = n0 > 0 && n1 > 0;
+    if (v.have_tops) {
+      v.bb = f.best0; v.bs = f.best1;
+      v.bv = best_level_volume(b, 0, n0); v.sv = best_level_volume(b, 1, n1);
+      double imb; v.price = microprice(v.bb, v.bs, v.bv, v.sv, imb);
+    } else { v.bb = v.bs = v.bv = v.sv = 0; v.price = NAN; }
+  };
+  if (p.reset_mode == 2) { // State(...) + _reset_features, HOE.py:152-154,218-221
+    StepView v; tops(v);
+    v.inventory = h->inventory; v.now_us = sv->st_t0_us + (long long)now_step * c.step_us;
+    v.n_ext0 = v.n_ext1 = v.vol_ext0 = v.vol_ext1 = v.n_int0 = v.n_int1 = v.vol_int0 = v.vol_int1 = 0;
+    __syncwarp();
+    if (lane == 0) sv->price = v.price;
+    feat_cur = features_step<RARE>(&ec, fstate_env, rings_env, lane, v, sv->episode_start_us, 1);
+    __syncwarp();
+  }
+
+  // ---- message pipeline ----------------------------------------------------------------------------------------------
+  const int T = p.T;
+  const int n_grid = (int)stp->n_grid_steps;   // steps beyond the end: the existing ones are run, the first one past the end sets END_OF_STREAM
+  if ((now_step < 0 || now_step > n_grid) && !f.dead && T > 0) { f.err |= LOBSIM_ERR_END_OF_STREAM; f.dead = 1; }
+  unsigned g = 0, g_end_all = 0;
+  if (!f.dead && T > 0) { g = __ldg(&st_step_off[now_step]); g_end_all = __ldg(&st_step_off[min((long long)now_step + T, (long long)n_grid)]); }
+  const unsigned tile0 = g / MSG_TILE;
+  unsigned next_issue = 0, next_wait = 0;
+  auto issue_tile = [&]() {
+    const unsigned first = (tile0 + next_issue) * MSG_TILE;
+    if (first >= g_end_all) return;
+    if (lane == 0) {
+      const unsigned n_total = (unsigned)stp->n_msgs;
+      const unsigned cnt = n_total - first < MSG_TILE ? n_total - first : MSG_TILE;
+      uint64_t* bar = &bars[next_issue & 1];
+      mbar_expect_tx(bar, cnt * 16);
+      tma_load(msgbuf + (next_issue & 1) * MSG_TILE_BYTES, st_msgs + first, cnt * 16, bar);
+    }
+    next_issue++;
+  };
+  auto wait_tile = [&]() { mbar_wait(&bars[next_wait & 1], (next_wait >> 1) & 1); next_wait++; };
+  if (g < g_end_all) { issue_tile(); issue_tile(); }
+  __syncwarp();
+  if (SYNC) PHASE_SYNC();
+  const int steps_per_sec = ec.steps_per_sec;
+  int sub = now_step >= 0 ? now_step % steps_per_sec : 0;
+
+  AgentGen gen; gen.side = 3;
+  bool agent_phase = false;
+#pragma unroll 1
+  for (int t = 0; t < T; t++) {
+    if (SYNC) PHASE_SYNC(); // ---- phase A: action -> ladders (fp64) --------------------------------------------------------
+    __syncwarp();
+    if (lane == 0) { sv->cash0 = h->cash; sv->p0 = sv->price; sv->inv0 = h->inventory; } // deepcopy(self.state), HOE.py:166
+    if (lane < 8) h->flow[lane] = 0;
+    __syncwarp();
+    if (p.agent_kind != LOBSIM_AGENT_NONE) {
+      double* act_sm = reinterpret_cast<double*>(scratch);
+      if (p.agent_kind == LOBSIM_AGENT_EXTERNAL) {
+        const double* a = p.actions_in + ((size_t)t * p.n_sel + sel) * ec.action_dim;
+        if (lane < 5) act_sm[lane] = lane < ec.action_dim ? __ldg(&a[lane]) : 0.0;
+      } else {
+        const lobsim_agent_t* agp = p.agents ? p.agents + sel : &p.agent;
+        const double inv_obs = __shfl_sync(FULL_MASK, feat_cur, agp->inventory_index & 31);
+        if (lane == 0) agent_action_cold(agp, inv_obs, act_sm);
+      }
+      __syncwarp();
+      const double a0 = act_sm[0], a1 = act_sm[1], a2 = act_sm[2], a3 = act_sm[3], a4 = act_sm[4];
+      const double mine = lane < 5 ? act_sm[lane] : 0.0;
+      __syncwarp();
+      if (p.act && p.agent_kind != LOBSIM_AGENT_EXTERNAL && lane < ec.action_dim) p.act[((size_t)t * p.n_sel + sel) * ec.action_dim + lane] = mine;
+      if (p.obs && !p.out_final_obs_only && c.inc_prev_action_in_obs && lane < ec.action_dim)
+        p.obs[((size_t)t * p.n_sel + sel) * ec.obs_dim + F + lane] = mine;
+      if (!f.dead) {
+        gen = agent_prepare(b, h->cnt[0][0], h->cnt[1][0], h->nag[0], h->nag[1], h->inventory, &ec, a0, a1, a2, a3, a4);
+        f.err |= gen.err_out; if (gen.dead_out) f.dead = 1;
+        agent_phase = true;
+      }
+    }
+    if (SYNC) PHASE_SYNC(); // ---- phase B: the step's orders: the agent's first, then the historical messages of (now, now + step]
+    {
+      if (!f.dead && now_step >= (int)stp->n_grid_steps) { f.err |= LOBSIM_ERR_END_OF_STREAM; f.dead = 1; } // re-read: keeps a register free
+      const unsigned g_step_end = f.dead ? g : __ldg(&st_step_off[now_step + 1]);
+#pragma unroll 1
+      for (;;) {
+        int type, side, oprice, vol; uint32_t ref; bool is_agent;
+        if (agent_phase) {
+          if (!agent_next_fast(fb, f, gen, type, side, oprice, vol, ref)) { agent_phase = false; continue; }
+          is_agent = true;
+        } else {
+          if (f.dead || g >= g_step_end) break;
+          const unsigned tile = g / MSG_TILE - tile0;
+          if (tile == next_wait) wait_tile();
+          const uint4 m = *reinterpret_cast<const uint4*>(msgbuf + (tile & 1) * MSG_TILE_BYTES + (g % MSG_TILE) * 16);
+          oprice = (int)m.x; vol = (int)m.y; ref = m.z; type = (int)(m.w & 7u); side = (int)((m.w >> 3) & 1u);
+          is_agent = false;
+          g++;
+          if (g % MSG_TILE == 0) { __syncwarp(); issue_tile(); }
+        }
+        if (!f.dead) fast_order_full<LT, true>(fb, f, type, side, oprice, vol, ref, is_agent);
+      }
+    }
+    if (!f.dead) {
+      now_step++;
+      if (++sub == steps_per_sec) {                          // whole second: outer-level resync, OrderbookSimulator.py:86-87
+        sub = 0;
+        if (c.resync && (!p.resync_last_only || t == T - 1)) {
+          const double prop = ec.outer_prop;
+          const double bbd = f.best0 == INT32_MIN ? 0.0 : (double)f.best0;
+          const double bsd = f.best1 == INT32_MAX ? (double)INFINITY : (double)f.best1;
+          if (bbd < (double)h->min_buy + prop * (double)h->init_buy_range || bsd > (double)h->max_sell - prop * (double)h->init_sell_range) {
+            const int sec = now_step / steps_per_sec;
+            if (sec <= (int)stp->n_seconds && stp->snap_valid[sec]) {
+              const int32_t* row = stp->snapshots + (size_t)sec * 2 * c.n_levels * 2;
+              fast_resync_tracked(fb, f, row, c.n_levels, scratch);
+            }
+          }
+        }
+      }
+    }
+    if (SYNC) PHASE_SYNC(); // ---- phase C: update_internal_state + _update_features + reward, HOE.py:163-178,199-204 -------------
+    StepView v; tops(v);
+    if (!v.have_tops) f.err |= LOBSIM_ERR_EMPTY_BOOK;
+    const double price = v.price;
+    if (lane == 0) sv->price = price;
+    v.inventory = h->inventory; v.now_us = sv->st_t0_us + (long long)now_step * c.step_us;
+    v.n_ext0 = h->flow[0]; v.n_ext1 = h->flow[1]; v.vol_ext0 = h->flow[2]; v.vol_ext1 = h->flow[3];
+    v.n_int0 = h->flow[4]; v.n_int1 = h->flow[5]; v.vol_int0 = h->flow[6]; v.vol_int1 = h->flow[7];
+    __syncwarp(); // every lane has read this step's flow counters before lanes 0-7 zero them for the next step
+    feat_cur = features_step<RARE>(&ec, fstate_env, rings_env, lane, v, sv->episode_start_us, 0);
+    const bool write_now = !p.out_final_obs_only || t == T - 1;
+    if (p.obs && write_now) {
+      double* o = p.obs + ((size_t)(p.out_final_obs_only ? 0 : t) * p.n_sel + sel) * ec.obs_dim;
+      if (lane < F) o[lane] = feat_cur;
+      if (c.inc_prev_action_in_obs && lane < ec.action_dim && (p.agent_kind == LOBSIM_AGENT_NONE || p.out_final_obs_only)) o[F + lane] = 0.0;
+    }
+    if (p.agent_kind != LOBSIM_AGENT_NONE) {
+      const double cash1 = h->cash; const long long inv1 = h->inventory;
+      const bool d = now_step >= h->episode_start_step + c.episode_steps; // terminal_time - now < step/2, HOE.py:172
+      const double r = step_reward<RARE>(p, c, env, lane, d, sv->cash0, sv->inv0, sv->p0, cash1, inv1, price, f.err);
+      if (lane == 0) {
+        if (p.rew) p.rew[(size_t)t * p.n_sel + sel] = r;
+        if (p.done) p.done[(size_t)t * p.n_sel + sel] = d ? 1 : 0;
+      }
+      if (p.info) write_info(p.info + ((size_t)t * p.n_sel + sel) * LOBSIM_INFO_DIM, lane, v, cash1, inv1, f.err);
+    }
+  }
+  if (T == 0 && p.obs && p.reset_mode == 2) { // reset with no warm-up: obs straight after _reset_features
+    double* o = p.obs + (size_t)sel * ec.obs_dim;
+    if (lane < F) o[lane] = feat_cur;
+    if (c.inc_prev_action_in_obs && lane < ec.action_dim) o[F + lane] = 0.0;
+  }
+  while (next_wait < next_issue) wait_tile();
+  __syncwarp();
+  if (lane == 0) {
+    if (f.fill_log && h->n_fills > f.fill_cap) f.err |= LOBSIM_ERR_FILL_LOG_FULL;
+    h->now_step = now_step; h->price = sv->price; h->err = f.err; h->dead = f.dead;
+    if (p.fill_count) p.fill_count[env] = h->n_fills;
+  }
+  __syncwarp();
+  fence_proxy_async();
+  __syncwarp();
+  if (lane == 0) { tma_store(gblob, base, (uint32_t)LT::blob_bytes); tma_store_wait(); }
+  __syncwarp();
+}

@@ -219,6 +219,12 @@ class LobSim:
         return self.state()["err"].copy()
 
     @property
+    def kernel_path(self) -> str:
+        """"fast": the straight-line static-layout kernels serve this handle; "general": the runtime-layout kernel
+        (capacities without a compiled layout, csrc/layouts.h, or LOBSIM_FORCE_GENERAL=1)."""
+        return "fast" if lib().lobsim_kernel_path(self._h) == abi.PATH_FAST else "general"
+
+    @property
     def launch_count(self) -> int:
         return int(lib().lobsim_launch_count(self._h))
 

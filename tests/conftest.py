@@ -11,6 +11,24 @@ for p in (str(ROOT), str(ROOT / "tests")):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with `-m gpu`)")
+    config.addinivalue_line("markers", "fast_only: GPU test that is about the straight-line kernels only (not repeated "
+                                       "on the general kernel family)")
+
+
+def pytest_generate_tests(metafunc):
+    """Every GPU test runs twice: on the straight-line static-layout kernels ("fast") and, with LOBSIM_FORCE_GENERAL=1,
+    on the general runtime-layout kernel ("general") -- two independent implementations of the same semantics."""
+    if "kernel_family" in metafunc.fixturenames and metafunc.definition.get_closest_marker("gpu"):
+        fams = ["fast"] if metafunc.definition.get_closest_marker("fast_only") else ["fast", "general"]
+        metafunc.parametrize("kernel_family", fams, indirect=True)
+
+
+@pytest.fixture(autouse=True)
+def kernel_family(request, monkeypatch):
+    fam = getattr(request, "param", None)
+    if fam is not None:
+        monkeypatch.setenv("LOBSIM_FORCE_GENERAL", "1" if fam == "general" else "0")
+    return fam
 
 
 @pytest.fixture(scope="session")

@@ -133,6 +133,24 @@ def test_config3_rollout_65536_envs():
     total = rew.sum(0).cpu().numpy()
     mtm = st["cash"] + st["inventory"] * st["price"]
     assert np.allclose(total, mtm - 1000.0, rtol=1e-9, atol=1e-3)
+    # a sample of 8 envs against the CPU oracle: reset obs, every step's obs / reward / done, final book and portfolio
+    from oracle.oracle import Oracle
+
+    ocfg = abi.default_cfg(n_levels=10, episode_steps=64, warmup_steps=100, features=feats, step_reward=abi.Reward(abi.REWARD_PNL, 0, 0),
+                           terminal_reward=abi.Reward(abi.REWARD_PNL, 0, 0), portfolio_carryover=0)
+    obs0_h, obs_h, rew_h, done_h = obs0.cpu().numpy(), obs.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy()
+    for env in (0, 1, 4098, 20_001, 33_333, 48_000, 65_534, 65_535):
+        o = Oracle(ocfg, s)
+        r0 = o.reset(int(starts[env]))
+        assert np.allclose(obs0_h[env], r0, rtol=1e-6, atol=1e-9), env
+        oo, oa, orw, od = o.rollout(64, agent)
+        assert np.allclose(obs_h[:, env], oo, rtol=1e-6, atol=1e-9, equal_nan=True), env
+        assert np.allclose(rew_h[:, env], orw, rtol=1e-6, atol=1e-9), env
+        assert np.array_equal(done_h[:, env], od), env
+        for side in (0, 1):
+            assert np.array_equal(sim.dump_book(env, side)[["price", "volume"]], o.dump_book(side)[["price", "volume"]]), (env, side)
+        os_ = o.state()
+        assert st["inventory"][env] == os_["inventory"] and st["cash"][env] == os_["cash"], env
 
 
 def test_config4_collect_rollouts_example_single_gpu():

@@ -93,6 +93,7 @@ def test_random_env_case(seed):
     sim.close()
 
 
+@pytest.mark.fast_only          # the test itself runs both kernel families
 @pytest.mark.parametrize("seed", range(SEED0, SEED0 + N_REPLAY_CASES))
 def test_random_replay_case(seed, monkeypatch):
     """Pure replay (both kernel families: the straight-line k_replay_fast and, forced, the general k_advance) vs the oracle."""
