@@ -49,6 +49,25 @@ def episode_stats(rew: torch.Tensor, done: torch.Tensor, state: np.ndarray, obs_
     return out
 
 
+def episode_stats_dev(rew: torch.Tensor, done: torch.Tensor, state_dev: torch.Tensor, obs_spread: torch.Tensor = None) -> torch.Tensor:
+    """`episode_stats` without leaving the device: ``state_dev`` is ``LobSim.state_dev()`` ([N, 80] uint8 =
+    lobsim_env_state_t records); no host synchronisation, so it can sit between a rollout and the all-gather."""
+    T, N = rew.shape
+    i64, f64, i32 = state_dev.view(torch.int64), state_dev.view(torch.float64), state_dev.view(torch.int32)
+    inv, cash, price, err = i64[:, 0].to(torch.float64), f64[:, 1], f64[:, 2], i32[:, 14]
+    out = torch.zeros((N, len(STAT_FIELDS)), dtype=torch.float32, device=rew.device)
+    out[:, 0] = rew.sum(dim=0).to(torch.float32)
+    out[:, 1] = float(T)
+    out[:, 2] = inv.to(torch.float32)
+    out[:, 3] = cash.to(torch.float32)
+    out[:, 4] = (cash + price * inv).to(torch.float32)
+    if obs_spread is not None:
+        out[:, 5] = obs_spread.to(torch.float32).mean(dim=0)
+    out[:, 6] = done.to(torch.float32).sum(dim=0)
+    out[:, 7] = err.to(torch.float32)
+    return out
+
+
 def gather_episode_stats(stats_local: torch.Tensor, n_envs_total: int = None) -> torch.Tensor:
     """All-gather [N_local, K] -> [N_total, K] in GLOBAL env order (env i is row i).  Requires equal N_local on all
     ranks (pad the last shard) -- one `all_gather_into_tensor` per rollout, latency-bound (32 B per env)."""
