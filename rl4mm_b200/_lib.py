@@ -23,12 +23,15 @@ def lib():
     global _LIB
     if _LIB is not None:
         return _LIB
-    if not _NATIVE.exists():
+    import os
+
+    native = Path(os.environ["LOBSIM_NATIVE_LIB"]) if os.environ.get("LOBSIM_NATIVE_LIB") else _NATIVE   # A/B builds (tools/)
+    if not native.exists():
         raise LobsimError(
-            f"{_NATIVE} is missing: build the CUDA extension first (python -m rl4mm_b200.build, or "
+            f"{native} is missing: build the CUDA extension first (python -m rl4mm_b200.build, or "
             "__graft_entry__.build()).  The lobsim hot path has no CPU fallback."
         )
-    L = C.CDLL(str(_NATIVE))
+    L = C.CDLL(str(native))
     vp, i32, u32, i64, u64 = C.c_void_p, C.c_int32, C.c_uint32, C.c_int64, C.c_uint64
     sig = {
         "lobsim_last_error": (C.c_char_p, []),
@@ -69,7 +72,7 @@ def lib():
     from .build import source_hash
 
     built_from, here = L.lobsim_source_hash().decode(), source_hash()
-    if built_from != here:
+    if built_from != here and native == _NATIVE:
         raise LobsimError(f"{_NATIVE} was built from other sources (stamp {built_from[:12]}, tree {here[:12]}): rebuild "
                           "(python -m rl4mm_b200.build, or __graft_entry__.build())")
     _LIB = L

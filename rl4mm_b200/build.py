@@ -76,16 +76,24 @@ def n_fast_layouts() -> int:
     return int(m.group(1))
 
 
-def build_lobsim(force: bool = False, verbose: bool = False) -> Path:
+def build_lobsim(force: bool = False, verbose: bool = False, variant: str = None, extra_flags=()) -> Path:
+    """`variant` + `extra_flags`: an experimental build (A/B of -D switches) into _native/variants/liblobsim_<variant>.so,
+    loaded instead of the product library when LOBSIM_NATIVE_LIB points at it (tools/gpu_ab.sh)."""
+    global OBJ
     OUT.mkdir(exist_ok=True)
     out, stamp = OUT / "liblobsim.so", OUT / "liblobsim.hash"
     want = source_hash()
+    if variant:
+        (OUT / "variants").mkdir(exist_ok=True)
+        out, stamp = OUT / "variants" / f"liblobsim_{variant}.so", OUT / "variants" / f"liblobsim_{variant}.hash"
+        OBJ = OUT / "variants" / f"obj_{variant}"
+        want = hashlib.sha256((want + " ".join(extra_flags)).encode()).hexdigest()
     if not force and out.exists() and stamp.exists() and stamp.read_text().strip() == want:
         return out
     OBJ.mkdir(exist_ok=True)
     nvcc = nvcc_path()
-    common = [nvcc, *NVCC_FLAGS, "-I", str(INCLUDE), "-I", str(CSRC)]
-    jobs = [("lobsim", common + [f'-DLOBSIM_SOURCE_HASH="{want}"', "-c", str(CSRC / "lobsim.cu")])]
+    common = [nvcc, *NVCC_FLAGS, *extra_flags, "-I", str(INCLUDE), "-I", str(CSRC)]
+    jobs = [("lobsim", common + [f'-DLOBSIM_SOURCE_HASH="{source_hash()}"', "-c", str(CSRC / "lobsim.cu")])]
     for i in range(n_fast_layouts()):
         for part in (0, 1):
             jobs.append((f"fast{i}_{part}", common + [f"-DLOBSIM_LAYOUT_INDEX={i}", f"-DLOBSIM_TU_PART={part}", "-c", str(CSRC / "fast_layout.cu")]))
@@ -124,4 +132,8 @@ def build_all(force: bool = False, verbose: bool = False) -> None:
 if __name__ == "__main__":
     import sys
 
-    build_all(force="--force" in sys.argv, verbose=True)
+    if "--variant" in sys.argv:      # python -m rl4mm_b200.build --variant NAME -DFOO=1 ...
+        i = sys.argv.index("--variant")
+        print(build_lobsim(force="--force" in sys.argv, variant=sys.argv[i + 1], extra_flags=[a for a in sys.argv[i + 2:] if a != "--force"]))
+    else:
+        build_all(force="--force" in sys.argv, verbose="-v" in sys.argv)

@@ -13,14 +13,18 @@ struct __align__(16) FeatState {
   long long diff;    // trade_diff / volume_imbalance
   int32_t len;       // deque length (bit 30: running sums valid)
   int32_t head;      // circular write position
-  // rolling z-score (Feature.normalise): shifted running sums over the history ring
+};
+static_assert(sizeof(FeatState) == 32, "FeatState layout");
+// rolling z-score (Feature.normalise): shifted running sums over the history ring.  A separate array that exists only for
+// configurations with normalisation_on features: the per-step feature phase of every other configuration moves 32 B per feature.
+struct __align__(16) NormState {
   double nK, nS1, nS2; // shift K (first history value), sum (x-K), sum (x-K)^2
   int32_t nlen, nhead; // history length, next write position (= oldest entry once full)
   int32_t nrun;        // number of equal trailing history values (constant window)
   int32_t pad;
   double nS2max;       // largest nS2 since the sums were last recomputed exactly (bounds their accumulated rounding error)
 };
-static_assert(sizeof(FeatState) == 80, "FeatState layout");
+static_assert(sizeof(NormState) == 48, "NormState layout");
 #define FEAT_SUMS_VALID (1 << 30)
 
 struct EnvConst { // what the device needs of lobsim_cfg_t, by value in the kernel parameters
@@ -31,6 +35,9 @@ struct EnvConst { // what the device needs of lobsim_cfg_t, by value in the kern
   int32_t action_dim, obs_dim;
   int32_t steps_per_sec;                 // 1000000 / step_us        } precomputed on the host: 64-bit and fp64 divisions are
   double outer_prop;                     // outer_levels / n_levels  } subroutine calls on the device, unwanted in the hot kernels
+  int32_t steps_per_min;                 // 60000000 / step_us
+  int32_t pad0;
+  long long feat_aux[LOBSIM_MAX_FEATURES]; // TIME_OF_DAY: the bucket width in microseconds (Features.py:526-536), else 0
 };
 
 __device__ __forceinline__ long long now_us_of(const lobsim_stream_t& st, const lobsim_cfg_t& c, int now_step) {
@@ -167,12 +174,14 @@ static __device__ __noinline__ WarpState init_book_cold(const Book b, WarpState 
 
 // ---- BetaOrderDistributor, rl4mm/gym/action_interpretation/OrderDistributors.py:23-56 ----------------------------
 // lane k < Q returns the lot size of quote level k.  The sum follows numpy's pairwise summation order.
-static __device__ __noinline__ int beta_ladder_lane(double a, double bpar, int Q, int active_volume, int lane) {
-  double x = 1.0 / (double)Q * ((double)lane + 0.5);
+// log_x / log1m_x: ln(x_k) and ln(1 - x_k) = log1p(-x_k) of this lane's level midpoint x_k = (k + 0.5) / Q -- constants of the
+// configuration, tabulated once by lobsim_create (the reference evaluates the Beta pdf at the same fixed midpoints every step,
+// OrderDistributors.py:37); what is left per step is one exp per level.
+static __device__ __noinline__ int beta_ladder_lane(double a, double bpar, int Q, int active_volume, int lane, double log_x, double log1m_x) {
   double A = -INFINITY;
   if (lane < Q) {
-    double lx = (a - 1.0) == 0.0 ? 0.0 : (a - 1.0) * log(x);
-    double l1 = (bpar - 1.0) == 0.0 ? 0.0 : (bpar - 1.0) * log1p(-x);
+    double lx = (a - 1.0) == 0.0 ? 0.0 : (a - 1.0) * log_x;
+    double l1 = (bpar - 1.0) == 0.0 ? 0.0 : (bpar - 1.0) * log1m_x;
     A = lx + l1;
   }
   double amax = A;
@@ -217,8 +226,9 @@ struct AgentGen {
 };
 
 // Cold (noinline, everything by value): the fp64 ladder math must not inflate the register budget of the hot loop.
+// beta_tab: [2][32] doubles (ln x_k, ln(1 - x_k)) in global memory; vol_scratch: per-warp int[64] in shared memory.
 static __device__ __noinline__ AgentGen agent_prepare(const Book b, int nlv0, int nlv1, int nag0, int nag1, long long inventory, const EnvConst* ecp,
-                                               double a0, double a1, double a2, double a3, double a4) {
+                                               double a0, double a1, double a2, double a3, double a4, const double* __restrict__ beta_tab, int* vol_scratch) {
   const EnvConst& ec = *ecp;
   const lobsim_cfg_t& c = ec.cfg;
   const double action[5] = {a0, a1, a2, a3, a4};
@@ -231,8 +241,9 @@ static __device__ __noinline__ AgentGen agent_prepare(const Book b, int nlv0, in
   if (c.concentration >= 0) {
     ab = action[0] + EPS; bbp = c.concentration - ab + EPS; as = action[1] + EPS; bsp = c.concentration - as + EPS;
   } else { ab = action[0] + EPS; bbp = action[1] + EPS; as = action[2] + EPS; bsp = action[3] + EPS; }
-  int desired0 = beta_ladder_lane(ab, bbp, Q, c.active_volume, b.lane);
-  int desired1 = beta_ladder_lane(as, bsp, Q, c.active_volume, b.lane);
+  const double log_x = __ldg(&beta_tab[b.lane]), log1m_x = __ldg(&beta_tab[32 + b.lane]);
+  int desired0 = beta_ladder_lane(ab, bbp, Q, c.active_volume, b.lane, log_x, log1m_x);
+  int desired1 = beta_ladder_lane(as, bsp, Q, c.active_volume, b.lane, log_x, log1m_x);
   long long absinv = inventory < 0 ? -inventory : inventory;
   const bool clearing = c.market_order_clearing && (double)absinv > pick5(action, ec.action_dim - 1);
   if (clearing) desired0 = desired1 = 0;
@@ -247,13 +258,24 @@ static __device__ __noinline__ AgentGen agent_prepare(const Book b, int nlv0, in
   }
   g.price0 = bb - (c.min_quote_level + b.lane) * tick; // ladder price of this lane's quote level
   g.price1 = bs + (c.min_quote_level + b.lane) * tick;
-  if (b.lane < Q) { // _get_current_internal_order_volumes :291-296
-    int cur0 = 0, cur1 = 0;
-    for (int i = 0; i < nag0; i++) cur0 += b.aprice(0)[i] == g.price0 ? b.avol(0)[i] : 0;
-    for (int i = 0; i < nag1; i++) cur1 += b.aprice(1)[i] == g.price1 ? b.avol(1)[i] : 0;
-    g.diff0 = desired0 - cur0; g.diff1 = desired1 - cur1;
+  { // _get_current_internal_order_volumes :291-296 -- one agent order per lane: its ladder index k = distance from the ladder's
+    // first price in ticks; the resting volume per ladder level is accumulated with shared-memory atomics (integers: order-free)
+    __syncwarp();
+    vol_scratch[b.lane] = 0; vol_scratch[32 + b.lane] = 0;
+    __syncwarp();
+    const int base0 = bb - c.min_quote_level * tick, base1 = bs + c.min_quote_level * tick;
+    for (int i = b.lane; i < nag0; i += 32) {
+      const int d = base0 - b.aprice(0)[i];
+      if (d >= 0) { const int q = d / tick; if (q * tick == d && q < Q) atomicAdd(&vol_scratch[q], b.avol(0)[i]); }
+    }
+    for (int i = b.lane; i < nag1; i += 32) {
+      const int d = b.aprice(1)[i] - base1;
+      if (d >= 0) { const int q = d / tick; if (q * tick == d && q < Q) atomicAdd(&vol_scratch[32 + q], b.avol(1)[i]); }
+    }
+    __syncwarp();
+    if (b.lane < Q) { g.diff0 = desired0 - vol_scratch[b.lane]; g.diff1 = desired1 - vol_scratch[32 + b.lane]; }
+    __syncwarp();
   }
-  __syncwarp();
   g.side = 0; g.Q = Q;
   g.clearing = clearing;
   g.clear_vol = clearing ? (int)rint((double)absinv * c.market_order_fraction_of_inventory) : 0;
@@ -353,11 +375,12 @@ __device__ __forceinline__ double reward_calc(const lobsim_reward_t& r, double c
 struct StepView { // uniform inputs of the feature updates
   int have_tops; int bb, bs, bv, sv;
   double price; long long inventory; long long now_us;
+  int us_in_min;   // now_us % 60 s (32-bit: the update-frequency gate of every feature, Features.py:102-105)
   int n_ext0, n_ext1, vol_ext0, vol_ext1, n_int0, n_int1, vol_int0, vol_int1;
 };
 
 // Feature._update of the concrete classes; `ring` is this (env, feature)'s circular buffer in global memory
-__device__ __forceinline__ void feature_update_raw(const lobsim_feature_t& fc, FeatState& f, double* ring, const StepView& v) {
+__device__ __forceinline__ void feature_update_raw(const lobsim_feature_t& fc, FeatState& f, double* ring, const StepView& v, long long aux) {
   const int k = fc.lookback;
   switch (fc.kind) {
     case LOBSIM_FEAT_SPREAD: f.cur = v.have_tops ? (double)(v.bs - v.bb) : NAN; break;
@@ -366,10 +389,8 @@ __device__ __forceinline__ void feature_update_raw(const lobsim_feature_t& fc, F
     case LOBSIM_FEAT_INVENTORY: f.cur = (double)v.inventory; break;
     case LOBSIM_FEAT_EPISODE_PROPORTION: f.cur += fc.dparam; break;
     case LOBSIM_FEAT_TIME_OF_DAY: {
-      const long long min_time = 10LL * 3600 * 1000000, max_time = (15LL * 3600 + 1800) * 1000000;
-      long long tot = max_time - min_time, nb = fc.iparam;
-      long long bucket = tot / nb, rem = tot % nb;
-      if (2 * rem > nb || (2 * rem == nb && (bucket & 1))) bucket++;
+      const long long min_time = 10LL * 3600 * 1000000;
+      const long long bucket = aux;   // (15:30 - 10:00) / n_buckets, rounded like timedelta division (host: time_of_day_bucket_us)
       long long d = v.now_us - min_time;
       long long q = d >= 0 ? d / bucket : -((-d + bucket - 1) / bucket);
       f.cur = (double)(q > 0 ? q : 0);
@@ -557,7 +578,7 @@ static __device__ __noinline__ double zscore_exact(const double* hist, int maxle
 }
 
 // exact shifted sums of the window around a new centre (sheds accumulated rounding and cancellation)
-static __device__ __noinline__ void zscore_recenter(FeatState& f, const double* hist, int maxlen, int start, int n, double centre) {
+static __device__ __noinline__ void zscore_recenter(NormState& f, const double* hist, int maxlen, int start, int n, double centre) {
   double s1 = 0.0, s2 = 0.0;
   for (int i = 0; i < n; i++) {
     int k = start + i; if (k >= maxlen) k -= maxlen;
@@ -567,10 +588,11 @@ static __device__ __noinline__ void zscore_recenter(FeatState& f, const double* 
   f.nK = centre; f.nS1 = s1; f.nS2 = s2; f.nS2max = s2;
 }
 
-// Cold and out of line, working on the FeatState in global memory after features_step has stored it: nothing of the caller
-// stays live across the (rare) calls into the exact paths, so the per-step feature code keeps its registers.
-static __device__ __noinline__ double feature_normalise(FeatState* fg, double* hist, int maxlen, double value) {
-  FeatState f = *fg;
+// Cold and out of line, working on the NormState in global memory: nothing of the caller stays live across the (rare) calls
+// into the exact paths, so the per-step feature code keeps its registers.  Returns the normalised current value.
+static __device__ __noinline__ double feature_normalise(NormState* fg, double* hist, int maxlen, double value) {
+  NormState f = *fg;
+  double cur;
   int n = f.nlen;
   int head = f.nhead;
   double last = NAN;
@@ -588,9 +610,9 @@ static __device__ __noinline__ double feature_normalise(FeatState* fg, double* h
   int start = head - n; if (start < 0) start += maxlen;      // ring index of the oldest entry
   if (f.nrun >= n) {                                          // the whole window holds one value
     f.nK = value; f.nS1 = 0.0; f.nS2 = 0.0; f.nS2max = 0.0;   // exact sums around the value itself
-    f.cur = zscore_exact(hist, maxlen, start, n, value, 1);
+    cur = zscore_exact(hist, maxlen, start, n, value, 1);
     *fg = f;
-    return f.cur;
+    return cur;
   }
   double d = value - f.nK;
   f.nS1 += d; f.nS2 += d * d;
@@ -607,28 +629,27 @@ static __device__ __noinline__ double feature_normalise(FeatState* fg, double* h
     d = value - f.nK; m1 = f.nS1 / (double)n; msq = f.nS2 / (double)n; var = msq - m1 * m1;
   }
   const double sd = sqrt(var);
-  if (!(sd > 1e-8 * fabs(f.nK + m1))) f.cur = zscore_exact(hist, maxlen, start, n, value, 0);   // noise-dominated (or NaN)
-  else f.cur = (d - m1) / sd;
+  if (!(sd > 1e-8 * fabs(f.nK + m1))) cur = zscore_exact(hist, maxlen, start, n, value, 0);   // noise-dominated (or NaN)
+  else cur = (d - m1) / sd;
   *fg = f;
-  return f.cur;
+  return cur;
 }
 
-// Feature.reset/_reset, Features.py:92-96
-__device__ __forceinline__ void feature_reset(const lobsim_feature_t& fc, FeatState& f, double* ring, const StepView& v) {
+// Feature.reset/_reset, Features.py:92-96 (the normalisation history is cleared by features_step)
+__device__ __forceinline__ void feature_reset(const lobsim_feature_t& fc, FeatState& f, double* ring, const StepView& v, long long aux) {
   f.len = 0; f.head = 0; f.total = 0; f.diff = 0;
-  f.nlen = 0; f.nhead = 0; f.nrun = 0; // history.clear()
   if (fc.kind == LOBSIM_FEAT_AMIHUD_LAMBDA) { f.len = (fc.iparam - 1) << 16; f.diff = __double_as_longlong(0.0); } // AmihudLambda.reset :278-283
-  feature_update_raw(fc, f, ring, v);
+  feature_update_raw(fc, f, ring, v, aux);
   if (fc.kind == LOBSIM_FEAT_EPISODE_PROPORTION) f.cur = 0.0;
 }
 
 // Feature.update, Features.py:80-86,102-105
 // returns true when the (clamped) value still has to go through Feature.normalise (done by the caller, out of line)
-__device__ __forceinline__ bool feature_update(const lobsim_feature_t& fc, FeatState& f, double* ring, const StepView& v, long long episode_start_us) {
+__device__ __forceinline__ bool feature_update(const lobsim_feature_t& fc, FeatState& f, double* ring, const StepView& v, long long episode_start_us, long long aux) {
   long long first_usage = episode_start_us - (long long)fc.lookback * fc.update_us;
   if (v.now_us < first_usage) return false;
-  if ((v.now_us % 60000000LL) % fc.update_us != 0) return false;
-  feature_update_raw(fc, f, ring, v);
+  if (v.us_in_min % (int)fc.update_us != 0) return false;   // (second * 1e6 + microsecond) % update_frequency, update_us <= 60 s
+  feature_update_raw(fc, f, ring, v, aux);
   f.cur = fmax(fmin(f.cur, fc.max_value), fc.min_value);
   return fc.norm_len > 0;
 }
@@ -638,8 +659,10 @@ __device__ __forceinline__ bool feature_update(const lobsim_feature_t& fc, FeatS
 // code (and its registers) away from the order-processing loop.
 // NORM == false instantiations contain no call into the z-score code: a callee subtree that is never executed still costs
 // the calling kernel registers around the call and I-cache footprint (measured: 3.7 % of the env step).
+// With normalisation the value a feature's recurrences continue from (Feature.current_value, e.g. Volatility) IS the
+// normalised one (Features.py:80-86 overwrites current_value), so it is written back into the FeatState.
 template <bool NORM>
-static __device__ __noinline__ double features_step(const EnvConst* ecp, FeatState* fstate_env, double* rings_env, int lane, const StepView v, long long episode_start_us, int mode) {
+static __device__ __noinline__ double features_step(const EnvConst* ecp, FeatState* fstate_env, NormState* nstate_env, double* rings_env, int lane, const StepView v, long long episode_start_us, int mode) {
   const EnvConst& ec = *ecp;
   double cur = 0.0;
   if (lane < ec.cfg.n_features) {
@@ -647,11 +670,13 @@ static __device__ __noinline__ double features_step(const EnvConst* ecp, FeatSta
     FeatState fs = fstate_env[lane];
     double* ring = rings_env + ec.ring_off[lane];
     bool norm = false;
-    if (mode == 1) feature_reset(fc, fs, ring, v);
-    else norm = feature_update(fc, fs, ring, v, episode_start_us);
+    if (mode == 1) {
+      feature_reset(fc, fs, ring, v, ec.feat_aux[lane]);
+      if (NORM && fc.norm_len > 0) { NormState z; z.nK = z.nS1 = z.nS2 = z.nS2max = 0.0; z.nlen = z.nhead = z.nrun = z.pad = 0; nstate_env[lane] = z; } // history.clear()
+    } else norm = feature_update(fc, fs, ring, v, episode_start_us, ec.feat_aux[lane]);
+    if (NORM && norm) fs.cur = feature_normalise(&nstate_env[lane], rings_env + ec.hist_off[lane], fc.norm_len, fs.cur);
     fstate_env[lane] = fs;
     cur = fs.cur;
-    if (NORM && norm) cur = feature_normalise(&fstate_env[lane], rings_env + ec.hist_off[lane], fc.norm_len, cur);
   }
   return cur;
 }

@@ -53,6 +53,10 @@ __device__ __forceinline__ void tma_store(void* dst_gmem, const void* src_smem, 
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
+__device__ __forceinline__ void tma_store_part(void* dst_gmem, const void* src_smem, uint32_t bytes) { // no commit: several parts, one group
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
 // ====================================================================================================================
@@ -66,10 +70,15 @@ __device__ __forceinline__ void tma_store_wait() { asm volatile("cp.async.bulk.w
 #endif
 #define MSG_TILE 32                      // records per TMA tile
 #define MSG_TILE_BYTES (MSG_TILE * 16)
+// per-warp scratch behind the message tiles: int2[2 * NA] for update_outer_levels (the agent's re-queued orders), at least
+// int[64] for the agent's resting volume per ladder level (agent_prepare) and the 5 action doubles
+__host__ __device__ constexpr int scratch_bytes(int NA) { return 2 * NA * 8 > 256 ? 2 * NA * 8 : 256; }
 
 struct AdvParams {
   unsigned char* blobs;             // [n_envs][blob_bytes]
   FeatState* fstate;                // [n_envs][LOBSIM_MAX_FEATURES]
+  NormState* nstate;                // [n_envs][LOBSIM_MAX_FEATURES] rolling z-score state, or null (no normalised feature configured)
+  const double* beta_tab;           // [2][32]: ln x_k, ln(1 - x_k) at the quote-level midpoints x_k = (k + 0.5) / Q
   double* rings;                    // [n_envs][ring_stride]
   double* rs_ring;                  // RollingSharpe [n_envs][3][LOBSIM_MAX_SHARPE_WINDOW]: two AUM windows + a scratch row of returns, or null
   int32_t* rs_state;                // [n_envs][2][2] = {n_filled, head}
@@ -130,6 +139,12 @@ __device__ __forceinline__ double step_reward(const AdvParams& p, const lobsim_c
   return r;
 }
 
+// (second * 1e6 + microsecond) of now = t0 + now_step * step_us, in 32-bit arithmetic (t0 % 60 s comes with the stream)
+__device__ __forceinline__ int us_in_minute(int t0_mod_min, int now_step, const EnvConst& ec) {
+  int u = t0_mod_min + (now_step % ec.steps_per_min) * (int)ec.cfg.step_us;
+  return u >= 60000000 ? u - 60000000 : u;
+}
+
 __device__ __forceinline__ unsigned char* warp_smem_base(unsigned char* smem, int warp, int warp_smem) { return smem + (size_t)warp * warp_smem; }
 
 // ====================================================================================================================
@@ -150,7 +165,7 @@ __global__ void __launch_bounds__(128, kEnv ? LOBSIM_ENV_MIN_BLOCKS : 4) k_advan
   Book b; b.blob = base; b.L = p.L; b.lane = lane;
   unsigned char* msgbuf = base + p.L.blob_bytes;                                   // 2 x 512 B
   int2* scratch = reinterpret_cast<int2*>(msgbuf + 2 * MSG_TILE_BYTES);             // [2*NA]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(scratch) + 2 * p.L.NA * 8); // 3 barriers
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(scratch) + scratch_bytes(p.L.NA)); // 3 barriers
   unsigned char* gblob = p.blobs + (size_t)env * p.L.blob_bytes;
 
   // ---- book blob: HBM -> shared memory ---------------------------------------------------------------------------
@@ -200,9 +215,11 @@ __global__ void __launch_bounds__(128, kEnv ? LOBSIM_ENV_MIN_BLOCKS : 4) k_advan
   const long long episode_start_us = st_t0_us + (long long)h->episode_start_step * c.step_us;
 
   FeatState* fstate_env = p.fstate + (size_t)env * LOBSIM_MAX_FEATURES;
+  NormState* nstate_env = p.nstate ? p.nstate + (size_t)env * LOBSIM_MAX_FEATURES : nullptr;
   double* rings_env = p.rings + (size_t)env * ec.ring_stride;
   double feat_cur = 0.0; // Feature.current_value of this lane's feature
   if (kEnv && lane < F) feat_cur = fstate_env[lane].cur;
+  const int t0_mod_min = (int)stp->reserved;   // t0_us % 60 s, filled in by lobsim_load_stream
 
   // price / tops of the current book
   auto tops = [&](StepView& v) {
@@ -218,9 +235,10 @@ __global__ void __launch_bounds__(128, kEnv ? LOBSIM_ENV_MIN_BLOCKS : 4) k_advan
   if (kEnv && p.reset_mode == 2) { // State(...) + _reset_features, HOE.py:152-154,218-221
     StepView v; tops(v);
     v.inventory = w.inventory; v.now_us = st_t0_us + (long long)now_step * c.step_us;
+    v.us_in_min = us_in_minute(t0_mod_min, now_step, ec);
     v.n_ext0 = v.n_ext1 = v.vol_ext0 = v.vol_ext1 = v.n_int0 = v.n_int1 = v.vol_int0 = v.vol_int1 = 0;
     price = v.price;
-    feat_cur = features_step<true>(&ec, fstate_env, rings_env, lane, v, episode_start_us, 1);
+    feat_cur = features_step<true>(&ec, fstate_env, nstate_env, rings_env, lane, v, episode_start_us, 1);
   }
 
   // ---- message pipeline ----------------------------------------------------------------------------------------------
@@ -278,7 +296,7 @@ __global__ void __launch_bounds__(128, kEnv ? LOBSIM_ENV_MIN_BLOCKS : 4) k_advan
         if (p.act && p.agent_kind != LOBSIM_AGENT_EXTERNAL && lane < ec.action_dim) p.act[((size_t)t * p.n_sel + sel) * ec.action_dim + lane] = mine;
         if (p.obs && !p.out_final_obs_only && c.inc_prev_action_in_obs && lane < ec.action_dim)
           p.obs[((size_t)t * p.n_sel + sel) * ec.obs_dim + F + lane] = mine; // get_observation(action), HOE.py:171
-        gen = agent_prepare(b, w.nlv0, w.nlv1, w.nag0, w.nag1, w.inventory, &ec, a0, a1, a2, a3, a4);
+        gen = agent_prepare(b, w.nlv0, w.nlv1, w.nag0, w.nag1, w.inventory, &ec, a0, a1, a2, a3, a4, p.beta_tab, reinterpret_cast<int*>(scratch));
         w.err |= gen.err_out; if (gen.dead_out) w.dead = 1;
         agent_phase = true;
       }
@@ -325,9 +343,10 @@ __global__ void __launch_bounds__(128, kEnv ? LOBSIM_ENV_MIN_BLOCKS : 4) k_advan
       if (!v.have_tops) w.err |= LOBSIM_ERR_EMPTY_BOOK;
       price = v.price;
       v.inventory = w.inventory; v.now_us = st_t0_us + (long long)now_step * c.step_us;
+      v.us_in_min = us_in_minute(t0_mod_min, now_step, ec);
       v.n_ext0 = w.n_ext0; v.n_ext1 = w.n_ext1; v.vol_ext0 = w.vol_ext0; v.vol_ext1 = w.vol_ext1;
       v.n_int0 = w.n_int0; v.n_int1 = w.n_int1; v.vol_int0 = w.vol_int0; v.vol_int1 = w.vol_int1;
-      feat_cur = features_step<true>(&ec, fstate_env, rings_env, lane, v, episode_start_us, 0);
+      feat_cur = features_step<true>(&ec, fstate_env, nstate_env, rings_env, lane, v, episode_start_us, 0);
       const bool write_now = !p.out_final_obs_only || t == T - 1;
       if (p.obs && write_now) {
         double* o = p.obs + ((size_t)(p.out_final_obs_only ? 0 : t) * p.n_sel + sel) * ec.obs_dim;
@@ -383,7 +402,7 @@ __global__ void __launch_bounds__(128, 7) k_replay_fast(const __grid_constant__ 
   unsigned char* base = warp_smem_base(smem, warp, p.warp_smem);
   unsigned char* msgbuf = base + LT::blob_bytes;
   int2* scratch = reinterpret_cast<int2*>(msgbuf + 2 * MSG_TILE_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(scratch) + 2 * LT::NA * 8);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(scratch) + scratch_bytes(LT::NA));
   unsigned char* gblob = p.blobs + (size_t)env * LT::blob_bytes;
   if (lane == 0) {
     mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
@@ -492,8 +511,45 @@ static __device__ __noinline__ uint32_t reset_book_cold(unsigned char* blob, con
   return pack_errdead(w.err, w.dead);
 }
 
+// ---- the OCCUPIED part of a book blob (env kernels: one blob round trip per env step when a policy runs between steps) ----
+// Only what the counters in the header say is in use moves between HBM and shared memory: per side the level prices, the
+// level ends and the order entries up to {nlv, nord}, and the agent tables up to nag -- about 1.5 KB of a 6.5 KB blob for a
+// 10-level book.  Sizes are rounded up to the 16-byte granularity of cp.async.bulk; every array of a StaticLayout starts
+// 16-byte aligned and its capacity is a multiple of 16 bytes, so a rounded-up part never leaves its array.
+// Lane 0 only.  LOAD: the header has already arrived in shared memory; returns the bytes expected on `bar` (0: nothing issued).
+template <class LT, bool LOAD>
+__device__ __forceinline__ uint32_t blob_body_copy(unsigned char* sm, unsigned char* gm, uint64_t* bar) {
+  static_assert(LT::NL % 8 == 0 && LT::NO % 2 == 0 && LT::NA % 4 == 0 && LT::ord_off % 16 == 0 && LT::side_stride % 16 == 0 && LT::agent_off % 16 == 0,
+                "StaticLayout arrays must be 16-byte aligned for the partial blob copies");
+  const BookHdr* h = reinterpret_cast<const BookHdr*>(sm);
+  uint32_t off[12], len[12];
+#pragma unroll
+  for (int s = 0; s < 2; s++) {
+    const uint32_t nlv = min((uint32_t)h->cnt[s][0], (uint32_t)LT::NL), nord = min((uint32_t)h->cnt[s][1], (uint32_t)LT::NO), nag = min((uint32_t)h->nag[s], (uint32_t)LT::NA);
+    const uint32_t so = LT::side_off + s * LT::side_stride, ao = LT::agent_off + s * LT::NA * 12, al = (nag * 4 + 15) & ~15u;
+    off[s * 6 + 0] = so;                  len[s * 6 + 0] = (nlv * 4 + 15) & ~15u;    // level prices
+    off[s * 6 + 1] = so + LT::lvend_off;  len[s * 6 + 1] = (nlv * 2 + 15) & ~15u;    // level ends
+    off[s * 6 + 2] = so + LT::ord_off;    len[s * 6 + 2] = (nord * 8 + 15) & ~15u;   // orders
+    off[s * 6 + 3] = ao;                  len[s * 6 + 3] = al;                       // agent price / volume / id arrays
+    off[s * 6 + 4] = ao + LT::NA * 4;     len[s * 6 + 4] = al;
+    off[s * 6 + 5] = ao + LT::NA * 8;     len[s * 6 + 5] = al;
+  }
+  uint32_t total = 0;
+#pragma unroll
+  for (int k = 0; k < 12; k++) total += len[k];
+  if (total == 0) return 0;
+  if (LOAD) mbar_expect_tx(bar, total);
+#pragma unroll
+  for (int k = 0; k < 12; k++)
+    if (len[k]) { if (LOAD) tma_load(sm + off[k], gm + off[k], len[k], bar); else tma_store_part(gm + off[k], sm + off[k], len[k]); }
+  return total;
+}
+
 #ifndef LOBSIM_ENVFAST_WARPS
 #define LOBSIM_ENVFAST_WARPS 4    // warps per CTA of the env fast kernel (four CTAs per SM at 128 registers; 8 measured 1.3 % slower)
+#endif
+#ifndef LOBSIM_ENVFAST_MINB
+#define LOBSIM_ENVFAST_MINB (16 / LOBSIM_ENVFAST_WARPS)   // resident CTAs per SM the register allocation aims at
 #endif
 #ifndef LOBSIM_PHASE_SYNC
 #define LOBSIM_PHASE_SYNC 1
@@ -510,7 +566,7 @@ static __device__ __noinline__ uint32_t reset_book_cold(unsigned char* blob, con
 struct StepSave { double cash0, p0, price; long long inv0, episode_start_us, st_t0_us; };
 // RARE: the configuration uses z-score normalisation or a RollingSharpe reward (their code is compiled out otherwise).
 template <class LT, bool SYNC, bool RARE>
-__global__ void __launch_bounds__(32 * LOBSIM_ENVFAST_WARPS, 16 / LOBSIM_ENVFAST_WARPS) k_env_fast(const __grid_constant__ AdvParams p, const __grid_constant__ EnvConst ec) {
+__global__ void __launch_bounds__(32 * LOBSIM_ENVFAST_WARPS, LOBSIM_ENVFAST_MINB) k_env_fast(const __grid_constant__ AdvParams p, const __grid_constant__ EnvConst ec) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int sel = p.sel_offset + blockIdx.x * (blockDim.x >> 5) + warp;
@@ -523,16 +579,24 @@ __global__ void __launch_bounds__(32 * LOBSIM_ENVFAST_WARPS, 16 / LOBSIM_ENVFAST
   unsigned char* base = warp_smem_base(smem, warp, p.warp_smem);
   unsigned char* msgbuf = base + LT::blob_bytes;
   int2* scratch = reinterpret_cast<int2*>(msgbuf + 2 * MSG_TILE_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(scratch) + 2 * LT::NA * 8);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(scratch) + scratch_bytes(LT::NA));
   unsigned char* gblob = p.blobs + (size_t)env * LT::blob_bytes;
+  // ---- book blob, HBM -> shared memory: the 128-byte header first, then only the occupied part of the arrays (a reset rebuilds
+  //      the book from the snapshot and needs the header alone)
   if (lane == 0) {
     mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
     fence_mbar_init();
-    mbar_expect_tx(&bars[2], (uint32_t)LT::blob_bytes);
-    tma_load(base, gblob, (uint32_t)LT::blob_bytes, &bars[2]);
+    mbar_expect_tx(&bars[2], (uint32_t)sizeof(BookHdr));
+    tma_load(base, gblob, (uint32_t)sizeof(BookHdr), &bars[2]);
   }
   __syncwarp();
   mbar_wait(&bars[2], 0);
+  if (!p.reset_mode) {
+    uint32_t body = 0;
+    if (lane == 0) body = blob_body_copy<LT, true>(base, gblob, &bars[2]);
+    body = __shfl_sync(FULL_MASK, body, 0);
+    if (body) mbar_wait(&bars[2], 1);
+  }
 
   FastBook<LT> fb; fb.blob = base; fb.lane = lane;
   Book b; b.blob = base; b.L = p.L; b.lane = lane;
@@ -566,9 +630,11 @@ __global__ void __launch_bounds__(32 * LOBSIM_ENVFAST_WARPS, 16 / LOBSIM_ENVFAST
   if (lane == 0) { sv->st_t0_us = stp->t0_us; sv->episode_start_us = stp->t0_us + (long long)h->episode_start_step * c.step_us; sv->price = h->price; }
   __syncwarp();
   FeatState* fstate_env = p.fstate + (size_t)env * LOBSIM_MAX_FEATURES;
+  NormState* nstate_env = RARE && p.nstate ? p.nstate + (size_t)env * LOBSIM_MAX_FEATURES : nullptr;
   double* rings_env = p.rings + (size_t)env * ec.ring_stride;
   double feat_cur = 0.0;
   if (lane < F) feat_cur = fstate_env[lane].cur;
+  const int t0_mod_min = (int)stp->reserved;   // t0_us % 60 s, filled in by lobsim_load_stream
 
   auto tops = [&](StepView& v) { // Orderbook.best_* / microprice, models.py:72-101
     const int n0 = h->cnt[0][0], n1 = h->cnt[1][0];
@@ -582,10 +648,11 @@ __global__ void __launch_bounds__(32 * LOBSIM_ENVFAST_WARPS, 16 / LOBSIM_ENVFAST
   if (p.reset_mode == 2) { // State(...) + _reset_features, HOE.py:152-154,218-221
     StepView v; tops(v);
     v.inventory = h->inventory; v.now_us = sv->st_t0_us + (long long)now_step * c.step_us;
+    v.us_in_min = us_in_minute(t0_mod_min, now_step, ec);
     v.n_ext0 = v.n_ext1 = v.vol_ext0 = v.vol_ext1 = v.n_int0 = v.n_int1 = v.vol_int0 = v.vol_int1 = 0;
     __syncwarp();
     if (lane == 0) sv->price = v.price;
-    feat_cur = features_step<RARE>(&ec, fstate_env, rings_env, lane, v, sv->episode_start_us, 1);
+    feat_cur = features_step<RARE>(&ec, fstate_env, nstate_env, rings_env, lane, v, sv->episode_start_us, 1);
     __syncwarp();
   }
 
@@ -643,7 +710,7 @@ __global__ void __launch_bounds__(32 * LOBSIM_ENVFAST_WARPS, 16 / LOBSIM_ENVFAST
       if (p.obs && !p.out_final_obs_only && c.inc_prev_action_in_obs && lane < ec.action_dim)
         p.obs[((size_t)t * p.n_sel + sel) * ec.obs_dim + F + lane] = mine;
       if (!f.dead) {
-        gen = agent_prepare(b, h->cnt[0][0], h->cnt[1][0], h->nag[0], h->nag[1], h->inventory, &ec, a0, a1, a2, a3, a4);
+        gen = agent_prepare(b, h->cnt[0][0], h->cnt[1][0], h->nag[0], h->nag[1], h->inventory, &ec, a0, a1, a2, a3, a4, p.beta_tab, reinterpret_cast<int*>(scratch));
         f.err |= gen.err_out; if (gen.dead_out) f.dead = 1;
         agent_phase = true;
       }
@@ -695,10 +762,11 @@ __global__ void __launch_bounds__(32 * LOBSIM_ENVFAST_WARPS, 16 / LOBSIM_ENVFAST
     const double price = v.price;
     if (lane == 0) sv->price = price;
     v.inventory = h->inventory; v.now_us = sv->st_t0_us + (long long)now_step * c.step_us;
+    v.us_in_min = us_in_minute(t0_mod_min, now_step, ec);
     v.n_ext0 = h->flow[0]; v.n_ext1 = h->flow[1]; v.vol_ext0 = h->flow[2]; v.vol_ext1 = h->flow[3];
     v.n_int0 = h->flow[4]; v.n_int1 = h->flow[5]; v.vol_int0 = h->flow[6]; v.vol_int1 = h->flow[7];
     __syncwarp(); // every lane has read this step's flow counters before lanes 0-7 zero them for the next step
-    feat_cur = features_step<RARE>(&ec, fstate_env, rings_env, lane, v, sv->episode_start_us, 0);
+    feat_cur = features_step<RARE>(&ec, fstate_env, nstate_env, rings_env, lane, v, sv->episode_start_us, 0);
     const bool write_now = !p.out_final_obs_only || t == T - 1;
     if (p.obs && write_now) {
       double* o = p.obs + ((size_t)(p.out_final_obs_only ? 0 : t) * p.n_sel + sel) * ec.obs_dim;
@@ -731,6 +799,11 @@ __global__ void __launch_bounds__(32 * LOBSIM_ENVFAST_WARPS, 16 / LOBSIM_ENVFAST
   __syncwarp();
   fence_proxy_async();
   __syncwarp();
-  if (lane == 0) { tma_store(gblob, base, (uint32_t)LT::blob_bytes); tma_store_wait(); }
+  if (lane == 0) {   // shared memory -> HBM: the header and the occupied part of the arrays
+    tma_store_part(gblob, base, (uint32_t)sizeof(BookHdr));
+    blob_body_copy<LT, false>(base, gblob, nullptr);
+    tma_store_commit();
+    tma_store_wait();
+  }
   __syncwarp();
 }

@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -165,6 +166,8 @@ struct lobsim {
   int warp_smem;
   unsigned char* blobs = nullptr;
   FeatState* fstate = nullptr;
+  NormState* nstate = nullptr;          // rolling z-score state: only with normalisation_on features
+  double* beta_tab = nullptr;           // [2][32] ln x_k, ln(1 - x_k) at the quote-level midpoints (BetaOrderDistributor)
   double* rings = nullptr;
   double* rs_ring = nullptr;
   int32_t* rs_state = nullptr;
@@ -233,7 +236,7 @@ int64_t lobsim_state_bytes(const lobsim_cfg_t* c) {
   return make_layout(c->max_levels_per_side, c->max_orders_per_side, c->max_agent_orders).blob_bytes;
 }
 
-static int warp_smem_bytes(const Layout& L) { return (L.blob_bytes + 2 * MSG_TILE_BYTES + 2 * L.NA * 8 + 32 + 128 + 127) & ~127; }
+static int warp_smem_bytes(const Layout& L) { return (L.blob_bytes + 2 * MSG_TILE_BYTES + scratch_bytes(L.NA) + 32 + 128 + 127) & ~127; }
 
 int lobsim_create(const lobsim_cfg_t* cfg, int device, lobsim_t** out) {
   if (!out) return fail(LOBSIM_E_INVALID, "out is null");
@@ -290,10 +293,36 @@ int lobsim_create(const lobsim_cfg_t* cfg, int device, lobsim_t** out) {
   h->ec.ring_stride = (slots + 1) & ~1;
   h->ec.action_dim = lobsim_action_dim(cfg); h->ec.obs_dim = lobsim_obs_dim(cfg);
   h->ec.steps_per_sec = (int)(1000000 / cfg->step_us); h->ec.outer_prop = (double)cfg->outer_levels / (double)cfg->n_levels;
+  h->ec.steps_per_min = (int)(60000000 / cfg->step_us);
+  bool any_norm = false;
+  for (int i = 0; i < cfg->n_features; i++) {
+    const lobsim_feature_t& ft = cfg->features[i];
+    any_norm = any_norm || ft.norm_len > 0;
+    if (ft.kind == LOBSIM_FEAT_TIME_OF_DAY) { // bucket_size = (15:30 - 10:00) / n_buckets: timedelta division rounds half to even (Features.py:526-536)
+      const long long tot = (15LL * 3600 + 1800 - 10LL * 3600) * 1000000, nb = ft.iparam;
+      long long bucket = tot / nb, rem = tot % nb;
+      if (2 * rem > nb || (2 * rem == nb && (bucket & 1))) bucket++;
+      h->ec.feat_aux[i] = bucket;
+    }
+  }
+  {
+    const int Q = cfg->max_quote_level - cfg->min_quote_level;
+    double tab[64];
+    for (int k = 0; k < 32; k++) {   // OrderDistributors.py:37: midpoints 1 / Q * (k + 0.5)
+      const double x = 1.0 / (double)Q * ((double)k + 0.5);
+      tab[k] = k < Q ? log(x) : 0.0; tab[32 + k] = k < Q ? log1p(-x) : 0.0;
+    }
+    CUDA_TRY(cudaMalloc(&h->beta_tab, sizeof tab));
+    CUDA_TRY(cudaMemcpy(h->beta_tab, tab, sizeof tab, cudaMemcpyHostToDevice));
+  }
   const size_t n = (size_t)cfg->n_envs;
   CUDA_TRY(cudaMalloc(&h->blobs, n * h->L.blob_bytes));
   CUDA_TRY(cudaMalloc(&h->fstate, n * LOBSIM_MAX_FEATURES * sizeof(FeatState)));
   CUDA_TRY(cudaMemset(h->fstate, 0, n * LOBSIM_MAX_FEATURES * sizeof(FeatState)));
+  if (any_norm) {
+    CUDA_TRY(cudaMalloc(&h->nstate, n * LOBSIM_MAX_FEATURES * sizeof(NormState)));
+    CUDA_TRY(cudaMemset(h->nstate, 0, n * LOBSIM_MAX_FEATURES * sizeof(NormState)));
+  }
   {
     size_t free_b = 0, total_b = 0;
     CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
@@ -323,7 +352,7 @@ int lobsim_create(const lobsim_cfg_t* cfg, int device, lobsim_t** out) {
 int lobsim_destroy(lobsim_t* h) {
   if (!h) return LOBSIM_OK;
   cudaSetDevice(h->device);
-  cudaFree(h->blobs); cudaFree(h->fstate); cudaFree(h->rings); cudaFree(h->rs_ring); cudaFree(h->rs_state); cudaFree(h->fill_log); cudaFree(h->fill_count); cudaFree(h->agents_dev);
+  cudaFree(h->blobs); cudaFree(h->fstate); cudaFree(h->nstate); cudaFree(h->beta_tab); cudaFree(h->rings); cudaFree(h->rs_ring); cudaFree(h->rs_state); cudaFree(h->fill_log); cudaFree(h->fill_count); cudaFree(h->agents_dev);
   cudaFree(h->streams_dev); cudaFree(h->st_actions); cudaFree(h->st_obs); cudaFree(h->st_rew); cudaFree(h->st_done);
   cudaFree(h->st_state); cudaFree(h->st_msgs);
   delete h;
@@ -343,6 +372,7 @@ int lobsim_load_stream(lobsim_t* h, int stream_id, const lobsim_stream_t* s) {
     h->streams.resize(stream_id + 1, empty);
   }
   h->streams[stream_id] = *s;
+  h->streams[stream_id].reserved = (uint32_t)(s->t0_us % 60000000);   // the kernels' 32-bit update-frequency gate (us_in_minute)
   if (h->streams_cap < (int)h->streams.size()) {
     CUDA_TRY(cudaDeviceSynchronize());
     cudaFree(h->streams_dev);
@@ -355,7 +385,7 @@ int lobsim_load_stream(lobsim_t* h, int stream_id, const lobsim_stream_t* s) {
 
 static void base_params(lobsim* h, AdvParams& p) {
   memset(&p, 0, sizeof p);
-  p.blobs = h->blobs; p.fstate = h->fstate; p.rings = h->rings; p.rs_ring = h->rs_ring; p.rs_state = h->rs_state; p.streams = h->streams_dev; p.n_streams = (int)h->streams.size();
+  p.blobs = h->blobs; p.fstate = h->fstate; p.nstate = h->nstate; p.beta_tab = h->beta_tab; p.rings = h->rings; p.rs_ring = h->rs_ring; p.rs_state = h->rs_state; p.streams = h->streams_dev; p.n_streams = (int)h->streams.size();
   p.fill_log = h->fill_log; p.fill_count = h->fill_count; p.fill_cap = h->cfg.fill_log_capacity;
   p.n_envs = h->cfg.n_envs; p.n_sel = h->cfg.n_envs; p.L = h->L; p.warp_smem = h->warp_smem;
 }
