@@ -689,55 +689,110 @@ static __device__ __noinline__ void agent_action_cold(const lobsim_agent_t* ag, 
   for (int i = 0; i < 5; i++) out5_smem[i] = a[i];
 }
 
-// agent_next for the straight-line path: the agent table counters live in the shared-memory header
+// ---- agent_next for the straight-line path -----------------------------------------------------------------------------
+// Same order sequence as agent_next (the reference's convert_action_to_orders, HOE.py:206-258), but the generator never walks
+// over things that yield nothing: the ladder levels whose volume difference is non-zero are a bitmask (one __ffs per yielded
+// order instead of a loop over all Q levels), and the agent's off-ladder ("wide") orders are found by ONE lane-parallel pass
+// over the agent table when the ladder stage of a side ends (instead of one scalar iteration per resting agent order).
+// The per-level differences live in the per-warp scratch (int[64]: buy levels, sell levels); the agent table counters in the
+// shared-memory header.
+struct AgentGenFast {
+  int side, stage, need;        // cursor: side 0/1 (2 = market order stage, 3 = done); stage 0 = ladder, 1 = wide cancels
+  unsigned todo0, todo1;        // ladder levels with a non-zero volume difference, per side
+  unsigned wm0, wm1;            // wide stage of the current side: off-ladder entries of the agent table (original indices 0..63)
+  int wide_removed, wide_pos;   // entries removed so far in this wide stage; table position of the cancel yielded last
+  uint32_t pending_id;          // id of that cancel (0: none)
+  int base0, base1;             // first ladder price per side: price of level k = base0 - k * tick / base1 + k * tick
+  int clear_vol, clear_side;    // inventory-clearing market order (clear_vol < 0: none)
+};
+
+// AgentGen (agent_prepare: one quote level per lane) -> the compact form; diffs go to the per-warp scratch
+__device__ __forceinline__ AgentGenFast agent_gen_fast_init(const AgentGen& g, int lane, int* diff_scratch) {
+  AgentGenFast a;
+  a.side = g.side; a.stage = 0; a.need = 0;
+  a.todo0 = __ballot_sync(FULL_MASK, lane < g.Q && g.diff0 != 0);
+  a.todo1 = __ballot_sync(FULL_MASK, lane < g.Q && g.diff1 != 0);
+  a.wm0 = a.wm1 = 0; a.wide_removed = 0; a.wide_pos = 0; a.pending_id = 0;
+  a.base0 = __shfl_sync(FULL_MASK, g.price0, 0); a.base1 = __shfl_sync(FULL_MASK, g.price1, 0);
+  a.clear_vol = g.clearing ? g.clear_vol : -1; a.clear_side = g.clear_side;
+  __syncwarp();
+  diff_scratch[lane] = g.diff0; diff_scratch[32 + lane] = g.diff1;
+  __syncwarp();
+  return a;
+}
+
 template <class LT>
-__device__ __forceinline__ bool agent_next_fast(const FastBook<LT>& fb, FastState& f, AgentGen& g, int& type, int& side, int& price, int& vol, uint32_t& ref) {
+__device__ __forceinline__ bool agent_next_fast(const FastBook<LT>& fb, FastState& f, AgentGenFast& g, const int* diff_scratch, int Q, int tick,
+                                                int& type, int& side, int& price, int& vol, uint32_t& ref) {
   BookHdr* h = reinterpret_cast<BookHdr*>(fb.blob);
   for (;;) {
     if (f.dead || g.side >= 3) return false;
     if (g.side == 2) { // _get_inventory_clearing_market_order :260-266
       g.side = 3;
-      if (!g.clearing) return false;
-      if (g.clear_vol <= 0) { f.err |= LOBSIM_ERR_BAD_VOLUME; return false; }
+      if (g.clear_vol < 0) return false;
+      if (g.clear_vol == 0) { f.err |= LOBSIM_ERR_BAD_VOLUME; return false; }
       type = LOBSIM_MSG_MARKET; side = g.clear_side; price = 0; vol = g.clear_vol; ref = 0;
       return true;
     }
     const int s = g.side;
-    const int myprice = s ? g.price1 : g.price0;
     const int32_t* ap = reinterpret_cast<const int32_t*>(fb.blob + LT::agent_off + s * LT::NA * 12);
     const int32_t* av = ap + LT::NA;
     const uint32_t* ai = reinterpret_cast<const uint32_t*>(ap + 2 * LT::NA);
     const int nag = h->nag[s];
-    if (g.k < g.Q) {
-      const int p = __shfl_sync(FULL_MASK, myprice, g.k);
+    const int base = s ? g.base1 : g.base0;
+    if (g.stage == 0) {
+      const unsigned todo = s ? g.todo1 : g.todo0;
+      if (todo == 0) {
+        // ladder done: agent orders off the ladder are cancelled in full, :250-257.  One pass: entry i is on the ladder iff its
+        // distance from the first ladder price is k * tick with 0 <= k < Q (orders placed during the ladder stage are).
+        __syncwarp();
+        bool off0 = false, off1 = false;
+        if (fb.lane < nag) { const int d = s ? ap[fb.lane] - base : base - ap[fb.lane]; const int q = d / tick; off0 = !(d >= 0 && q * tick == d && q < Q); }
+        if (fb.lane + 32 < nag) { const int d = s ? ap[fb.lane + 32] - base : base - ap[fb.lane + 32]; const int q = d / tick; off1 = !(d >= 0 && q * tick == d && q < Q); }
+        g.wm0 = __ballot_sync(FULL_MASK, off0); g.wm1 = __ballot_sync(FULL_MASK, off1);
+        g.stage = 1; g.wide_removed = 0; g.pending_id = 0;
+        continue;
+      }
+      const int k = __ffs(todo) - 1;
+      const int p = s ? base + k * tick : base - k * tick;
       if (g.need == 0) {
-        const int d = __shfl_sync(FULL_MASK, s ? g.diff1 : g.diff0, g.k);
-        if (d > 0) { type = LOBSIM_MSG_LIMIT; side = s; price = p; vol = d; ref = 0; g.k++; return true; }
-        if (d == 0) { g.k++; continue; }
+        const int d = diff_scratch[s * 32 + k];
+        if (d > 0) {
+          if (s) g.todo1 = todo & (todo - 1); else g.todo0 = todo & (todo - 1);
+          type = LOBSIM_MSG_LIMIT; side = s; price = p; vol = d; ref = 0;
+          return true;
+        }
         g.need = -d;
       }
       // cancel from the back of the agent's queue at this price, :239-249 (NA <= 64)
       const unsigned m1 = __ballot_sync(FULL_MASK, fb.lane + 32 < nag && ap[fb.lane + 32] == p);
       const unsigned m0 = __ballot_sync(FULL_MASK, fb.lane < nag && ap[fb.lane] == p);
-      if (!(m0 | m1)) { g.need = 0; g.k++; continue; }
+      if (!(m0 | m1)) { g.need = 0; if (s) g.todo1 = todo & (todo - 1); else g.todo0 = todo & (todo - 1); continue; }
       const int hit = m1 ? 63 - __clz(m1) : 31 - __clz(m0);
       const int a = av[hit];
       const uint32_t id = ai[hit];
       const int v = a < g.need ? a : g.need;
       g.need -= v;
-      if (g.need == 0) g.k++;
+      if (g.need == 0) { if (s) g.todo1 = todo & (todo - 1); else g.todo0 = todo & (todo - 1); }
       type = LOBSIM_MSG_CANCEL; side = s; price = p; vol = v; ref = LOBSIM_REF_AGENT | id;
       return true;
     }
-    // agent orders off the ladder are cancelled in full, :250-257
-    if (g.wide_i >= nag) { g.side = s + 1; g.k = 0; g.need = 0; g.wide_i = 0; g.pending_id = 0; continue; }
-    const int wp = ap[g.wide_i], wv = av[g.wide_i];
-    const uint32_t id = ai[g.wide_i];
-    __syncwarp();
-    if (id == g.pending_id) { fast_agent_reduce(fb, s, id, 0, true); g.pending_id = 0; continue; } // keep books consistent
-    const bool on_ladder = __ballot_sync(FULL_MASK, fb.lane < g.Q && myprice == wp) != 0;
-    if (on_ladder) { g.wide_i++; continue; }
-    g.pending_id = id;
+    // ---- wide stage --------------------------------------------------------------------------------------------------------
+    if (g.pending_id) {   // the cancel yielded last: if the book could not apply it, drop the entry here (keeps the books consistent)
+      const bool still = g.wide_pos < nag && ai[g.wide_pos] == g.pending_id;
+      __syncwarp();
+      if (still) fast_agent_reduce(fb, s, g.pending_id, 0, true);
+      g.pending_id = 0; g.wide_removed++;
+      continue;
+    }
+    if (!(g.wm0 | g.wm1)) { g.side = s + 1; g.stage = 0; g.need = 0; continue; }
+    int i;
+    if (g.wm0) { i = __ffs(g.wm0) - 1; g.wm0 &= g.wm0 - 1; } else { i = 32 + __ffs(g.wm1) - 1; g.wm1 &= g.wm1 - 1; }
+    const int pos = i - g.wide_removed;
+    if (pos < 0 || pos >= nag) continue;   // cannot happen while every wide cancel removes exactly its own entry
+    const int wp = ap[pos], wv = av[pos];
+    const uint32_t id = ai[pos];
+    g.pending_id = id; g.wide_pos = pos;
     type = LOBSIM_MSG_CANCEL; side = s; price = wp; vol = wv; ref = LOBSIM_REF_AGENT | id;
     return true;
   }

@@ -516,32 +516,28 @@ static __device__ __noinline__ uint32_t reset_book_cold(unsigned char* blob, con
 // level ends and the order entries up to {nlv, nord}, and the agent tables up to nag -- about 1.5 KB of a 6.5 KB blob for a
 // 10-level book.  Sizes are rounded up to the 16-byte granularity of cp.async.bulk; every array of a StaticLayout starts
 // 16-byte aligned and its capacity is a multiple of 16 bytes, so a rounded-up part never leaves its array.
-// Lane 0 only.  LOAD: the header has already arrived in shared memory; returns the bytes expected on `bar` (0: nothing issued).
+// Warp-collective: lane k < 12 owns part k (its offset and length are a few integer operations on the header counters) and
+// issues its own bulk copy; lane 0 posts the byte total on the mbarrier first.  LOAD: the header has already arrived in shared
+// memory; returns the bytes expected on `bar` (0: nothing was issued).
 template <class LT, bool LOAD>
-__device__ __forceinline__ uint32_t blob_body_copy(unsigned char* sm, unsigned char* gm, uint64_t* bar) {
+__device__ __forceinline__ uint32_t blob_body_copy(unsigned char* sm, unsigned char* gm, uint64_t* bar, int lane) {
   static_assert(LT::NL % 8 == 0 && LT::NO % 2 == 0 && LT::NA % 4 == 0 && LT::ord_off % 16 == 0 && LT::side_stride % 16 == 0 && LT::agent_off % 16 == 0,
                 "StaticLayout arrays must be 16-byte aligned for the partial blob copies");
   const BookHdr* h = reinterpret_cast<const BookHdr*>(sm);
-  uint32_t off[12], len[12];
-#pragma unroll
-  for (int s = 0; s < 2; s++) {
-    const uint32_t nlv = min((uint32_t)h->cnt[s][0], (uint32_t)LT::NL), nord = min((uint32_t)h->cnt[s][1], (uint32_t)LT::NO), nag = min((uint32_t)h->nag[s], (uint32_t)LT::NA);
-    const uint32_t so = LT::side_off + s * LT::side_stride, ao = LT::agent_off + s * LT::NA * 12, al = (nag * 4 + 15) & ~15u;
-    off[s * 6 + 0] = so;                  len[s * 6 + 0] = (nlv * 4 + 15) & ~15u;    // level prices
-    off[s * 6 + 1] = so + LT::lvend_off;  len[s * 6 + 1] = (nlv * 2 + 15) & ~15u;    // level ends
-    off[s * 6 + 2] = so + LT::ord_off;    len[s * 6 + 2] = (nord * 8 + 15) & ~15u;   // orders
-    off[s * 6 + 3] = ao;                  len[s * 6 + 3] = al;                       // agent price / volume / id arrays
-    off[s * 6 + 4] = ao + LT::NA * 4;     len[s * 6 + 4] = al;
-    off[s * 6 + 5] = ao + LT::NA * 8;     len[s * 6 + 5] = al;
+  const int s = lane >= 6 ? 1 : 0, part = lane - s * 6;     // parts 0-2: level prices, level ends, orders; 3-5: agent price / volume / id
+  uint32_t off = 0, len = 0;
+  if (lane < 12) {
+    const uint32_t so = LT::side_off + s * LT::side_stride, ao = LT::agent_off + s * LT::NA * 12;
+    if (part == 0)      { off = so;                 len = min((uint32_t)h->cnt[s][0], (uint32_t)LT::NL) * 4; }
+    else if (part == 1) { off = so + LT::lvend_off; len = min((uint32_t)h->cnt[s][0], (uint32_t)LT::NL) * 2; }
+    else if (part == 2) { off = so + LT::ord_off;   len = min((uint32_t)h->cnt[s][1], (uint32_t)LT::NO) * 8; }
+    else                { off = ao + (part - 3) * LT::NA * 4; len = min((uint32_t)h->nag[s], (uint32_t)LT::NA) * 4; }
+    len = (len + 15) & ~15u;
   }
-  uint32_t total = 0;
-#pragma unroll
-  for (int k = 0; k < 12; k++) total += len[k];
+  const uint32_t total = __reduce_add_sync(FULL_MASK, len);
   if (total == 0) return 0;
-  if (LOAD) mbar_expect_tx(bar, total);
-#pragma unroll
-  for (int k = 0; k < 12; k++)
-    if (len[k]) { if (LOAD) tma_load(sm + off[k], gm + off[k], len[k], bar); else tma_store_part(gm + off[k], sm + off[k], len[k]); }
+  if (LOAD) { if (lane == 0) mbar_expect_tx(bar, total); __syncwarp(); }
+  if (len) { if (LOAD) tma_load(sm + off, gm + off, len, bar); else tma_store_part(gm + off, sm + off, len); }
   return total;
 }
 
@@ -549,8 +545,15 @@ __device__ __forceinline__ uint32_t blob_body_copy(unsigned char* sm, unsigned c
 #define LOBSIM_ENVFAST_WARPS 4    // warps per CTA of the env fast kernel (four CTAs per SM at 128 registers; 8 measured 1.3 % slower)
 #endif
 #ifndef LOBSIM_ENVFAST_MINB
-#define LOBSIM_ENVFAST_MINB (16 / LOBSIM_ENVFAST_WARPS)   // resident CTAs per SM the register allocation aims at
-#endif
+#define LOBSIM_ENVFAST_MINB (24 / LOBSIM_ENVFAST_WARPS)   // resident CTAs per SM the register allocation aims at (80 registers: measured
+#endif                                                     // +9 % over 128 registers / 16 warps per SM, profiles/r02_env_ab.txt)
+// ... but never more CTAs than the shared memory of an SM can hold for this layout (deep 50-level books: 2 CTAs, no register cap)
+template <class LT>
+constexpr int env_min_blocks() {
+  const int warp_bytes = (LT::blob_bytes + 2 * MSG_TILE_BYTES + scratch_bytes(LT::NA) + 32 + 128 + 127) & ~127;
+  const int fit = (227 * 1024) / (LOBSIM_ENVFAST_WARPS * warp_bytes);
+  return fit < 1 ? 1 : (fit < LOBSIM_ENVFAST_MINB ? fit : LOBSIM_ENVFAST_MINB);
+}
 #ifndef LOBSIM_PHASE_SYNC
 #define LOBSIM_PHASE_SYNC 1
 #endif
@@ -566,7 +569,7 @@ __device__ __forceinline__ uint32_t blob_body_copy(unsigned char* sm, unsigned c
 struct StepSave { double cash0, p0, price; long long inv0, episode_start_us, st_t0_us; };
 // RARE: the configuration uses z-score normalisation or a RollingSharpe reward (their code is compiled out otherwise).
 template <class LT, bool SYNC, bool RARE>
-__global__ void __launch_bounds__(32 * LOBSIM_ENVFAST_WARPS, LOBSIM_ENVFAST_MINB) k_env_fast(const __grid_constant__ AdvParams p, const __grid_constant__ EnvConst ec) {
+__global__ void __launch_bounds__(32 * LOBSIM_ENVFAST_WARPS, env_min_blocks<LT>()) k_env_fast(const __grid_constant__ AdvParams p, const __grid_constant__ EnvConst ec) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int sel = p.sel_offset + blockIdx.x * (blockDim.x >> 5) + warp;
@@ -592,10 +595,7 @@ __global__ void __launch_bounds__(32 * LOBSIM_ENVFAST_WARPS, LOBSIM_ENVFAST_MINB
   __syncwarp();
   mbar_wait(&bars[2], 0);
   if (!p.reset_mode) {
-    uint32_t body = 0;
-    if (lane == 0) body = blob_body_copy<LT, true>(base, gblob, &bars[2]);
-    body = __shfl_sync(FULL_MASK, body, 0);
-    if (body) mbar_wait(&bars[2], 1);
+    if (blob_body_copy<LT, true>(base, gblob, &bars[2], lane)) mbar_wait(&bars[2], 1);
   }
 
   FastBook<LT> fb; fb.blob = base; fb.lane = lane;
@@ -683,7 +683,10 @@ __global__ void __launch_bounds__(32 * LOBSIM_ENVFAST_WARPS, LOBSIM_ENVFAST_MINB
   const int steps_per_sec = ec.steps_per_sec;
   int sub = now_step >= 0 ? now_step % steps_per_sec : 0;
 
-  AgentGen gen; gen.side = 3;
+  AgentGenFast gen; gen.side = 3; gen.stage = 0; gen.need = 0; gen.todo0 = gen.todo1 = gen.wm0 = gen.wm1 = 0; gen.wide_removed = gen.wide_pos = 0;
+  gen.pending_id = 0; gen.base0 = gen.base1 = 0; gen.clear_vol = -1; gen.clear_side = 0;
+  const int Q = c.max_quote_level - c.min_quote_level;
+  int* diff_scratch = reinterpret_cast<int*>(scratch);
   bool agent_phase = false;
 #pragma unroll 1
   for (int t = 0; t < T; t++) {
@@ -710,8 +713,9 @@ __global__ void __launch_bounds__(32 * LOBSIM_ENVFAST_WARPS, LOBSIM_ENVFAST_MINB
       if (p.obs && !p.out_final_obs_only && c.inc_prev_action_in_obs && lane < ec.action_dim)
         p.obs[((size_t)t * p.n_sel + sel) * ec.obs_dim + F + lane] = mine;
       if (!f.dead) {
-        gen = agent_prepare(b, h->cnt[0][0], h->cnt[1][0], h->nag[0], h->nag[1], h->inventory, &ec, a0, a1, a2, a3, a4, p.beta_tab, reinterpret_cast<int*>(scratch));
-        f.err |= gen.err_out; if (gen.dead_out) f.dead = 1;
+        const AgentGen g0 = agent_prepare(b, h->cnt[0][0], h->cnt[1][0], h->nag[0], h->nag[1], h->inventory, &ec, a0, a1, a2, a3, a4, p.beta_tab, diff_scratch);
+        f.err |= g0.err_out; if (g0.dead_out) f.dead = 1;
+        gen = agent_gen_fast_init(g0, lane, diff_scratch);
         agent_phase = true;
       }
     }
@@ -723,7 +727,7 @@ __global__ void __launch_bounds__(32 * LOBSIM_ENVFAST_WARPS, LOBSIM_ENVFAST_MINB
       for (;;) {
         int type, side, oprice, vol; uint32_t ref; bool is_agent;
         if (agent_phase) {
-          if (!agent_next_fast(fb, f, gen, type, side, oprice, vol, ref)) { agent_phase = false; continue; }
+          if (!agent_next_fast(fb, f, gen, diff_scratch, Q, c.tick_size, type, side, oprice, vol, ref)) { agent_phase = false; continue; }
           is_agent = true;
         } else {
           if (f.dead || g >= g_step_end) break;
@@ -799,11 +803,9 @@ __global__ void __launch_bounds__(32 * LOBSIM_ENVFAST_WARPS, LOBSIM_ENVFAST_MINB
   __syncwarp();
   fence_proxy_async();
   __syncwarp();
-  if (lane == 0) {   // shared memory -> HBM: the header and the occupied part of the arrays
-    tma_store_part(gblob, base, (uint32_t)sizeof(BookHdr));
-    blob_body_copy<LT, false>(base, gblob, nullptr);
-    tma_store_commit();
-    tma_store_wait();
-  }
+  // shared memory -> HBM: the header and the occupied part of the arrays; every issuing lane commits and waits for its own copy
+  if (lane == 12) tma_store_part(gblob, base, (uint32_t)sizeof(BookHdr));
+  blob_body_copy<LT, false>(base, gblob, nullptr, lane);
+  if (lane <= 12) { tma_store_commit(); tma_store_wait(); }
   __syncwarp();
 }
