@@ -67,7 +67,7 @@ def build_ingest(force: bool = False) -> Path:
     out = OUT / "libingest.so"
     srcs = [CSRC / "lobster_ingest.cpp"]
     if force or _newer(srcs, out):
-        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", str(out), str(srcs[0])], check=True)
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-o", str(out), str(srcs[0])], check=True)
     return out
 
 

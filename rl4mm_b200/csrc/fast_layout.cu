@@ -29,12 +29,16 @@ static cudaError_t set_attr(const void* k, int dyn) {
 #if LOBSIM_TU_PART == 0
 cudaError_t FN(_attrs)(int dyn_replay, int dyn_env) {
   cudaError_t e = set_attr((const void*)k_replay_fast<LT>, dyn_replay);
+  if (e == cudaSuccess) e = set_attr((const void*)k_replay_flat<LT>, dyn_replay);
   if (e == cudaSuccess) e = set_attr((const void*)k_env_fast<LT, true, false>, dyn_env);
   if (e == cudaSuccess) e = set_attr((const void*)k_env_fast<LT, false, false>, dyn_env);
   return e;
 }
 void FN(_replay)(int grid, int block, size_t dyn, cudaStream_t stream, const AdvParams& p, const EnvConst& ec) {
   k_replay_fast<LT><<<grid, block, dyn, stream>>>(p, ec);
+}
+void FN(_replay_flat)(int grid, int block, size_t dyn, cudaStream_t stream, const AdvParams& p, const EnvConst& ec) {
+  k_replay_flat<LT><<<grid, block, dyn, stream>>>(p, ec);
 }
 void FN(_env)(bool sync, int grid, int block, size_t dyn, cudaStream_t stream, const AdvParams& p, const EnvConst& ec) {
   if (sync) k_env_fast<LT, true, false><<<grid, block, dyn, stream>>>(p, ec);

@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "book_flat.cuh"
 #include "env.cuh"
 #include "lobsim.h"
 
@@ -486,6 +487,136 @@ __global__ void __launch_bounds__(128, 7) k_replay_fast(const __grid_constant__ 
       }
     }
   }
+  while (next_wait < next_issue) wait_tile();                // drain TMA loads still in flight (aborted episode)
+  __syncwarp();
+  if (lane == 0) { h->now_step = now_step; h->err = f.err; h->dead = f.dead; }
+  __syncwarp();
+  fence_proxy_async();
+  __syncwarp();
+  if (lane == 0) { tma_store(gblob, base, (uint32_t)LT::blob_bytes); tma_store_wait(); }
+  __syncwarp();
+}
+
+// ====================================================================================================================
+//  the replay FLAT kernel: k_replay_fast with the flat order pools of book_flat.cuh for every book that fits them (at most
+//  FLAT_CAP resting orders per side), the sorted straight-line path for the others -- per book, re-decided every second.
+//  The blob in HBM is the canonical sorted layout on entry and on exit.
+// ====================================================================================================================
+template <class LT>
+__global__ void __launch_bounds__(128, 7) k_replay_flat(const __grid_constant__ AdvParams p, const __grid_constant__ EnvConst ec) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int env = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (env >= p.n_sel) return;
+  const lobsim_cfg_t& c = ec.cfg;
+  unsigned char* base = warp_smem_base(smem, warp, p.warp_smem);
+  unsigned char* msgbuf = base + LT::blob_bytes;
+  int2* scratch = reinterpret_cast<int2*>(msgbuf + 2 * MSG_TILE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(scratch) + scratch_bytes(LT::NA));
+  unsigned char* gblob = p.blobs + (size_t)env * LT::blob_bytes;
+  if (lane == 0) {
+    mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
+    fence_mbar_init();
+    mbar_expect_tx(&bars[2], (uint32_t)LT::blob_bytes);
+    tma_load(base, gblob, (uint32_t)LT::blob_bytes, &bars[2]);
+  }
+  __syncwarp();
+  mbar_wait(&bars[2], 0);
+
+  FastBook<LT> fb; fb.blob = base; fb.lane = lane;
+  BookHdr* h = reinterpret_cast<BookHdr*>(base);
+  FastState f; f.err = h->err; f.dead = h->dead; f.bail = 0; f.bail_vol = 0;
+  fast_refresh_best(fb, f);
+  FlatState fs; fs.n0 = fs.n1 = 0; fs.seq = 0;
+  bool flat = false;
+  const lobsim_stream_t* stp = &p.streams[h->stream_id];
+  const lobsim_msg_t* __restrict__ st_msgs = stp->msgs;
+  const uint32_t* __restrict__ st_step_off = stp->step_off;
+  int now_step = h->now_step;
+  const int T = p.T;
+  const int n_grid = (int)stp->n_grid_steps;
+  if ((now_step < 0 || now_step > n_grid) && !f.dead && T > 0) { f.err |= LOBSIM_ERR_END_OF_STREAM; f.dead = 1; }
+  unsigned g = 0, g_end_all = 0;
+  if (!f.dead && T > 0) { g = __ldg(&st_step_off[now_step]); g_end_all = __ldg(&st_step_off[min((long long)now_step + T, (long long)n_grid)]); }
+  if (g < g_end_all && flat_fits(fb, 0)) { flat_enter(fb, fs); flat = true; }
+  const unsigned tile0 = g / MSG_TILE;
+  unsigned next_issue = 0, next_wait = 0;
+  auto issue_tile = [&]() {
+    const unsigned first = (tile0 + next_issue) * MSG_TILE;
+    if (first >= g_end_all) return;
+    if (lane == 0) {
+      const unsigned n_total = (unsigned)stp->n_msgs;
+      const unsigned cnt = n_total - first < MSG_TILE ? n_total - first : MSG_TILE;
+      uint64_t* bar = &bars[next_issue & 1];
+      mbar_expect_tx(bar, cnt * 16);
+      tma_load(msgbuf + (next_issue & 1) * MSG_TILE_BYTES, st_msgs + first, cnt * 16, bar);
+    }
+    next_issue++;
+  };
+  auto wait_tile = [&]() { mbar_wait(&bars[next_wait & 1], (next_wait >> 1) & 1); next_wait++; };
+  if (g < g_end_all) { issue_tile(); issue_tile(); }
+  __syncwarp();
+  const int steps_per_sec = ec.steps_per_sec;
+  int sub = now_step >= 0 ? now_step % steps_per_sec : 0;
+
+#pragma unroll 1
+  for (int t = 0; t < T && !f.dead; t++) {
+    if (now_step >= n_grid) { f.err |= LOBSIM_ERR_END_OF_STREAM; f.dead = 1; break; }
+    const unsigned g_step_end = __ldg(&st_step_off[now_step + 1]);
+#pragma unroll 1
+    while (g < g_step_end) {
+      const unsigned tile = g / MSG_TILE - tile0;
+      if (tile == next_wait) wait_tile();
+      const unsigned tile_end = (g / MSG_TILE + 1) * MSG_TILE;
+      const unsigned lim = g_step_end < tile_end ? g_step_end : tile_end;
+      const uint4* mp = reinterpret_cast<const uint4*>(msgbuf + (tile & 1) * MSG_TILE_BYTES) + (g % MSG_TILE);
+      const unsigned cnt = lim - g;
+      unsigned i = 0;
+      if (flat) {
+#pragma unroll 1
+        for (; i < cnt; i++) {
+          const uint4 m = mp[i];
+          if (!flat_message<LT>(base, lane, f, fs, (int)m.x, (int)m.y, m.z, m.w)) break;   // pool full: this message runs on the sorted book
+          if (f.dead) break;
+        }
+        if (i < cnt && !f.dead) { flat_leave(fb, fs); flat = false; }
+      }
+      if (!flat && !f.dead) {
+#pragma unroll 1
+        for (; i < cnt; i++) {
+          const uint4 m = mp[i];
+          fast_message(fb, f, (int)m.x, (int)m.y, m.z, m.w);
+          if (f.dead) break;
+        }
+      }
+      if (f.dead) break;
+      g = lim;
+      if (g == tile_end) { __syncwarp(); issue_tile(); }
+    }
+    if (f.dead) break;
+    now_step++;
+    if (++sub == steps_per_sec) {                            // whole second: outer-level resync, OrderbookSimulator.py:86-87
+      sub = 0;
+      if (c.resync && (!p.resync_last_only || t == T - 1)) {
+        const double prop = ec.outer_prop;
+        const double bb = f.best0 == INT32_MIN ? 0.0 : (double)f.best0;
+        const double bs = f.best1 == INT32_MAX ? (double)INFINITY : (double)f.best1;
+        if (bb < (double)h->min_buy + prop * (double)h->init_buy_range || bs > (double)h->max_sell - prop * (double)h->init_sell_range) {
+          const int sec = now_step / steps_per_sec;
+          if (sec <= (int)stp->n_seconds && stp->snap_valid[sec]) {
+            const int32_t* row = stp->snapshots + (size_t)sec * 2 * c.n_levels * 2;
+            if (flat && !flat_resync_needed(h, row, c.n_levels, lane)) flat_update_trackers<LT>(base, lane, fs);
+            else {
+              if (flat) { flat_leave(fb, fs); flat = false; }
+              fast_resync(fb, f, row, c.n_levels);
+            }
+          }
+        }
+      }
+      if (!flat && flat_fits(fb, 8)) { flat_enter(fb, fs); flat = true; }   // back to the flat pools once the book has shrunk
+    }
+  }
+  if (flat) flat_leave(fb, fs);
   while (next_wait < next_issue) wait_tile();                // drain TMA loads still in flight (aborted episode)
   __syncwarp();
   if (lane == 0) { h->now_step = now_step; h->err = f.err; h->dead = f.dead; }

@@ -36,6 +36,7 @@ struct FastLayoutOps {
   cudaError_t (*attrs)(int dyn_replay, int dyn_env);
   cudaError_t (*attrs_rare)(int dyn_env);
   void (*replay)(int grid, int block, size_t dyn, cudaStream_t stream, const AdvParams& p, const EnvConst& ec);
+  void (*replay_flat)(int grid, int block, size_t dyn, cudaStream_t stream, const AdvParams& p, const EnvConst& ec);
   void (*env)(bool sync, int grid, int block, size_t dyn, cudaStream_t stream, const AdvParams& p, const EnvConst& ec);
   void (*env_rare)(bool sync, int grid, int block, size_t dyn, cudaStream_t stream, const AdvParams& p, const EnvConst& ec);
 };
@@ -43,11 +44,12 @@ struct FastLayoutOps {
   cudaError_t lobsim_fast##i##_attrs(int, int);                                                                            \
   cudaError_t lobsim_fast##i##_attrs_rare(int);                                                                            \
   void lobsim_fast##i##_replay(int, int, size_t, cudaStream_t, const AdvParams&, const EnvConst&);                         \
+  void lobsim_fast##i##_replay_flat(int, int, size_t, cudaStream_t, const AdvParams&, const EnvConst&);                    \
   void lobsim_fast##i##_env(bool, int, int, size_t, cudaStream_t, const AdvParams&, const EnvConst&);                      \
   void lobsim_fast##i##_env_rare(bool, int, int, size_t, cudaStream_t, const AdvParams&, const EnvConst&);
 LOBSIM_FAST_LAYOUTS(X)
 #undef X
-#define X(i, nl, no, na) {nl, no, na, lobsim_fast##i##_attrs, lobsim_fast##i##_attrs_rare, lobsim_fast##i##_replay, lobsim_fast##i##_env, lobsim_fast##i##_env_rare},
+#define X(i, nl, no, na) {nl, no, na, lobsim_fast##i##_attrs, lobsim_fast##i##_attrs_rare, lobsim_fast##i##_replay, lobsim_fast##i##_replay_flat, lobsim_fast##i##_env, lobsim_fast##i##_env_rare},
 static const FastLayoutOps g_fast_layouts[LOBSIM_N_FAST_LAYOUTS] = {LOBSIM_FAST_LAYOUTS(X)};
 #undef X
 static const FastLayoutOps* find_fast_layout(const Layout& L) {
@@ -184,6 +186,7 @@ struct lobsim {
   lobsim_msg_t* st_msgs = nullptr; uint64_t st_msgs_cap = 0;
   bool has_reset = false;
   bool force_general = false;         // LOBSIM_FORCE_GENERAL=1: always use the runtime-layout kernels (testing)
+  bool replay_flat = true;            // LOBSIM_REPLAY_FLAT=0: the replay fast path keeps every book in the sorted level arrays (A/B, testing)
   bool agent_orders_possible = false; // an agent order may rest in some book (disables the replay fast path)
   const FastLayoutOps* fast = nullptr; // compiled straight-line kernels for these capacities, or null: general kernel
   int64_t launches = 0;
@@ -250,6 +253,7 @@ int lobsim_create(const lobsim_cfg_t* cfg, int device, lobsim_t** out) {
   if (!h) return fail(LOBSIM_E_NOMEM, "out of host memory");
   h->cfg = *cfg; h->device = device;
   { const char* e = getenv("LOBSIM_FORCE_GENERAL"); h->force_general = e && e[0] == '1'; }
+  { const char* e = getenv("LOBSIM_REPLAY_FLAT"); h->replay_flat = !(e && e[0] == '0'); }
   h->rare_paths = cfg->step_reward.kind == LOBSIM_REWARD_ROLLING_SHARPE || cfg->terminal_reward.kind == LOBSIM_REWARD_ROLLING_SHARPE;
   for (int i = 0; i < cfg->n_features; i++) h->rare_paths = h->rare_paths || cfg->features[i].norm_len > 0;
   h->L = make_layout(cfg->max_levels_per_side, cfg->max_orders_per_side, cfg->max_agent_orders);
@@ -411,7 +415,7 @@ static int launch_replay_fast(lobsim* h, const AdvParams& p, cudaStream_t stream
   CUDA_TRY(cudaSetDevice(h->device));
   const int wpc = h->warps_per_cta, grid = (p.n_sel + wpc - 1) / wpc;
   if (grid <= 0) return LOBSIM_OK;
-  h->fast->replay(grid, wpc * 32, (size_t)wpc * h->warp_smem, stream, p, h->ec);
+  (h->replay_flat ? h->fast->replay_flat : h->fast->replay)(grid, wpc * 32, (size_t)wpc * h->warp_smem, stream, p, h->ec);
   CUDA_TRY(cudaGetLastError());
   h->launches++;
   return LOBSIM_OK;

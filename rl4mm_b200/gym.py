@@ -292,8 +292,25 @@ class HistoricalOrderbookEnvironment:
         if self.info_calculator is not None:
             info = self.info_calculator.calculate(internal_state=self.sim.state(), action=a)
         if self._squeeze:
-            return obs[0], float(rew[0]), bool(done[0]), info
+            return obs[0], float(rew[0]), bool(done[0]), self._squeeze_info(info)
         return obs, rew, done, info
+
+    @staticmethod
+    def _squeeze_info(info: dict) -> dict:
+        """n_envs == 1: the reference's info shapes (InfoCalculators.py:31-59) -- scalars for the per-env values and
+        1-tuples of 1-D arrays for the action slices -- so that ``extract_array_from_infos`` / ``get_sharpe`` see a
+        [T] series, not [T, 1].  Deviation kept on purpose: ``agent_weighted_spread`` is the computed value; the reference
+        returns the literal ``[1]`` there (InfoCalculators.py:40)."""
+        out = {}
+        for k, v in info.items():
+            a = np.asarray(v)
+            if k in ("bid_action", "ask_action", "market_order_action"):
+                out[k] = (a.reshape(-1),)
+            elif a.ndim >= 1 and a.size == 1:
+                out[k] = a.reshape(-1)[0].item()
+            else:
+                out[k] = v
+        return out
 
     def step_torch(self, actions):
         """Hot-loop variant: torch CUDA tensors in and out, no host round trip, no error polling."""

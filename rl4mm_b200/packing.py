@@ -207,6 +207,14 @@ def _ingest_lib():
         L.lobingest_count_lines.argtypes = [C.c_char_p]
         L.lobingest_parse_messages.argtypes = [C.c_char_p, C.c_int64] + [C.c_void_p] * 6 + [C.POINTER(C.c_int64)]
         L.lobingest_parse_book_rows.argtypes = [C.c_char_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
+        L.lobingest_count_rows.restype = C.c_int64
+        L.lobingest_count_rows.argtypes = [C.c_char_p]
+        L.lobingest_pack_open.restype = C.c_void_p
+        L.lobingest_pack_open.argtypes = [C.c_char_p, C.c_char_p, C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_int64, C.c_int64,
+                                          C.POINTER(C.c_int32), C.c_char_p, C.c_int32]
+        L.lobingest_pack_sizes.argtypes = [C.c_void_p, C.c_void_p]
+        L.lobingest_pack_copy.argtypes = [C.c_void_p] * 6
+        L.lobingest_pack_close.argtypes = [C.c_void_p]
         _INGEST = L
     return _INGEST
 
@@ -218,7 +226,7 @@ def read_lobster_messages(message_csv, max_rows: Optional[int] = None):
 
     L = _ingest_lib()
     path = str(message_csv).encode()
-    n = L.lobingest_count_lines(path)
+    n = L.lobingest_count_rows(path)
     if n < 0:
         raise FileNotFoundError(message_csv)
     if max_rows is not None:
@@ -246,12 +254,52 @@ def read_lobster_book_rows(orderbook_csv, row_idx: np.ndarray, n_levels: int) ->
     return out
 
 
-def pack_lobster(message_csv, orderbook_csv, n_levels: int, max_rows: Optional[int] = None, fast: bool = True, **kw) -> PackedStream:
+def pack_lobster_native(message_csv, orderbook_csv, n_levels: int, max_rows: Optional[int] = None, step_us: int = 100_000,
+                        t0_us: Optional[int] = None, tie_order: str = "reference", db_batch_size: int = 1_000_000,
+                        ticker: str = "", date: str = "") -> PackedStream:
+    """The whole packer in C++ (csrc/lobster_ingest.cpp::lobingest_pack_open): CSV parse, type map, direction flip,
+    microsecond truncation, the reference's lexicographic tie order, hidden-execution drop, dense order references,
+    CSR step offsets and the per-second snapshot alignment -- bit-identical to :func:`pack_arrays`."""
+    import ctypes as C
+
+    if tie_order not in ("reference", "file"):
+        raise ValueError(tie_order)
+    L = _ingest_lib()
+    rc, err = C.c_int32(0), C.create_string_buffer(256)
+    h = L.lobingest_pack_open(str(message_csv).encode(), str(orderbook_csv).encode(), n_levels, step_us,
+                              -1 if t0_us is None else int(t0_us), int(tie_order == "reference"), db_batch_size,
+                              -1 if max_rows is None else int(max_rows), C.byref(rc), err, 256)
+    if not h:
+        msg = err.value.decode() or f"rc {rc.value}"
+        raise (FileNotFoundError if rc.value == -1 else ValueError)(f"{message_csv}: {msg}")
+    try:
+        sizes = np.zeros(6, np.int64)
+        L.lobingest_pack_sizes(h, sizes.ctypes.data)
+        n_msgs, n_grid, n_sec, n_ids, t0, _ = (int(x) for x in sizes)
+        msgs = np.zeros(n_msgs, abi.MSG_DTYPE)
+        step_off = np.zeros(n_grid + 1, np.uint32)
+        snapshots = np.zeros((n_sec + 1, 2, n_levels, 2), np.int32)
+        snap_valid = np.zeros(n_sec + 1, np.uint8)
+        ext_ids = np.zeros(n_ids, np.int64)
+        L.lobingest_pack_copy(h, msgs.ctypes.data, step_off.ctypes.data, snapshots.ctypes.data, snap_valid.ctypes.data, ext_ids.ctypes.data)
+    finally:
+        L.lobingest_pack_close(h)
+    out = PackedStream(msgs, step_off, snapshots, snap_valid, t0, int(step_us), n_levels, ext_ids, ticker, date)
+    out.validate()
+    return out
+
+
+def pack_lobster(message_csv, orderbook_csv, n_levels: int, max_rows: Optional[int] = None, fast=True, **kw) -> PackedStream:
     """Pack a LOBSTER ``*_message_L.csv`` / ``*_orderbook_L.csv`` pair (populate_database.py:71-78 column layout).
-    ``fast=True`` reads the files with the C++ reader (and only the orderbook rows the snapshots need); ``fast=False``
-    is the pure-Python path (kept as the cross-check in the tests)."""
+    ``fast=True``: the native packer (:func:`pack_lobster_native`); ``fast="reader"``: the C++ CSV reader (only the
+    orderbook rows the snapshots need) + the numpy packer :func:`pack_arrays`; ``fast=False``: the pure-Python path.
+    All three give bit-identical streams (tests/test_abi_cpu.py)."""
+    if fast is True:
+        return pack_lobster_native(message_csv, orderbook_csv, n_levels, max_rows, **kw)
     if fast:
         t, ty, oid, sz, pr, di = read_lobster_messages(message_csv, max_rows)
+        if max_rows is None and _ingest_lib().lobingest_count_rows(str(orderbook_csv).encode()) != len(t):
+            raise ValueError("message file and orderbook file have different row counts")
         return pack_arrays(t, ty, oid, sz, pr, di, lambda idx: read_lobster_book_rows(orderbook_csv, idx, n_levels),
                            n_levels, **kw)
     t, ty, oid, sz, pr, di = [], [], [], [], [], []

@@ -7,7 +7,13 @@ the env step is the CUDA path (``LobSim.step`` on device tensors, no host round 
 * rollouts: all envs of a rank step in lock-step for T steps (fixed episode length => every env finishes together and
   the batch is reset at once, i.e. the reference's env.reset() per worker);
 * update: GAE(lambda) + clipped surrogate + value loss + entropy bonus, minibatch Adam; with world_size > 1 the
-  modules are wrapped in DistributedDataParallel so gradients are all-reduced over NVLink.
+  modules are wrapped in DistributedDataParallel so gradients are all-reduced over NVLink;
+* observation normalisation: the batch stores the observations AS THE POLICY SAW THEM (normalised with the running
+  statistics in force during collection); the statistics are updated only after the PPO epochs, so ratio == 1 at the
+  first minibatch and returns / values share one input scaling;
+* device errors: ``step_torch`` does not poll, so the per-env error column is read once per rollout and before every
+  batch reset (the reset kernel clears the flags): EmptyOrderbookError / overflow / bad-action envs raise, exactly as
+  ``env.step`` would have (``on_error="raise"``), or are masked out of the update (``on_error="mask"``).
 """
 from __future__ import annotations
 
@@ -99,9 +105,10 @@ def gae(rew: torch.Tensor, val: torch.Tensor, last_val: torch.Tensor, done: torc
 
 
 class PPOTrainer:
-    def __init__(self, env, cfg: PPOConfig = PPOConfig(), seed: int = 0):
+    def __init__(self, env, cfg: PPOConfig = PPOConfig(), seed: int = 0, on_error: str = "raise"):
         """`env`: rl4mm_b200.gym.HistoricalOrderbookEnvironment (batched).  One trainer per rank / GPU."""
-        self.env, self.cfg = env, cfg
+        assert on_error in ("raise", "mask")
+        self.env, self.cfg, self.on_error = env, cfg, on_error
         self.device = env.sim.device
         torch.manual_seed(seed)
         low = torch.as_tensor(env.action_space.low, device=self.device)
@@ -116,11 +123,26 @@ class PPOTrainer:
         self.steps_left = 0
         self.episode_return = torch.zeros(env.n_envs, dtype=torch.float64, device=self.device)
         self.finished_returns = []
+        self.bad_envs = torch.zeros(env.n_envs, dtype=torch.bool, device=self.device)   # envs that died in the current episode
+
+    def _poll_errors(self) -> None:
+        """Read the per-env error flags (one D2H copy).  Must run BEFORE a reset: the reset kernel clears them."""
+        from . import abi
+
+        err = torch.as_tensor(self.env.sim.errors().astype("int64"), device=self.device)
+        fatal = abi.ERR_EMPTY_BOOK | abi.ERR_LEVEL_OVERFLOW | abi.ERR_ORDER_OVERFLOW | abi.ERR_AGENT_OVERFLOW | abi.ERR_BAD_ACTION \
+            | abi.ERR_END_OF_STREAM | abi.ERR_NO_SNAPSHOT
+        bad = (err & fatal) != 0
+        if bool(bad.any()):
+            if self.on_error == "raise":
+                self.env._raise_on_errors()
+            self.bad_envs |= bad
 
     def _reset(self):
         self.obs = torch.as_tensor(self.env.reset(), device=self.device).reshape(self.env.n_envs, -1)
         self.steps_left = self.env.n_steps
         self.episode_return.zero_()
+        self.bad_envs.zero_()
 
     @torch.no_grad()
     def collect(self) -> Dict[str, torch.Tensor]:
@@ -128,6 +150,8 @@ class PPOTrainer:
         if self.obs is None:
             self._reset()
         obs_b = torch.empty((T, N, self.env.sim.obs_dim), dtype=torch.float64, device=self.device)
+        obsn_b = torch.empty((T, N, self.env.sim.obs_dim), device=self.device)
+        valid_b = torch.ones((T, N), dtype=torch.bool, device=self.device)
         x_b = torch.empty((T, N, self.env.sim.action_dim), device=self.device)
         logp_b, val_b, rew_b = (torch.empty((T, N), device=self.device) for _ in range(3))
         done_b = torch.zeros((T, N), dtype=torch.bool, device=self.device)
@@ -135,27 +159,38 @@ class PPOTrainer:
             self.norm.update(self.obs)
         for t in range(T):
             obs_b[t] = self.obs
-            dist, val = self.policy(self.norm(self.obs))
+            obsn_b[t] = self.norm(self.obs)
+            dist, val = self.policy(obsn_b[t])
             x = dist.sample()
             obs, rew, done = self.env.step_torch(self.policy.to_env(x).double())
             x_b[t], logp_b[t], val_b[t] = x, dist.log_prob(x.clamp(1e-6, 1 - 1e-6)).sum(-1), val
+            finite = torch.isfinite(rew)                # an empty book side has no price: the reward of a dead env is NaN
+            valid_b[t] = finite
+            rew = torch.where(finite, rew, torch.zeros_like(rew))
             rew_b[t], done_b[t] = (rew * cfg.reward_scale).float(), done.bool()
             self.episode_return += rew
             self.obs = obs
             self.steps_left -= 1
             if self.steps_left == 0:                    # every env ends together: batch reset (env.reset per worker)
-                self.finished_returns.append(float(self.episode_return.mean()))
+                self._poll_errors()                     # before the reset kernel clears the flags
+                valid_b[: t + 1] &= ~self.bad_envs
+                good = ~self.bad_envs
+                self.finished_returns.append(float(self.episode_return[good].mean()) if bool(good.any()) else float("nan"))
                 self._reset()
-        self.norm.update(obs_b)
+        self._poll_errors()
+        valid_b &= ~self.bad_envs                       # (conservative: the whole rollout of an env that died in it)
         last_val = self.policy(self.norm(self.obs))[1]
         adv, ret = gae(rew_b, val_b, last_val, done_b, cfg.gamma, cfg.lam)
-        return dict(obs=obs_b, x=x_b, logp=logp_b, adv=adv, ret=ret, rew=rew_b)
+        return dict(obs=obs_b, obs_n=obsn_b, x=x_b, logp=logp_b, adv=adv, ret=ret, rew=rew_b, valid=valid_b)
 
     def update(self, batch: Dict[str, torch.Tensor]) -> Dict[str, float]:
         cfg = self.cfg
-        obs = self.norm(batch["obs"]).flatten(0, 1)
+        obs = batch["obs_n"].flatten(0, 1)              # as seen by the policy during collection
         x, logp0 = batch["x"].flatten(0, 1).clamp(1e-6, 1 - 1e-6), batch["logp"].flatten()
         adv, ret = batch["adv"].flatten(), batch["ret"].flatten()
+        keep = batch["valid"].flatten()
+        if not bool(keep.all()):                        # dead envs (on_error="mask") / non-finite rewards stay out of the update
+            obs, x, logp0, adv, ret = obs[keep], x[keep], logp0[keep], adv[keep], ret[keep]
         adv = (adv - adv.mean()) / (adv.std() + 1e-8)
         n = obs.shape[0]
         stats = {}
@@ -175,6 +210,8 @@ class PPOTrainer:
                 self.opt.step()
                 stats = dict(loss=loss.item(), pg=pg.item(), vf=vf.item(), entropy=ent.item(),
                              kl=(logp0[idx] - logp).mean().item())
+        self.norm.update(batch["obs"])                  # running statistics move only after the PPO epochs
+        stats["masked_fraction"] = 1.0 - float(keep.float().mean())
         return stats
 
     def train(self, iterations: int, log=None):

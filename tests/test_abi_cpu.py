@@ -215,12 +215,104 @@ def test_fast_lobster_reader_matches_python_packer(tmp_path):
     idx = np.array([0, 0, 5, 17, 17, 599])
     assert np.array_equal(read_lobster_book_rows(book, idx, L), rows[idx])
     for tie in ("reference", "file"):
-        a = pack_lobster(msg, book, L, fast=True, tie_order=tie)
-        b = pack_lobster(msg, book, L, fast=False, tie_order=tie)
+        a = pack_lobster(msg, book, L, fast=True, tie_order=tie)          # the native packer (lobingest_pack_open)
+        r = pack_lobster(msg, book, L, fast="reader", tie_order=tie)      # C++ reader + numpy packer
+        b = pack_lobster(msg, book, L, fast=False, tie_order=tie)         # pure Python
         for f_ in ("msgs", "step_off", "snapshots", "snap_valid", "ext_ids"):
             assert np.array_equal(getattr(a, f_), getattr(b, f_)), (tie, f_)
-        assert a.t0_us == b.t0_us == 34_200_000_000
+            assert np.array_equal(getattr(r, f_), getattr(b, f_)), (tie, f_)
+        assert a.t0_us == r.t0_us == b.t0_us == 34_200_000_000
+    for kw in (dict(max_rows=250), dict(step_us=50_000), dict(t0_us=34_199_000_000), dict(db_batch_size=100)):
+        a, b = pack_lobster(msg, book, L, fast=True, **kw), pack_lobster(msg, book, L, fast=False, **kw)
+        for f_ in ("msgs", "step_off", "snapshots", "snap_valid", "ext_ids"):
+            assert np.array_equal(getattr(a, f_), getattr(b, f_)), (kw, f_)
     assert np.array_equal(read_lobster_messages(msg, max_rows=10)[0], t[:10])
+
+    # blank / "\r"-only lines are not data rows in EITHER file (the readers used to count them differently, which
+    # silently shifted the snapshots against the messages); an empty field is malformed; unequal row counts are an error
+    msg2, book2 = tmp_path / "blank_message_3.csv", tmp_path / "blank_orderbook_3.csv"
+    ml, bl = open(msg).read().splitlines(), open(book).read().splitlines()
+    with open(msg2, "w") as f:
+        f.write("\n".join(ml[:50] + ["", "\r"] + ml[50:]) + "\n\n")
+    with open(book2, "w") as f:
+        f.write("\n".join(bl[:300] + [""] + bl[300:]) + "\n")
+    ref = pack_lobster(msg, book, L, fast=True)
+    for fast in (True, "reader"):
+        got = pack_lobster(msg2, book2, L, fast=fast)
+        for f_ in ("msgs", "step_off", "snapshots", "snap_valid", "ext_ids"):
+            assert np.array_equal(getattr(got, f_), getattr(ref, f_)), (fast, f_)
+    with open(book2, "w") as f:
+        f.write("\n".join(bl[:-1]) + "\n")
+    for fast in (True, "reader"):
+        with pytest.raises(ValueError, match="different row counts"):
+            pack_lobster(msg, book2, L, fast=fast)
+    with open(msg2, "w") as f:
+        f.write("\n".join(ml[:10] + ["34203.5,1,,100,3000000,1"] + ml[10:]) + "\n")
+    with pytest.raises(ValueError, match="malformed"):
+        pack_lobster(msg2, book, L, fast=True)
+    with pytest.raises(ValueError, match="malformed"):
+        read_lobster_messages(msg2)
+
+
+def test_native_packer_on_the_msft_fixture_and_a_1e6_row_day(tmp_path):
+    """the native packer == the numpy packer on the reference's own MSFT fixture, and on a 1e6-row synthetic
+    LOBSTER file pair (written from a packed synthetic stream), where it also has to be much faster."""
+    import time
+
+    from pathlib import Path
+
+    from parity_helpers import load_fixture_stream
+    from rl4mm_b200 import synthetic
+    from rl4mm_b200.packing import pack_lobster
+
+    ref_dir = Path("/root/reference/test_data")       # present in the build container only; the packed fixture is committed
+    m = ref_dir / "MSFT_2012-06-21_34200000_37800000_message_50.csv"
+    b = ref_dir / "MSFT_2012-06-21_34200000_37800000_orderbook_50.csv"
+    if m.exists():
+        for tie in ("reference", "file"):
+            x, y = pack_lobster(m, b, 50, max_rows=1000, fast=True, tie_order=tie), load_fixture_stream(tie)
+            for f_ in ("msgs", "step_off", "snapshots", "snap_valid", "ext_ids"):
+                assert np.array_equal(getattr(x, f_), getattr(y, f_)), (tie, f_)
+    n, L = 1_000_000, 10
+    s = synthetic.generate(synthetic.spy_day(seed=3, n_msgs=n, duration_s=2340))
+    # a LOBSTER file pair carrying that stream: time inside the step, LOBSTER's resting-order direction for executions
+    step = np.repeat(np.arange(s.n_grid_steps), np.diff(s.step_off.astype(np.int64)))
+    us = s.t0_us + step * s.step_us + 1 + (np.arange(n) - s.step_off.astype(np.int64)[step])   # strictly increasing inside (k*step, (k+1)*step]
+    assert np.all(np.diff(us) > 0) and np.all(us <= s.t0_us + (step + 1) * s.step_us)
+    ty = (s.msgs["meta"] & 7).astype(np.int64)
+    side = ((s.msgs["meta"] >> 3) & 1).astype(np.int64)
+    lob_dir = np.where(ty == 4, 1 - side, side)
+    di = np.where(lob_dir == 0, 1, -1)
+    msg, book = tmp_path / "SYN_message_10.csv", tmp_path / "SYN_orderbook_10.csv"
+    sec_of = (us - s.t0_us) // 1_000_000
+    with open(msg, "w") as f:
+        f.write("".join(f"{u // 1_000_000}.{u % 1_000_000:06d}000,{t},{r},{v},{p},{d}\n" for u, t, r, v, p, d in
+                        zip(us.tolist(), ty.tolist(), s.msgs["ref"].tolist(), s.msgs["volume"].tolist(), s.msgs["price"].tolist(), di.tolist())))
+    snap = s.snapshots.astype(np.int64)
+    snap_rows = np.zeros((snap.shape[0], 4 * L), np.int64)
+    for lv in range(L):
+        ap, av, bp, bv = snap[:, 1, lv, 0], snap[:, 1, lv, 1], snap[:, 0, lv, 0], snap[:, 0, lv, 1]
+        snap_rows[:, 4 * lv + 0] = np.where(ap == abi.NO_PRICE, 9999999999, ap)
+        snap_rows[:, 4 * lv + 1] = av
+        snap_rows[:, 4 * lv + 2] = np.where(bp == abi.NO_PRICE, -9999999999, bp)
+        snap_rows[:, 4 * lv + 3] = bv
+    lines = [",".join(map(str, r)) for r in snap_rows.tolist()]
+    with open(book, "w") as f:
+        f.write("".join(lines[k] + "\n" for k in sec_of.tolist()))
+    t0 = time.perf_counter()
+    a = pack_lobster(msg, book, L, fast=True, t0_us=s.t0_us)
+    t_native = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    r = pack_lobster(msg, book, L, fast="reader", t0_us=s.t0_us)
+    t_numpy = time.perf_counter() - t0
+    for f_ in ("msgs", "step_off", "snapshots", "snap_valid", "ext_ids"):
+        assert np.array_equal(getattr(a, f_), getattr(r, f_)), f_
+    # round trip: the packed stream is the one the files were written from (refs are re-ranked densely: same order)
+    assert np.array_equal(a.step_off, s.step_off)
+    for f_ in ("price", "volume", "meta"):
+        assert np.array_equal(a.msgs[f_], s.msgs[f_]), f_
+    assert np.array_equal(a.ext_ids[a.msgs["ref"]], s.msgs["ref"].astype(np.int64))
+    print(f"native packer: {n / t_native:.3g} rows/s, C++ reader + numpy packer: {n / t_numpy:.3g} rows/s")
 
 
 def test_gae_matches_naive_sum():

@@ -29,6 +29,7 @@ def _order(env, type, direction, price, volume, is_external, ref):
     return o
 
 
+@pytest.mark.replay_path
 def test_message_free_steps_and_zero_step_calls():
     """A stream with no messages at all: replay / rollout advance the clock and leave the snapshot book untouched."""
     s = H.snapshot_stream([[0, 1000, 5], [0, 900, 7], [1, 1100, 3]], n_levels=50)
@@ -48,6 +49,7 @@ def test_message_free_steps_and_zero_step_calls():
     assert o.shape == (0, 5, 1)
 
 
+@pytest.mark.replay_path
 def test_stepping_past_the_grid_sets_end_of_stream():
     s = H.snapshot_stream([[0, 1000, 5], [1, 1100, 3]], n_levels=50)
     sim = _sim(abi.default_cfg(n_envs=2), [s])

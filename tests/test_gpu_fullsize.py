@@ -29,6 +29,7 @@ def _sim(cfg, streams):
     return sim
 
 
+@pytest.mark.replay_path
 def test_config2_full_day_replay_4096_books():
     from oracle.oracle import Oracle
     from rl4mm_b200 import synthetic
@@ -181,3 +182,66 @@ def test_ppo_training_loop_runs_on_device_env():
         assert all(np.isfinite(h[k]) for k in ("loss", "pg", "vf", "entropy", "kl", "mean_step_reward")), h
         assert h["env_steps_per_sec"] > 0
     assert np.isfinite(hist[-1]["episode_reward_mean"])          # 96 steps >= one 50-step episode
+
+
+def _ppo_env(n_envs, max_orders=256, max_agent=64, seed=7, episode_seconds=5.0):
+    from datetime import datetime, timedelta
+
+    from rl4mm_b200 import synthetic
+    from rl4mm_b200.features import Portfolio
+    from rl4mm_b200.gym import HistoricalOrderbookEnvironment
+    from rl4mm_b200.rewards import PnL
+    from rl4mm_b200.simulation import DeviceDatabase
+
+    day = datetime(2019, 1, 2)
+    db = DeviceDatabase()
+    db.add_stream("SPY", day, synthetic.generate(synthetic.spy_day(seed=0, n_msgs=300_000, duration_s=900)))
+    step, ep = timedelta(seconds=0.1), timedelta(seconds=episode_seconds)
+    feats = HistoricalOrderbookEnvironment.get_default_features(step, ep)
+    warm = max(f.window_size for f in feats)
+    return HistoricalOrderbookEnvironment(
+        features=feats, ticker="SPY", step_size=step, episode_length=ep, min_date=day, max_date=day,
+        initial_portfolio=Portfolio(inventory=0, cash=1_000_000), n_levels=10, database=db, n_envs=n_envs, device=0,
+        min_start_timedelta=timedelta(hours=9, minutes=30) + warm + timedelta(seconds=10),
+        max_end_timedelta=timedelta(hours=9, minutes=30, seconds=890),
+        per_step_reward_function=PnL(), terminal_reward_function=PnL(),
+        max_levels_per_side=64, max_orders_per_side=max_orders, max_agent_orders=max_agent, portfolio_carryover=False, seed=seed)
+
+
+def test_ppo_batch_keeps_the_observations_the_policy_saw():
+    """logp / values are computed with the normalisation statistics in force during collection, so the update
+    must see the same normalised observations: with unchanged parameters the importance ratio is exactly 1."""
+    import torch
+
+    from rl4mm_b200.ppo import PPOConfig, PPOTrainer
+
+    env = _ppo_env(256)
+    tr = PPOTrainer(env, PPOConfig(rollout_steps=16, epochs=1, minibatches=1, lr=0.0), seed=0)
+    batch = tr.collect()
+    n_before = float(tr.norm.n)
+    with torch.no_grad():
+        dist, val = tr.policy(batch["obs_n"].flatten(0, 1))
+        logp = dist.log_prob(batch["x"].flatten(0, 1).clamp(1e-6, 1 - 1e-6)).sum(-1)
+    assert torch.allclose(logp, batch["logp"].flatten(), atol=1e-5)
+    stats = tr.update(batch)
+    assert abs(stats["kl"]) < 1e-6 and stats["masked_fraction"] == 0.0
+    assert float(tr.norm.n) == n_before + 16 * 256            # the running statistics moved only after the epochs
+
+
+def test_ppo_surfaces_dead_envs():
+    """an env that dies mid-episode (here: 4-order agent table => AGENT_OVERFLOW) must not be lost at the
+    batch reset: on_error="raise" raises like env.step would, on_error="mask" keeps it out of the update."""
+    import torch
+
+    from rl4mm_b200.ppo import PPOConfig, PPOTrainer
+
+    env = _ppo_env(128, max_orders=128, max_agent=4, episode_seconds=2.0)
+    tr = PPOTrainer(env, PPOConfig(rollout_steps=32, epochs=1, minibatches=1), seed=0, on_error="raise")
+    with pytest.raises(RuntimeError, match="AGENT_OVERFLOW"):
+        tr.collect()
+    env2 = _ppo_env(128, max_orders=128, max_agent=4, episode_seconds=2.0)
+    tr2 = PPOTrainer(env2, PPOConfig(rollout_steps=32, epochs=1, minibatches=1), seed=0, on_error="mask")
+    batch = tr2.collect()
+    assert not bool(batch["valid"].all()) and torch.isfinite(batch["rew"]).all()
+    stats = tr2.update(batch) if bool(batch["valid"].any()) else {"masked_fraction": 1.0}
+    assert stats["masked_fraction"] > 0.0

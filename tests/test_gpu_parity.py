@@ -74,6 +74,7 @@ class DeviceExchange:
 # ---------------------------------------------------------------------------------------------------------------------
 #  golden vectors from the reference
 # ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.replay_path
 @pytest.mark.parametrize("case_idx", range(4))
 def test_fixture_replay_l3_and_fills(case_idx, torch_cuda):
     case = H.load_golden("fixture_replay.json.gz")[case_idx]
@@ -94,6 +95,7 @@ def test_fixture_replay_l3_and_fills(case_idx, torch_cuda):
         assert np.all(st["min_buy_price"] == step["min_buy"]) and np.all(st["max_sell_price"] == step["max_sell"])
 
 
+@pytest.mark.replay_path
 def test_fixture_replay_in_one_launch(torch_cuda):
     """27 steps fused in one launch == 27 single-step launches (the TMA message pipeline crosses step boundaries)."""
     case = H.load_golden("fixture_replay.json.gz")[0]
@@ -197,6 +199,7 @@ def compare_books(sim, env, oracle, what):
         assert np.array_equal(ad["price"], ao["price"]) and np.array_equal(ad["volume"], ao["volume"]), (what, side)
 
 
+@pytest.mark.replay_path
 @pytest.mark.parametrize("which", ["spy", "heavy"])
 def test_synthetic_replay_vs_oracle(which, torch_cuda):
     from oracle.oracle import Oracle

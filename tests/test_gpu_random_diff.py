@@ -96,7 +96,8 @@ def test_random_env_case(seed):
 @pytest.mark.fast_only          # the test itself runs both kernel families
 @pytest.mark.parametrize("seed", range(SEED0, SEED0 + N_REPLAY_CASES))
 def test_random_replay_case(seed, monkeypatch):
-    """Pure replay (both kernel families: the straight-line k_replay_fast and, forced, the general k_advance) vs the oracle."""
+    """Pure replay on all three implementations -- the flat order pools (k_replay_flat), the sorted level arrays
+    (k_replay_fast, LOBSIM_REPLAY_FLAT=0) and, forced, the general k_advance -- vs the oracle."""
     from oracle.oracle import Oracle
     from rl4mm_b200 import synthetic
     from test_gpu_parity import compare_books, make_sim
@@ -105,8 +106,9 @@ def test_random_replay_case(seed, monkeypatch):
     s = synthetic.generate(c["synth"])
     n = c["n_envs"]
     okw = {k: v for k, v in c["cfg_kw"].items() if not k.startswith("max_")}
-    for force_general in ("0", "1"):
+    for force_general, flat in (("0", "1"), ("0", "0"), ("1", "1")):
         monkeypatch.setenv("LOBSIM_FORCE_GENERAL", force_general)
+        monkeypatch.setenv("LOBSIM_REPLAY_FLAT", flat)
         sim = make_sim(abi.default_cfg(n_envs=n, **c["cfg_kw"]), [s])
         oracles = [Oracle(abi.default_cfg(n_envs=1, **okw), s) for _ in range(n)]
         sim.reset_book(0, c["starts"])
@@ -116,7 +118,7 @@ def test_random_replay_case(seed, monkeypatch):
             sim.replay(chunk)
             st = sim.state()
             for env, o in enumerate(oracles):
-                what = f"replay seed {seed} general={force_general} env {env} chunk {chunk}"
+                what = f"replay seed {seed} general={force_general} flat={flat} env {env} chunk {chunk}"
                 o.replay(chunk)
                 os_ = o.state()
                 overflow = int(st["err"][env]) & (abi.ERR_LEVEL_OVERFLOW | abi.ERR_ORDER_OVERFLOW)

@@ -362,7 +362,11 @@ def test_env_episode_runs_to_done_and_info(m):
     assert len(traj["rewards"]) == 10 and len(traj["observations"]) == 11
     info = traj["infos"][-1]
     assert {"asset_price", "inventory", "cash", "aum", "market_spread", "agent_spread", "midprice_offset"} <= set(info)
-    assert info["market_spread"][0] == 100.0
+    # n_envs == 1: the reference's shapes (InfoCalculators.py:31-59) -- scalars, and 1-tuples of 1-D action slices
+    assert info["market_spread"] == 100.0 and np.isscalar(info["aum"]) and isinstance(info["inventory"], int)
+    assert isinstance(info["bid_action"], tuple) and info["bid_action"][0].shape == (2,) and info["ask_action"][0].shape == (2,)
+    aum = np.array([i["aum"] for i in traj["infos"]])
+    assert aum.shape == (10,) and np.diff(aum).shape == (9,)          # a [T] series: get_sharpe(aum_array) works as in the reference
 
 
 def test_trade_imbalance_goldens(m):
