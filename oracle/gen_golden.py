@@ -468,6 +468,48 @@ def golden_episode_summary():
     save("episode_summary.json.gz", cases)
 
 
+def golden_generator_merge():
+    """Multi-generator merge (rl4mm/simulation/OrderbookSimulator.py:137-148): random 2- and 3-generator step windows through
+    the reference's own ``OrderbookSimulator._compress_order_dict`` with the reference's Order dataclasses.  Timestamps are
+    drawn from a handful of microseconds, and orders are sometimes duplicated across generators, so that the lexicographic
+    deque comparison (equal heads defer to the next elements, ties keep the first generator) is what decides."""
+    from collections import deque
+
+    from rl4mm.orderbook.create_order import create_order
+    from rl4mm.simulation.OrderbookSimulator import OrderbookSimulator
+
+    rng = np.random.default_rng(20260101)
+    kinds = {1: "limit", 2: "cancellation", 3: "deletion", 4: "market"}
+    cases = []
+    for c in range(200):
+        n_gen = int(rng.integers(2, 4))
+        pool = []                                             # shared pool => cross-generator duplicates
+        for _ in range(int(rng.integers(2, 7))):
+            pool.append(dict(us=int(rng.integers(1, 5)), type=int(rng.choice([1, 2, 3, 4])), direction=int(rng.choice([-1, 1])),
+                             ext_id=int(rng.integers(1, 4)), size=int(rng.integers(1, 3)) * 100, price=int(rng.integers(1, 3)) * 100))
+        gens = []
+        for g in range(n_gen):
+            k = int(rng.integers(1, 6))
+            rows = [dict(pool[int(rng.integers(0, len(pool)))]) if rng.random() < 0.6 else
+                    dict(us=int(rng.integers(1, 5)), type=int(rng.choice([1, 2, 3, 4])), direction=int(rng.choice([-1, 1])),
+                         ext_id=int(rng.integers(1, 50)), size=int(rng.integers(1, 9)) * 100, price=int(rng.integers(1, 9)) * 100)
+                    for _ in range(k)]
+            rows.sort(key=lambda r: r["us"])                  # a generator hands its orders out in time order
+            gens.append(rows)
+        od = {}
+        for g, rows in enumerate(gens):
+            dq = deque()
+            for i, r in enumerate(rows):
+                o = create_order(kinds[r["type"]], dict(timestamp=DAY + timedelta(hours=10, microseconds=r["us"]), price=r["price"], volume=r["size"],
+                                                        direction="buy" if r["direction"] == 1 else "sell", ticker="MSFT", internal_id=None,
+                                                        external_id=r["ext_id"], is_external=True))
+                o._src = (g, i)
+                dq.append(o)
+            od[f"gen_{g}"] = dq
+        merged = OrderbookSimulator._compress_order_dict(od)
+        cases.append(dict(generators=gens, merged=[list(o._src) for o in merged]))
+    save("generator_merge.json.gz", cases)
+
 
 def main():
     refshim.install()
@@ -486,6 +528,7 @@ def main():
         golden_beta_ladders()
         golden_exchange_fuzz()
         golden_episode_summary()
+        golden_generator_merge()
     for p in sorted(GOLDEN.glob("*.gz")):
         print(p.name, p.stat().st_size)
 

@@ -44,6 +44,7 @@ class PackedStream:
     ext_ids: np.ndarray = field(default_factory=lambda: np.zeros(1, np.int64))  # ref -> original external id
     ticker: str = ""
     date: str = ""
+    generators: tuple = ("historical",)   # names of the OrderGenerators merged into this stream (pack_merged)
 
     @property
     def n_msgs(self) -> int:
@@ -98,6 +99,136 @@ def _lexicographic_tie_order(ts_us: np.ndarray, row_ids: np.ndarray) -> np.ndarr
     return order
 
 
+@dataclass
+class RawMessages:
+    """The messages of ONE OrderGenerator (rl4mm/simulation/OrderGenerator.py:9-21) as LOBSTER columns."""
+    time_ns: np.ndarray
+    msg_type: np.ndarray
+    ext_id: np.ndarray
+    size: np.ndarray
+    price: np.ndarray
+    direction: np.ndarray
+
+    def take(self, idx) -> "RawMessages":
+        return RawMessages(*(np.asarray(getattr(self, f))[idx] for f in ("time_ns", "msg_type", "ext_id", "size", "price", "direction")))
+
+    def __len__(self):
+        return len(self.time_ns)
+
+
+class _MergeOrder:
+    """What ``min(order_dict, key=order_dict.get)`` sees of an Order (rl4mm/orderbook/models.py:17-52): ``==`` is the dataclass
+    equality over every field (same class, i.e. same message type; a market order has no price), ``<`` is
+    ``Order.__lt__`` = the timestamp alone (:27-28)."""
+    __slots__ = ("ts", "fields", "idx")
+
+    def __init__(self, ts, fields, idx):
+        self.ts, self.fields, self.idx = ts, fields, idx
+
+    def __eq__(self, other):
+        return self.fields == other.fields
+
+    def __lt__(self, other):
+        return self.ts < other.ts
+
+
+def compress_order_dict(order_dict):
+    """``OrderbookSimulator._compress_order_dict`` (rl4mm/simulation/OrderbookSimulator.py:137-148): the orders of several
+    generators for one step, merged by repeatedly taking the head of the SMALLEST deque -- deques compare
+    lexicographically (first unequal pair decides by ``<`` = timestamp; equal prefixes => the shorter one), and ``min``
+    keeps the first generator of the dict on a tie.  Works on deques of anything with that ``==`` / ``<`` (the façade's
+    Order dataclasses, or :class:`_MergeOrder`).  Consumes ``order_dict``."""
+    if len(order_dict) == 1:
+        return list(next(iter(order_dict.values())))
+    merged = []
+    while order_dict:
+        key = min(order_dict, key=order_dict.get)
+        merged.append(order_dict[key].popleft())
+        if not order_dict[key]:
+            del order_dict[key]
+    return merged
+
+
+def generator_order(raw: RawMessages, t0_us: int, tie_order: str = "reference", db_batch_size: int = 1_000_000) -> RawMessages:
+    """One generator's messages in the order ``generate_orders`` hands them out (HistoricalOrderGenerator.py:32-57):
+    ``ORDER BY (timestamp, id-string)``, hidden executions dropped, nothing at or before the grid origin."""
+    time_ns, mt = np.asarray(raw.time_ns, np.int64), np.asarray(raw.msg_type, np.int64)
+    ts_us = time_ns // 1000
+    row_ids = np.arange(len(raw), dtype=np.int64)
+    row_ids = row_ids + (row_ids // db_batch_size) * db_batch_size
+    order = _lexicographic_tie_order(ts_us, row_ids) if tie_order == "reference" else np.argsort(ts_us, kind="stable")
+    keep = order[(ts_us[order] > t0_us) & (mt[order] != 5)]
+    return raw.take(keep)
+
+
+def compress_order_sources(sources, t0_us: int, step_us: int) -> RawMessages:
+    """Pack-time form of ``forward_step``'s merge (OrderbookSimulator.py:74-75,137-148): ``sources`` maps generator name ->
+    :class:`RawMessages` already in generator order (:func:`generator_order`); every step window
+    ``(t0 + k*step, t0 + (k+1)*step]`` is merged with :func:`compress_order_dict`, exactly what the reference does when it
+    pulls that window from each generator.  Returns the merged messages (time truncated to microseconds)."""
+    from collections import deque
+
+    names = list(sources)
+    srcs = [sources[k] for k in names]
+    ts = [np.asarray(s.time_ns, np.int64) // 1000 for s in srcs]
+    if len(srcs) == 1:
+        out = srcs[0].take(slice(None))
+        out.time_ns = ts[0] * 1000
+        return out
+    steps = [-(-(t - t0_us) // step_us) - 1 for t in ts]
+    for st in steps:
+        assert np.all(np.diff(st) >= 0), "a generator's messages must be time ordered"
+    n_steps = max(int(st[-1]) + 1 if len(st) else 0 for st in steps)
+    bounds = [np.searchsorted(st, np.arange(n_steps + 1)) for st in steps]
+    cols = [[np.asarray(getattr(s, f), np.int64) for f in ("msg_type", "ext_id", "size", "price", "direction")] for s in srcs]
+    picks = []                                       # (source, index) in merged order, as array chunks
+    for k in range(n_steps):
+        live = [g for g in range(len(srcs)) if bounds[g][k + 1] > bounds[g][k]]
+        if not live:
+            continue
+        if len(live) == 1:
+            g = live[0]
+            idx = np.arange(bounds[g][k], bounds[g][k + 1])
+            picks.append(np.stack([np.full(len(idx), g), idx], 1))
+            continue
+        od = {}
+        for g in live:
+            mt, eid, sz, pr, di = cols[g]
+            od[names[g]] = deque(
+                _MergeOrder(int(ts[g][i]), (int(ts[g][i]), int(mt[i]), int(di[i]), int(eid[i]), int(sz[i]), None if mt[i] == 4 else int(pr[i])), (g, i))
+                for i in range(bounds[g][k], bounds[g][k + 1]))
+        picks.append(np.array([o.idx for o in compress_order_dict(od)], np.int64).reshape(-1, 2))
+    pick = np.concatenate(picks) if picks else np.zeros((0, 2), np.int64)
+    out = {}
+    for f in ("time_ns", "msg_type", "ext_id", "size", "price", "direction"):
+        col = np.zeros(len(pick), np.int64)
+        for g, s in enumerate(srcs):
+            m = pick[:, 0] == g
+            src = ts[g] * 1000 if f == "time_ns" else np.asarray(getattr(s, f), np.int64)
+            col[m] = src[pick[m, 1]]
+        out[f] = col
+    return RawMessages(**out)
+
+
+def pack_merged(sources, book_rows, n_levels: int, step_us: int = 100_000, t0_us: Optional[int] = None, tie_order: str = "reference",
+                db_batch_size: int = 1_000_000, snapshot_source: Optional[str] = None, **kw) -> PackedStream:
+    """Several OrderGenerators -> ONE packed stream (the reference's ``order_generators`` list, OrderbookSimulator.py:24-53):
+    each source is put in generator order, the sources are merged step by step with the reference's comparison, and the
+    result is packed as is.  ``book_rows`` (and the per-second snapshots) belong to ``snapshot_source`` (default: the first
+    source, the historical one -- snapshots come from the database, not from the generators)."""
+    names = list(sources)
+    snapshot_source = snapshot_source or names[0]
+    first = min(int(np.asarray(s.time_ns)[0]) for s in sources.values() if len(s))
+    if t0_us is None:
+        t0_us = first // 1000 // 1_000_000 * 1_000_000
+    ordered = {k: generator_order(v, t0_us, tie_order, db_batch_size) for k, v in sources.items()}
+    merged = compress_order_sources(ordered, t0_us, step_us)
+    out = pack_arrays(merged.time_ns, merged.msg_type, merged.ext_id, merged.size, merged.price, merged.direction, book_rows, n_levels,
+                      step_us=step_us, t0_us=t0_us, tie_order="file", snapshot_time_ns=np.asarray(sources[snapshot_source].time_ns, np.int64), **kw)
+    out.generators = tuple(names)
+    return out
+
+
 def pack_arrays(
     time_ns: np.ndarray,
     msg_type: np.ndarray,
@@ -113,15 +244,19 @@ def pack_arrays(
     db_batch_size: int = 1_000_000,
     ticker: str = "",
     date: str = "",
+    snapshot_time_ns: Optional[np.ndarray] = None,
 ) -> PackedStream:
     """Pack raw LOBSTER columns.  ``book_rows`` is the orderbook file as int64 [n_rows, 4*n_levels] (one row per
     message row, columns ask price, ask size, bid price, bid size per level -- rl4mm/orderbook/helpers.py:52-55), or a
-    callable ``rows(idx) -> int64 [len(idx), 4*n_levels]`` that loads just the requested (ascending) row indices."""
+    callable ``rows(idx) -> int64 [len(idx), 4*n_levels]`` that loads just the requested (ascending) row indices.
+    ``snapshot_time_ns``: the time column the orderbook rows are aligned with when it is not ``time_ns`` (merged streams:
+    the snapshots follow the historical source, :func:`pack_merged`)."""
     time_ns = np.asarray(time_ns, np.int64)
     msg_type = np.asarray(msg_type, np.int64)
     n = len(time_ns)
     assert np.all(np.diff(time_ns) >= 0), "LOBSTER messages must be time ordered"
-    assert callable(book_rows) or book_rows.shape == (n, 4 * n_levels)
+    snap_time = time_ns if snapshot_time_ns is None else np.asarray(snapshot_time_ns, np.int64)
+    assert callable(book_rows) or book_rows.shape == (len(snap_time), 4 * n_levels)
     if 1_000_000 % step_us:
         raise ValueError("step_us must divide one second")
     ts_us = time_ns // 1000
@@ -175,7 +310,7 @@ def pack_arrays(
 
     # --- per-second snapshots ----------------------------------------------------------------------------------
     sec_ns = (t0_us + np.arange(n_seconds + 1, dtype=np.int64) * 1_000_000) * 1000
-    idx = np.searchsorted(time_ns, sec_ns, side="right") - 1
+    idx = np.searchsorted(snap_time, sec_ns, side="right") - 1
     snap_valid = (idx >= 0).astype(np.uint8)
     need = np.maximum(idx, 0)
     rows = book_rows(need) if callable(book_rows) else np.asarray(book_rows, np.int64)[need]

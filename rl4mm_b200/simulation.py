@@ -10,7 +10,7 @@ import numpy as np
 
 from . import abi
 from .orderbook import Exchange, FilledOrders, LimitOrder, MarketOrder, Order, Orderbook, _DIR
-from .packing import PackedStream, pack_lobster
+from .packing import PackedStream, RawMessages, compress_order_dict, pack_lobster, pack_merged, read_lobster_book_rows, read_lobster_messages
 
 
 class DeviceDatabase:
@@ -30,6 +30,19 @@ class DeviceDatabase:
 
     def add_lobster_files(self, ticker: str, trading_date: datetime, message_csv, orderbook_csv, n_levels: int, **kw) -> int:
         s = pack_lobster(message_csv, orderbook_csv, n_levels, **kw)
+        s.ticker, s.date = ticker, trading_date.strftime("%Y-%m-%d")
+        return self.add_stream(ticker, trading_date, s)
+
+    def add_merged_lobster_files(self, ticker: str, trading_date: datetime, message_csv, orderbook_csv, n_levels: int,
+                                 extra_generators: Dict[str, RawMessages], **kw) -> int:
+        """The reference's ``order_generators=[historical, ...]`` (OrderbookSimulator.py:24-53,74-75): the LOBSTER files plus
+        the messages of further generators, merged at pack time with the reference's comparison
+        (``_compress_order_dict``, :137-148) into one device-resident stream."""
+        t, ty, oid, sz, pr, di = read_lobster_messages(message_csv, kw.pop("max_rows", None))
+        sources = {"historical": RawMessages(t, ty, oid, sz, pr, di)}
+        assert "historical" not in extra_generators
+        sources.update(extra_generators)
+        s = pack_merged(sources, lambda idx: read_lobster_book_rows(orderbook_csv, idx, n_levels), n_levels, **kw)
         s.ticker, s.date = ticker, trading_date.strftime("%Y-%m-%d")
         return self.add_stream(ticker, trading_date, s)
 
@@ -70,9 +83,24 @@ class HistoricalOrderGenerator(OrderGenerator):
         self.exchange_name = "NASDAQ"
 
 
+class PackedOrderGenerator(OrderGenerator):
+    """A further OrderGenerator (rl4mm/simulation/OrderGenerator.py:9-21) next to the historical one.  Its messages were merged
+    into the device-resident stream at pack time (``DeviceDatabase.add_merged_lobster_files``); the object is the name the
+    simulator checks against ``PackedStream.generators``."""
+
+    def __init__(self, name: str):
+        self._name = name
+
+    @property
+    def name(self):
+        return self._name
+
+
 class OrderbookSimulator:
     """rl4mm/simulation/OrderbookSimulator.py:23-188 for one book (env 0 of its own LobSim, or a view of one env of a
     batched LobSim)."""
+
+    _compress_order_dict = staticmethod(compress_order_dict)   # OrderbookSimulator.py:137-148 (the device path merges at pack time)
 
     def __init__(self, ticker: str = "MSFT", exchange: Exchange = None, order_generators=None, n_levels: int = 50,
                  database: DeviceDatabase = None, preload_orders: bool = True,
@@ -94,6 +122,11 @@ class OrderbookSimulator:
         for i, s in enumerate(database.streams):
             self.sim.load_stream(i, s)
         self.order_generators = {gen.name: gen for gen in (order_generators or [HistoricalOrderGenerator(ticker, database, preload_orders)])}
+        for s in database.streams:                          # several generators: their messages must be IN the packed streams
+            missing = set(self.order_generators) - set(s.generators)
+            if missing:
+                raise ValueError(f"order generators {sorted(missing)} are not part of the packed stream {s.ticker} {s.date} "
+                                 f"(it holds {list(s.generators)}): pack with DeviceDatabase.add_merged_lobster_files")
         self.now_is: datetime = datetime(2000, 1, 1)
         self._sid = 0
 

@@ -389,3 +389,75 @@ def test_episode_summary_shapes_and_reference_quirks():
     assert esd["actions"][1].shape == (3,) and np.allclose(esd["actions"][1], act[:, 1, :].mean(axis=0)[:-1])
     assert esd["inventory"][2] == 2.0 and np.allclose(esd["rewards"][0], rew[:, 0].mean())
     assert np.isfinite(evaluation.get_sharpe(np.stack(esd["equity_curves"]))).all()
+
+
+def test_compress_order_dict_reference_test():
+    """rl4mm/simulation/tests/testOrderbookSimulator.py:110-114 (test_compare_order_dict), on the façade's Order classes."""
+    from collections import deque
+    from datetime import datetime
+
+    from rl4mm_b200.orderbook import Cancellation, LimitOrder
+    from rl4mm_b200.simulation import OrderbookSimulator
+
+    limit_1 = LimitOrder(datetime(2012, 6, 21, 12, 0), "buy", "MSFT", None, 50, True, int(30.1 * 10000), 1000)
+    limit_2 = LimitOrder(datetime(2012, 6, 21, 12, 1), "buy", "MSFT", None, 100, True, int(30.1 * 10000), 200)
+    cancellation_1 = Cancellation(datetime(2012, 6, 21, 12, 1), "buy", "MSFT", None, 50, True, int(30.1 * 10000), 200)
+    cancellation_2 = Cancellation(datetime(2012, 6, 21, 12, 2), "buy", "MSFT", None, 50, False, int(30.1 * 10000), 1100)
+    order_dict = {"gen_1": deque([limit_1, cancellation_1]), "gen_2": deque([limit_2, cancellation_2])}
+    assert OrderbookSimulator._compress_order_dict(order_dict) == [limit_1, cancellation_1, limit_2, cancellation_2]
+    assert OrderbookSimulator._compress_order_dict({"only": deque([limit_2, limit_1])}) == [limit_2, limit_1]   # one generator: as is
+
+
+def test_generator_merge_matches_reference_golden():
+    """The pack-time merge (packing.compress_order_sources) == the reference's ``_compress_order_dict`` on 200 random 2- / 3-generator
+    step windows with colliding timestamps and cross-generator duplicate orders (tests/golden/generator_merge.json.gz, generated
+    by oracle/gen_golden.py::golden_generator_merge from the unmodified reference)."""
+    import gzip
+    import json
+    from pathlib import Path
+
+    from rl4mm_b200.packing import RawMessages, compress_order_sources
+
+    cases = json.loads(gzip.open(Path(__file__).parent / "golden" / "generator_merge.json.gz").read())
+    assert len(cases) == 200
+    t0_us, step_us = 36_000_000_000, 100_000
+    n_multi = 0
+    for c in cases:
+        sources = {}
+        for g, rows in enumerate(c["generators"]):
+            col = lambda k: np.array([r[k] for r in rows], np.int64)        # noqa: E731
+            sources[f"gen_{g}"] = RawMessages((t0_us + col("us")) * 1000, col("type"), col("ext_id"), col("size"), col("price"), col("direction"))
+        merged = compress_order_sources(sources, t0_us, step_us)
+        exp = [c["generators"][g][i] for g, i in c["merged"]]
+        assert len(merged) == len(exp)
+        for k, r in enumerate(exp):
+            got = (int(merged.time_ns[k] // 1000 - t0_us), int(merged.msg_type[k]), int(merged.direction[k]), int(merged.ext_id[k]),
+                   int(merged.size[k]), int(merged.price[k]))
+            assert got == (r["us"], r["type"], r["direction"], r["ext_id"], r["size"], r["price"]), (c, k)
+        n_multi += len(c["generators"]) > 1
+    assert n_multi == 200
+
+
+def test_pack_merged_two_generators():
+    """Two generators end to end: per-source generator order (hidden dropped, lexicographic ties), step-wise merge, one packed
+    stream whose snapshots follow the historical source."""
+    from rl4mm_b200.packing import RawMessages, pack_arrays, pack_merged
+
+    L = 2
+    t0 = 34_200_000_000
+    hist = RawMessages(np.array([t0 + 50_000, t0 + 50_000, t0 + 150_000, t0 + 1_250_000], np.int64) * 1000, np.array([1, 5, 3, 4]),
+                       np.array([7, 8, 7, 9]), np.array([10, 10, 10, 5]), np.array([1000, 1000, 1000, 1100]), np.array([1, 1, 1, -1]))
+    synth = RawMessages(np.array([t0 + 40_000, t0 + 50_000, t0 + 1_250_000], np.int64) * 1000, np.array([1, 1, 1]),
+                        np.array([100, 101, 102]), np.array([3, 4, 5]), np.array([900, 1000, 1200]), np.array([1, 1, -1]))
+    books = np.tile(np.array([1100, 5, 1000, 7, 9999999999, 0, -9999999999, 0], np.int64), (4, 1))
+    books[:, 1] = np.arange(4)
+    s = pack_merged({"historical": hist, "synthetic": synth}, books, L, t0_us=t0)
+    assert s.generators == ("historical", "synthetic")
+    # step 0: synth@40ms, then the two 50 ms orders -- equal timestamps keep the first generator (historical) first; the hidden
+    # execution is gone; step 1: the deletion; step 12: equal timestamps again: historical first
+    assert [int(x) for x in s.ext_ids[s.msgs["ref"]]] == [100, 7, 101, 7, 9, 102]
+    assert list(s.step_off[:3]) == [0, 3, 4] and s.step_off[13] == 6 and s.step_off[12] == 4
+    alone = pack_arrays(hist.time_ns, hist.msg_type, hist.ext_id, hist.size, hist.price, hist.direction, books, L, t0_us=t0)
+    assert np.array_equal(s.snapshots, alone.snapshots) and np.array_equal(s.snap_valid, alone.snap_valid)
+    one = pack_merged({"historical": hist}, books, L, t0_us=t0)
+    assert np.array_equal(one.msgs, alone.msgs) and np.array_equal(one.step_off, alone.step_off)
