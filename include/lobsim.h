@@ -124,16 +124,20 @@ enum {
   LOBSIM_AGENT_NONE = 0,       /* empty action list every step (warm-up, replay)       */
   LOBSIM_AGENT_FIXED = 1,      /* FixedActionAgent, baseline_agents.py:21-30            */
   LOBSIM_AGENT_TERADACTYL = 2, /* Teradactyl, baseline_agents.py:33-108                 */
-  LOBSIM_AGENT_EXTERNAL = 3    /* actions supplied by the caller (act tensor is input)  */
+  LOBSIM_AGENT_EXTERNAL = 3,   /* actions supplied by the caller (act tensor is input)  */
+  LOBSIM_AGENT_RANDOM = 4      /* RandomAgent, baseline_agents.py:9-18: action_space.sample() = uniform in the action box
+                                  [0, fixed_action[i]); here a counter-based stream, Philox4x32-10 keyed by
+                                  (seed = `reserved`, env index, absolute grid step), so a rollout does not depend on how it
+                                  is cut into launches and the CPU oracle draws the same numbers                       */
 };
 typedef struct {
   int32_t kind;
   int32_t inventory_index;  /* Teradactyl: index of the inventory feature in obs        */
-  double fixed_action[5];   /* FIXED                                                    */
+  double fixed_action[5];   /* FIXED: the action; RANDOM: the upper bounds of the action box (lower bounds are 0, HOE.py:85-93) */
   double max_inventory;     /* Teradactyl (<= 0: None => denom 100)                     */
   double default_kappa, default_omega, max_kappa, exponent;
   int32_t market_clearing;
-  int32_t reserved;
+  int32_t reserved;         /* RANDOM: the seed                                          */
 } lobsim_agent_t;
 
 /* ---- environment configuration: kwargs of HistoricalOrderbookEnvironment.__init__ (HOE.py:54-81) and

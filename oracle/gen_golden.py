@@ -158,7 +158,7 @@ def feature_specs():
 
 
 def run_env_case(name, actions, env_kwargs, reward_step, reward_term, features=None, episode_seconds=1.5,
-                 start_seconds=36001.0, n_episodes=1, outer_levels=20, portfolio=None):
+                 start_seconds=36001.0, n_episodes=1, outer_levels=20, portfolio=None, step_hook=None):
     from rl4mm.features.Features import Portfolio
     from rl4mm.gym.HistoricalOrderbookEnvironment import HistoricalOrderbookEnvironment
     from rl4mm.rewards.RewardFunctions import InventoryAdjustedPnL, PnL
@@ -204,6 +204,8 @@ def run_env_case(name, actions, env_kwargs, reward_step, reward_term, features=N
                 price=float(env.state.price), book=dump_book(env.central_orderbook),
                 agent_book=dump_book(env.internal_orderbook), fills=dump_fills(env.state.filled_orders),
             ))
+            if step_hook is not None:
+                step_hook(env, ep["steps"][-1])
             if done:
                 break
         episodes.append(ep)
@@ -468,6 +470,50 @@ def golden_episode_summary():
     save("episode_summary.json.gz", cases)
 
 
+def golden_rolling_sharpe_1e12():
+    """RollingSharpe at the reference's DEFAULT cash (initial_cash = 1e12, rl4mm/helpers/main_helper.py:78).  There the window
+    holds AUMs of ~1e12 whose step-to-step returns are 1e-10..1e-8, and get_sharpe (RewardFunctions.py:10-22) takes
+    ``np.diff(np.log(aum))``: log(1e12) = 27.6 carries an absolute rounding error of up to one ulp = 3.6e-15, i.e. up to 1e-4
+    RELATIVE on such a return -- the reference's own reward depends on whose ``log`` it links (numpy's SIMD loop, glibc, ...).
+    Every step records, besides the reward of the unmodified reference: the same formula with glibc's scalar log / exp
+    (``reward_libm``), and the first-order bound on |delta reward| between two implementations whose log is good to one ulp
+    (``bound``) -- the tolerance tests/ hold the CUDA path and the oracle to."""
+    import math
+    import sys as _sys
+
+    from rl4mm.rewards.RewardFunctions import RollingSharpe
+
+    def hook(env, rec):
+        d = done_flag = rec["done"]
+        rf = env.terminal_reward_function if d else env.per_step_reward_function
+        rec["reward_libm"], rec["bound"] = None, None
+        if not isinstance(rf, RollingSharpe) or rf.n_filled < rf.min_window_size:
+            return
+        aum = rf.aum_array[~np.isnan(rf.aum_array)]
+        n = len(aum) - 1
+        if n < 2 or np.min(aum) <= 0:
+            return
+        logs = [math.log(float(a)) for a in aum]
+        r = np.array([math.exp(logs[i + 1] - logs[i]) - 1 for i in range(n)])
+        sd = float(np.std(r, ddof=1))
+        rec["reward_libm"] = float(np.mean(r) / (sd + _sys.float_info.min))
+        ulp = float(np.spacing(np.log(np.max(aum))))
+        e = 2.0 * ulp                                  # two implementations, each within one ulp of the true log
+        if sd > 0:
+            S = abs(rec["reward"])
+            rec["bound"] = float(2 * e / (n * sd) + S * 2 * e * math.sqrt(n / (n - 1)) / sd)
+
+    rng = np.random.default_rng(77)
+    rand4 = rng.uniform(0.0, 10.0, size=(64, 4)).tolist()
+    cases = [
+        run_env_case("rolling_sharpe_default_cash", rand4, {}, ("RS", 12, 5), ("RS", 8, 3), features=[14, 9, 0, 7], n_episodes=3,
+                     episode_seconds=1.0, start_seconds=36001.0, portfolio=(0, 1e12), step_hook=hook),
+        run_env_case("rolling_sharpe_default_cash_inventory", rand4[9:], {}, ("RS", 20, 4), ("RS", 20, 4), features=[14, 9, 0, 7],
+                     episode_seconds=1.5, start_seconds=36001.0, portfolio=(500, 1e12), step_hook=hook),
+    ]
+    save("rolling_sharpe_1e12.json.gz", cases)
+
+
 def golden_generator_merge():
     """Multi-generator merge (rl4mm/simulation/OrderbookSimulator.py:137-148): random 2- and 3-generator step windows through
     the reference's own ``OrderbookSimulator._compress_order_dict`` with the reference's Order dataclasses.  Timestamps are
@@ -529,6 +575,7 @@ def main():
         golden_exchange_fuzz()
         golden_episode_summary()
         golden_generator_merge()
+        golden_rolling_sharpe_1e12()
     for p in sorted(GOLDEN.glob("*.gz")):
         print(p.name, p.stat().st_size)
 

@@ -168,6 +168,7 @@ struct lo {
   int64_t counter;          /* OrderIdConvertor.counter */
   /* simulator */
   int64_t now_step;
+  int32_t env_index;   /* which env of the batch this oracle stands for: part of the RandomAgent stream key */
   int64_t min_buy_price, max_sell_price, init_buy_range, init_sell_range;
   /* env */
   int64_t episode_start_step;
@@ -946,6 +947,36 @@ int lo_step(lo_t* o, const double* action, double* obs, double* reward, uint8_t*
 
 /* Agents -- rl4mm/agents/baseline_agents.py */
 static double clamp_to_unit(double x) { const double eps = 0.00001; double m = x < 1 - eps ? x : 1 - eps; return m > -1 + eps ? m : -1 + eps; } /* :96-100 */
+/* Philox4x32-10 (Salmon, Moraes, Dror, Shaw: "Parallel random numbers: as easy as 1, 2, 3", SC'11), written from the paper:
+ * ten rounds of  (L, R) pairs  c0,c1,c2,c3 -> hi(M1*c2)^c1^k0, lo(M1*c2), hi(M0*c0)^c3^k1, lo(M0*c0), keys bumped by the Weyl
+ * constants.  Known-answer vectors of the Random123 distribution are checked in tests/test_oracle_golden.py. */
+void lo_philox4x32_10(uint32_t ctr[4], uint32_t key0, uint32_t key1) {
+  for (int round = 0; round < 10; round++) {
+    uint64_t prod0 = (uint64_t)0xD2511F53u * (uint64_t)ctr[0];
+    uint64_t prod1 = (uint64_t)0xCD9E8D57u * (uint64_t)ctr[2];
+    uint32_t out0 = (uint32_t)(prod1 >> 32) ^ ctr[1] ^ key0;
+    uint32_t out1 = (uint32_t)prod1;
+    uint32_t out2 = (uint32_t)(prod0 >> 32) ^ ctr[3] ^ key1;
+    uint32_t out3 = (uint32_t)prod0;
+    ctr[0] = out0; ctr[1] = out1; ctr[2] = out2; ctr[3] = out3;
+    key0 += 0x9E3779B9u; key1 += 0xBB67AE85u;
+  }
+}
+/* RandomAgent.get_action = action_space.sample() (baseline_agents.py:9-18) for Box(0, high): uniform in [0, high_i).  The
+ * device kernels have no global numpy RNG to share, so "random" is DEFINED as: dimension 2b / 2b+1 = the two 53-bit uniforms
+ * of Philox(counter = (grid step, env index, b, 0), key = (seed, "LOBS")).  No reference parity target; this twin pins the
+ * device implementation bit for bit. */
+void lo_random_action(const lobsim_agent_t* ag, int32_t env_index, int64_t now_step, double* action) {
+  for (uint32_t b = 0; b < 3; b++) {
+    uint32_t ctr[4] = {(uint32_t)now_step, (uint32_t)env_index, b, 0u};
+    lo_philox4x32_10(ctr, (uint32_t)ag->reserved, 0x4C4F4253u);
+    uint64_t w0 = ((uint64_t)ctr[0] << 32) | ctr[1], w1 = ((uint64_t)ctr[2] << 32) | ctr[3];
+    action[2 * b] = ag->fixed_action[2 * b] * ((double)(w0 >> 11) / 9007199254740992.0);
+    if (2 * b + 1 < 5) action[2 * b + 1] = ag->fixed_action[2 * b + 1] * ((double)(w1 >> 11) / 9007199254740992.0);
+  }
+}
+void lo_set_env_index(lo_t* o, int32_t env_index) { o->env_index = env_index; }
+
 void lo_agent_action(const lobsim_agent_t* ag, const double* obs, double* action) {
   if (ag->kind == LOBSIM_AGENT_FIXED) { for (int i = 0; i < 5; i++) action[i] = ag->fixed_action[i]; return; }
   if (ag->kind == LOBSIM_AGENT_TERADACTYL) { /* :51-87 */
@@ -998,6 +1029,7 @@ int lo_rollout_info(lo_t* o, int T, const lobsim_agent_t* ag, double* obs, doubl
       continue;
     }
     if (ag->kind == LOBSIM_AGENT_EXTERNAL) memcpy(a, act + (size_t)t * ad, sizeof(double) * (size_t)ad);
+    else if (ag->kind == LOBSIM_AGENT_RANDOM) lo_random_action(ag, o->env_index, o->now_step, a);
     else lo_agent_action(ag, cur_obs, a);
     double r; uint8_t d;
     lo_step(o, a, cur_obs, &r, &d);

@@ -16,6 +16,9 @@ int lo_replay(lo_t* o, int n_steps);
 int lo_rollout(lo_t* o, int T, const lobsim_agent_t* agent, double* obs, double* act, double* rew, uint8_t* done);
 int lo_rollout_info(lo_t* o, int T, const lobsim_agent_t* agent, double* obs, double* act, double* rew, uint8_t* done, double* info);
 void lo_agent_action(const lobsim_agent_t* agent, const double* obs, double* action);
+void lo_philox4x32_10(uint32_t ctr[4], uint32_t key0, uint32_t key1);
+void lo_random_action(const lobsim_agent_t* agent, int32_t env_index, int64_t now_step, double* action);
+void lo_set_env_index(lo_t* o, int32_t env_index);
 void lo_action_to_ladders(const lo_t* o, const double* action, int64_t* buy, int64_t* sell);
 int lo_process_order(lo_t* o, const lobsim_order_t* order, uint32_t* ref_out);
 void lo_clear_fills(lo_t* o);

@@ -43,6 +43,9 @@ def lib():
         L.lo_rollout_info.argtypes = [C.c_void_p, C.c_int, C.POINTER(abi.Agent), C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p]
         L.lo_agent_action.argtypes = [C.POINTER(abi.Agent), C.c_void_p, C.c_void_p]
+        L.lo_philox4x32_10.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
+        L.lo_random_action.argtypes = [C.POINTER(abi.Agent), C.c_int32, C.c_int64, C.c_void_p]
+        L.lo_set_env_index.argtypes = [C.c_void_p, C.c_int32]
         L.lo_action_to_ladders.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.lo_process_order.argtypes = [C.c_void_p, C.POINTER(abi.Order), C.POINTER(C.c_uint32)]
         L.lo_clear_fills.argtypes = [C.c_void_p]
@@ -61,9 +64,10 @@ def _ptr(a: np.ndarray):
 
 
 class Oracle:
-    def __init__(self, cfg: abi.Cfg, stream: PackedStream | None = None):
+    def __init__(self, cfg: abi.Cfg, stream: PackedStream | None = None, env_index: int = 0):
         self.cfg = cfg
         self._h = lib().lo_create(C.byref(cfg))
+        lib().lo_set_env_index(self._h, env_index)        # part of the RandomAgent stream key
         self._keep = None
         self.obs_dim = lib().lo_obs_dim(C.byref(cfg))
         self.action_dim = lib().lo_action_dim(C.byref(cfg))
@@ -156,6 +160,18 @@ class Oracle:
         st = np.zeros(1, abi.ENV_STATE_DTYPE)
         lib().lo_get_state(self._h, _ptr(st))
         return st[0]
+
+
+def philox4x32_10(ctr, key) -> list:
+    c = np.array(ctr, np.uint32)
+    lib().lo_philox4x32_10(_ptr(c), int(key[0]), int(key[1]))
+    return [int(x) for x in c]
+
+
+def random_action(agent: abi.Agent, env_index: int, now_step: int) -> np.ndarray:
+    a = np.zeros(5)
+    lib().lo_random_action(C.byref(agent), env_index, now_step, _ptr(a))
+    return a
 
 
 def agent_action(agent: abi.Agent, obs) -> np.ndarray:

@@ -47,7 +47,7 @@ MAX_SHARPE_WINDOW = 256
 FEAT_AMIHUD_LAMBDA = 11
 INFO_FIELDS = ("asset_price", "inventory", "cash", "aum", "market_spread", "best_buy", "best_sell", "err")
 INFO_DIM = len(INFO_FIELDS)
-AGENT_NONE, AGENT_FIXED, AGENT_TERADACTYL, AGENT_EXTERNAL = 0, 1, 2, 3
+AGENT_NONE, AGENT_FIXED, AGENT_TERADACTYL, AGENT_EXTERNAL, AGENT_RANDOM = 0, 1, 2, 3, 4
 PATH_GENERAL, PATH_FAST = 0, 1
 
 MSG_DTYPE = np.dtype([("price", "<i4"), ("volume", "<i4"), ("ref", "<u4"), ("meta", "<u4")])

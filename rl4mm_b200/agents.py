@@ -20,18 +20,29 @@ class Agent(metaclass=abc.ABCMeta):
 
 
 class RandomAgent(Agent):
-    """baseline_agents.py:9-18"""
+    """baseline_agents.py:9-18.  ``get_action`` samples the env's action box on the host (one vectorised draw for a batch of
+    states); ``env.rollout(agent, T)`` runs the same kind of agent fused on the device (``LOBSIM_AGENT_RANDOM``: a
+    counter-based Philox stream keyed by (seed, env, grid step) -- a different stream than the host generator's)."""
 
     def __init__(self, env, seed: int = None):
         self.action_space = env.action_space
         self.action_space.seed(seed)
         self.n_envs = getattr(env, "n_envs", 1)
+        self.seed = 0 if seed is None else int(seed)
+        self._rng = np.random.default_rng(seed)
 
     def get_action(self, state: np.ndarray) -> np.ndarray:
         state = np.asarray(state)
         if state.ndim == 1:
             return self.action_space.sample()
-        return np.stack([self.action_space.sample() for _ in range(state.shape[0])])
+        low, high = np.asarray(self.action_space.low, np.float64), np.asarray(self.action_space.high, np.float64)
+        return low + (high - low) * self._rng.random((state.shape[0], len(low)))
+
+    def to_abi(self):
+        high = [float(x) for x in np.asarray(self.action_space.high, np.float64).reshape(-1)]
+        assert np.all(np.asarray(self.action_space.low) == 0), "the device RandomAgent samples Box(0, high)"
+        return abi.Agent(kind=abi.AGENT_RANDOM, fixed_action=(ctypes.c_double * 5)(*(high + [0.0] * (5 - len(high)))),
+                         reserved=self.seed & 0x7FFFFFFF)
 
     def get_name(self):
         return "RandomAgent"

@@ -6,6 +6,7 @@
 
 #include "book.cuh"
 #include "book_fast.cuh"
+#include "crmath.cuh"
 
 struct __align__(16) FeatState {
   double cur;        // Feature.current_value
@@ -337,10 +338,36 @@ __device__ __forceinline__ bool agent_next(const Book& b, WarpState& w, AgentGen
 
 // ---- agents, rl4mm/agents/baseline_agents.py -----------------------------------------------------------------------
 __device__ __forceinline__ double clamp_to_unit(double x) { const double eps = 0.00001; return fmax(fmin(x, 1 - eps), -1 + eps); }
-__device__ __forceinline__ void agent_action(const lobsim_agent_t& ag, double inventory_obs, double* a) {
+// Philox4x32-10 (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3", SC'11): counter c[4], key (k0, k1)
+__device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+#pragma unroll 1
+  for (int r = 0; r < 10; r++) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+    c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+// RandomAgent (baseline_agents.py:9-18): action_space.sample() for the env's Box(0, high) -- uniform in [0, high_i) per
+// dimension, 53 random bits each, from the stream keyed by (seed, env, grid step)
+__device__ __forceinline__ void random_action(const lobsim_agent_t& ag, int env, int now_step, double* a) {
+#pragma unroll 1
+  for (int blk = 0; blk < 3; blk++) {
+    uint32_t c[4] = {(uint32_t)now_step, (uint32_t)env, (uint32_t)blk, 0u};
+    philox4x32_10(c, (uint32_t)ag.reserved, 0x4C4F4253u);
+    const double u0 = (double)((((unsigned long long)c[0] << 32) | c[1]) >> 11) * (1.0 / 9007199254740992.0);
+    const double u1 = (double)((((unsigned long long)c[2] << 32) | c[3]) >> 11) * (1.0 / 9007199254740992.0);
+    a[2 * blk] = ag.fixed_action[2 * blk] * u0;
+    if (2 * blk + 1 < 5) a[2 * blk + 1] = ag.fixed_action[2 * blk + 1] * u1;
+  }
+}
+__device__ __forceinline__ void agent_action(const lobsim_agent_t& ag, double inventory_obs, double* a, int env, int now_step) {
   if (ag.kind == LOBSIM_AGENT_FIXED) {
 #pragma unroll
     for (int i = 0; i < 5; i++) a[i] = ag.fixed_action[i];
+  } else if (ag.kind == LOBSIM_AGENT_RANDOM) {
+    random_action(ag, env, now_step, a);
   } else { // Teradactyl.get_action :76-87
     double denom = ag.max_inventory > 0 ? ag.max_inventory : 100.0;
     double wd = ag.default_omega, ob, oa;
@@ -682,9 +709,9 @@ static __device__ __noinline__ double features_step(const EnvConst* ecp, FeatSta
 }
 
 // Agent.get_action for the fused rollout (cold)
-static __device__ __noinline__ void agent_action_cold(const lobsim_agent_t* ag, double inventory_obs, double* out5_smem) {
+static __device__ __noinline__ void agent_action_cold(const lobsim_agent_t* ag, double inventory_obs, double* out5_smem, int env, int now_step) {
   double a[5] = {0, 0, 0, 0, 0};
-  agent_action(*ag, inventory_obs, a);
+  agent_action(*ag, inventory_obs, a, env, now_step);
 #pragma unroll
   for (int i = 0; i < 5; i++) out5_smem[i] = a[i];
 }
@@ -822,7 +849,7 @@ static __device__ __noinline__ SharpeOut rolling_sharpe_step(double* ring, int* 
   for (int i = lane; i < m; i += 32) {
     int k0 = first + i; if (k0 >= maxw) k0 -= maxw;
     int k1 = k0 + 1 == maxw ? 0 : k0 + 1;
-    tmp[i] = exp(log(ring[k1]) - log(ring[k0])) - 1.0;
+    tmp[i] = cr_exp(cr_log(ring[k1]) - cr_log(ring[k0])) - 1.0;   // correctly rounded: crmath.cuh
   }
   __syncwarp();
   double r = 0.0;

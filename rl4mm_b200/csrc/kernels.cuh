@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(128, kEnv ? LOBSIM_ENV_MIN_BLOCKS : 4) k_advan
         } else {
           const lobsim_agent_t* agp = p.agents ? p.agents + sel : &p.agent;
           const double inv_obs = __shfl_sync(FULL_MASK, feat_cur, agp->inventory_index & 31);
-          if (lane == 0) agent_action_cold(agp, inv_obs, act_sm);
+          if (lane == 0) agent_action_cold(agp, inv_obs, act_sm, env, now_step);
         }
         __syncwarp();
         const double a0 = act_sm[0], a1 = act_sm[1], a2 = act_sm[2], a3 = act_sm[3], a4 = act_sm[4];
@@ -834,7 +834,7 @@ __global__ void __launch_bounds__(32 * LOBSIM_ENVFAST_WARPS, env_min_blocks<LT>(
       } else {
         const lobsim_agent_t* agp = p.agents ? p.agents + sel : &p.agent;
         const double inv_obs = __shfl_sync(FULL_MASK, feat_cur, agp->inventory_index & 31);
-        if (lane == 0) agent_action_cold(agp, inv_obs, act_sm);
+        if (lane == 0) agent_action_cold(agp, inv_obs, act_sm, env, now_step);
       }
       __syncwarp();
       const double a0 = act_sm[0], a1 = act_sm[1], a2 = act_sm[2], a3 = act_sm[3], a4 = act_sm[4];

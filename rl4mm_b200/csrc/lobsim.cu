@@ -510,6 +510,7 @@ int lobsim_rollout(lobsim_t* h, int32_t T, const lobsim_agent_t* agent, double* 
 int lobsim_rollout_info(lobsim_t* h, int32_t T, const lobsim_agent_t* agent, double* obs, double* act, double* rew, uint8_t* done, double* info, void* stream) {
   if (!h || !agent || T < 0) return fail(LOBSIM_E_INVALID, "bad argument");
   if (!h->has_reset) return fail(LOBSIM_E_STATE, "rollout before reset");
+  if (agent->kind < LOBSIM_AGENT_NONE || agent->kind > LOBSIM_AGENT_RANDOM) return fail(LOBSIM_E_INVALID, "unknown agent kind");
   if (agent->kind == LOBSIM_AGENT_EXTERNAL && !act) return fail(LOBSIM_E_INVALID, "EXTERNAL agent needs the act tensor as input");
   if (agent->kind == LOBSIM_AGENT_TERADACTYL && (agent->inventory_index < 0 || agent->inventory_index >= h->cfg.n_features)) return fail(LOBSIM_E_INVALID, "bad inventory_index");
   AdvParams p; base_params(h, p);
@@ -525,7 +526,7 @@ int lobsim_rollout_agents(lobsim_t* h, int32_t T, const lobsim_agent_t* agents_h
   const int n = h->cfg.n_envs;
   for (int i = 0; i < n; i++) {
     const lobsim_agent_t& a = agents_host[i];
-    if (a.kind != LOBSIM_AGENT_FIXED && a.kind != LOBSIM_AGENT_TERADACTYL) return fail(LOBSIM_E_INVALID, "per-env agents must be FIXED or TERADACTYL");
+    if (a.kind != LOBSIM_AGENT_FIXED && a.kind != LOBSIM_AGENT_TERADACTYL && a.kind != LOBSIM_AGENT_RANDOM) return fail(LOBSIM_E_INVALID, "per-env agents must be FIXED, TERADACTYL or RANDOM");
     if (a.kind == LOBSIM_AGENT_TERADACTYL && (a.inventory_index < 0 || a.inventory_index >= h->cfg.n_features)) return fail(LOBSIM_E_INVALID, "bad inventory_index");
   }
   CUDA_TRY(cudaSetDevice(h->device));

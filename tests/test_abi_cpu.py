@@ -461,3 +461,37 @@ def test_pack_merged_two_generators():
     assert np.array_equal(s.snapshots, alone.snapshots) and np.array_equal(s.snap_valid, alone.snap_valid)
     one = pack_merged({"historical": hist}, books, L, t0_us=t0)
     assert np.array_equal(one.msgs, alone.msgs) and np.array_equal(one.step_off, alone.step_off)
+
+
+def test_correctly_rounded_log_and_exp(tmp_path):
+    """csrc/crmath.cuh (the RollingSharpe log / exp of the device path) compiled for the host: correctly rounded against
+    60-digit decimal arithmetic on 2e4 arguments (AUM-like values around 1e12, the whole double range, values near 1; log-return
+    sized exp arguments).  glibc's log -- what numpy calls -- is the same value except for a few arguments in 1e4."""
+    import ctypes
+    import math
+    import subprocess
+    from decimal import Decimal, getcontext
+    from pathlib import Path
+
+    src = tmp_path / "cr.cpp"
+    src.write_text('#include "crmath.cuh"\nextern "C" double t_log(double x) { return cr_log(x); }\n'
+                   'extern "C" double t_exp(double x) { return cr_exp(x); }\n')
+    so = tmp_path / "libcr.so"
+    csrc = Path(__file__).resolve().parent.parent / "rl4mm_b200" / "csrc"
+    subprocess.run(["g++", "-O2", "-ffp-contract=off", "-mfma", "-fPIC", "-shared", "-I", str(csrc), "-o", str(so), str(src)], check=True)
+    L = ctypes.CDLL(str(so))
+    for f in (L.t_log, L.t_exp):
+        f.restype, f.argtypes = ctypes.c_double, [ctypes.c_double]
+    getcontext().prec = 60
+    rng = np.random.default_rng(0)
+    xs = np.concatenate([rng.uniform(0.5, 2, 3000), 10 ** rng.uniform(-300, 300, 3000), 1e12 + rng.uniform(-1e6, 1e6, 6000),
+                         rng.uniform(0.99, 1.01, 2000), [1.0, 2.0, 0.5, 1e12, 1.4142135623730951, 1.414213562373095, 5e-324 * 2 ** 60]])
+    glibc_differs = 0
+    for x in xs.tolist():
+        cr = float(Decimal(x).ln())
+        assert L.t_log(x) == cr, x
+        glibc_differs += math.log(x) != cr
+    assert glibc_differs < len(xs) // 500
+    for x in np.concatenate([rng.uniform(-0.015625, 0.015625, 3000), rng.uniform(-1e-8, 1e-8, 3000), [0.0, 0.015625, -0.015625]]).tolist():
+        assert L.t_exp(x) == float(Decimal(x).exp()), x
+    assert L.t_exp(0.5) == math.exp(0.5) and math.isnan(L.t_log(-1.0)) and L.t_log(float("inf")) == float("inf")

@@ -115,6 +115,7 @@ def test_env_episodes(golden, case_idx, torch_cuda):
     n = 3
     sim = make_sim(H.cfg_from_env_case(case, n_envs=n), [s])
     start = s.step_of_time(case["start_seconds"])
+    n_rewards = n_tight = 0
     for ep in case["episodes"]:
         obs = sim.reset(0, start).cpu().numpy()
         for env in range(n):
@@ -137,11 +138,16 @@ def test_env_episodes(golden, case_idx, torch_cuda):
             assert np.all(st["inventory"] == step["inventory"]), (case["name"], k)
             assert H.close(st["cash"][env], step["cash"]) and H.close(st["price"][env], step["price"])
             H.assert_close_vec(obs[env], step["obs"], f"{case['name']} step {k} obs")
-            assert H.close(rew[env], step["reward"]), (case["name"], k, rew[env], step["reward"])
+            assert H.reward_close(rew[env], step), (case["name"], k, rew[env], step["reward"], step.get("bound"))
+            n_rewards += 1
+            n_tight += H.close(rew[env], step["reward"])
             assert bool(done[env]) == step["done"]
             # identical replicas stay identical (RollingSharpe over a single return is NaN in the reference too)
             assert np.array_equal(obs, np.broadcast_to(obs[0], obs.shape), equal_nan=True)
             assert np.array_equal(rew, np.full_like(rew, rew[0]), equal_nan=True)
+    # the correctly rounded log / exp of the device (crmath.cuh) keep nearly every RollingSharpe reward at 1e12 cash within 1e-6
+    # of the reference; the analytic bound is needed only where glibc's log is not the correctly rounded value
+    assert n_tight >= 0.9 * n_rewards, (case["name"], n_tight, n_rewards)
 
 
 @pytest.mark.parametrize("case_idx", range(120))
@@ -250,7 +256,7 @@ def rollout_features():
     ]
 
 
-@pytest.mark.parametrize("agent_kind", ["fixed", "teradactyl", "external"])
+@pytest.mark.parametrize("agent_kind", ["fixed", "teradactyl", "external", "random"])
 def test_synthetic_rollout_vs_oracle(agent_kind, torch_cuda):
     """Full env path (agent orders, fills, portfolio, features, rewards, resync) on a synthetic SPY-shaped stream."""
     torch = torch_cuda
@@ -267,7 +273,7 @@ def test_synthetic_rollout_vs_oracle(agent_kind, torch_cuda):
               market_order_clearing=1 if agent_kind == "teradactyl" else 0,
               market_order_fraction_of_inventory=0.25 if agent_kind == "teradactyl" else 0.0)
     sim = make_sim(abi.default_cfg(n_envs=len(starts), **kw), [s])
-    oracles = [Oracle(abi.default_cfg(**kw), s) for _ in starts]
+    oracles = [Oracle(abi.default_cfg(**kw), s, env_index=i) for i in range(len(starts))]
     obs_d = sim.reset(0, np.array(starts, np.int32)).cpu().numpy()
     for env, (o, st) in enumerate(zip(oracles, starts)):
         H.assert_close_vec(obs_d[env], o.reset(st), f"reset obs env {env}")
@@ -279,6 +285,8 @@ def test_synthetic_rollout_vs_oracle(agent_kind, torch_cuda):
     elif agent_kind == "teradactyl":
         agent = abi.Agent(kind=abi.AGENT_TERADACTYL, inventory_index=5, max_inventory=300.0, default_kappa=7.0,
                           default_omega=0.4, max_kappa=12.0, exponent=1.5, market_clearing=1)
+    elif agent_kind == "random":   # device RandomAgent (Philox keyed by seed, env, grid step) == its oracle twin, bit for bit
+        agent = abi.Agent(kind=abi.AGENT_RANDOM, fixed_action=(ctypes.c_double * 5)(10, 10, 10, 10, 0), reserved=1234)
     else:
         agent = abi.Agent(kind=abi.AGENT_EXTERNAL)
         acts = np.random.default_rng(0).uniform(0, 10, size=(T, len(starts), ad))
@@ -291,6 +299,8 @@ def test_synthetic_rollout_vs_oracle(agent_kind, torch_cuda):
             oo, oa, orw, od = o.rollout(half, agent, None if acts is None else acts[sl, env])
             for t in range(half):
                 H.assert_close_vec(act[t, env], oa[t], f"{agent_kind} env {env} t {t} action")
+                if agent_kind == "random":
+                    assert np.array_equal(act[t, env], oa[t]) and np.all(act[t, env] >= 0) and np.all(act[t, env] < 10)
                 H.assert_close_vec(obs[t, env], oo[t], f"{agent_kind} env {env} t {part * half + t} obs")
                 assert H.close(rew[t, env], orw[t]), (agent_kind, env, t, rew[t, env], orw[t])
                 assert done[t, env] == od[t]
@@ -298,3 +308,5 @@ def test_synthetic_rollout_vs_oracle(agent_kind, torch_cuda):
             st, os_ = sim.state(env, 1)[0], o.state()
             assert st["err"] == os_["err"] == 0
             assert st["inventory"] == os_["inventory"] and H.close(st["cash"], os_["cash"])
+        if agent_kind == "random":    # envs 2 and 3 start 10 steps apart: different env index => different action streams
+            assert not np.array_equal(act[:, 2], act[:, 3]) and not np.array_equal(act[10:, 2], act[:-10, 3])

@@ -36,10 +36,12 @@ def test_random_env_case(seed):
     oracles = [Oracle(abi.default_cfg(n_envs=1, **c["cfg_kw"]), s) for _ in range(n)]
     agent, external = c["agent"], c["agent_kind"] == "external"
     # RollingSharpe takes exp(log(aum') - log(aum)) - 1 of AUMs around 1e9..1e12 against returns of 1e-10..1e-12: one ulp of log()
-    # (CUDA libm vs glibc vs numpy's SIMD loops) moves a return by up to 1e-3 relative, so the reward itself is only defined
-    # to ~1e-4 there (compared at 1e-3); everything else keeps the 1e-6 tolerance
+    # moves a return by up to 1e-3 relative.  The device rounds its log / exp correctly (crmath.cuh); the oracle calls glibc's
+    # (what numpy does), which is the correctly rounded value except for a few arguments in 1e4 -- so nearly every reward is
+    # within 1e-6 (counted below), and the rare others within 1e-3; everything else keeps the 1e-6 tolerance
     sharpe = abi.REWARD_ROLLING_SHARPE in (c["cfg_kw"]["step_reward"].kind, c["cfg_kw"]["terminal_reward"].kind)
     rew_close = (lambda a, b: H.close(a, b, rel=1e-3)) if sharpe else H.close
+    n_rew = n_rew_tight = 0
     skipped = set()   # envs whose device book hit a fixed capacity (flagged): with portfolio carry-over they stay different
     for part in range(2):
         starts = (c["starts"] + part * 10).astype(np.int32)
@@ -82,6 +84,8 @@ def test_random_env_case(seed):
                 H.assert_close_vec(act[t, env], oa[t], f"{what} t {t} action")
                 H.assert_close_vec(obs[t, env], oo[t], f"{what} t {t} obs")
                 assert rew_close(rew[t, env], orw[t]), (what, t, rew[t, env], orw[t])
+                n_rew += 1
+                n_rew_tight += H.close(rew[t, env], orw[t])
                 assert done[t, env] == od[t], (what, t)
                 if t >= k:
                     H.assert_close_vec(info_b[t - k, env], oi[t], f"{what} t {t} info")
@@ -90,6 +94,7 @@ def test_random_env_case(seed):
             assert H.close(st["price"][env], os_["price"]), what
             for f in ("now_step", "min_buy_price", "max_sell_price", "best_buy", "best_sell", "best_buy_volume", "best_sell_volume"):
                 assert st[f][env] == os_[f], (what, f, st[f][env], os_[f])
+    assert n_rew_tight >= 0.97 * n_rew, (seed, n_rew_tight, n_rew)
     sim.close()
 
 
