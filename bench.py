@@ -656,7 +656,7 @@ def run_collect(ctx: Ctx, stream):
 def run_multiticker(ctx: Ctx):
     """BASELINE.json configs[4]: 8 synthetic tickers (seeds 0-7, mids $30-$500), 50 levels, heavy cancel / modify flow,
     deep queues; `multiticker_envs` books per GPU, ticker = book index mod 8, a random start second per book.  Replay
-    (messages/s, k_replay_fast<128,1536,32>) and a fused FixedActionAgent([1,2,1,2]) rollout (env steps/s)."""
+    (messages/s, k_replay_flat / k_replay_fast<128,1536,64>) and a fused FixedActionAgent([1,2,1,2]) rollout (env steps/s)."""
     args, torch = ctx.args, ctx.torch
     import ctypes
 
@@ -670,7 +670,7 @@ def run_multiticker(ctx: Ctx):
     feats = [abi.feature(abi.FEAT_SPREAD, 0, 100000, 0, 5000), abi.feature(abi.FEAT_BOOK_IMBALANCE, 0, 100000, -1, 1),
              abi.feature(abi.FEAT_INVENTORY, 0, 100000, -1e6, 1e6)]
     cfg = abi.default_cfg(n_envs=n_envs, n_levels=50, outer_levels=20, max_levels_per_side=128, max_orders_per_side=1536,
-                          max_agent_orders=32, features=feats, episode_steps=18000, warmup_steps=0,
+                          max_agent_orders=64, features=feats, episode_steps=18000, warmup_steps=0,
                           step_reward=abi.Reward(abi.REWARD_PNL, 0, 0.0), terminal_reward=abi.Reward(abi.REWARD_PNL, 0, 0.0))
     sim = LobSim(cfg, ctx.local_rank)
     path = sim.kernel_path
@@ -706,9 +706,9 @@ def run_multiticker(ctx: Ctx):
                                "%d books per GPU, ticker = book mod %d, random start second per book, %d grid steps per bench step"
                                % (n_streams, args.multiticker_msgs, n_envs, n_streams, seg),
                    "envs_per_gpu": n_envs, "n_levels": 50, "n_streams": n_streams, "segment_steps": seg,
-                   "capacities": [128, 1536, 32]},
+                   "capacities": [128, 1536, 64]},
         "gpu_launches": int(launches), "clocks": clocks,
-        "roofline": roofline(algo, 1e3 * t_dev / steps, "k_replay_fast<StaticLayout<128,1536,32>>",
+        "roofline": roofline(algo, 1e3 * t_dev / steps, "k_replay_fast<StaticLayout<128,1536,64>>",
                              "k_replay_fast_L50" if n_envs == 8192 else None),
     }
     ctx.launches += launches
@@ -730,7 +730,7 @@ def run_multiticker(ctx: Ctx):
                   "ms_per_step": 1e3 * t_env / steps, "lob_messages_per_sec": msgs * world / t_env, "T": T,
                   "agent": "FixedActionAgent([1,2,1,2]) fused on the device", "features": "Spread, BookImbalance, Inventory; PnL",
                   "agent_overflow_envs": int((st["err"] & abi.ERR_AGENT_OVERFLOW != 0).sum()), "gpu_launches": int(launches),
-                  "roofline": roofline(algo, 1e3 * t_env / steps, "k_env_fast<StaticLayout<128,1536,32>> (one launch = 128 env steps)")}
+                  "roofline": roofline(algo, 1e3 * t_env / steps, "k_env_fast<StaticLayout<128,1536,64>> (one launch = 128 env steps)")}
     ctx.launches += launches
     if ctx.rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1

@@ -31,6 +31,8 @@ def main(argv=None):
     ap.add_argument("--episode-seconds", type=float, default=60.0)
     ap.add_argument("--n-msgs", type=int, default=2_000_000)
     ap.add_argument("--duration-s", type=int, default=4680)
+    ap.add_argument("--cuda-graph", choices=["auto", "on", "off"], default="auto",
+                    help="capture one collection step (policy forward + lobsim_step) in a CUDA graph; auto: n_envs <= 16384")
     args = ap.parse_args(argv)
 
     rank, world, local_rank = parallel.init_from_env()
@@ -48,7 +50,8 @@ def main(argv=None):
         max_end_timedelta=timedelta(hours=9, minutes=30, seconds=args.duration_s - 10),
         per_step_reward_function=InventoryAdjustedPnL(inventory_aversion=1e-4), terminal_reward_function=InventoryAdjustedPnL(inventory_aversion=0.1),
         max_levels_per_side=64, max_orders_per_side=256, max_agent_orders=64, portfolio_carryover=False, seed=1234 + rank)
-    trainer = PPOTrainer(env, PPOConfig(rollout_steps=args.rollout_steps, reward_scale=1e-3), seed=rank)
+    trainer = PPOTrainer(env, PPOConfig(rollout_steps=args.rollout_steps, reward_scale=1e-3), seed=rank,
+                         use_cuda_graph={"auto": None, "on": True, "off": False}[args.cuda_graph])
     hist = trainer.train(args.iterations, log=(lambda s: print(json.dumps(s))) if rank == 0 else None)
     if world > 1:
         torch.distributed.destroy_process_group()

@@ -10,7 +10,8 @@
   X(0, 64, 256, 32)    /* BASELINE config 2: 10-level books, replay                               */ \
   X(1, 128, 512, 64)   /* the default capacities of lobsim_cfg_t (50-level books)                 */ \
   X(2, 64, 256, 64)    /* 10-level books with a 64-order agent table (configs 3 and 4)            */ \
-  X(3, 128, 1536, 32)  /* BASELINE config 5: 50-level books, deep queues, heavy cancel flow       */ \
+  X(3, 128, 1536, 64)  /* BASELINE config 5: 50-level books, deep queues, heavy cancel flow (its      \
+                          FixedActionAgent holds up to ~45 resting orders per side: 32 overflows) */ \
   X(4, 128, 1024, 64)  /* 50-level books with deep queues and a 64-order agent table              */
 
 #define LOBSIM_N_FAST_LAYOUTS 5

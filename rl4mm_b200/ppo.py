@@ -11,6 +11,11 @@ the env step is the CUDA path (``LobSim.step`` on device tensors, no host round 
 * observation normalisation: the batch stores the observations AS THE POLICY SAW THEM (normalised with the running
   statistics in force during collection); the statistics are updated only after the PPO epochs, so ratio == 1 at the
   first minibatch and returns / values share one input scaling;
+* small batches are launch-bound (about 40 small torch kernels + one env kernel per step, 2.8 ms per step of Python and launch
+  overhead at 4 096 envs): with ``use_cuda_graph`` (default for n_envs <= 16 384) ONE collection step -- normalise, policy
+  forward, Beta sample, ``lobsim_step`` on the capturing stream, and the writes into slot t of the rollout tensors through a
+  device-side step counter -- is captured once in a CUDA graph and replayed T times (the reference's per-step caller is
+  rl4mm/gym/utils.py:100-117);
 * device errors: ``step_torch`` does not poll, so the per-env error column is read once per rollout and before every
   batch reset (the reset kernel clears the flags): EmptyOrderbookError / overflow / bad-action envs raise, exactly as
   ``env.step`` would have (``on_error="raise"``), or are masked out of the update (``on_error="mask"``).
@@ -81,9 +86,10 @@ class RunningNorm:
         m2b = qb - nb * mb * mb
         delta = mb - self.mean
         tot = self.n + nb
-        self.mean = self.mean + delta * nb / tot
-        self.m2 = self.m2 + m2b + delta * delta * self.n * nb / tot
-        self.n = tot
+        # in place: a captured CUDA graph of the collection step keeps reading these tensors
+        self.m2.add_(m2b + delta * delta * self.n * nb / tot)
+        self.mean.add_(delta * nb / tot)
+        self.n.copy_(tot)
 
     def __call__(self, x: torch.Tensor) -> torch.Tensor:
         std = torch.sqrt(self.m2 / torch.clamp(self.n, min=1.0)).clamp(min=1e-8)
@@ -105,10 +111,12 @@ def gae(rew: torch.Tensor, val: torch.Tensor, last_val: torch.Tensor, done: torc
 
 
 class PPOTrainer:
-    def __init__(self, env, cfg: PPOConfig = PPOConfig(), seed: int = 0, on_error: str = "raise"):
+    def __init__(self, env, cfg: PPOConfig = PPOConfig(), seed: int = 0, on_error: str = "raise", use_cuda_graph: Optional[bool] = None):
         """`env`: rl4mm_b200.gym.HistoricalOrderbookEnvironment (batched).  One trainer per rank / GPU."""
         assert on_error in ("raise", "mask")
         self.env, self.cfg, self.on_error = env, cfg, on_error
+        self.use_cuda_graph = env.n_envs <= 16_384 if use_cuda_graph is None else bool(use_cuda_graph)
+        self._graph = None
         self.device = env.sim.device
         torch.manual_seed(seed)
         low = torch.as_tensor(env.action_space.low, device=self.device)
@@ -139,37 +147,79 @@ class PPOTrainer:
             self.bad_envs |= bad
 
     def _reset(self):
-        self.obs = torch.as_tensor(self.env.reset(), device=self.device).reshape(self.env.n_envs, -1)
+        obs = torch.as_tensor(self.env.reset(), device=self.device).reshape(self.env.n_envs, -1)
+        if self.obs is None:
+            self.obs = obs.clone()
+        else:
+            self.obs.copy_(obs)                         # in place: the captured step reads this tensor
         self.steps_left = self.env.n_steps
         self.episode_return.zero_()
         self.bad_envs.zero_()
+
+    def _one_step(self, b: Dict[str, torch.Tensor], t_idx: torch.Tensor) -> None:
+        """One collection step into slot ``t_idx`` (a 1-element device tensor) of the rollout tensors; reads and rewrites
+        ``self.obs`` in place.  Pure device work on the current stream: this is the body of the captured CUDA graph."""
+        cfg = self.cfg
+        obsn = self.norm(self.obs)
+        dist, val = self.policy(obsn)
+        x = dist.sample()
+        obs, rew, done = self.env.step_torch(self.policy.to_env(x).double())
+        logp = dist.log_prob(x.clamp(1e-6, 1 - 1e-6)).sum(-1)
+        finite = torch.isfinite(rew)                    # an empty book side has no price: the reward of a dead env is NaN
+        rew = torch.where(finite, rew, torch.zeros_like(rew))
+        for key, v in (("obs", self.obs), ("obs_n", obsn), ("x", x), ("logp", logp), ("val", val), ("valid", finite),
+                       ("rew", (rew * cfg.reward_scale).float()), ("done", done.bool())):
+            b[key].index_copy_(0, t_idx, v.unsqueeze(0))
+        self.episode_return += rew
+        self.obs.copy_(obs)
+        t_idx += 1
+
+    def _capture(self, b: Dict[str, torch.Tensor]) -> None:
+        """Capture ``_one_step`` once (after the side-stream warm-up torch asks for); the warm-up steps really step the envs,
+        so it runs at construction-time state and the envs are reset afterwards."""
+        self._t_idx = torch.zeros(1, dtype=torch.long, device=self.device)
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                self._t_idx.zero_()
+                self._one_step(b, self._t_idx)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        self._graph = torch.cuda.CUDAGraph()
+        self._t_idx.zero_()
+        with torch.cuda.graph(self._graph):
+            self._one_step(b, self._t_idx)
+        self._graph_bufs = b
+        self._poll_errors()
+        self._reset()                                   # the warm-up / capture steps moved the envs: start the episode afresh
 
     @torch.no_grad()
     def collect(self) -> Dict[str, torch.Tensor]:
         T, N, cfg = self.cfg.rollout_steps, self.env.n_envs, self.cfg
         if self.obs is None:
             self._reset()
-        obs_b = torch.empty((T, N, self.env.sim.obs_dim), dtype=torch.float64, device=self.device)
-        obsn_b = torch.empty((T, N, self.env.sim.obs_dim), device=self.device)
-        valid_b = torch.ones((T, N), dtype=torch.bool, device=self.device)
-        x_b = torch.empty((T, N, self.env.sim.action_dim), device=self.device)
-        logp_b, val_b, rew_b = (torch.empty((T, N), device=self.device) for _ in range(3))
-        done_b = torch.zeros((T, N), dtype=torch.bool, device=self.device)
         if float(self.norm.n) == 0:                     # first rollout: seed the statistics with the reset observations
             self.norm.update(self.obs)
+        if self.use_cuda_graph and self._graph is not None:
+            b = self._graph_bufs                        # the captured graph writes into these tensors
+        else:
+            b = dict(obs=torch.empty((T, N, self.env.sim.obs_dim), dtype=torch.float64, device=self.device),
+                     obs_n=torch.empty((T, N, self.env.sim.obs_dim), device=self.device),
+                     valid=torch.ones((T, N), dtype=torch.bool, device=self.device),
+                     x=torch.empty((T, N, self.env.sim.action_dim), device=self.device),
+                     logp=torch.empty((T, N), device=self.device), val=torch.empty((T, N), device=self.device),
+                     rew=torch.empty((T, N), device=self.device), done=torch.zeros((T, N), dtype=torch.bool, device=self.device))
+            if self.use_cuda_graph:
+                self._capture(b)
+        obs_b, obsn_b, valid_b, x_b, logp_b, val_b, rew_b, done_b = (b[k] for k in ("obs", "obs_n", "valid", "x", "logp", "val", "rew", "done"))
+        t_idx = self._t_idx if self.use_cuda_graph else torch.zeros(1, dtype=torch.long, device=self.device)
+        t_idx.zero_()
         for t in range(T):
-            obs_b[t] = self.obs
-            obsn_b[t] = self.norm(self.obs)
-            dist, val = self.policy(obsn_b[t])
-            x = dist.sample()
-            obs, rew, done = self.env.step_torch(self.policy.to_env(x).double())
-            x_b[t], logp_b[t], val_b[t] = x, dist.log_prob(x.clamp(1e-6, 1 - 1e-6)).sum(-1), val
-            finite = torch.isfinite(rew)                # an empty book side has no price: the reward of a dead env is NaN
-            valid_b[t] = finite
-            rew = torch.where(finite, rew, torch.zeros_like(rew))
-            rew_b[t], done_b[t] = (rew * cfg.reward_scale).float(), done.bool()
-            self.episode_return += rew
-            self.obs = obs
+            if self.use_cuda_graph:
+                self._graph.replay()
+            else:
+                self._one_step(b, t_idx)
             self.steps_left -= 1
             if self.steps_left == 0:                    # every env ends together: batch reset (env.reset per worker)
                 self._poll_errors()                     # before the reset kernel clears the flags

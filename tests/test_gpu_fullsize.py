@@ -85,7 +85,7 @@ def test_config5_multi_ticker_heavy_cancel_general_path():
     streams = [synthetic.generate(synthetic.heavy_cancel_ticker(seed=k, n_msgs=1_000_000, duration_s=4680)) for k in range(3)]
     n = 1536
     cfg = abi.default_cfg(n_envs=n, n_levels=50, outer_levels=20, max_levels_per_side=128, max_orders_per_side=1536,
-                          max_agent_orders=32)
+                          max_agent_orders=64)
     sim = _sim(cfg, streams)
     sid = (np.arange(n) % 3).astype(np.int32)
     start = ((np.arange(n) // 3) % 4 * 1000).astype(np.int32)   # four different start seconds per ticker
@@ -166,9 +166,10 @@ def test_config4_collect_rollouts_example_single_gpu():
     assert out["errors"] == 0 and out["gathered_shape"] == [4096, 8] and np.isfinite(out["mean_return"])
 
 
-def test_ppo_training_loop_runs_on_device_env():
+@pytest.mark.parametrize("cuda_graph", ["on", "off"])
+def test_ppo_training_loop_runs_on_device_env(cuda_graph):
     """the policy-update loop (examples/train_ppo.py) -- three PPO iterations on 512 envs; losses finite,
-    parameters move, no env error."""
+    parameters move, no env error.  Both with the collection step captured in a CUDA graph and eagerly."""
     import importlib.util
     from pathlib import Path
 
@@ -176,7 +177,7 @@ def test_ppo_training_loop_runs_on_device_env():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     hist = mod.main(["--envs", "512", "--iterations", "3", "--rollout-steps", "32", "--episode-seconds", "5", "--n-msgs", "300000",
-                     "--duration-s", "900"])
+                     "--duration-s", "900", "--cuda-graph", cuda_graph])
     assert len(hist) == 3
     for h in hist:
         assert all(np.isfinite(h[k]) for k in ("loss", "pg", "vf", "entropy", "kl", "mean_step_reward")), h
