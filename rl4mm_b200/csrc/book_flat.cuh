@@ -55,18 +55,21 @@ __device__ __forceinline__ int flat_best_of(const uint4& e0, const uint4& e1, in
   return S ? __reduce_min_sync(FULL_MASK, k0 < k1 ? k0 : k1) : __reduce_max_sync(FULL_MASK, k0 > k1 ? k0 : k1);
 }
 
-// One order of side S (0 buy, 1 sell) through the flat book.  Same results as fast_order_full<LT,false> on the sorted book.
+// One order of side S (0 buy, 1 sell) through the flat book.  Same results as fast_order_full<LT,TR> on the sorted book; TR: fills /
+// flows / the agent's order tables are tracked (env kernels), exactly as in book_fast.cuh.
 // Returns false -- with the book untouched -- when the order may have to rest and the pool of its side is full: the caller
 // converts the book to the sorted form and runs the order there.
-template <class LT, int S>
-__device__ __forceinline__ bool flat_order(unsigned char* blob, int lane, FastState& f, FlatState& st, int type, int price, int vol, uint32_t ref) {
+template <class LT, int S, bool TR>
+__device__ __forceinline__ bool flat_order(unsigned char* blob, int lane, FastState& f, FlatState& st, int type, int price, int vol, uint32_t ref, bool is_agent) {
   constexpr int OPP = S ^ 1;
+  if (!TR) is_agent = false;
   int& n_own = S ? st.n1 : st.n0;
   int& n_opp = S ? st.n0 : st.n1;
   int& best_own = S ? f.best1 : f.best0;
   int& best_opp = S ? f.best0 : f.best1;
   uint4* own = flat_pool<LT>(blob, S);
   uint4* opp = flat_pool<LT>(blob, OPP);
+  FastBook<LT> fb; fb.blob = blob; fb.lane = lane;
   if (vol <= 0) { f.err |= LOBSIM_ERR_BAD_VOLUME; return true; }          // assert order.volume > 0, Exchange.py:59-60
   __syncwarp();                                                             // the previous order's stores are visible
   if (type == LOBSIM_MSG_LIMIT || type == LOBSIM_MSG_MARKET) {
@@ -90,22 +93,48 @@ __device__ __forceinline__ bool flat_order(unsigned char* blob, int lane, FastSt
         const unsigned b0 = __ballot_sync(FULL_MASK, q0 == head_seq), b1 = __ballot_sync(FULL_MASK, q1 == head_seq);
         const int i = b0 ? __ffs(b0) - 1 : 32 + __ffs(b1) - 1;              // the head of the best queue
         const int hv = (int)__shfl_sync(FULL_MASK, b0 ? e0.y : e1.y, i & 31);
-        if (rem < hv) {                                                    // partial fill of the head
-          if (lane == 0) opp[i].y = (unsigned)(hv - rem);
-          rem = 0;
-          break;
+        const uint32_t href = TR ? __shfl_sync(FULL_MASK, b0 ? e0.z : e1.z, i & 31) : 0u;
+        const bool hagent = TR && (href & LOBSIM_REF_AGENT) != 0;
+        const bool self_match = TR && is_agent && hagent;                  // cannot fill our own order => delete it, :91-94
+        if (!self_match) {
+          const int v = rem < hv ? rem : hv;
+          if (TR) {
+            if (hagent) fast_record(fb, f, 0, OPP, bp, v, 0, href);
+            else fast_record(fb, f, 1, OPP, bp, v, 0, href);
+            if (is_agent) fast_record(fb, f, 0, S, bp, v, 1, href);         // the synthetic MarketOrder fill, :111-115
+          }
+          if (rem < hv) {                                                  // partial fill of the head
+            if (lane == 0) opp[i].y = (unsigned)(hv - rem);
+            if (TR && hagent) { __syncwarp(); fast_agent_reduce(fb, OPP, href & 0x7fffffffu, rem, false); }
+            rem = 0;
+            break;
+          }
+          rem -= hv;                                                       // the head is consumed
         }
-        rem -= hv;                                                         // the head is consumed
         const int at_best = __popc(__ballot_sync(FULL_MASK, q0 != 0xffffffffu)) + __popc(__ballot_sync(FULL_MASK, q1 != 0xffffffffu));
         if (at_best == 1) best_opp = flat_best_of<OPP>(e0, e1, n_opp, lane, i);   // the level emptied
         if (lane == 0) opp[i] = opp[n_opp - 1];
         n_opp -= 1;
         __syncwarp();
+        if (TR && hagent) fast_agent_reduce(fb, OPP, href & 0x7fffffffu, 0, true);   // the resting agent order is gone
       }
       if (!(rem > 0 && type == LOBSIM_MSG_LIMIT && !f.dead)) return true;
       // the remainder of a crossing limit order rests (Exchange.py:116-119)
     }
     // ---- the order rests at the back of its price's queue (Exchange.py:74-83) ------------------------------------------
+    if (TR && is_agent) {   // OrderIdConvertor.add_internal_id_to_order_and_track + internal book append
+      BookHdr* h = reinterpret_cast<BookHdr*>(blob);
+      const int nag = h->nag[S];
+      if (nag >= LT::NA) { f.err |= LOBSIM_ERR_AGENT_OVERFLOW; return true; }
+      const uint32_t id = h->next_agent_id;
+      ref = LOBSIM_REF_AGENT | id;
+      __syncwarp();
+      if (lane == 0) {
+        int32_t* ap = reinterpret_cast<int32_t*>(blob + LT::agent_off + S * LT::NA * 12);
+        ap[nag] = price; ap[LT::NA + nag] = rem; reinterpret_cast<uint32_t*>(ap)[2 * LT::NA + nag] = id;
+        h->nag[S] = nag + 1; h->next_agent_id = id + 1;
+      }
+    }
     if (lane == 0) own[n_own] = make_uint4((unsigned)price, (unsigned)rem, ref, st.seq);
     n_own += 1; st.seq += 1;
     if (S ? price < best_own : price > best_own) best_own = price;
@@ -115,31 +144,51 @@ __device__ __forceinline__ bool flat_order(unsigned char* blob, int lane, FastSt
   uint4 e0, e1;
   flat_load(own, n_own, lane, e0, e1);
   unsigned m0 = __ballot_sync(FULL_MASK, (int)e0.x == price && e0.z == ref), m1 = __ballot_sync(FULL_MASK, (int)e1.x == price && e1.z == ref);
+  bool aggregate = false;
   if (!(m0 | m1)) {
     // unknown id: the level's snapshot aggregate (internal_id -1, always the head of its level) takes the hit (:133-137);
     // no such level, or no aggregate left at it: nothing happens (:129-132,138-139)
     m0 = __ballot_sync(FULL_MASK, lane < n_own && (int)e0.x == price && e0.z == LOBSIM_REF_AGGREGATE);
     m1 = __ballot_sync(FULL_MASK, lane + 32 < n_own && (int)e1.x == price && e1.z == LOBSIM_REF_AGGREGATE);
     if (!(m0 | m1)) return true;
+    aggregate = true;
   }
   const int i = m0 ? __ffs(m0) - 1 : 32 + __ffs(m1) - 1;
   const int cur = (int)__shfl_sync(FULL_MASK, m0 ? e0.y : e1.y, i & 31);
   if (vol < cur) {                                                         // partial: reduce in place
     if (lane == 0) own[i].y = (unsigned)(cur - vol);
+    if (TR && is_agent && !aggregate) { __syncwarp(); fast_agent_reduce(fb, S, ref & 0x7fffffffu, vol, false); }
     return true;
   }
   // full removal (over-size requests remove the resting volume, :142-146): the last order of the pool fills the hole
   if (price == best_own) best_own = flat_best_of<S>(e0, e1, n_own, lane, i);
   if (lane == 0) own[i] = own[n_own - 1];
   n_own -= 1;
+  if (TR && is_agent && !aggregate) { __syncwarp(); fast_agent_reduce(fb, S, ref & 0x7fffffffu, cur, true); }
   return true;
 }
 
 template <class LT>
 __device__ __forceinline__ bool flat_message(unsigned char* blob, int lane, FastState& f, FlatState& st, int price, int vol, uint32_t ref, uint32_t meta) {
   const int type = (int)(meta & 7u);
-  if (meta & 8u) return flat_order<LT, 1>(blob, lane, f, st, type, price, vol, ref);
-  return flat_order<LT, 0>(blob, lane, f, st, type, price, vol, ref);
+  if (meta & 8u) return flat_order<LT, 1, false>(blob, lane, f, st, type, price, vol, ref, false);
+  return flat_order<LT, 0, false>(blob, lane, f, st, type, price, vol, ref, false);
+}
+// the tracked form (env kernels): historical messages and the agent's own orders
+template <class LT>
+__device__ __forceinline__ bool flat_order_tracked(unsigned char* blob, int lane, FastState& f, FlatState& st, int type, int side, int price, int vol, uint32_t ref, bool is_agent) {
+  if (side) return flat_order<LT, 1, true>(blob, lane, f, st, type, price, vol, ref, is_agent);
+  return flat_order<LT, 0, true>(blob, lane, f, st, type, price, vol, ref, is_agent);
+}
+
+// volume resting at the best price of side S (Orderbook.best_buy_volume / best_sell_volume, models.py:80-85)
+template <class LT, int S>
+__device__ __forceinline__ int flat_best_volume(unsigned char* blob, int lane, const FastState& f, const FlatState& st) {
+  const int n = S ? st.n1 : st.n0, best = S ? f.best1 : f.best0;
+  uint4 e0, e1;
+  flat_load(flat_pool<LT>(blob, S), n, lane, e0, e1);
+  const int v = ((lane < n && (int)e0.x == best) ? (int)e0.y : 0) + ((lane + 32 < n && (int)e1.x == best) ? (int)e1.y : 0);
+  return __reduce_add_sync(FULL_MASK, v);
 }
 
 // ---- sorted -> flat (kernel entry, and after a resync / when a book has shrunk) ---------------------------------------------

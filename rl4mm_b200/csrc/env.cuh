@@ -228,7 +228,9 @@ struct AgentGen {
 
 // Cold (noinline, everything by value): the fp64 ladder math must not inflate the register budget of the hot loop.
 // beta_tab: [2][32] doubles (ln x_k, ln(1 - x_k)) in global memory; vol_scratch: per-warp int[64] in shared memory.
-static __device__ __noinline__ AgentGen agent_prepare(const Book b, int nlv0, int nlv1, int nag0, int nag1, long long inventory, const EnvConst* ecp,
+// best_buy / best_sell: the best prices of the central book (INT32_MIN / INT32_MAX: that side is empty) -- passed in, because the
+// caller's book may be in the flat form (book_flat.cuh), which has no level arrays to read them from.
+static __device__ __noinline__ AgentGen agent_prepare(const Book b, int best_buy, int best_sell, int nag0, int nag1, long long inventory, const EnvConst* ecp,
                                                double a0, double a1, double a2, double a3, double a4, const double* __restrict__ beta_tab, int* vol_scratch) {
   const EnvConst& ec = *ecp;
   const lobsim_cfg_t& c = ec.cfg;
@@ -249,8 +251,8 @@ static __device__ __noinline__ AgentGen agent_prepare(const Book b, int nlv0, in
   const bool clearing = c.market_order_clearing && (double)absinv > pick5(action, ec.action_dim - 1);
   if (clearing) desired0 = desired1 = 0;
   if (__any_sync(FULL_MASK, desired0 == INT32_MIN || desired1 == INT32_MIN)) { g.err_out = LOBSIM_ERR_BAD_ACTION; g.dead_out = 1; return g; }
-  if (nlv0 == 0 || nlv1 == 0) { g.err_out = LOBSIM_ERR_EMPTY_BOOK; g.dead_out = 1; return g; }
-  int bb = b.lvp(0)[nlv0 - 1], bs = b.lvp(1)[nlv1 - 1];
+  if (best_buy == INT32_MIN || best_sell == INT32_MAX) { g.err_out = LOBSIM_ERR_EMPTY_BOOK; g.dead_out = 1; return g; }
+  int bb = best_buy, bs = best_sell;
   const int tick = c.tick_size;
   if (c.enter_spread) { // _get_best_prices :298-309
     double mid = (double)(bs + bb) / 2.0;

@@ -30,6 +30,7 @@ static cudaError_t set_attr(const void* k, int dyn) {
 cudaError_t FN(_attrs)(int dyn_replay, int dyn_env) {
   cudaError_t e = set_attr((const void*)k_replay_fast<LT>, dyn_replay);
   if (e == cudaSuccess) e = set_attr((const void*)k_replay_flat<LT>, dyn_replay);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)k_to_sorted<LT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * LT::blob_bytes <= 227 * 1024 ? 4 * LT::blob_bytes : LT::blob_bytes);
   if (e == cudaSuccess) e = set_attr((const void*)k_env_fast<LT, true, false>, dyn_env);
   if (e == cudaSuccess) e = set_attr((const void*)k_env_fast<LT, false, false>, dyn_env);
   return e;
@@ -39,6 +40,10 @@ void FN(_replay)(int grid, int block, size_t dyn, cudaStream_t stream, const Adv
 }
 void FN(_replay_flat)(int grid, int block, size_t dyn, cudaStream_t stream, const AdvParams& p, const EnvConst& ec) {
   k_replay_flat<LT><<<grid, block, dyn, stream>>>(p, ec);
+}
+void FN(_to_sorted)(unsigned char* blobs, int n_envs, cudaStream_t stream) {
+  const int wpc = 4 * LT::blob_bytes <= 227 * 1024 ? 4 : 1;
+  k_to_sorted<LT><<<(n_envs + wpc - 1) / wpc, wpc * 32, (size_t)wpc * LT::blob_bytes, stream>>>(blobs, n_envs);
 }
 void FN(_env)(bool sync, int grid, int block, size_t dyn, cudaStream_t stream, const AdvParams& p, const EnvConst& ec) {
   if (sync) k_env_fast<LT, true, false><<<grid, block, dyn, stream>>>(p, ec);

@@ -99,6 +99,7 @@ struct AdvParams {
   int32_t agent_kind;               // LOBSIM_AGENT_*
   int32_t out_final_obs_only;       // reset: write obs once, after the warm-up
   int32_t resync_last_only;         // forward_step over several grid steps: resync check only at the end
+  int32_t allow_flat;               // fast kernels: books that fit run on -- and are stored in -- the flat order pools (book_flat.cuh)
   const double* actions_in;         // EXTERNAL: [T][n_sel][action_dim]
   double* obs; double* act; double* rew; uint8_t* done; // [T][n_sel][...] (any may be null)
   double* info;                     // [T][n_sel][LOBSIM_INFO_DIM] per-step info series (SimpleInfoCalculator source) or null
@@ -297,7 +298,7 @@ __global__ void __launch_bounds__(128, kEnv ? LOBSIM_ENV_MIN_BLOCKS : 4) k_advan
         if (p.act && p.agent_kind != LOBSIM_AGENT_EXTERNAL && lane < ec.action_dim) p.act[((size_t)t * p.n_sel + sel) * ec.action_dim + lane] = mine;
         if (p.obs && !p.out_final_obs_only && c.inc_prev_action_in_obs && lane < ec.action_dim)
           p.obs[((size_t)t * p.n_sel + sel) * ec.obs_dim + F + lane] = mine; // get_observation(action), HOE.py:171
-        gen = agent_prepare(b, w.nlv0, w.nlv1, w.nag0, w.nag1, w.inventory, &ec, a0, a1, a2, a3, a4, p.beta_tab, reinterpret_cast<int*>(scratch));
+        gen = agent_prepare(b, w.nlv0 ? b.lvp(0)[w.nlv0 - 1] : INT32_MIN, w.nlv1 ? b.lvp(1)[w.nlv1 - 1] : INT32_MAX, w.nag0, w.nag1, w.inventory, &ec, a0, a1, a2, a3, a4, p.beta_tab, reinterpret_cast<int*>(scratch));
         w.err |= gen.err_out; if (gen.dead_out) w.dead = 1;
         agent_phase = true;
       }
@@ -497,6 +498,76 @@ __global__ void __launch_bounds__(128, 7) k_replay_fast(const __grid_constant__ 
   __syncwarp();
 }
 
+// ---- the flat form of a blob in HBM (book_flat.cuh): header with cnt[0] = {-1, n0}, cnt[1] = {seq, n1}; per side the order pool
+//      (n x 16 B at the start of the side's order array); the agent tables as always.  Parts: lanes 0-1 the pools, 2-7 the agent tables.
+__device__ __forceinline__ bool hdr_is_flat(const BookHdr* h) { return h->cnt[0][0] < 0; }
+template <class LT, bool LOAD>
+__device__ __forceinline__ uint32_t flat_body_copy(unsigned char* sm, unsigned char* gm, uint64_t* bar, int lane, int n0, int n1) {
+  const BookHdr* h = reinterpret_cast<const BookHdr*>(sm);
+  uint32_t off = 0, len = 0;
+  if (lane < 2) { off = LT::side_off + lane * LT::side_stride + LT::ord_off; len = (uint32_t)(lane ? n1 : n0) * 16u; }
+  else if (lane < 8) {
+    const int s = (lane - 2) / 3, part = (lane - 2) % 3;
+    off = LT::agent_off + s * LT::NA * 12 + part * LT::NA * 4;
+    len = (min((uint32_t)h->nag[s], (uint32_t)LT::NA) * 4 + 15) & ~15u;
+  }
+  const uint32_t total = __reduce_add_sync(FULL_MASK, len);
+  if (total == 0) return 0;
+  if (LOAD) { if (lane == 0) mbar_expect_tx(bar, total); __syncwarp(); }
+  if (len) { if (LOAD) tma_load(sm + off, gm + off, len, bar); else tma_store_part(gm + off, sm + off, len); }
+  return total;
+}
+// FlatState of a flat blob whose header and pools are in shared memory; the best prices are recomputed from the pools
+template <class LT>
+__device__ __forceinline__ void flat_adopt(unsigned char* sm, int lane, FastState& f, FlatState& fs) {
+  const BookHdr* h = reinterpret_cast<const BookHdr*>(sm);
+  fs.n0 = h->cnt[0][1]; fs.n1 = h->cnt[1][1]; fs.seq = (uint32_t)h->cnt[1][0];
+  uint4 e0, e1;
+  flat_load(flat_pool<LT>(sm, 0), fs.n0, lane, e0, e1);
+  f.best0 = flat_best_of<0>(e0, e1, fs.n0, lane, -1);
+  flat_load(flat_pool<LT>(sm, 1), fs.n1, lane, e0, e1);
+  f.best1 = flat_best_of<1>(e0, e1, fs.n1, lane, -1);
+}
+__device__ __forceinline__ void flat_mark(BookHdr* h, const FlatState& fs) {   // lane 0, before the blob goes back to HBM
+  h->cnt[0][0] = -1; h->cnt[0][1] = fs.n0; h->cnt[1][0] = (int32_t)fs.seq; h->cnt[1][1] = fs.n1;
+}
+
+// Every flat blob back to the canonical sorted layout, in place (run by the host before anything that reads the level arrays:
+// the general kernels, k_process_orders, the sorted-only replay kernel, the L3 dump).  One warp per book; sorted books: nothing.
+template <class LT>
+__global__ void __launch_bounds__(128) k_to_sorted(unsigned char* blobs, int n_envs) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int env = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (env >= n_envs) return;
+  unsigned char* gblob = blobs + (size_t)env * LT::blob_bytes;
+  if (!hdr_is_flat(reinterpret_cast<const BookHdr*>(gblob))) return;
+  unsigned char* base = smem + (size_t)warp * LT::blob_bytes;
+  if (lane < 8) reinterpret_cast<uint4*>(base)[lane] = reinterpret_cast<const uint4*>(gblob)[lane];   // the 128-byte header
+  __syncwarp();
+  const BookHdr* h = reinterpret_cast<const BookHdr*>(base);
+  FlatState fs; fs.n0 = h->cnt[0][1]; fs.n1 = h->cnt[1][1]; fs.seq = (uint32_t)h->cnt[1][0];
+#pragma unroll
+  for (int s = 0; s < 2; s++) {
+    const int n = s ? fs.n1 : fs.n0;
+    const uint4* gp = flat_pool<LT>(gblob, s); uint4* sp = flat_pool<LT>(base, s);
+    if (lane < n) sp[lane] = gp[lane];
+    if (lane + 32 < n) sp[lane + 32] = gp[lane + 32];
+  }
+  __syncwarp();
+  FastBook<LT> fb; fb.blob = base; fb.lane = lane;
+  flat_leave(fb, fs);
+  __syncwarp();
+  if (lane == 0) reinterpret_cast<uint4*>(gblob)[0] = reinterpret_cast<const uint4*>(base)[0];          // cnt[2][2]
+#pragma unroll
+  for (int s = 0; s < 2; s++) {
+    const int2 c = *fb.cnt(s);
+    unsigned char* ss = fb.side(s); unsigned char* gs = gblob + LT::side_off + s * LT::side_stride;
+    for (int i = lane; i < c.x; i += 32) { fb.P(gs)[i] = fb.P(ss)[i]; fb.LE(gs)[i] = fb.LE(ss)[i]; }
+    for (int i = lane; i < c.y; i += 32) fb.O(gs)[i] = fb.O(ss)[i];
+  }
+}
+
 // ====================================================================================================================
 //  the replay FLAT kernel: k_replay_fast with the flat order pools of book_flat.cuh for every book that fits them (at most
 //  FLAT_CAP resting orders per side), the sorted straight-line path for the others -- per book, re-decided every second.
@@ -526,9 +597,10 @@ __global__ void __launch_bounds__(128, 7) k_replay_flat(const __grid_constant__ 
   FastBook<LT> fb; fb.blob = base; fb.lane = lane;
   BookHdr* h = reinterpret_cast<BookHdr*>(base);
   FastState f; f.err = h->err; f.dead = h->dead; f.bail = 0; f.bail_vol = 0;
-  fast_refresh_best(fb, f);
+  if (!hdr_is_flat(h)) fast_refresh_best(fb, f);
   FlatState fs; fs.n0 = fs.n1 = 0; fs.seq = 0;
   bool flat = false;
+  if (hdr_is_flat(h)) { flat_adopt<LT>(base, lane, f, fs); flat = true; }   // the blob was stored in the flat form
   const lobsim_stream_t* stp = &p.streams[h->stream_id];
   const lobsim_msg_t* __restrict__ st_msgs = stp->msgs;
   const uint32_t* __restrict__ st_step_off = stp->step_off;
@@ -538,7 +610,7 @@ __global__ void __launch_bounds__(128, 7) k_replay_flat(const __grid_constant__ 
   if ((now_step < 0 || now_step > n_grid) && !f.dead && T > 0) { f.err |= LOBSIM_ERR_END_OF_STREAM; f.dead = 1; }
   unsigned g = 0, g_end_all = 0;
   if (!f.dead && T > 0) { g = __ldg(&st_step_off[now_step]); g_end_all = __ldg(&st_step_off[min((long long)now_step + T, (long long)n_grid)]); }
-  if (g < g_end_all && flat_fits(fb, 0)) { flat_enter(fb, fs); flat = true; }
+  if (!flat && g < g_end_all && flat_fits(fb, 0)) { flat_enter(fb, fs); flat = true; }
   const unsigned tile0 = g / MSG_TILE;
   unsigned next_issue = 0, next_wait = 0;
   auto issue_tile = [&]() {
@@ -616,10 +688,10 @@ __global__ void __launch_bounds__(128, 7) k_replay_flat(const __grid_constant__ 
       if (!flat && flat_fits(fb, 8)) { flat_enter(fb, fs); flat = true; }   // back to the flat pools once the book has shrunk
     }
   }
-  if (flat) flat_leave(fb, fs);
+  if (flat && !p.allow_flat) { flat_leave(fb, fs); flat = false; }   // the caller wants the canonical sorted layout in HBM
   while (next_wait < next_issue) wait_tile();                // drain TMA loads still in flight (aborted episode)
   __syncwarp();
-  if (lane == 0) { h->now_step = now_step; h->err = f.err; h->dead = f.dead; }
+  if (lane == 0) { h->now_step = now_step; h->err = f.err; h->dead = f.dead; if (flat) flat_mark(h, fs); }
   __syncwarp();
   fence_proxy_async();
   __syncwarp();
@@ -673,7 +745,10 @@ __device__ __forceinline__ uint32_t blob_body_copy(unsigned char* sm, unsigned c
 }
 
 #ifndef LOBSIM_ENVFAST_WARPS
-#define LOBSIM_ENVFAST_WARPS 4    // warps per CTA of the env fast kernel (four CTAs per SM at 128 registers; 8 measured 1.3 % slower)
+#define LOBSIM_ENVFAST_WARPS 8    // warps per CTA of the env fast kernel: the warps of a CTA move through the phases of a step together, so
+                                  // fewer, larger CTAs = fewer phases in flight per SM = a warmer instruction cache ("no instruction" is the
+                                  // top stall).  Measured at 80 registers / 24 resident warps per SM (profiles/r02_env_ab.txt): 4 warps per CTA
+                                  // 4.36e7 env steps/s, 8: 4.77e7, 12: 4.53e7, 24: 4.21e7; no phase sync at all: 3.41e7
 #endif
 #ifndef LOBSIM_ENVFAST_MINB
 #define LOBSIM_ENVFAST_MINB (24 / LOBSIM_ENVFAST_WARPS)   // resident CTAs per SM the register allocation aims at (80 registers: measured
@@ -725,13 +800,20 @@ __global__ void __launch_bounds__(32 * LOBSIM_ENVFAST_WARPS, env_min_blocks<LT>(
   }
   __syncwarp();
   mbar_wait(&bars[2], 0);
-  if (!p.reset_mode) {
-    if (blob_body_copy<LT, true>(base, gblob, &bars[2], lane)) mbar_wait(&bars[2], 1);
-  }
-
   FastBook<LT> fb; fb.blob = base; fb.lane = lane;
   Book b; b.blob = base; b.L = p.L; b.lane = lane;
   BookHdr* h = reinterpret_cast<BookHdr*>(base);
+  // flat: the book is in the flat order pools of book_flat.cuh (every book that fits them, when the handle allows it) -- in shared
+  // memory during the launch AND in HBM between launches (one launch = one env step when a policy runs in between, so a
+  // conversion per launch would cost more than the flat order path saves)
+  bool flat = false;
+  FlatState fs; fs.n0 = fs.n1 = 0; fs.seq = 0;
+  if (!p.reset_mode) {
+    if (hdr_is_flat(h)) {
+      if (flat_body_copy<LT, true>(base, gblob, &bars[2], lane, h->cnt[0][1], h->cnt[1][1])) mbar_wait(&bars[2], 1);
+      flat = true;
+    } else if (blob_body_copy<LT, true>(base, gblob, &bars[2], lane)) mbar_wait(&bars[2], 1);
+  }
   FastState f; f.err = h->err; f.dead = h->dead; f.bail = 0; f.bail_vol = 0;
   f.fill_log = p.fill_log ? p.fill_log + (size_t)env * p.fill_cap : nullptr; f.fill_cap = p.fill_cap;
   if (lane == 0) h->n_fills = 0;
@@ -752,7 +834,11 @@ __global__ void __launch_bounds__(32 * LOBSIM_ENVFAST_WARPS, env_min_blocks<LT>(
     }
     __syncwarp();
   }
-  fast_refresh_best(fb, f);
+  if (flat) flat_adopt<LT>(base, lane, f, fs);
+  else {
+    fast_refresh_best(fb, f);
+    if (p.allow_flat && flat_fits(fb, 8)) { flat_enter(fb, fs); flat = true; }
+  }
   const lobsim_stream_t* stp = &p.streams[stream_id];
   const lobsim_msg_t* __restrict__ st_msgs = stp->msgs;
   const uint32_t* __restrict__ st_step_off = stp->step_off;
@@ -768,11 +854,12 @@ __global__ void __launch_bounds__(32 * LOBSIM_ENVFAST_WARPS, env_min_blocks<LT>(
   const int t0_mod_min = (int)stp->reserved;   // t0_us % 60 s, filled in by lobsim_load_stream
 
   auto tops = [&](StepView& v) { // Orderbook.best_* / microprice, models.py:72-101
-    const int n0 = h->cnt[0][0], n1 = h->cnt[1][0];
-    v.have_tops = n0 > 0 && n1 > 0;
+    v.have_tops = f.best0 != INT32_MIN && f.best1 != INT32_MAX;
     if (v.have_tops) {
       v.bb = f.best0; v.bs = f.best1;
-      v.bv = best_level_volume(b, 0, n0); v.sv = best_level_volume(b, 1, n1);
+      __syncwarp();
+      if (flat) { v.bv = flat_best_volume<LT, 0>(base, lane, f, fs); v.sv = flat_best_volume<LT, 1>(base, lane, f, fs); }
+      else { v.bv = best_level_volume(b, 0, h->cnt[0][0]); v.sv = best_level_volume(b, 1, h->cnt[1][0]); }
       double imb; v.price = microprice(v.bb, v.bs, v.bv, v.sv, imb);
     } else { v.bb = v.bs = v.bv = v.sv = 0; v.price = NAN; }
   };
@@ -844,7 +931,7 @@ __global__ void __launch_bounds__(32 * LOBSIM_ENVFAST_WARPS, env_min_blocks<LT>(
       if (p.obs && !p.out_final_obs_only && c.inc_prev_action_in_obs && lane < ec.action_dim)
         p.obs[((size_t)t * p.n_sel + sel) * ec.obs_dim + F + lane] = mine;
       if (!f.dead) {
-        const AgentGen g0 = agent_prepare(b, h->cnt[0][0], h->cnt[1][0], h->nag[0], h->nag[1], h->inventory, &ec, a0, a1, a2, a3, a4, p.beta_tab, diff_scratch);
+        const AgentGen g0 = agent_prepare(b, f.best0, f.best1, h->nag[0], h->nag[1], h->inventory, &ec, a0, a1, a2, a3, a4, p.beta_tab, diff_scratch);
         f.err |= g0.err_out; if (g0.dead_out) f.dead = 1;
         gen = agent_gen_fast_init(g0, lane, diff_scratch);
         agent_phase = true;
@@ -870,7 +957,10 @@ __global__ void __launch_bounds__(32 * LOBSIM_ENVFAST_WARPS, env_min_blocks<LT>(
           g++;
           if (g % MSG_TILE == 0) { __syncwarp(); issue_tile(); }
         }
-        if (!f.dead) fast_order_full<LT, true>(fb, f, type, side, oprice, vol, ref, is_agent);
+        if (!f.dead) {
+          if (flat && !flat_order_tracked<LT>(base, lane, f, fs, type, side, oprice, vol, ref, is_agent)) { flat_leave(fb, fs); flat = false; }   // pool full
+          if (!flat) fast_order_full<LT, true>(fb, f, type, side, oprice, vol, ref, is_agent);
+        }
       }
     }
     if (!f.dead) {
@@ -885,7 +975,12 @@ __global__ void __launch_bounds__(32 * LOBSIM_ENVFAST_WARPS, env_min_blocks<LT>(
             const int sec = now_step / steps_per_sec;
             if (sec <= (int)stp->n_seconds && stp->snap_valid[sec]) {
               const int32_t* row = stp->snapshots + (size_t)sec * 2 * c.n_levels * 2;
-              fast_resync_tracked(fb, f, row, c.n_levels, scratch);
+              if (flat && !flat_resync_needed(h, row, c.n_levels, lane)) flat_update_trackers<LT>(base, lane, fs);
+              else {
+                if (flat) { flat_leave(fb, fs); flat = false; }
+                fast_resync_tracked(fb, f, row, c.n_levels, scratch);
+                if (p.allow_flat && flat_fits(fb, 8)) { flat_enter(fb, fs); flat = true; }
+              }
             }
           }
         }
@@ -930,13 +1025,15 @@ __global__ void __launch_bounds__(32 * LOBSIM_ENVFAST_WARPS, env_min_blocks<LT>(
     if (f.fill_log && h->n_fills > f.fill_cap) f.err |= LOBSIM_ERR_FILL_LOG_FULL;
     h->now_step = now_step; h->price = sv->price; h->err = f.err; h->dead = f.dead;
     if (p.fill_count) p.fill_count[env] = h->n_fills;
+    if (flat) flat_mark(h, fs);
   }
   __syncwarp();
   fence_proxy_async();
   __syncwarp();
   // shared memory -> HBM: the header and the occupied part of the arrays; every issuing lane commits and waits for its own copy
   if (lane == 12) tma_store_part(gblob, base, (uint32_t)sizeof(BookHdr));
-  blob_body_copy<LT, false>(base, gblob, nullptr, lane);
+  if (flat) flat_body_copy<LT, false>(base, gblob, nullptr, lane, fs.n0, fs.n1);
+  else blob_body_copy<LT, false>(base, gblob, nullptr, lane);
   if (lane <= 12) { tma_store_commit(); tma_store_wait(); }
   __syncwarp();
 }

@@ -37,6 +37,7 @@ struct FastLayoutOps {
   cudaError_t (*attrs_rare)(int dyn_env);
   void (*replay)(int grid, int block, size_t dyn, cudaStream_t stream, const AdvParams& p, const EnvConst& ec);
   void (*replay_flat)(int grid, int block, size_t dyn, cudaStream_t stream, const AdvParams& p, const EnvConst& ec);
+  void (*to_sorted)(unsigned char* blobs, int n_envs, cudaStream_t stream);
   void (*env)(bool sync, int grid, int block, size_t dyn, cudaStream_t stream, const AdvParams& p, const EnvConst& ec);
   void (*env_rare)(bool sync, int grid, int block, size_t dyn, cudaStream_t stream, const AdvParams& p, const EnvConst& ec);
 };
@@ -45,11 +46,12 @@ struct FastLayoutOps {
   cudaError_t lobsim_fast##i##_attrs_rare(int);                                                                            \
   void lobsim_fast##i##_replay(int, int, size_t, cudaStream_t, const AdvParams&, const EnvConst&);                         \
   void lobsim_fast##i##_replay_flat(int, int, size_t, cudaStream_t, const AdvParams&, const EnvConst&);                    \
+  void lobsim_fast##i##_to_sorted(unsigned char*, int, cudaStream_t);                                                      \
   void lobsim_fast##i##_env(bool, int, int, size_t, cudaStream_t, const AdvParams&, const EnvConst&);                      \
   void lobsim_fast##i##_env_rare(bool, int, int, size_t, cudaStream_t, const AdvParams&, const EnvConst&);
 LOBSIM_FAST_LAYOUTS(X)
 #undef X
-#define X(i, nl, no, na) {nl, no, na, lobsim_fast##i##_attrs, lobsim_fast##i##_attrs_rare, lobsim_fast##i##_replay, lobsim_fast##i##_replay_flat, lobsim_fast##i##_env, lobsim_fast##i##_env_rare},
+#define X(i, nl, no, na) {nl, no, na, lobsim_fast##i##_attrs, lobsim_fast##i##_attrs_rare, lobsim_fast##i##_replay, lobsim_fast##i##_replay_flat, lobsim_fast##i##_to_sorted, lobsim_fast##i##_env, lobsim_fast##i##_env_rare},
 static const FastLayoutOps g_fast_layouts[LOBSIM_N_FAST_LAYOUTS] = {LOBSIM_FAST_LAYOUTS(X)};
 #undef X
 static const FastLayoutOps* find_fast_layout(const Layout& L) {
@@ -123,7 +125,16 @@ __global__ void k_get_state(const unsigned char* blobs, Layout L, int first, int
   s.err = h->err; s.stream_id = h->stream_id; s.n_agent_orders[0] = h->nag[0]; s.n_agent_orders[1] = h->nag[1];
   s.next_agent_id = h->next_agent_id; s.reserved = 0;
   int best[2] = {0, INT32_MAX}, bvol[2] = {0, 0};
-  for (int side = 0; side < 2; side++) {
+  const bool flat = h->cnt[0][0] < 0;   // the flat form (book_flat.cuh): cnt[side][1] orders {price, volume, ref, seq} at the order array
+  for (int side = 0; flat && side < 2; side++) {
+    const int n = h->cnt[side][1];
+    const uint4* pool = reinterpret_cast<const uint4*>(blob + L.side_off + side * L.side_stride + L.ord_off);
+    int bp = side ? INT32_MAX : INT32_MIN, v = 0;
+    for (int k = 0; k < n; k++) { const int pr = (int)pool[k].x; if (side ? pr < bp : pr > bp) bp = pr; }
+    for (int k = 0; k < n; k++) if ((int)pool[k].x == bp) v += (int)pool[k].y;
+    if (n) { best[side] = bp; bvol[side] = v; }
+  }
+  for (int side = 0; !flat && side < 2; side++) {
     int nlv = h->cnt[side][0];
     if (!nlv) continue;
     const unsigned char* sb = blob + L.side_off + side * L.side_stride;
@@ -187,6 +198,9 @@ struct lobsim {
   bool has_reset = false;
   bool force_general = false;         // LOBSIM_FORCE_GENERAL=1: always use the runtime-layout kernels (testing)
   bool replay_flat = true;            // LOBSIM_REPLAY_FLAT=0: the replay fast path keeps every book in the sorted level arrays (A/B, testing)
+  bool flat_blobs = true;             // LOBSIM_FLAT_BLOBS=0: the fast kernels never keep a book in the flat order pools across launches
+                                      // (env kernels: sorted path only; replay: converts back at the end of every launch)
+  bool maybe_flat = false;            // some blob in HBM may be in the flat form: ensure_sorted() before anything that reads level arrays
   bool agent_orders_possible = false; // an agent order may rest in some book (disables the replay fast path)
   const FastLayoutOps* fast = nullptr; // compiled straight-line kernels for these capacities, or null: general kernel
   int64_t launches = 0;
@@ -254,6 +268,7 @@ int lobsim_create(const lobsim_cfg_t* cfg, int device, lobsim_t** out) {
   h->cfg = *cfg; h->device = device;
   { const char* e = getenv("LOBSIM_FORCE_GENERAL"); h->force_general = e && e[0] == '1'; }
   { const char* e = getenv("LOBSIM_REPLAY_FLAT"); h->replay_flat = !(e && e[0] == '0'); }
+  { const char* e = getenv("LOBSIM_FLAT_BLOBS"); h->flat_blobs = !(e && e[0] == '0'); }
   h->rare_paths = cfg->step_reward.kind == LOBSIM_REWARD_ROLLING_SHARPE || cfg->terminal_reward.kind == LOBSIM_REWARD_ROLLING_SHARPE;
   for (int i = 0; i < cfg->n_features; i++) h->rare_paths = h->rare_paths || cfg->features[i].norm_len > 0;
   h->L = make_layout(cfg->max_levels_per_side, cfg->max_orders_per_side, cfg->max_agent_orders);
@@ -392,12 +407,25 @@ static void base_params(lobsim* h, AdvParams& p) {
   p.blobs = h->blobs; p.fstate = h->fstate; p.nstate = h->nstate; p.beta_tab = h->beta_tab; p.rings = h->rings; p.rs_ring = h->rs_ring; p.rs_state = h->rs_state; p.streams = h->streams_dev; p.n_streams = (int)h->streams.size();
   p.fill_log = h->fill_log; p.fill_count = h->fill_count; p.fill_cap = h->cfg.fill_log_capacity;
   p.n_envs = h->cfg.n_envs; p.n_sel = h->cfg.n_envs; p.L = h->L; p.warp_smem = h->warp_smem;
+  p.allow_flat = h->fast && h->flat_blobs ? 1 : 0;
+}
+
+// Flat blobs (book_flat.cuh) exist only between launches of the straight-line kernels; everything else reads the level arrays.
+static int ensure_sorted(lobsim* h, cudaStream_t stream) {
+  if (!h->maybe_flat || !h->fast) return LOBSIM_OK;
+  CUDA_TRY(cudaSetDevice(h->device));
+  h->fast->to_sorted(h->blobs, h->cfg.n_envs, stream);
+  CUDA_TRY(cudaGetLastError());
+  h->launches++;
+  h->maybe_flat = false;
+  return LOBSIM_OK;
 }
 
 } // extern "C"
 
 template <bool kEnv, bool kTrack>
 static int launch_advance(lobsim* h, const AdvParams& p, cudaStream_t stream) {
+  { int rc = ensure_sorted(h, stream); if (rc) return rc; }
   if (h->streams.empty()) return fail(LOBSIM_E_STATE, "no stream loaded");
   CUDA_TRY(cudaSetDevice(h->device));
   int wpc = h->warps_per_cta;
@@ -415,6 +443,8 @@ static int launch_replay_fast(lobsim* h, const AdvParams& p, cudaStream_t stream
   CUDA_TRY(cudaSetDevice(h->device));
   const int wpc = h->warps_per_cta, grid = (p.n_sel + wpc - 1) / wpc;
   if (grid <= 0) return LOBSIM_OK;
+  if (!h->replay_flat) { int rc = ensure_sorted(h, stream); if (rc) return rc; }
+  else if (p.allow_flat) h->maybe_flat = true;
   (h->replay_flat ? h->fast->replay_flat : h->fast->replay)(grid, wpc * 32, (size_t)wpc * h->warp_smem, stream, p, h->ec);
   CUDA_TRY(cudaGetLastError());
   h->launches++;
@@ -431,6 +461,8 @@ static int launch_env(lobsim* h, const AdvParams& p, cudaStream_t stream) {
   const size_t dyn = (size_t)wpc * h->warp_smem;
   const int full = p.n_sel / wpc, tail = p.n_sel % wpc;
   auto launch = h->rare_paths ? h->fast->env_rare : h->fast->env;
+  if (p.allow_flat) h->maybe_flat = true;
+  else { int rc = ensure_sorted(h, stream); if (rc) return rc; }
   if (full > 0) { // full CTAs: phase-synchronous
     launch(true, full, wpc * 32, dyn, stream, p, h->ec);
     CUDA_TRY(cudaGetLastError());
@@ -563,6 +595,7 @@ int lobsim_set_book(lobsim_t* h, int32_t env, const lobsim_book_entry_t* buy, in
   const Layout& L = h->L;
   if (n_buy > L.NO || n_sell > L.NO) return fail(LOBSIM_E_INVALID, "more orders than max_orders_per_side");
   CUDA_TRY(cudaSetDevice(h->device));
+  { int rc = ensure_sorted(h, 0); if (rc) return rc; }
   CUDA_TRY(cudaDeviceSynchronize());
   std::vector<unsigned char> buf(L.blob_bytes);
   unsigned char* gblob = h->blobs + (size_t)env * L.blob_bytes;
@@ -675,6 +708,7 @@ int lobsim_process_orders(lobsim_t* h, const lobsim_order_t* orders, int32_t n, 
   OrdParams p; p.blobs = h->blobs; p.L = h->L; p.n_envs = h->cfg.n_envs; p.orders = d_orders; p.n = n;
   p.fills = max_fills > 0 ? d_fills : nullptr; p.max_fills = max_fills; p.n_fills = d_nf; p.refs_out = d_refs;
   h->agent_orders_possible = true;
+  { int rc = ensure_sorted(h, 0); if (rc) return rc; }
   k_process_orders<<<1, 32, h->L.blob_bytes>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
@@ -693,6 +727,7 @@ int lobsim_process_orders(lobsim_t* h, const lobsim_order_t* orders, int32_t n, 
 static int fetch_blob(lobsim* h, int env, std::vector<unsigned char>& buf) {
   if (env < 0 || env >= h->cfg.n_envs) return fail(LOBSIM_E_INVALID, "bad env index");
   CUDA_TRY(cudaSetDevice(h->device));
+  { CUDA_TRY(cudaDeviceSynchronize()); int rc = ensure_sorted(h, 0); if (rc) return rc; }
   buf.resize(h->L.blob_bytes);
   CUDA_TRY(cudaMemcpy(buf.data(), h->blobs + (size_t)env * h->L.blob_bytes, h->L.blob_bytes, cudaMemcpyDeviceToHost));
   return LOBSIM_OK;

@@ -56,7 +56,7 @@ class BetaPolicy(nn.Module):
 
     def dist(self, obs: torch.Tensor) -> torch.distributions.Beta:
         a, b = (nn.functional.softplus(self.pi(obs)) + 1.0).chunk(2, dim=-1)      # unimodal: a, b > 1
-        return torch.distributions.Beta(a, b)
+        return torch.distributions.Beta(a, b, validate_args=False)   # (validation synchronises: not allowed while a CUDA graph is captured)
 
     def forward(self, obs: torch.Tensor):
         return self.dist(obs), self.vf(obs).squeeze(-1)
@@ -92,7 +92,7 @@ class RunningNorm:
         self.n.copy_(tot)
 
     def __call__(self, x: torch.Tensor) -> torch.Tensor:
-        std = torch.sqrt(self.m2 / torch.clamp(self.n, min=1.0)).clamp(min=1e-8)
+        std = torch.sqrt(torch.clamp(self.m2, min=0.0) / torch.clamp(self.n, min=1.0)).clamp(min=1e-8)   # (m2 of a constant feature can round below 0)
         z = (torch.nan_to_num(x.double(), nan=0.0, posinf=0.0, neginf=0.0) - self.mean) / std
         return z.clamp(-10.0, 10.0).float()
 

@@ -11,22 +11,18 @@ for p in (str(ROOT), str(ROOT / "tests")):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with `-m gpu`)")
-    config.addinivalue_line("markers", "replay_path: GPU test that goes through lobsim_replay -- also run with "
-                                       "LOBSIM_REPLAY_FLAT=0 (every book on the sorted level arrays of k_replay_fast instead "
-                                       "of the flat order pools of k_replay_flat)")
+    config.addinivalue_line("markers", "replay_path: GPU test that goes through lobsim_replay (kept for selection with -m)")
     config.addinivalue_line("markers", "fast_only: GPU test that is about the straight-line kernels only (not repeated "
                                        "on the general kernel family)")
 
 
 def pytest_generate_tests(metafunc):
-    """Every GPU test runs twice: on the straight-line static-layout kernels ("fast") and, with LOBSIM_FORCE_GENERAL=1,
-    on the general runtime-layout kernel ("general") -- two independent implementations of the same semantics.  Tests
-    marked `replay_path` run a third time on the sorted-array replay kernel ("sorted": LOBSIM_REPLAY_FLAT=0), since
-    "fast" replays on the flat order pools (book_flat.cuh) -- a third implementation of the order semantics."""
+    """Every GPU test runs on three independent implementations of the order semantics: "fast" = the straight-line static-layout
+    kernels with every book that fits in the flat order pools of book_flat.cuh (in shared memory and in HBM); "sorted" = the same
+    kernels on the sorted level arrays only (LOBSIM_REPLAY_FLAT=0, LOBSIM_FLAT_BLOBS=0); "general" = the runtime-layout kernel
+    (LOBSIM_FORCE_GENERAL=1)."""
     if "kernel_family" in metafunc.fixturenames and metafunc.definition.get_closest_marker("gpu"):
-        fams = ["fast"] if metafunc.definition.get_closest_marker("fast_only") else ["fast", "general"]
-        if metafunc.definition.get_closest_marker("replay_path"):
-            fams.insert(1, "sorted")
+        fams = ["fast"] if metafunc.definition.get_closest_marker("fast_only") else ["fast", "sorted", "general"]
         metafunc.parametrize("kernel_family", fams, indirect=True)
 
 
@@ -36,6 +32,7 @@ def kernel_family(request, monkeypatch):
     if fam is not None:
         monkeypatch.setenv("LOBSIM_FORCE_GENERAL", "1" if fam == "general" else "0")
         monkeypatch.setenv("LOBSIM_REPLAY_FLAT", "0" if fam == "sorted" else "1")
+        monkeypatch.setenv("LOBSIM_FLAT_BLOBS", "0" if fam == "sorted" else "1")
     return fam
 
 

@@ -114,6 +114,7 @@ def test_random_replay_case(seed, monkeypatch):
     for force_general, flat in (("0", "1"), ("0", "0"), ("1", "1")):
         monkeypatch.setenv("LOBSIM_FORCE_GENERAL", force_general)
         monkeypatch.setenv("LOBSIM_REPLAY_FLAT", flat)
+        monkeypatch.setenv("LOBSIM_FLAT_BLOBS", flat)
         sim = make_sim(abi.default_cfg(n_envs=n, **c["cfg_kw"]), [s])
         oracles = [Oracle(abi.default_cfg(n_envs=1, **okw), s) for _ in range(n)]
         sim.reset_book(0, c["starts"])
