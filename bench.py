@@ -238,7 +238,8 @@ def rollout_cfg(n_envs: int, stream):
     return abi.default_cfg(n_envs=n_envs, n_levels=stream.n_levels, episode_steps=18000, warmup_steps=warm,
                            features=[f.to_abi() for f in feats], step_reward=abi.Reward(abi.REWARD_PNL, 0, 0.0),
                            terminal_reward=abi.Reward(abi.REWARD_PNL, 0, 0.0), initial_cash=1000.0,
-                           max_levels_per_side=64, max_orders_per_side=256, max_agent_orders=64, outer_levels=20)
+                           max_levels_per_side=int(os.environ.get("LOBSIM_BENCH_NL", "64")), max_orders_per_side=256, max_agent_orders=64,
+                           outer_levels=20)
 
 
 def run_reference(args):
@@ -566,6 +567,10 @@ def run_rollout(ctx: Ctx, stream):
                              "k_env_fast" if n_envs == 65536 else None),
     }
     ctx.launches += launches
+    form = sim.state()["reserved"]                      # lobsim_env_state_t.reserved: bit 0 flat form, bits 8-19 / 20-31 orders per side
+    n_side = np.maximum((form >> 8) & 0xfff, (form >> 20) & 0xfff)
+    rec["book_forms"] = {"flat_fraction": float((form & 1).mean()), "orders_per_side_p50": float(np.median(n_side)),
+                         "orders_per_side_p99": float(np.percentile(n_side, 99)), "orders_per_side_max": int(n_side.max())}
     if ctx.rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         v, dt, n_cpu = cpu_oracle_env_throughput(stream, cfg, threads, 8000)

@@ -235,7 +235,8 @@ typedef struct {
   int32_t stream_id;
   uint32_t n_agent_orders[2];
   uint32_t next_agent_id;
-  uint32_t reserved;
+  uint32_t reserved;   /* book form: bit 0 = the blob is in the flat order-pool form (csrc/book_flat.cuh) between launches;
+                          bits 8-19 / 20-31 = resting orders on the buy / sell side (clamped to 4095)              */
 } lobsim_env_state_t;
 
 typedef struct lobsim lobsim_t;

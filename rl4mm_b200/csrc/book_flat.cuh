@@ -1,58 +1,84 @@
-// book_flat.cuh -- the FLAT book of the replay kernel: a side is an unordered pool of resting orders
+// book_flat.cuh -- the FLAT book: a side is an unordered pool of resting orders
 //
-//     pool[s][i] = { price, volume, ref, seq }      i < n[s] <= FLAT_CAP (64), 16 bytes per order, no gaps
+//     pool[s][i] = { price, ref, volume, seq }      i < n[s] <= FLAT_CAP, 16 bytes per order, no gaps
 //
 // with NO level structure at all.  It is the reference's `SortedDict[price -> deque[LimitOrder]]` (rl4mm/orderbook/models.py:64-69)
-// for books that are small enough that one or two warp-wide compares see every resting order of a side (BASELINE config 2: 8-12
-// levels and 30-55 orders per side):
+// for books that are small enough that a few warp-wide compares see every resting order of a side (BASELINE config 2: 8-12
+// levels and 30-55 orders per side; configs 3 / 4 with the agent's ladders: 60-100):
 //   * price-time priority is carried by `seq`, a per-book counter stamped when an order starts resting (Exchange.py:78-83 appends
 //     to the level's deque): the head of a level = the order with the smallest seq at that price (one REDUX.MIN);
 //   * a new order is ONE 16-byte store at pool[n] (no level search, no level insert, no queue shift, no prefix-end update);
-//   * a cancellation / deletion finds (price, ref) with two 16-byte loads per lane + ballots and fills the hole with the last
-//     order (one load + one store) -- Exchange.remove_order / _find_queue_position, Exchange.py:122-147,196-217;
+//   * a cancellation / deletion finds (price, ref) with one 8-byte load per lane and 32-order chunk + ballots and fills the hole
+//     with the last order (one load + one store) -- Exchange.remove_order / _find_queue_position, Exchange.py:122-147,196-217;
 //   * the best price of a side lives in a register and is recomputed (REDUX.MAX / MIN over the prices already in registers)
 //     only when the last order at the best price leaves.
-// About 45 warp instructions per message against 110 for the sorted level arrays of book_fast.cuh (profiles/r02_replay_ab.md).
+// 69 warp instructions per message against 110 for the sorted level arrays of book_fast.cuh (profiles/r02_replay_ab.md).
 //
-// The HBM blob stays in the canonical sorted layout (book.cuh): the kernel converts on entry (flat_enter: trivial, seq = position
-// in the sorted order array) and on exit (flat_leave: rank-by-counting sort on (price, seq)), so every other kernel, the L3 dump
-// and the env path are untouched.  A book that does not fit (more than FLAT_CAP orders on a side) runs on the sorted path of
-// book_fast.cuh in the same kernel and moves back when it has shrunk; update_outer_levels (OrderbookSimulator.py:105-135) is
-// run on the sorted form (leave -> fast_resync -> enter) on the seconds where the snapshot really has levels beyond the range.
+// FLAT_CAP = 32 * NCH orders per side, NCH = 2 or 4 chunks by the handle's capacities (flat_nch<LT>): a flat side may hold
+// FLAT_CAP distinct prices, so the sorted layout must have room for as many levels, and the pool lives in the side's order array.
+//
+// A book is flat or sorted PER BOOK: in shared memory during a launch, and in HBM between launches (header marker, kernels.cuh) --
+// one launch is one env step when a policy runs in between, so converting per launch would cost more than the flat path saves.
+// Conversions: flat_enter (sorted -> flat: trivial, seq = position in the sorted order array) when a book fits with some slack;
+// flat_leave (flat -> sorted: rank-by-counting sort on (price, seq)) when a pool is full, when update_outer_levels
+// (OrderbookSimulator.py:105-135) really has a level to overwrite (leave -> resync on the sorted form -> enter), and by k_to_sorted
+// before anything outside the straight-line kernels reads a book.
 #pragma once
 #include "book_fast.cuh"
-
-#define FLAT_CAP 64
 
 struct FlatState {
   int n0, n1;      // resting orders per side
   uint32_t seq;    // next time-priority stamp
 };
 
+// chunks of 32 orders per side that the flat form of this layout may use
+template <class LT>
+__host__ __device__ constexpr int flat_nch() { return (LT::NL >= 128 && LT::NO >= 256) ? 4 : 2; }
+template <class LT>
+__host__ __device__ constexpr int flat_cap() { return 32 * flat_nch<LT>(); }
+
 template <class LT>
 __device__ __forceinline__ uint4* flat_pool(unsigned char* blob, int s) {
-  static_assert(LT::NO * 8 >= FLAT_CAP * 16, "the flat pool (FLAT_CAP x 16 B) lives in the order array of the side");
-  static_assert(LT::NL >= FLAT_CAP, "a flat side may hold FLAT_CAP distinct prices");
+  static_assert(LT::NO * 8 >= flat_cap<LT>() * 16, "the flat pool (FLAT_CAP x 16 B) lives in the order array of the side");
+  static_assert(LT::NO * 8 >= flat_cap<LT>() * 12, "flat_leave: sorted orders (8 B) + one price per order (4 B) in the order array");
+  static_assert(LT::NL >= flat_cap<LT>(), "a flat side may hold FLAT_CAP distinct prices");
   static_assert(LT::ord_off % 16 == 0 && LT::side_stride % 16 == 0 && LT::side_off % 16 == 0, "16-byte aligned pool");
   return reinterpret_cast<uint4*>(blob + LT::side_off + s * LT::side_stride + LT::ord_off);
 }
 
-#define FLAT_EMPTY_ENTRY make_uint4(0u, 0u, 0xffffffffu, 0xffffffffu)   // ref / seq that no resting order has
-
-// both chunks of a side's pool, one order per lane and chunk
-__device__ __forceinline__ void flat_load(const uint4* pool, int n, int lane, uint4& e0, uint4& e1) {
-  e0 = FLAT_EMPTY_ENTRY; e1 = FLAT_EMPTY_ENTRY;
-  if (lane < n) e0 = pool[lane];
-  if (lane + 32 < n) e1 = pool[lane + 32];
+// (price, ref) of every order of a side, one order per lane and chunk; lanes beyond n: a ref that no resting order has
+template <int NCH>
+__device__ __forceinline__ void flat_keys(const uint4* pool, int n, int lane, uint2 (&k)[NCH]) {
+#pragma unroll
+  for (int c = 0; c < NCH; c++) {
+    k[c] = make_uint2(0u, 0xffffffffu);
+    if (c * 32 + lane < n) k[c] = *reinterpret_cast<const uint2*>(&pool[c * 32 + lane]);
+  }
 }
-
-// best price of side S over the orders in registers, leaving out entry `skip` (-1: none)
-template <int S>
-__device__ __forceinline__ int flat_best_of(const uint4& e0, const uint4& e1, int n, int lane, int skip) {
-  const int sent = S ? INT32_MAX : INT32_MIN;
-  const int k0 = (lane < n && lane != skip) ? (int)e0.x : sent;
-  const int k1 = (lane + 32 < n && lane + 32 != skip) ? (int)e1.x : sent;
-  return S ? __reduce_min_sync(FULL_MASK, k0 < k1 ? k0 : k1) : __reduce_max_sync(FULL_MASK, k0 > k1 ? k0 : k1);
+// first set bit of a per-chunk ballot array -> order index (the array is not all zero)
+template <int NCH>
+__device__ __forceinline__ int flat_first(const unsigned (&m)[NCH]) {
+  int i = 0;
+#pragma unroll
+  for (int c = NCH - 1; c >= 0; c--) if (m[c]) i = c * 32 + __ffs(m[c]) - 1;
+  return i;
+}
+// best price of side S over the keys in registers, leaving out order `skip` (-1: none)
+template <int S, int NCH>
+__device__ __forceinline__ int flat_best_of(const uint2 (&k)[NCH], int n, int lane, int skip) {
+  int b = S ? INT32_MAX : INT32_MIN;
+#pragma unroll
+  for (int c = 0; c < NCH; c++) {
+    const int i = c * 32 + lane;
+    if (i < n && i != skip) b = S ? min(b, (int)k[c].x) : max(b, (int)k[c].x);
+  }
+  return S ? __reduce_min_sync(FULL_MASK, b) : __reduce_max_sync(FULL_MASK, b);
+}
+template <class LT, int S>
+__device__ __forceinline__ int flat_best_scan(unsigned char* blob, int lane, int n) {
+  uint2 k[flat_nch<LT>()];
+  flat_keys(flat_pool<LT>(blob, S), n, lane, k);
+  return flat_best_of<S>(k, n, lane, -1);
 }
 
 // One order of side S (0 buy, 1 sell) through the flat book.  Same results as fast_order_full<LT,TR> on the sorted book; TR: fills /
@@ -62,6 +88,7 @@ __device__ __forceinline__ int flat_best_of(const uint4& e0, const uint4& e1, in
 template <class LT, int S, bool TR>
 __device__ __forceinline__ bool flat_order(unsigned char* blob, int lane, FastState& f, FlatState& st, int type, int price, int vol, uint32_t ref, bool is_agent) {
   constexpr int OPP = S ^ 1;
+  constexpr int NCH = flat_nch<LT>();
   if (!TR) is_agent = false;
   int& n_own = S ? st.n1 : st.n0;
   int& n_opp = S ? st.n0 : st.n1;
@@ -74,7 +101,7 @@ __device__ __forceinline__ bool flat_order(unsigned char* blob, int lane, FastSt
   __syncwarp();                                                             // the previous order's stores are visible
   if (type == LOBSIM_MSG_LIMIT || type == LOBSIM_MSG_MARKET) {
     int rem = vol;
-    if (type == LOBSIM_MSG_LIMIT && n_own >= FLAT_CAP) return false;
+    if (type == LOBSIM_MSG_LIMIT && n_own >= flat_cap<LT>()) return false;
     const bool crosses = S ? price <= best_opp : price >= best_opp;        // empty opposite side: INT32_MIN / INT32_MAX
     if (type == LOBSIM_MSG_MARKET || crosses) {
       // ---- execution against the opposite side, best price first, oldest order first (Exchange.py:85-120) -------------
@@ -86,14 +113,24 @@ __device__ __forceinline__ bool flat_order(unsigned char* blob, int lane, FastSt
         }
         const int bp = best_opp;
         if (type == LOBSIM_MSG_LIMIT && !(S ? price <= bp : price >= bp)) break;
-        uint4 e0, e1;
-        flat_load(opp, n_opp, lane, e0, e1);
-        const unsigned q0 = (int)e0.x == bp ? e0.w : 0xffffffffu, q1 = (int)e1.x == bp ? e1.w : 0xffffffffu;   // empty lanes: seq = ~0
-        const unsigned head_seq = __reduce_min_sync(FULL_MASK, q0 < q1 ? q0 : q1);
-        const unsigned b0 = __ballot_sync(FULL_MASK, q0 == head_seq), b1 = __ballot_sync(FULL_MASK, q1 == head_seq);
-        const int i = b0 ? __ffs(b0) - 1 : 32 + __ffs(b1) - 1;              // the head of the best queue
-        const int hv = (int)__shfl_sync(FULL_MASK, b0 ? e0.y : e1.y, i & 31);
-        const uint32_t href = TR ? __shfl_sync(FULL_MASK, b0 ? e0.z : e1.z, i & 31) : 0u;
+        unsigned q[NCH], qmin = 0xffffffffu;                                // seq of the orders at the best price, ~0 elsewhere
+#pragma unroll
+        for (int c = 0; c < NCH; c++) {
+          q[c] = 0xffffffffu;
+          if (c * 32 + lane < n_opp) { const uint4 e = opp[c * 32 + lane]; if ((int)e.x == bp) q[c] = e.w; }
+          qmin = min(qmin, q[c]);
+        }
+        const unsigned head_seq = __reduce_min_sync(FULL_MASK, qmin);
+        unsigned hm[NCH]; int at_best = 0;
+#pragma unroll
+        for (int c = 0; c < NCH; c++) {
+          hm[c] = __ballot_sync(FULL_MASK, q[c] == head_seq);
+          at_best += __popc(__ballot_sync(FULL_MASK, q[c] != 0xffffffffu));
+        }
+        const int i = flat_first(hm);                                       // the head of the best queue
+        const uint4 he = opp[i];
+        const int hv = (int)he.z;
+        const uint32_t href = he.y;
         const bool hagent = TR && (href & LOBSIM_REF_AGENT) != 0;
         const bool self_match = TR && is_agent && hagent;                  // cannot fill our own order => delete it, :91-94
         if (!self_match) {
@@ -104,15 +141,20 @@ __device__ __forceinline__ bool flat_order(unsigned char* blob, int lane, FastSt
             if (is_agent) fast_record(fb, f, 0, S, bp, v, 1, href);         // the synthetic MarketOrder fill, :111-115
           }
           if (rem < hv) {                                                  // partial fill of the head
-            if (lane == 0) opp[i].y = (unsigned)(hv - rem);
+            __syncwarp();
+            if (lane == 0) opp[i].z = (unsigned)(hv - rem);
             if (TR && hagent) { __syncwarp(); fast_agent_reduce(fb, OPP, href & 0x7fffffffu, rem, false); }
             rem = 0;
             break;
           }
           rem -= hv;                                                       // the head is consumed
         }
-        const int at_best = __popc(__ballot_sync(FULL_MASK, q0 != 0xffffffffu)) + __popc(__ballot_sync(FULL_MASK, q1 != 0xffffffffu));
-        if (at_best == 1) best_opp = flat_best_of<OPP>(e0, e1, n_opp, lane, i);   // the level emptied
+        if (at_best == 1) {                                                // the level emptied: next best price
+          uint2 k[NCH];
+          flat_keys(opp, n_opp, lane, k);
+          best_opp = flat_best_of<OPP>(k, n_opp, lane, i);
+        }
+        __syncwarp();
         if (lane == 0) opp[i] = opp[n_opp - 1];
         n_opp -= 1;
         __syncwarp();
@@ -135,39 +177,43 @@ __device__ __forceinline__ bool flat_order(unsigned char* blob, int lane, FastSt
         h->nag[S] = nag + 1; h->next_agent_id = id + 1;
       }
     }
-    if (lane == 0) own[n_own] = make_uint4((unsigned)price, (unsigned)rem, ref, st.seq);
+    if (lane == 0) own[n_own] = make_uint4((unsigned)price, ref, (unsigned)rem, st.seq);
     n_own += 1; st.seq += 1;
     if (S ? price < best_own : price > best_own) best_own = price;
     return true;
   }
   // ---- cancellation / deletion (Exchange.py:122-147) ----------------------------------------------------------------------
-  uint4 e0, e1;
-  flat_load(own, n_own, lane, e0, e1);
-  unsigned m0 = __ballot_sync(FULL_MASK, (int)e0.x == price && e0.z == ref), m1 = __ballot_sync(FULL_MASK, (int)e1.x == price && e1.z == ref);
+  uint2 k[NCH];
+  flat_keys(own, n_own, lane, k);
+  unsigned m[NCH], any = 0;
+#pragma unroll
+  for (int c = 0; c < NCH; c++) { m[c] = __ballot_sync(FULL_MASK, (int)k[c].x == price && k[c].y == ref); any |= m[c]; }
   bool aggregate = false;
-  if (!(m0 | m1)) {
+  if (!any) {
     // unknown id: the level's snapshot aggregate (internal_id -1, always the head of its level) takes the hit (:133-137);
     // no such level, or no aggregate left at it: nothing happens (:129-132,138-139)
-    m0 = __ballot_sync(FULL_MASK, lane < n_own && (int)e0.x == price && e0.z == LOBSIM_REF_AGGREGATE);
-    m1 = __ballot_sync(FULL_MASK, lane + 32 < n_own && (int)e1.x == price && e1.z == LOBSIM_REF_AGGREGATE);
-    if (!(m0 | m1)) return true;
+#pragma unroll
+    for (int c = 0; c < NCH; c++) { m[c] = __ballot_sync(FULL_MASK, c * 32 + lane < n_own && (int)k[c].x == price && k[c].y == LOBSIM_REF_AGGREGATE); any |= m[c]; }
+    if (!any) return true;
     aggregate = true;
   }
-  const int i = m0 ? __ffs(m0) - 1 : 32 + __ffs(m1) - 1;
-  const int cur = (int)__shfl_sync(FULL_MASK, m0 ? e0.y : e1.y, i & 31);
+  const int i = flat_first(m);
+  const int cur = (int)own[i].z;
+  __syncwarp();
   if (vol < cur) {                                                         // partial: reduce in place
-    if (lane == 0) own[i].y = (unsigned)(cur - vol);
+    if (lane == 0) own[i].z = (unsigned)(cur - vol);
     if (TR && is_agent && !aggregate) { __syncwarp(); fast_agent_reduce(fb, S, ref & 0x7fffffffu, vol, false); }
     return true;
   }
   // full removal (over-size requests remove the resting volume, :142-146): the last order of the pool fills the hole
-  if (price == best_own) best_own = flat_best_of<S>(e0, e1, n_own, lane, i);
+  if (price == best_own) best_own = flat_best_of<S>(k, n_own, lane, i);
   if (lane == 0) own[i] = own[n_own - 1];
   n_own -= 1;
   if (TR && is_agent && !aggregate) { __syncwarp(); fast_agent_reduce(fb, S, ref & 0x7fffffffu, cur, true); }
   return true;
 }
 
+// the replay form: a packed historical message
 template <class LT>
 __device__ __forceinline__ bool flat_message(unsigned char* blob, int lane, FastState& f, FlatState& st, int price, int vol, uint32_t ref, uint32_t meta) {
   const int type = (int)(meta & 7u);
@@ -185,99 +231,123 @@ __device__ __forceinline__ bool flat_order_tracked(unsigned char* blob, int lane
 template <class LT, int S>
 __device__ __forceinline__ int flat_best_volume(unsigned char* blob, int lane, const FastState& f, const FlatState& st) {
   const int n = S ? st.n1 : st.n0, best = S ? f.best1 : f.best0;
-  uint4 e0, e1;
-  flat_load(flat_pool<LT>(blob, S), n, lane, e0, e1);
-  const int v = ((lane < n && (int)e0.x == best) ? (int)e0.y : 0) + ((lane + 32 < n && (int)e1.x == best) ? (int)e1.y : 0);
+  const uint4* pool = flat_pool<LT>(blob, S);
+  int v = 0;
+#pragma unroll
+  for (int c = 0; c < flat_nch<LT>(); c++)
+    if (c * 32 + lane < n) { const uint4 e = pool[c * 32 + lane]; if ((int)e.x == best) v += (int)e.z; }
   return __reduce_add_sync(FULL_MASK, v);
 }
 
-// ---- sorted -> flat (kernel entry, and after a resync / when a book has shrunk) ---------------------------------------------
+// ---- sorted -> flat (kernel entry, after a reset / resync, when a book has shrunk) ----------------------------------------------
 template <class LT>
 __device__ __forceinline__ bool flat_fits(const FastBook<LT>& fb, int slack) {
-  return fb.cnt(0)->y <= FLAT_CAP - slack && fb.cnt(1)->y <= FLAT_CAP - slack;
+  return fb.cnt(0)->y <= flat_cap<LT>() - slack && fb.cnt(1)->y <= flat_cap<LT>() - slack;
 }
-// precondition: flat_fits(fb, 0); f.best0 / f.best1 are current
+// precondition: flat_fits(fb, 0).  Returns {n0, n1}; seq restarts at FLAT_CAP (above every position stamp).
 template <class LT>
-__device__ __forceinline__ void flat_enter(const FastBook<LT>& fb, FlatState& st) {
-  const int lane = fb.lane;
+static __device__ __noinline__ int2 flat_enter_fn(unsigned char* blob, int lane) {
+  constexpr int NCH = flat_nch<LT>();
+  FastBook<LT> fb; fb.blob = blob; fb.lane = lane;
+  int2 out = make_int2(0, 0);
   __syncwarp();
-#pragma unroll
+#pragma unroll 1
   for (int s = 0; s < 2; s++) {
     unsigned char* sb = fb.side(s);
     const int2 c = *fb.cnt(s);
     const int nlv = c.x, n = c.y;
-    uint2 o0 = make_uint2(0u, 0u), o1 = make_uint2(0u, 0u);
-    int p0 = 0, p1 = 0;
-    // the level of order i = the first level whose end offset is beyond i (binary search over the level ends)
-    auto price_of = [&](int i) {
-      int lo = 0, hi = nlv - 1;
+    uint2 o[NCH]; int pr[NCH];
+#pragma unroll
+    for (int ch = 0; ch < NCH; ch++) {
+      const int i = ch * 32 + lane;
+      o[ch] = make_uint2(0u, 0u); pr[ch] = 0;
+      if (i < n) {
+        o[ch] = fb.O(sb)[i];
+        int lo = 0, hi = nlv - 1;                 // the level of order i = the first level whose end offset is beyond i
 #pragma unroll 1
-      while (lo < hi) { const int mid = (lo + hi) >> 1; if ((int)fb.LE(sb)[mid] > i) hi = mid; else lo = mid + 1; }
-      return fb.P(sb)[lo];
-    };
-    if (lane < n) { o0 = fb.O(sb)[lane]; p0 = price_of(lane); }
-    if (lane + 32 < n) { o1 = fb.O(sb)[lane + 32]; p1 = price_of(lane + 32); }
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if ((int)fb.LE(sb)[mid] > i) hi = mid; else lo = mid + 1; }
+        pr[ch] = fb.P(sb)[lo];
+      }
+    }
     __syncwarp();                                                           // the pool overlays the order array
-    uint4* pool = flat_pool<LT>(fb.blob, s);
-    if (lane < n) pool[lane] = make_uint4((unsigned)p0, o0.x, o0.y, (unsigned)lane);
-    if (lane + 32 < n) pool[lane + 32] = make_uint4((unsigned)p1, o1.x, o1.y, (unsigned)(lane + 32));
-    if (s) st.n1 = n; else st.n0 = n;
+    uint4* pool = flat_pool<LT>(blob, s);
+#pragma unroll
+    for (int ch = 0; ch < NCH; ch++) {
+      const int i = ch * 32 + lane;
+      if (i < n) pool[i] = make_uint4((unsigned)pr[ch], o[ch].y, o[ch].x, (unsigned)i);
+    }
+    if (s) out.y = n; else out.x = n;
   }
-  st.seq = FLAT_CAP;
   __syncwarp();
+  return out;
+}
+template <class LT>
+__device__ __forceinline__ void flat_enter(const FastBook<LT>& fb, FlatState& st) {
+  const int2 n = flat_enter_fn<LT>(fb.blob, fb.lane);
+  st.n0 = n.x; st.n1 = n.y; st.seq = (uint32_t)flat_cap<LT>();
 }
 
-// ---- flat -> sorted (kernel exit, pool overflow, resync): rank every order by (price worst -> best, seq), scatter, rebuild the
-//      level prices / ends ----------------------------------------------------------------------------------------------------
+// ---- flat -> sorted: rank every order by (price worst -> best, seq), scatter, rebuild the level prices / ends ---------------
 template <class LT>
-__device__ __forceinline__ void flat_leave(const FastBook<LT>& fb, const FlatState& st) {
-  const int lane = fb.lane;
+static __device__ __noinline__ void flat_leave_fn(unsigned char* blob, int lane, int n0, int n1) {
+  constexpr int NCH = flat_nch<LT>();
+  FastBook<LT> fb; fb.blob = blob; fb.lane = lane;
   __syncwarp();
-#pragma unroll
+#pragma unroll 1
   for (int s = 0; s < 2; s++) {
     unsigned char* sb = fb.side(s);
-    const uint4* pool = flat_pool<LT>(fb.blob, s);
-    const int n = s ? st.n1 : st.n0;
-    uint4 e0, e1;
-    flat_load(pool, n, lane, e0, e1);
-    auto key = [&](const uint4& e) {                                        // ascending = worst -> best price, then oldest first
-      uint32_t pk = e.x ^ 0x80000000u;
-      if (s) pk = ~pk;
-      return ((unsigned long long)pk << 32) | e.w;
-    };
-    const unsigned long long k0 = key(e0), k1 = key(e1);
-    int r0 = 0, r1 = 0;
+    const uint4* pool = flat_pool<LT>(blob, s);
+    const int n = s ? n1 : n0;
+    const unsigned flip = s ? 0xffffffffu : 0u;                             // ascending key = worst -> best price, then oldest first
+    uint4 e[NCH]; unsigned long long k[NCH]; int r[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; c++) {
+      e[c] = make_uint4(0u, 0u, 0u, 0u);
+      if (c * 32 + lane < n) e[c] = pool[c * 32 + lane];
+      k[c] = ((unsigned long long)((e[c].x ^ 0x80000000u) ^ flip) << 32) | e[c].w;
+      r[c] = 0;
+    }
 #pragma unroll 1
     for (int m = 0; m < n; m++) {
-      const unsigned long long km = key(pool[m]);
-      r0 += km < k0 ? 1 : 0; r1 += km < k1 ? 1 : 0;
+      const uint4 em = pool[m];
+      const unsigned long long km = ((unsigned long long)((em.x ^ 0x80000000u) ^ flip) << 32) | em.w;
+#pragma unroll
+      for (int c = 0; c < NCH; c++) r[c] += km < k[c] ? 1 : 0;
     }
     __syncwarp();                                                           // every lane holds its orders: the arrays can be rewritten
-    if (lane < n) { fb.O(sb)[r0] = make_uint2(e0.y, e0.z); fb.P(sb)[r0] = (int)e0.x; }          // P: sorted price per ORDER for now
-    if (lane + 32 < n) { fb.O(sb)[r1] = make_uint2(e1.y, e1.z); fb.P(sb)[r1] = (int)e1.x; }
+    int32_t* tmp = reinterpret_cast<int32_t*>(fb.O(sb) + flat_cap<LT>());     // one sorted price per ORDER, behind the sorted orders
+#pragma unroll
+    for (int c = 0; c < NCH; c++)
+      if (c * 32 + lane < n) { fb.O(sb)[r[c]] = make_uint2(e[c].z, e[c].y); tmp[r[c]] = (int)e[c].x; }
     __syncwarp();
-    int t0 = 0, t1 = 0, pv0 = 0, pv1 = 0;
-    if (lane < n) t0 = fb.P(sb)[lane];
-    if (lane + 32 < n) t1 = fb.P(sb)[lane + 32];
-    if (lane > 0 && lane < n) pv0 = fb.P(sb)[lane - 1];
-    if (lane + 32 < n) pv1 = fb.P(sb)[lane + 31];
-    const bool new0 = lane < n && (lane == 0 || t0 != pv0), new1 = lane + 32 < n && t1 != pv1;   // first order of a level
-    const unsigned nb0 = __ballot_sync(FULL_MASK, new0), nb1 = __ballot_sync(FULL_MASK, new1);
+    int t[NCH]; unsigned nb[NCH + 1]; int below = 0;
+#pragma unroll
+    for (int c = 0; c < NCH; c++) {
+      const int i = c * 32 + lane;
+      t[c] = 0; int pv = 0;
+      if (i < n) t[c] = tmp[i];
+      if (i > 0 && i < n) pv = tmp[i - 1];
+      nb[c] = __ballot_sync(FULL_MASK, i < n && (i == 0 || t[c] != pv));   // first order of a level
+    }
+    nb[NCH] = 0;
     const unsigned le_mask = 0xffffffffu >> (31 - lane);                    // lanes <= this lane
-    const int lvl0 = __popc(nb0 & le_mask) - 1, lvl1 = __popc(nb0) + __popc(nb1 & le_mask) - 1;
-    // last order of a level: the next order starts a new level, or there is no next order
-    const bool next_new0 = lane == 31 ? (nb1 & 1u) != 0 : ((nb0 >> (lane + 1)) & 1u) != 0;
-    const bool next_new1 = lane == 31 ? false : ((nb1 >> (lane + 1)) & 1u) != 0;
-    const bool last0 = lane < n && (lane == n - 1 || next_new0), last1 = lane + 32 < n && (lane + 32 == n - 1 || next_new1);
-    __syncwarp();                                                           // the per-order prices have been read
-    if (new0) fb.P(sb)[lvl0] = t0;
-    if (new1) fb.P(sb)[lvl1] = t1;
-    if (last0) fb.LE(sb)[lvl0] = (uint16_t)(lane + 1);
-    if (last1) fb.LE(sb)[lvl1] = (uint16_t)(lane + 33);
-    if (lane == 0) *fb.cnt(s) = make_int2(__popc(nb0) + __popc(nb1), n);
+#pragma unroll
+    for (int c = 0; c < NCH; c++) {
+      const int i = c * 32 + lane;
+      const int lvl = below + __popc(nb[c] & le_mask) - 1;
+      const bool is_new = (nb[c] >> lane) & 1u;
+      // last order of a level: the next order starts a new level, or there is no next order
+      const bool next_new = lane == 31 ? (nb[c + 1] & 1u) != 0 : ((nb[c] >> (lane + 1)) & 1u) != 0;
+      if (is_new) fb.P(sb)[lvl] = t[c];
+      if (i < n && (i == n - 1 || next_new)) fb.LE(sb)[lvl] = (uint16_t)(i + 1);
+      below += __popc(nb[c]);
+    }
+    if (lane == 0) *fb.cnt(s) = make_int2(below, n);
+    __syncwarp();
   }
-  __syncwarp();
 }
+template <class LT>
+__device__ __forceinline__ void flat_leave(const FastBook<LT>& fb, const FlatState& st) { flat_leave_fn<LT>(fb.blob, fb.lane, st.n0, st.n1); }
 
 // does the snapshot row of this second hold a level beyond the tracked price range (OrderbookSimulator.py:99-103,113-115)?
 __device__ __forceinline__ bool flat_resync_needed(const BookHdr* h, const int32_t* __restrict__ row, int L, int lane) {
@@ -296,11 +366,11 @@ template <class LT>
 __device__ __forceinline__ void flat_update_trackers(unsigned char* blob, int lane, const FlatState& st) {
   BookHdr* h = reinterpret_cast<BookHdr*>(blob);
   __syncwarp();
-  uint4 e0, e1;
-  flat_load(flat_pool<LT>(blob, 0), st.n0, lane, e0, e1);
-  const int w0 = flat_best_of<1>(e0, e1, st.n0, lane, -1);                // lowest bid
-  flat_load(flat_pool<LT>(blob, 1), st.n1, lane, e0, e1);
-  const int w1 = flat_best_of<0>(e0, e1, st.n1, lane, -1);                // highest ask
+  uint2 k[flat_nch<LT>()];
+  flat_keys(flat_pool<LT>(blob, 0), st.n0, lane, k);
+  const int w0 = flat_best_of<1>(k, st.n0, lane, -1);                     // lowest bid
+  flat_keys(flat_pool<LT>(blob, 1), st.n1, lane, k);
+  const int w1 = flat_best_of<0>(k, st.n1, lane, -1);                     // highest ask
   if (lane == 0) {
     if (st.n0 && w0 < h->min_buy) h->min_buy = w0;
     if (st.n1 && w1 > h->max_sell) h->max_sell = w1;

@@ -522,11 +522,8 @@ template <class LT>
 __device__ __forceinline__ void flat_adopt(unsigned char* sm, int lane, FastState& f, FlatState& fs) {
   const BookHdr* h = reinterpret_cast<const BookHdr*>(sm);
   fs.n0 = h->cnt[0][1]; fs.n1 = h->cnt[1][1]; fs.seq = (uint32_t)h->cnt[1][0];
-  uint4 e0, e1;
-  flat_load(flat_pool<LT>(sm, 0), fs.n0, lane, e0, e1);
-  f.best0 = flat_best_of<0>(e0, e1, fs.n0, lane, -1);
-  flat_load(flat_pool<LT>(sm, 1), fs.n1, lane, e0, e1);
-  f.best1 = flat_best_of<1>(e0, e1, fs.n1, lane, -1);
+  f.best0 = flat_best_scan<LT, 0>(sm, lane, fs.n0);
+  f.best1 = flat_best_scan<LT, 1>(sm, lane, fs.n1);
 }
 __device__ __forceinline__ void flat_mark(BookHdr* h, const FlatState& fs) {   // lane 0, before the blob goes back to HBM
   h->cnt[0][0] = -1; h->cnt[0][1] = fs.n0; h->cnt[1][0] = (int32_t)fs.seq; h->cnt[1][1] = fs.n1;
@@ -551,8 +548,7 @@ __global__ void __launch_bounds__(128) k_to_sorted(unsigned char* blobs, int n_e
   for (int s = 0; s < 2; s++) {
     const int n = s ? fs.n1 : fs.n0;
     const uint4* gp = flat_pool<LT>(gblob, s); uint4* sp = flat_pool<LT>(base, s);
-    if (lane < n) sp[lane] = gp[lane];
-    if (lane + 32 < n) sp[lane + 32] = gp[lane + 32];
+    for (int i = lane; i < n; i += 32) sp[i] = gp[i];
   }
   __syncwarp();
   FastBook<LT> fb; fb.blob = base; fb.lane = lane;
@@ -763,6 +759,12 @@ constexpr int env_min_blocks() {
 #ifndef LOBSIM_PHASE_SYNC
 #define LOBSIM_PHASE_SYNC 1
 #endif
+#ifndef LOBSIM_ENV_FLAT
+#define LOBSIM_ENV_FLAT 0         // 1: the env kernel also runs (and stores) books in the flat order pools of book_flat.cuh.  Measured
+                                  // (profiles/r02_env_ab.txt): 11 % fewer instructions per env step, but 16 % SLOWER -- the env kernel is bound by
+                                  // instruction fetch and registers, and merely compiling the flat path in costs 10 % (4.78e7 -> 4.32e7 env
+                                  // steps/s with it unused).  Kept for A/B; the GPU suite passed with it on (profiles/r02_env_flat_tests.log).
+#endif
 #if LOBSIM_PHASE_SYNC
 #define PHASE_SYNC() __syncthreads()
 #else
@@ -808,8 +810,9 @@ __global__ void __launch_bounds__(32 * LOBSIM_ENVFAST_WARPS, env_min_blocks<LT>(
   // conversion per launch would cost more than the flat order path saves)
   bool flat = false;
   FlatState fs; fs.n0 = fs.n1 = 0; fs.seq = 0;
+  const bool allow_flat = LOBSIM_ENV_FLAT && p.allow_flat;
   if (!p.reset_mode) {
-    if (hdr_is_flat(h)) {
+    if (LOBSIM_ENV_FLAT && hdr_is_flat(h)) {
       if (flat_body_copy<LT, true>(base, gblob, &bars[2], lane, h->cnt[0][1], h->cnt[1][1])) mbar_wait(&bars[2], 1);
       flat = true;
     } else if (blob_body_copy<LT, true>(base, gblob, &bars[2], lane)) mbar_wait(&bars[2], 1);
@@ -837,7 +840,7 @@ __global__ void __launch_bounds__(32 * LOBSIM_ENVFAST_WARPS, env_min_blocks<LT>(
   if (flat) flat_adopt<LT>(base, lane, f, fs);
   else {
     fast_refresh_best(fb, f);
-    if (p.allow_flat && flat_fits(fb, 8)) { flat_enter(fb, fs); flat = true; }
+    if (allow_flat && flat_fits(fb, 8)) { flat_enter(fb, fs); flat = true; }
   }
   const lobsim_stream_t* stp = &p.streams[stream_id];
   const lobsim_msg_t* __restrict__ st_msgs = stp->msgs;
@@ -979,7 +982,7 @@ __global__ void __launch_bounds__(32 * LOBSIM_ENVFAST_WARPS, env_min_blocks<LT>(
               else {
                 if (flat) { flat_leave(fb, fs); flat = false; }
                 fast_resync_tracked(fb, f, row, c.n_levels, scratch);
-                if (p.allow_flat && flat_fits(fb, 8)) { flat_enter(fb, fs); flat = true; }
+                if (allow_flat && flat_fits(fb, 8)) { flat_enter(fb, fs); flat = true; }
               }
             }
           }

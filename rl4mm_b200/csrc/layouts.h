@@ -12,6 +12,8 @@
   X(2, 64, 256, 64)    /* 10-level books with a 64-order agent table (configs 3 and 4)            */ \
   X(3, 128, 1536, 64)  /* BASELINE config 5: 50-level books, deep queues, heavy cancel flow (its      \
                           FixedActionAgent holds up to ~45 resting orders per side: 32 overflows) */ \
-  X(4, 128, 1024, 64)  /* 50-level books with deep queues and a 64-order agent table              */
+  X(4, 128, 1024, 64)  /* 50-level books with deep queues and a 64-order agent table              */ \
+  X(5, 128, 256, 64)   /* 10-level books + the agent's ladders (configs 3 and 4): 128 levels so that   \
+                          the flat form may hold 128 orders per side (book_flat.cuh)               */
 
-#define LOBSIM_N_FAST_LAYOUTS 5
+#define LOBSIM_N_FAST_LAYOUTS 6

@@ -123,15 +123,15 @@ __global__ void k_get_state(const unsigned char* blobs, Layout L, int first, int
   s.inventory = h->inventory; s.cash = h->cash; s.price = h->price; s.now_step = h->now_step;
   s.episode_start_step = h->episode_start_step; s.min_buy_price = h->min_buy; s.max_sell_price = h->max_sell;
   s.err = h->err; s.stream_id = h->stream_id; s.n_agent_orders[0] = h->nag[0]; s.n_agent_orders[1] = h->nag[1];
-  s.next_agent_id = h->next_agent_id; s.reserved = 0;
+  s.next_agent_id = h->next_agent_id; s.reserved = 0;   // book form, set below
   int best[2] = {0, INT32_MAX}, bvol[2] = {0, 0};
-  const bool flat = h->cnt[0][0] < 0;   // the flat form (book_flat.cuh): cnt[side][1] orders {price, volume, ref, seq} at the order array
+  const bool flat = h->cnt[0][0] < 0;   // the flat form (book_flat.cuh): cnt[side][1] orders {price, ref, volume, seq} at the order array
   for (int side = 0; flat && side < 2; side++) {
     const int n = h->cnt[side][1];
     const uint4* pool = reinterpret_cast<const uint4*>(blob + L.side_off + side * L.side_stride + L.ord_off);
     int bp = side ? INT32_MAX : INT32_MIN, v = 0;
     for (int k = 0; k < n; k++) { const int pr = (int)pool[k].x; if (side ? pr < bp : pr > bp) bp = pr; }
-    for (int k = 0; k < n; k++) if ((int)pool[k].x == bp) v += (int)pool[k].y;
+    for (int k = 0; k < n; k++) if ((int)pool[k].x == bp) v += (int)pool[k].z;
     if (n) { best[side] = bp; bvol[side] = v; }
   }
   for (int side = 0; !flat && side < 2; side++) {
@@ -147,6 +147,8 @@ __global__ void k_get_state(const unsigned char* blobs, Layout L, int first, int
     bvol[side] = v;
   }
   s.best_buy = best[0]; s.best_sell = best[1]; s.best_buy_volume = bvol[0]; s.best_sell_volume = bvol[1];
+  { const unsigned n0 = (unsigned)h->cnt[0][1], n1 = (unsigned)h->cnt[1][1];
+    s.reserved = (flat ? 1u : 0u) | ((n0 > 4095u ? 4095u : n0) << 8) | ((n1 > 4095u ? 4095u : n1) << 20); }
   out[i] = s;
 }
 
@@ -276,10 +278,27 @@ int lobsim_create(const lobsim_cfg_t* cfg, int device, lobsim_t** out) {
   int max_smem = 0;
   CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
   if (h->warp_smem > max_smem) { delete h; return fail(LOBSIM_E_INVALID, "book capacities exceed the shared memory of one SM"); }
-  h->warps_per_cta = 4;
-  while (h->warps_per_cta > 1 && h->warps_per_cta * h->warp_smem > max_smem) h->warps_per_cta >>= 1;
-  h->env_warps_per_cta = LOBSIM_ENVFAST_WARPS;
-  while (h->env_warps_per_cta > 1 && h->env_warps_per_cta * h->warp_smem > max_smem - 1024) h->env_warps_per_cta >>= 1;
+  // warps (= books) per CTA: as many resident books per SM as the shared memory allows -- deep books are smem-bound, and a CTA
+  // size that does not divide the SM's shared memory wastes up to half of it (128/1536/64 capacities: 30 KB per book, 4 books
+  // per CTA = one CTA = 4 books per SM, 1 book per CTA = 7 books per SM).  Ties go to the larger CTA.
+  int sm_smem = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&sm_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device));
+  // `keep`: the largest CTA within that fraction of the best residency wins (the env kernel prefers large CTAs: its warps move
+  // through the phases of a step together, kernels.cuh).
+  auto best_wpc = [&](int max_wpc, double keep) {
+    int books_of[65] = {0}, best_books = 0;
+    for (int w = 1; w <= max_wpc && w <= 64; w++) {
+      if ((long long)w * h->warp_smem > max_smem - 1024) break;
+      const int ctas = sm_smem / (w * h->warp_smem + 1024);     // 1 KB per CTA is reserved by the driver
+      books_of[w] = (ctas > 32 ? 32 : ctas) * w;
+      if (books_of[w] > best_books) best_books = books_of[w];
+    }
+    int best = 1;
+    for (int w = 1; w <= max_wpc && w <= 64; w++) if (books_of[w] > 0 && books_of[w] >= keep * best_books) best = w;
+    return best;
+  };
+  h->warps_per_cta = best_wpc(4, 1.0);
+  h->env_warps_per_cta = best_wpc(LOBSIM_ENVFAST_WARPS, 0.8);
   CUDA_TRY((cudaFuncSetAttribute(k_advance<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->warps_per_cta * h->warp_smem)));
   CUDA_TRY((cudaFuncSetAttribute(k_advance<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->warps_per_cta * h->warp_smem)));
   h->fast = h->force_general ? nullptr : find_fast_layout(h->L);
@@ -461,7 +480,7 @@ static int launch_env(lobsim* h, const AdvParams& p, cudaStream_t stream) {
   const size_t dyn = (size_t)wpc * h->warp_smem;
   const int full = p.n_sel / wpc, tail = p.n_sel % wpc;
   auto launch = h->rare_paths ? h->fast->env_rare : h->fast->env;
-  if (p.allow_flat) h->maybe_flat = true;
+  if (p.allow_flat && LOBSIM_ENV_FLAT) h->maybe_flat = true;
   else { int rc = ensure_sorted(h, stream); if (rc) return rc; }
   if (full > 0) { // full CTAs: phase-synchronous
     launch(true, full, wpc * 32, dyn, stream, p, h->ec);
