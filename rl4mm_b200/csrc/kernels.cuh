@@ -401,16 +401,17 @@ __global__ void __launch_bounds__(128, 7) k_replay_fast(const __grid_constant__ 
   const int env = blockIdx.x * (blockDim.x >> 5) + warp;
   if (env >= p.n_sel) return;
   const lobsim_cfg_t& c = ec.cfg;
+  // a replay book holds no agent orders: the agent tables at the end of the blob stay in HBM (deep books are shared-memory bound:
+  // 128/1536/64 capacities = 8 instead of 7 resident books per SM)
   unsigned char* base = warp_smem_base(smem, warp, p.warp_smem);
-  unsigned char* msgbuf = base + LT::blob_bytes;
-  int2* scratch = reinterpret_cast<int2*>(msgbuf + 2 * MSG_TILE_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(scratch) + scratch_bytes(LT::NA));
+  unsigned char* msgbuf = base + LT::agent_off;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(msgbuf + 2 * MSG_TILE_BYTES);
   unsigned char* gblob = p.blobs + (size_t)env * LT::blob_bytes;
   if (lane == 0) {
     mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
     fence_mbar_init();
-    mbar_expect_tx(&bars[2], (uint32_t)LT::blob_bytes);
-    tma_load(base, gblob, (uint32_t)LT::blob_bytes, &bars[2]);
+    mbar_expect_tx(&bars[2], (uint32_t)LT::agent_off);
+    tma_load(base, gblob, (uint32_t)LT::agent_off, &bars[2]);
   }
   __syncwarp();
   mbar_wait(&bars[2], 0);
@@ -494,7 +495,7 @@ __global__ void __launch_bounds__(128, 7) k_replay_fast(const __grid_constant__ 
   __syncwarp();
   fence_proxy_async();
   __syncwarp();
-  if (lane == 0) { tma_store(gblob, base, (uint32_t)LT::blob_bytes); tma_store_wait(); }
+  if (lane == 0) { tma_store(gblob, base, (uint32_t)LT::agent_off); tma_store_wait(); }
   __syncwarp();
 }
 
@@ -576,16 +577,17 @@ __global__ void __launch_bounds__(128, 7) k_replay_flat(const __grid_constant__ 
   const int env = blockIdx.x * (blockDim.x >> 5) + warp;
   if (env >= p.n_sel) return;
   const lobsim_cfg_t& c = ec.cfg;
+  // a replay book holds no agent orders: the agent tables at the end of the blob stay in HBM (deep books are shared-memory bound:
+  // 128/1536/64 capacities = 8 instead of 7 resident books per SM)
   unsigned char* base = warp_smem_base(smem, warp, p.warp_smem);
-  unsigned char* msgbuf = base + LT::blob_bytes;
-  int2* scratch = reinterpret_cast<int2*>(msgbuf + 2 * MSG_TILE_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(scratch) + scratch_bytes(LT::NA));
+  unsigned char* msgbuf = base + LT::agent_off;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(msgbuf + 2 * MSG_TILE_BYTES);
   unsigned char* gblob = p.blobs + (size_t)env * LT::blob_bytes;
   if (lane == 0) {
     mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
     fence_mbar_init();
-    mbar_expect_tx(&bars[2], (uint32_t)LT::blob_bytes);
-    tma_load(base, gblob, (uint32_t)LT::blob_bytes, &bars[2]);
+    mbar_expect_tx(&bars[2], (uint32_t)LT::agent_off);
+    tma_load(base, gblob, (uint32_t)LT::agent_off, &bars[2]);
   }
   __syncwarp();
   mbar_wait(&bars[2], 0);
@@ -691,7 +693,7 @@ __global__ void __launch_bounds__(128, 7) k_replay_flat(const __grid_constant__ 
   __syncwarp();
   fence_proxy_async();
   __syncwarp();
-  if (lane == 0) { tma_store(gblob, base, (uint32_t)LT::blob_bytes); tma_store_wait(); }
+  if (lane == 0) { tma_store(gblob, base, (uint32_t)LT::agent_off); tma_store_wait(); }
   __syncwarp();
 }
 

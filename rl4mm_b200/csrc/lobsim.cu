@@ -179,6 +179,8 @@ struct lobsim {
   int warps_per_cta;
   int env_warps_per_cta;
   int warp_smem;
+  int replay_warp_smem;              // straight-line replay kernels: the blob WITHOUT the agent tables + message tiles + barriers
+  int replay_warps_per_cta;
   unsigned char* blobs = nullptr;
   FeatState* fstate = nullptr;
   NormState* nstate = nullptr;          // rolling z-score state: only with normalisation_on features
@@ -256,6 +258,7 @@ int64_t lobsim_state_bytes(const lobsim_cfg_t* c) {
 }
 
 static int warp_smem_bytes(const Layout& L) { return (L.blob_bytes + 2 * MSG_TILE_BYTES + scratch_bytes(L.NA) + 32 + 128 + 127) & ~127; }
+static int replay_warp_smem_bytes(const Layout& L) { return (L.agent_off + 2 * MSG_TILE_BYTES + 32 + 127) & ~127; }
 
 int lobsim_create(const lobsim_cfg_t* cfg, int device, lobsim_t** out) {
   if (!out) return fail(LOBSIM_E_INVALID, "out is null");
@@ -285,11 +288,12 @@ int lobsim_create(const lobsim_cfg_t* cfg, int device, lobsim_t** out) {
   CUDA_TRY(cudaDeviceGetAttribute(&sm_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device));
   // `keep`: the largest CTA within that fraction of the best residency wins (the env kernel prefers large CTAs: its warps move
   // through the phases of a step together, kernels.cuh).
-  auto best_wpc = [&](int max_wpc, double keep) {
+  h->replay_warp_smem = replay_warp_smem_bytes(h->L);
+  auto best_wpc = [&](int max_wpc, double keep, int ws) {
     int books_of[65] = {0}, best_books = 0;
     for (int w = 1; w <= max_wpc && w <= 64; w++) {
-      if ((long long)w * h->warp_smem > max_smem - 1024) break;
-      const int ctas = sm_smem / (w * h->warp_smem + 1024);     // 1 KB per CTA is reserved by the driver
+      if ((long long)w * ws > max_smem - 1024) break;
+      const int ctas = sm_smem / (w * ws + 1024);               // 1 KB per CTA is reserved by the driver
       books_of[w] = (ctas > 32 ? 32 : ctas) * w;
       if (books_of[w] > best_books) best_books = books_of[w];
     }
@@ -297,13 +301,14 @@ int lobsim_create(const lobsim_cfg_t* cfg, int device, lobsim_t** out) {
     for (int w = 1; w <= max_wpc && w <= 64; w++) if (books_of[w] > 0 && books_of[w] >= keep * best_books) best = w;
     return best;
   };
-  h->warps_per_cta = best_wpc(4, 1.0);
-  h->env_warps_per_cta = best_wpc(LOBSIM_ENVFAST_WARPS, 0.8);
+  h->warps_per_cta = best_wpc(4, 1.0, h->warp_smem);
+  h->replay_warps_per_cta = best_wpc(4, 1.0, h->replay_warp_smem);
+  h->env_warps_per_cta = best_wpc(LOBSIM_ENVFAST_WARPS, 0.8, h->warp_smem);
   CUDA_TRY((cudaFuncSetAttribute(k_advance<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->warps_per_cta * h->warp_smem)));
   CUDA_TRY((cudaFuncSetAttribute(k_advance<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->warps_per_cta * h->warp_smem)));
   h->fast = h->force_general ? nullptr : find_fast_layout(h->L);
   if (h->fast) {
-    CUDA_TRY(h->fast->attrs(h->warps_per_cta * h->warp_smem, h->env_warps_per_cta * h->warp_smem));
+    CUDA_TRY(h->fast->attrs(h->replay_warps_per_cta * h->replay_warp_smem, h->env_warps_per_cta * h->warp_smem));
     if (h->rare_paths) CUDA_TRY(h->fast->attrs_rare(h->env_warps_per_cta * h->warp_smem));
   } else if (!h->force_general) {
     static bool warned = false;   // once per process
@@ -460,11 +465,13 @@ static int launch_replay_fast(lobsim* h, const AdvParams& p, cudaStream_t stream
   if (h->streams.empty()) return fail(LOBSIM_E_STATE, "no stream loaded");
   if (!h->fast) return 1;
   CUDA_TRY(cudaSetDevice(h->device));
-  const int wpc = h->warps_per_cta, grid = (p.n_sel + wpc - 1) / wpc;
+  const int wpc = h->replay_warps_per_cta, grid = (p.n_sel + wpc - 1) / wpc;
   if (grid <= 0) return LOBSIM_OK;
+  AdvParams pr = p;
+  pr.warp_smem = h->replay_warp_smem;
   if (!h->replay_flat) { int rc = ensure_sorted(h, stream); if (rc) return rc; }
   else if (p.allow_flat) h->maybe_flat = true;
-  (h->replay_flat ? h->fast->replay_flat : h->fast->replay)(grid, wpc * 32, (size_t)wpc * h->warp_smem, stream, p, h->ec);
+  (h->replay_flat ? h->fast->replay_flat : h->fast->replay)(grid, wpc * 32, (size_t)wpc * h->replay_warp_smem, stream, pr, h->ec);
   CUDA_TRY(cudaGetLastError());
   h->launches++;
   return LOBSIM_OK;
