@@ -421,7 +421,7 @@ def run_replay(ctx: Ctx, stream, line):
         "e2e": {"value": env_msgs / t_e2e, "unit": "messages/s", "h2d_bytes_per_step": h2d // args.steps,
                 "d2h_bytes_per_step": d2h // args.steps, "api": "lobsim_replay_host (C ABI, pinned host buffers)"},
         "gpu_launches": int(launches), "clocks": clocks,
-        "roofline": roofline(algo, 1e3 * t_dev / args.steps, "k_replay_fast<StaticLayout<64,256,32>>",
+        "roofline": roofline(algo, 1e3 * t_dev / args.steps, ("k_replay_flat" if os.environ.get("LOBSIM_REPLAY_FLAT", "1") != "0" else "k_replay_fast") + "<StaticLayout<64,256,32>>",
                              "k_replay_fast" if (n_envs, seg) == (4096, 2340) else None,
                              note="16 B per env-message + 4 B per env-step + 2 x 1216 B book state per book per launch; all books "
                                   "of a GPU replay the same stream, so DRAM traffic (ncu) is far BELOW the algorithmic bytes (L2 "
@@ -713,7 +713,7 @@ def run_multiticker(ctx: Ctx):
                    "envs_per_gpu": n_envs, "n_levels": 50, "n_streams": n_streams, "segment_steps": seg,
                    "capacities": [128, 1536, 64]},
         "gpu_launches": int(launches), "clocks": clocks,
-        "roofline": roofline(algo, 1e3 * t_dev / steps, "k_replay_fast<StaticLayout<128,1536,64>>",
+        "roofline": roofline(algo, 1e3 * t_dev / steps, "k_replay_flat<StaticLayout<128,1536,64>> (deep books: its sorted-array path)",
                              "k_replay_fast_L50" if n_envs == 8192 else None),
     }
     ctx.launches += launches

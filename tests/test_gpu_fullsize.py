@@ -13,6 +13,7 @@ import numpy as np
 import pytest
 
 from rl4mm_b200 import abi
+import parity_helpers as H
 
 pytestmark = pytest.mark.gpu
 
@@ -103,6 +104,66 @@ def test_config5_multi_ticker_heavy_cancel_general_path():
         o.replay(20_000)
         for side in (0, 1):
             assert np.array_equal(sim.dump_book(env, side)[["price", "volume", "ref"]], o.dump_book(side)[["price", "volume", "ref"]]), (env, side)
+
+
+@pytest.mark.fast_only
+def test_config5_full_size_8_tickers_8192_books():
+    """BASELINE configs[4] at size: 8 synthetic tickers x 5e6 messages (50 levels, heavy cancel / modify flow, mean queue 12),
+    8 192 books per GPU, ticker = book mod 8, a random start second per book, on the straight-line kernels of the 128/1536/64
+    layout (kernel_path "fast").  Replay, then a fused FixedActionAgent rollout; a sample of books against the oracle."""
+    import ctypes
+
+    from oracle.oracle import Oracle
+    from rl4mm_b200 import synthetic
+    from test_gpu_parity import compare_books
+
+    n, n_streams = 8192, 8
+    streams = [synthetic.generate(synthetic.heavy_cancel_ticker(seed=k, n_msgs=5_000_000)) for k in range(n_streams)]
+    feats = [abi.feature(abi.FEAT_SPREAD, 0, 100000, 0, 5000), abi.feature(abi.FEAT_BOOK_IMBALANCE, 0, 100000, -1, 1),
+             abi.feature(abi.FEAT_INVENTORY, 0, 100000, -1e6, 1e6)]
+    kw = dict(n_levels=50, outer_levels=20, features=feats, episode_steps=18000, warmup_steps=0,
+              step_reward=abi.Reward(abi.REWARD_PNL, 0, 0.0), terminal_reward=abi.Reward(abi.REWARD_PNL, 0, 0.0))
+    cfg = abi.default_cfg(n_envs=n, max_levels_per_side=128, max_orders_per_side=1536, max_agent_orders=64, **kw)
+    sim = _sim(cfg, streams)
+    assert sim.kernel_path == "fast"
+    rng = np.random.default_rng(7)
+    sps = streams[0].steps_per_second
+    sid = (np.arange(n) % n_streams).astype(np.int32)
+    starts = (rng.integers(0, streams[0].n_seconds - 1300, size=n) * sps).astype(np.int32)
+    sample = [0, 1, 4099, 8191]
+    # ---- replay: 5 850 grid steps (585 s) of every book
+    sim.reset_book(sid, starts)
+    sim.replay(5850)
+    st = sim.state()
+    assert np.all(st["err"] == 0), np.unique(st["err"])
+    assert np.all(st["now_step"] == starts + 5850)
+    for env in sample:
+        o = Oracle(abi.default_cfg(n_levels=50, outer_levels=20), streams[int(sid[env])])
+        o.reset_book(int(starts[env]))
+        o.replay(5850)
+        os_ = o.state()
+        for f in ("min_buy_price", "max_sell_price", "best_buy", "best_sell", "best_buy_volume", "best_sell_volume"):
+            assert st[f][env] == os_[f], (env, f)
+        for side in (0, 1):
+            assert np.array_equal(sim.dump_book(env, side)[["price", "volume", "ref"]], o.dump_book(side)[["price", "volume", "ref"]]), (env, side)
+    # ---- env: reset + 96 fused FixedActionAgent steps
+    agent = abi.Agent(kind=abi.AGENT_FIXED, fixed_action=(ctypes.c_double * 5)(1, 2, 1, 2, 0))
+    starts2 = (rng.integers(600, streams[0].n_seconds - 100, size=n) * sps).astype(np.int32)
+    obs0 = sim.reset(sid, starts2).cpu().numpy()
+    obs, act, rew, done = (x.cpu().numpy() for x in sim.rollout(96, agent))
+    st = sim.state()
+    assert np.all(st["err"] == 0), np.unique(st["err"])            # in particular no AGENT_OVERFLOW with the 64-order agent table
+    for env in sample:
+        o = Oracle(abi.default_cfg(**kw), streams[int(sid[env])])
+        H.assert_close_vec(obs0[env], o.reset(int(starts2[env])), f"reset obs env {env}")
+        oo, oa, orw, od = o.rollout(96, agent)
+        for t in range(96):
+            H.assert_close_vec(obs[t, env], oo[t], f"env {env} t {t} obs")
+            assert H.close(rew[t, env], orw[t]), (env, t, rew[t, env], orw[t])
+        compare_books(sim, env, o, f"config 5 env {env}")        # (agent ids are implementation-defined: queue order is compared)
+        os_ = o.state()
+        assert st["inventory"][env] == os_["inventory"] and H.close(st["cash"][env], os_["cash"])
+    sim.close()
 
 
 def test_config3_rollout_65536_envs():
