@@ -514,6 +514,28 @@ def golden_rolling_sharpe_1e12():
     save("rolling_sharpe_1e12.json.gz", cases)
 
 
+def golden_episode_starts():
+    """Seeded episode starts of the unmodified reference (HOE.py:196,333-351: np.random.choice over the business days, then
+    np.random.randint over the step offsets, from numpy's GLOBAL state): for a few np.random.seed values the first four
+    ``_get_random_start_time()`` of an env -- one trading day, and a two-week date range."""
+    from rl4mm.gym.HistoricalOrderbookEnvironment import HistoricalOrderbookEnvironment
+
+    out = []
+    for min_date, max_date, t0, t1, ep in ((DAY, DAY, timedelta(hours=10), timedelta(hours=15, minutes=30), timedelta(minutes=30)),
+                                           (datetime(2012, 6, 11), datetime(2012, 6, 22), timedelta(hours=9, minutes=45), timedelta(hours=12), timedelta(seconds=90)),
+                                           (DAY, DAY, timedelta(hours=10), timedelta(hours=10, minutes=1), timedelta(minutes=1))):
+        db = make_db("S", "reference")
+        sim = make_sim(db, 20, preload=True, episode_length=ep, warm_up=timedelta(0))
+        env = HistoricalOrderbookEnvironment(ticker="MSFT", step_size=timedelta(seconds=0.1), episode_length=ep, min_date=min_date,
+                                             max_date=max_date, min_start_timedelta=t0, max_end_timedelta=t1, simulator=sim, n_levels=50)
+        for seed in range(6):
+            np.random.seed(seed)
+            out.append(dict(seed=seed, min_date=min_date.isoformat(), max_date=max_date.isoformat(), min_start_s=t0.total_seconds(),
+                            max_end_s=t1.total_seconds(), episode_s=ep.total_seconds(),
+                            starts=[env._get_random_start_time().isoformat() for _ in range(4)]))
+    save("episode_starts.json.gz", out)
+
+
 def golden_generator_merge():
     """Multi-generator merge (rl4mm/simulation/OrderbookSimulator.py:137-148): random 2- and 3-generator step windows through
     the reference's own ``OrderbookSimulator._compress_order_dict`` with the reference's Order dataclasses.  Timestamps are
@@ -576,6 +598,7 @@ def main():
         golden_episode_summary()
         golden_generator_merge()
         golden_rolling_sharpe_1e12()
+        golden_episode_starts()
     for p in sorted(GOLDEN.glob("*.gz")):
         print(p.name, p.stat().st_size)
 

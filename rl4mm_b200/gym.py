@@ -183,6 +183,9 @@ class HistoricalOrderbookEnvironment:
         outer_levels: int = 20,
         device: int = 0,
         seed: Optional[int] = None,
+        start_rng: str = "generator",
+        auto_reset: bool = False,
+        on_error: str = "raise",
         portfolio_carryover: bool = True,
         max_levels_per_side: int = 128,
         max_orders_per_side: int = 512,
@@ -230,6 +233,17 @@ class HistoricalOrderbookEnvironment:
         self.max_feature_window_size = max([f.window_size for f in self.features])
         self.n_envs, self.database = n_envs, database
         self.np_random = np.random.default_rng(seed)
+        # "generator": episode starts from this env's own seeded Generator (vectorised for a batch); "numpy_global": drawn from
+        # numpy's GLOBAL state with the reference's own call sequence (HOE.py:196,333-351), so that a run seeded with
+        # np.random.seed(k) starts its episodes exactly where the reference would (one draw pair per env, env 0 first)
+        assert start_rng in ("generator", "numpy_global")
+        self.start_rng = start_rng
+        # batched envs (n_envs > 1), vector-env conventions on top of the reference's single-env API: auto_reset -- an env whose episode
+        # ended (done) or died (EmptyOrderbookError, overflow, ...) is reset inside step(): its returned observation is the first one of
+        # the new episode, the last one of the old episode goes to info["terminal_observation"]; on_error="flag" -- device errors
+        # do not raise for the whole batch but are reported per env in info["err"] (lobsim error bits)
+        assert on_error in ("raise", "flag")
+        self.auto_reset, self.on_error = auto_reset, on_error
         self._squeeze = n_envs == 1
 
         from .device import LobSim
@@ -259,7 +273,7 @@ class HistoricalOrderbookEnvironment:
     def reset(self, env_ids=None):
         n = self.n_envs if env_ids is None else len(env_ids)
         sids, starts = np.zeros(n, np.int32), np.zeros(n, np.int32)
-        if n > 64 and self.min_date == self.max_date:          # one trading day: draw all the offsets at once
+        if n > 64 and self.min_date == self.max_date and self.start_rng == "generator":   # one trading day: draw all the offsets at once
             day = self._get_random_trading_day()
             sid = self.database.stream_id(self.ticker, day)
             step_us = self.step_size // timedelta(microseconds=1)
@@ -287,10 +301,24 @@ class HistoricalOrderbookEnvironment:
         a = a.reshape(self.n_envs, -1)
         obs, rew, done = self.sim.step(torch.from_numpy(a))
         obs, rew, done = obs.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy().astype(bool)
-        self._raise_on_errors()
+        err = None
+        if self.on_error == "raise":
+            self._raise_on_errors()
+        else:
+            err = self.sim.errors()
         info = {}
         if self.info_calculator is not None:
             info = self.info_calculator.calculate(internal_state=self.sim.state(), action=a)
+        if err is not None:
+            info["err"] = err
+        if self.auto_reset:
+            dead = np.zeros(self.n_envs, bool) if err is None else (err & (abi.ERR_EMPTY_BOOK | abi.ERR_BAD_ACTION | abi.ERR_END_OF_STREAM | abi.ERR_NO_SNAPSHOT)) != 0
+            ids = np.flatnonzero(done | dead)
+            if len(ids):
+                info["terminal_observation"] = {int(i): obs[i].copy() for i in ids}
+                done = done | dead
+                obs = obs.copy()
+                obs[ids] = np.asarray(self.reset(env_ids=ids)).reshape(len(ids), -1)
         if self._squeeze:
             return obs[0], float(rew[0]), bool(done[0]), self._squeeze_info(info)
         return obs, rew, done, info
@@ -341,6 +369,10 @@ class HistoricalOrderbookEnvironment:
 
     # ---- random episode start, HOE.py:196,333-351 ----------------------------------------------------------------------
     def _get_random_start_time(self):
+        if self.start_rng == "numpy_global":
+            days = sorted(d for d, t in zip(self.database.dates, self.database.tickers) if t == self.ticker)
+            return reference_random_start_time(self.min_date, self.max_date, self.min_start_timedelta, self.max_end_timedelta,
+                                               self.episode_length, self.step_size, days)
         return self._get_random_trading_day() + self._random_offset_timestamp()
 
     def _random_offset_timestamp(self):
@@ -410,6 +442,30 @@ class HistoricalOrderbookEnvironment:
             TradeDirectionImbalance(update_frequency=timedelta(seconds=0.1), lookback_periods=int(60 * 10), normalisation_on=n),
             TradeVolumeImbalance(update_frequency=timedelta(seconds=0.1), lookback_periods=int(60 * 10), normalisation_on=n),
         ]
+
+
+def reference_random_start_time(min_date, max_date, min_start_timedelta, max_end_timedelta, episode_length, step_size, trading_days):
+    """``HistoricalOrderbookEnvironment._get_random_start_time`` (HOE.py:196,333-351) with the reference's own draws from numpy's
+    GLOBAL random state, in the reference's order: ``np.random.choice(pd.bdate_range(min_date, max_date))`` (one bounded integer
+    draw over the business days), mapped to the next trading day (here: the next day that has packed data, the role of
+    ``get_next_trading_dt``), then ``np.random.randint(0, max_offset_steps)`` (no draw when the range is empty, :337-340);
+    the start is floored to the whole second (:342)."""
+    import pandas as pd
+
+    bdays = pd.bdate_range(min_date, max_date)
+    day = pd.Timestamp(np.random.choice(bdays)).to_pydatetime()
+    day = datetime.combine(day.date(), datetime.min.time())
+    later = [d for d in trading_days if d >= day]
+    assert later, f"no packed data on or after {day.date()}"
+    day = later[0]
+    max_offset_steps = int((max_end_timedelta - episode_length - min_start_timedelta) / step_size)
+    try:
+        random_offset_steps = int(np.random.randint(low=0, high=max_offset_steps))
+    except ValueError:
+        random_offset_steps = 0
+    ts = min_start_timedelta + random_offset_steps * step_size
+    ts -= timedelta(microseconds=ts.microseconds)
+    return day + ts
 
 
 def generate_trajectory(agent, env):

@@ -495,3 +495,27 @@ def test_correctly_rounded_log_and_exp(tmp_path):
     for x in np.concatenate([rng.uniform(-0.015625, 0.015625, 3000), rng.uniform(-1e-8, 1e-8, 3000), [0.0, 0.015625, -0.015625]]).tolist():
         assert L.t_exp(x) == float(Decimal(x).exp()), x
     assert L.t_exp(0.5) == math.exp(0.5) and math.isnan(L.t_log(-1.0)) and L.t_log(float("inf")) == float("inf")
+
+
+def test_reference_seeded_episode_starts():
+    """with start_rng="numpy_global" the env draws its episode starts from numpy's global state with the reference's own
+    call sequence (HOE.py:196,333-351), so np.random.seed(k) reproduces the reference's starts -- golden from the unmodified
+    reference (oracle/gen_golden.py::golden_episode_starts): single day, a two-week range, and an empty offset range."""
+    import gzip
+    import json
+    from datetime import datetime, timedelta
+    from pathlib import Path
+
+    import pandas as pd
+
+    from rl4mm_b200.gym import reference_random_start_time
+
+    cases = json.loads(gzip.open(Path(__file__).parent / "golden" / "episode_starts.json.gz").read())
+    assert len(cases) == 18
+    for c in cases:
+        lo, hi = datetime.fromisoformat(c["min_date"]), datetime.fromisoformat(c["max_date"])
+        days = [d.to_pydatetime() for d in pd.bdate_range(lo, hi)]           # every business day has packed data
+        np.random.seed(c["seed"])
+        got = [reference_random_start_time(lo, hi, timedelta(seconds=c["min_start_s"]), timedelta(seconds=c["max_end_s"]),
+                                           timedelta(seconds=c["episode_s"]), timedelta(seconds=0.1), days).isoformat() for _ in range(4)]
+        assert got == c["starts"], c

@@ -32,7 +32,8 @@ sys.exit(0 if json.dumps(new, sort_keys=True) == json.dumps(old, sort_keys=True)
                                                ("golden_episode_summary", "episode_summary.json.gz"),
                                                ("golden_fixture_replay", "fixture_replay.json.gz"),
                                                ("golden_generator_merge", "generator_merge.json.gz"),
-                                               ("golden_rolling_sharpe_1e12", "rolling_sharpe_1e12.json.gz")])
+                                               ("golden_rolling_sharpe_1e12", "rolling_sharpe_1e12.json.gz"),
+                                               ("golden_episode_starts", "episode_starts.json.gz")])
 def test_goldens_regenerate_identically(fn_name, file_name, tmp_path):
     res = subprocess.run([sys.executable, "-c", SCRIPT, str(ROOT), str(tmp_path), fn_name, file_name], capture_output=True, text=True,
                          timeout=600)

