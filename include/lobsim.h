@@ -356,6 +356,7 @@ int64_t lobsim_launch_count(lobsim_t* h);
  * instructions per order.  lobsim_create prints one warning per process when it has to select the general kernel.   */
 #define LOBSIM_PATH_GENERAL 0
 #define LOBSIM_PATH_FAST 1
+#define LOBSIM_PATH_DEEP 2   /* capacities whose book exceeds the shared memory of an SM: the general kernel works on the blob in place in HBM */
 int lobsim_kernel_path(lobsim_t* h);
 
 /* sha256 (hex) of the sources (rl4mm_b200/csrc/ and include/) this library was built from; rl4mm_b200/_lib.py compares

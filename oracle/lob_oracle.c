@@ -858,7 +858,7 @@ static double np_pairwise_sum(const double* a, int n) {
 
 /* get_sharpe -- rl4mm/rewards/RewardFunctions.py:10-22 */
 static double get_sharpe(lo_t* o, const double* aum, int n) {
-  double simple[LOBSIM_MAX_SHARPE_WINDOW];
+  double simple[LOBSIM_MAX_SHARPE_WINDOW] = {0};
   for (int i = 0; i < n; i++) if (aum[i] <= 0) { o->err |= LOBSIM_ERR_AUM_NONPOSITIVE; return NAN; } /* raise Exception */
   for (int i = 0; i + 1 < n; i++) simple[i] = exp(log(aum[i + 1]) - log(aum[i])) - 1.0;
   int m = n - 1;

@@ -21,8 +21,15 @@ _LIB = None
 def build(force: bool = False) -> Path:
     so = _HERE / "_build" / "liblob_oracle.so"
     src = [_HERE / "lob_oracle.c", _HERE / "lob_oracle.h", _HERE.parent / "include" / "lobsim.h"]
-    if force or not so.exists() or any(s.stat().st_mtime > so.stat().st_mtime for s in src):
-        subprocess.run(["make", "-C", str(_HERE), "-s", "-B"], check=True)
+    stale = lambda: force or not so.exists() or any(s.stat().st_mtime > so.stat().st_mtime for s in src)   # noqa: E731
+    if stale():
+        import fcntl
+
+        (_HERE / "_build").mkdir(exist_ok=True)
+        with open(_HERE / "_build" / ".lock", "w") as lock:        # pytest-xdist workers: one builds, the others wait and re-check
+            fcntl.flock(lock, fcntl.LOCK_EX)
+            if stale():
+                subprocess.run(["make", "-C", str(_HERE), "-s", "-B"], check=True)
     return so
 
 

@@ -48,7 +48,7 @@ FEAT_AMIHUD_LAMBDA = 11
 INFO_FIELDS = ("asset_price", "inventory", "cash", "aum", "market_spread", "best_buy", "best_sell", "err")
 INFO_DIM = len(INFO_FIELDS)
 AGENT_NONE, AGENT_FIXED, AGENT_TERADACTYL, AGENT_EXTERNAL, AGENT_RANDOM = 0, 1, 2, 3, 4
-PATH_GENERAL, PATH_FAST = 0, 1
+PATH_GENERAL, PATH_FAST, PATH_DEEP = 0, 1, 2
 
 MSG_DTYPE = np.dtype([("price", "<i4"), ("volume", "<i4"), ("ref", "<u4"), ("meta", "<u4")])
 assert MSG_DTYPE.itemsize == 16

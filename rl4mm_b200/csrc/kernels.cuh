@@ -99,6 +99,7 @@ struct AdvParams {
   int32_t agent_kind;               // LOBSIM_AGENT_*
   int32_t out_final_obs_only;       // reset: write obs once, after the warm-up
   int32_t resync_last_only;         // forward_step over several grid steps: resync check only at the end
+  int32_t blob_in_global;           // deep books: the blob does not fit in the shared memory of an SM and is worked on in place in HBM / L2
   int32_t allow_flat;               // fast kernels: books that fit run on -- and are stored in -- the flat order pools (book_flat.cuh)
   const double* actions_in;         // EXTERNAL: [T][n_sel][action_dim]
   double* obs; double* act; double* rew; uint8_t* done; // [T][n_sel][...] (any may be null)
@@ -163,22 +164,28 @@ __global__ void __launch_bounds__(128, kEnv ? LOBSIM_ENV_MIN_BLOCKS : 4) k_advan
   const int env = p.env_ids ? p.env_ids[sel] : sel;
   const lobsim_cfg_t& c = ec.cfg;
 
-  unsigned char* base = warp_smem_base(smem, warp, p.warp_smem);
+  // Deep-book mode (p.blob_in_global): capacities whose blob exceeds the shared memory of an SM (thousands of resting orders per side,
+  // rl4mm/orderbook/models.py:66-67 is unbounded) -- the book is worked on IN PLACE in HBM / L2 through the same routines (generic
+  // addressing), only the message tiles / scratch / barriers live in shared memory.  Slower per order, but no capacity cliff.
+  unsigned char* wbase = warp_smem_base(smem, warp, p.warp_smem);
+  unsigned char* gblob = p.blobs + (size_t)env * p.L.blob_bytes;
+  unsigned char* base = p.blob_in_global ? gblob : wbase;
   Book b; b.blob = base; b.L = p.L; b.lane = lane;
-  unsigned char* msgbuf = base + p.L.blob_bytes;                                   // 2 x 512 B
+  unsigned char* msgbuf = p.blob_in_global ? wbase : wbase + p.L.blob_bytes;       // 2 x 512 B
   int2* scratch = reinterpret_cast<int2*>(msgbuf + 2 * MSG_TILE_BYTES);             // [2*NA]
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(scratch) + scratch_bytes(p.L.NA)); // 3 barriers
-  unsigned char* gblob = p.blobs + (size_t)env * p.L.blob_bytes;
 
   // ---- book blob: HBM -> shared memory ---------------------------------------------------------------------------
   if (lane == 0) {
     mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
     fence_mbar_init();
-    mbar_expect_tx(&bars[2], (uint32_t)p.L.blob_bytes);
-    tma_load(base, gblob, (uint32_t)p.L.blob_bytes, &bars[2]);
+    if (!p.blob_in_global) {
+      mbar_expect_tx(&bars[2], (uint32_t)p.L.blob_bytes);
+      tma_load(base, gblob, (uint32_t)p.L.blob_bytes, &bars[2]);
+    }
   }
   __syncwarp();
-  mbar_wait(&bars[2], 0);
+  if (!p.blob_in_global) mbar_wait(&bars[2], 0);
 
 #if LOBSIM_WS_IN_SMEM
   // the uniform per-warp state lives in shared memory (not registers): every lane stores identical values, so plain
@@ -385,7 +392,7 @@ __global__ void __launch_bounds__(128, kEnv ? LOBSIM_ENV_MIN_BLOCKS : 4) k_advan
   store_state<kTrack>(b, w);
   fence_proxy_async();
   __syncwarp();
-  if (lane == 0) { tma_store(gblob, base, (uint32_t)p.L.blob_bytes); tma_store_wait(); }
+  if (lane == 0 && !p.blob_in_global) { tma_store(gblob, base, (uint32_t)p.L.blob_bytes); tma_store_wait(); }
   __syncwarp();
 }
 

@@ -64,7 +64,7 @@ static const FastLayoutOps* find_fast_layout(const Layout& L) {
 //  Exchange.process_order for a list of orders (drop-in / test entry point; one warp, sequential)
 // ====================================================================================================================
 struct OrdParams {
-  unsigned char* blobs; Layout L; int32_t n_envs;
+  unsigned char* blobs; Layout L; int32_t n_envs; int32_t blob_in_global;
   const lobsim_order_t* orders; int32_t n;
   lobsim_fill_t* fills; int32_t max_fills; int32_t* n_fills; uint32_t* refs_out;
 };
@@ -76,9 +76,12 @@ __global__ void __launch_bounds__(32) k_process_orders(const __grid_constant__ O
   WarpState w;
   int cur_env = -1, total_fills = 0;
   auto load_env = [&](int env) {
-    const uint4* src = reinterpret_cast<const uint4*>(p.blobs + (size_t)env * p.L.blob_bytes);
-    uint4* dst = reinterpret_cast<uint4*>(smem);
-    for (int i = lane; i < p.L.blob_bytes / 16; i += 32) dst[i] = src[i];
+    if (p.blob_in_global) b.blob = p.blobs + (size_t)env * p.L.blob_bytes;   // deep-book mode: in place
+    else {
+      const uint4* src = reinterpret_cast<const uint4*>(p.blobs + (size_t)env * p.L.blob_bytes);
+      uint4* dst = reinterpret_cast<uint4*>(smem);
+      for (int i = lane; i < p.L.blob_bytes / 16; i += 32) dst[i] = src[i];
+    }
     __syncwarp();
     load_state<true>(b, w);
     w.fill_log = p.fills ? p.fills + total_fills : nullptr;
@@ -86,9 +89,11 @@ __global__ void __launch_bounds__(32) k_process_orders(const __grid_constant__ O
   };
   auto store_env = [&](int env) {
     store_state<true>(b, w);
-    uint4* dst = reinterpret_cast<uint4*>(p.blobs + (size_t)env * p.L.blob_bytes);
-    const uint4* src = reinterpret_cast<const uint4*>(smem);
-    for (int i = lane; i < p.L.blob_bytes / 16; i += 32) dst[i] = src[i];
+    if (!p.blob_in_global) {
+      uint4* dst = reinterpret_cast<uint4*>(p.blobs + (size_t)env * p.L.blob_bytes);
+      const uint4* src = reinterpret_cast<const uint4*>(smem);
+      for (int i = lane; i < p.L.blob_bytes / 16; i += 32) dst[i] = src[i];
+    }
     __syncwarp();
     total_fills += w.n_fills < w.fill_cap ? w.n_fills : w.fill_cap;
   };
@@ -204,6 +209,7 @@ struct lobsim {
   bool replay_flat = true;            // LOBSIM_REPLAY_FLAT=0: the replay fast path keeps every book in the sorted level arrays (A/B, testing)
   bool flat_blobs = true;             // LOBSIM_FLAT_BLOBS=0: the fast kernels never keep a book in the flat order pools across launches
                                       // (env kernels: sorted path only; replay: converts back at the end of every launch)
+  bool blob_in_global = false;        // deep-book mode: the blob exceeds the shared memory of an SM and is worked on in place in HBM
   bool maybe_flat = false;            // some blob in HBM may be in the flat form: ensure_sorted() before anything that reads level arrays
   bool agent_orders_possible = false; // an agent order may rest in some book (disables the replay fast path)
   const FastLayoutOps* fast = nullptr; // compiled straight-line kernels for these capacities, or null: general kernel
@@ -280,7 +286,20 @@ int lobsim_create(const lobsim_cfg_t* cfg, int device, lobsim_t** out) {
   h->warp_smem = warp_smem_bytes(h->L);
   int max_smem = 0;
   CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-  if (h->warp_smem > max_smem) { delete h; return fail(LOBSIM_E_INVALID, "book capacities exceed the shared memory of one SM"); }
+  if (h->L.NO > 65535 || h->L.NL > 65535) { delete h; return fail(LOBSIM_E_INVALID, "at most 65535 levels / orders per side (16-bit level ends)"); }
+  if (h->warp_smem > max_smem - 1024) {
+    // deep-book mode: the blob stays in HBM / L2 and the general kernel works on it in place (k_advance, blob_in_global)
+    h->blob_in_global = true;
+    h->force_general = true;
+    h->warp_smem = (2 * MSG_TILE_BYTES + scratch_bytes(h->L.NA) + 32 + 128 + 127) & ~127;
+    static bool warned_deep = false;
+    if (!warned_deep) {
+      warned_deep = true;
+      fprintf(stderr, "lobsim: capacities {levels %d, orders %d, agent orders %d} = %d bytes per book exceed the shared memory of an SM: "
+                      "deep-book mode, the books are worked on in place in HBM (same results, several times slower per order)\n",
+              h->L.NL, h->L.NO, h->L.NA, h->L.blob_bytes);
+    }
+  }
   // warps (= books) per CTA: as many resident books per SM as the shared memory allows -- deep books are smem-bound, and a CTA
   // size that does not divide the SM's shared memory wastes up to half of it (128/1536/64 capacities: 30 KB per book, 4 books
   // per CTA = one CTA = 4 books per SM, 1 book per CTA = 7 books per SM).  Ties go to the larger CTA.
@@ -321,7 +340,7 @@ int lobsim_create(const lobsim_cfg_t* cfg, int device, lobsim_t** out) {
   }
   CUDA_TRY((cudaFuncSetAttribute(k_advance<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)));
   CUDA_TRY((cudaFuncSetAttribute(k_advance<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)));
-  CUDA_TRY(cudaFuncSetAttribute(k_process_orders, cudaFuncAttributeMaxDynamicSharedMemorySize, h->L.blob_bytes));
+  if (!h->blob_in_global) CUDA_TRY(cudaFuncSetAttribute(k_process_orders, cudaFuncAttributeMaxDynamicSharedMemorySize, h->L.blob_bytes));
   // feature rings
   memset(&h->ec, 0, sizeof h->ec);
   h->ec.cfg = *cfg;
@@ -432,6 +451,7 @@ static void base_params(lobsim* h, AdvParams& p) {
   p.fill_log = h->fill_log; p.fill_count = h->fill_count; p.fill_cap = h->cfg.fill_log_capacity;
   p.n_envs = h->cfg.n_envs; p.n_sel = h->cfg.n_envs; p.L = h->L; p.warp_smem = h->warp_smem;
   p.allow_flat = h->fast && h->flat_blobs ? 1 : 0;
+  p.blob_in_global = h->blob_in_global ? 1 : 0;
 }
 
 // Flat blobs (book_flat.cuh) exist only between launches of the straight-line kernels; everything else reads the level arrays.
@@ -731,11 +751,11 @@ int lobsim_process_orders(lobsim_t* h, const lobsim_order_t* orders, int32_t n, 
   CUDA_TRY(cudaMalloc(&d_refs, (size_t)n * sizeof(uint32_t)));
   CUDA_TRY(cudaMemcpy(d_orders, orders, (size_t)n * sizeof(lobsim_order_t), cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemset(d_nf, 0, sizeof(int32_t)));
-  OrdParams p; p.blobs = h->blobs; p.L = h->L; p.n_envs = h->cfg.n_envs; p.orders = d_orders; p.n = n;
+  OrdParams p; p.blobs = h->blobs; p.L = h->L; p.n_envs = h->cfg.n_envs; p.blob_in_global = h->blob_in_global ? 1 : 0; p.orders = d_orders; p.n = n;
   p.fills = max_fills > 0 ? d_fills : nullptr; p.max_fills = max_fills; p.n_fills = d_nf; p.refs_out = d_refs;
   h->agent_orders_possible = true;
   { int rc = ensure_sorted(h, 0); if (rc) return rc; }
-  k_process_orders<<<1, 32, h->L.blob_bytes>>>(p);
+  k_process_orders<<<1, 32, h->blob_in_global ? 16 : h->L.blob_bytes>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
   h->launches++;
@@ -822,7 +842,7 @@ int lobsim_errors(lobsim_t* h, uint32_t* err_out) {
 
 int64_t lobsim_launch_count(lobsim_t* h) { return h ? h->launches : 0; }
 
-int lobsim_kernel_path(lobsim_t* h) { return h && h->fast ? LOBSIM_PATH_FAST : LOBSIM_PATH_GENERAL; }
+int lobsim_kernel_path(lobsim_t* h) { return h && h->fast ? LOBSIM_PATH_FAST : (h && h->blob_in_global ? LOBSIM_PATH_DEEP : LOBSIM_PATH_GENERAL); }
 
 #ifndef LOBSIM_SOURCE_HASH
 #define LOBSIM_SOURCE_HASH "unstamped"

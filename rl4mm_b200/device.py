@@ -221,8 +221,9 @@ class LobSim:
     @property
     def kernel_path(self) -> str:
         """"fast": the straight-line static-layout kernels serve this handle; "general": the runtime-layout kernel
-        (capacities without a compiled layout, csrc/layouts.h, or LOBSIM_FORCE_GENERAL=1)."""
-        return "fast" if lib().lobsim_kernel_path(self._h) == abi.PATH_FAST else "general"
+        (capacities without a compiled layout, csrc/layouts.h, or LOBSIM_FORCE_GENERAL=1); "deep": capacities whose book exceeds
+        the shared memory of an SM -- the general kernel works on the blobs in place in HBM (no capacity cliff, slower)."""
+        return {abi.PATH_FAST: "fast", abi.PATH_DEEP: "deep"}.get(lib().lobsim_kernel_path(self._h), "general")
 
     @property
     def launch_count(self) -> int:

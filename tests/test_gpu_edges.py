@@ -120,8 +120,11 @@ def test_call_order_and_argument_errors():
         sim.step(torch.zeros((2, 4), dtype=torch.float64, device="cuda"))   # step before reset
     with pytest.raises(LobsimError):
         LobSim(abi.default_cfg(n_envs=2, max_quote_level=40), 0)
+    deep = LobSim(abi.default_cfg(n_envs=2, max_levels_per_side=4096, max_orders_per_side=60000), 0)   # > smem of an SM: deep-book mode
+    assert deep.kernel_path == "deep"
+    deep.close()
     with pytest.raises(LobsimError):
-        LobSim(abi.default_cfg(n_envs=2, max_levels_per_side=4096, max_orders_per_side=60000), 0)   # > smem of an SM
+        LobSim(abi.default_cfg(n_envs=2, max_levels_per_side=4096, max_orders_per_side=70000), 0)   # level ends are 16-bit
 
 
 def test_env_subset_reset_and_odd_env_counts():
@@ -150,3 +153,47 @@ def test_env_subset_reset_and_odd_env_counts():
     o, a, r, d = sim.rollout(5, agent)
     assert bool((o[:, others] == o[:, others[:1]]).all()) and bool((o[:, ids] == o[:, ids[:1]]).all())
     assert np.all(sim.state()["err"] == 0)
+
+
+def test_deep_books_in_hbm_match_oracle():
+    """books deeper than the shared memory of an SM allows (the reference's SortedDict / deque are unbounded,
+    rl4mm/orderbook/models.py:66-67).  Capacities of 256 levels x 16 384 orders per side = 265 KB per book put the handle in
+    deep-book mode (blob worked on in place in HBM); a synthetic stream with a mean queue of 80 orders per level and ~6 000
+    resting orders: replay and a fused agent rollout against the (unbounded) oracle, no ORDER_OVERFLOW."""
+    from oracle.oracle import Oracle
+    from rl4mm_b200 import synthetic
+    from test_gpu_parity import compare_books
+
+    sc = synthetic.SynthConfig(seed=11, n_msgs=300_000, duration_s=600, n_levels=50, mid0=2_000_000, p_limit=0.40, p_cancel=0.15,
+                               p_delete=0.37, p_exec=0.08, geom_p=0.10, init_levels=70, mean_queue=80, target_orders=6000,
+                               max_offset_ticks=80)
+    s = synthetic.generate(sc)
+    feats = [abi.feature(abi.FEAT_SPREAD, 0, 100000, 0, 5000), abi.feature(abi.FEAT_BOOK_IMBALANCE, 0, 100000, -1, 1),
+             abi.feature(abi.FEAT_INVENTORY, 0, 100000, -1e6, 1e6)]
+    kw = dict(n_levels=50, outer_levels=20, features=feats, episode_steps=600, warmup_steps=0)
+    starts = [0, 500, 1500]
+    sim = _sim(abi.default_cfg(n_envs=len(starts), max_levels_per_side=256, max_orders_per_side=16384, max_agent_orders=64, **kw), [s])
+    assert sim.kernel_path == "deep"
+    sim.reset_book(0, np.array(starts, np.int32))
+    oracles = [Oracle(abi.default_cfg(**kw), s) for _ in starts]
+    for o, st in zip(oracles, starts):
+        o.reset_book(st)
+    for chunk in (1, 99, 1900):
+        sim.replay(chunk)
+        st = sim.state()
+        assert np.all(st["err"] == 0), st["err"]
+        for env, o in enumerate(oracles):
+            o.replay(chunk)
+            compare_books(sim, env, o, ("deep replay", env, chunk))
+    n_side = [len(sim.dump_book(0, side)) for side in (0, 1)]
+    assert max(n_side) > 1600, n_side                       # deeper than the largest compiled shared-memory layout (1 536)
+    agent = abi.Agent(kind=abi.AGENT_FIXED, fixed_action=(ctypes.c_double * 5)(1, 2, 1, 2, 0))
+    obs0 = sim.reset(0, np.array([1000, 2000, 3000], np.int32)).cpu().numpy()
+    obs, act, rew, done = (x.cpu().numpy() for x in sim.rollout(50, agent))
+    assert np.all(sim.state()["err"] == 0)
+    for env, start in enumerate((1000, 2000, 3000)):
+        o = Oracle(abi.default_cfg(**kw), s)
+        o.reset(start)
+        oo, oa, orw, od = o.rollout(50, agent)
+        assert np.allclose(obs[:, env], oo, rtol=1e-6, atol=1e-9) and np.allclose(rew[:, env], orw, rtol=1e-6, atol=1e-9)
+        compare_books(sim, env, o, ("deep env", env))
