@@ -83,10 +83,12 @@ __device__ __forceinline__ int flat_best_scan(unsigned char* blob, int lane, int
 
 // One order of side S (0 buy, 1 sell) through the flat book.  Same results as fast_order_full<LT,TR> on the sorted book; TR: fills /
 // flows / the agent's order tables are tracked (env kernels), exactly as in book_fast.cuh.
-// Returns false -- with the book untouched -- when the order may have to rest and the pool of its side is full: the caller
-// converts the book to the sorted form and runs the order there.
+// Sets f.bail = FLAT_BAIL_FULL -- with the book untouched -- when the order may have to rest and the pool of its side is full: the
+// caller converts the book to the sorted form and runs the order there.  (A status in FastState instead of a return value: the hot
+// loop tests `f.bail | f.dead` once per message.)
+#define FLAT_BAIL_FULL 3
 template <class LT, int S, bool TR>
-__device__ __forceinline__ bool flat_order(unsigned char* blob, int lane, FastState& f, FlatState& st, int type, int price, int vol, uint32_t ref, bool is_agent) {
+__device__ __forceinline__ void flat_order(unsigned char* blob, int lane, FastState& f, FlatState& st, int type, int price, int vol, uint32_t ref, bool is_agent) {
   constexpr int OPP = S ^ 1;
   constexpr int NCH = flat_nch<LT>();
   if (!TR) is_agent = false;
@@ -97,11 +99,11 @@ __device__ __forceinline__ bool flat_order(unsigned char* blob, int lane, FastSt
   uint4* own = flat_pool<LT>(blob, S);
   uint4* opp = flat_pool<LT>(blob, OPP);
   FastBook<LT> fb; fb.blob = blob; fb.lane = lane;
-  if (vol <= 0) { f.err |= LOBSIM_ERR_BAD_VOLUME; return true; }          // assert order.volume > 0, Exchange.py:59-60
+  if (__builtin_expect(vol <= 0, 0)) { f.err |= LOBSIM_ERR_BAD_VOLUME; return; }   // assert order.volume > 0, Exchange.py:59-60
   __syncwarp();                                                             // the previous order's stores are visible
   if (type == LOBSIM_MSG_LIMIT || type == LOBSIM_MSG_MARKET) {
     int rem = vol;
-    if (type == LOBSIM_MSG_LIMIT && n_own >= flat_cap<LT>()) return false;
+    if (type == LOBSIM_MSG_LIMIT && n_own >= flat_cap<LT>()) { f.bail = FLAT_BAIL_FULL; return; }
     const bool crosses = S ? price <= best_opp : price >= best_opp;        // empty opposite side: INT32_MIN / INT32_MAX
     if (type == LOBSIM_MSG_MARKET || crosses) {
       // ---- execution against the opposite side, best price first, oldest order first (Exchange.py:85-120) -------------
@@ -160,14 +162,14 @@ __device__ __forceinline__ bool flat_order(unsigned char* blob, int lane, FastSt
         __syncwarp();
         if (TR && hagent) fast_agent_reduce(fb, OPP, href & 0x7fffffffu, 0, true);   // the resting agent order is gone
       }
-      if (!(rem > 0 && type == LOBSIM_MSG_LIMIT && !f.dead)) return true;
+      if (!(rem > 0 && type == LOBSIM_MSG_LIMIT && !f.dead)) return;
       // the remainder of a crossing limit order rests (Exchange.py:116-119)
     }
     // ---- the order rests at the back of its price's queue (Exchange.py:74-83) ------------------------------------------
     if (TR && is_agent) {   // OrderIdConvertor.add_internal_id_to_order_and_track + internal book append
       BookHdr* h = reinterpret_cast<BookHdr*>(blob);
       const int nag = h->nag[S];
-      if (nag >= LT::NA) { f.err |= LOBSIM_ERR_AGENT_OVERFLOW; return true; }
+      if (nag >= LT::NA) { f.err |= LOBSIM_ERR_AGENT_OVERFLOW; return; }
       const uint32_t id = h->next_agent_id;
       ref = LOBSIM_REF_AGENT | id;
       __syncwarp();
@@ -180,7 +182,7 @@ __device__ __forceinline__ bool flat_order(unsigned char* blob, int lane, FastSt
     if (lane == 0) own[n_own] = make_uint4((unsigned)price, ref, (unsigned)rem, st.seq);
     n_own += 1; st.seq += 1;
     if (S ? price < best_own : price > best_own) best_own = price;
-    return true;
+    return;
   }
   // ---- cancellation / deletion (Exchange.py:122-147) ----------------------------------------------------------------------
   uint2 k[NCH];
@@ -194,7 +196,7 @@ __device__ __forceinline__ bool flat_order(unsigned char* blob, int lane, FastSt
     // no such level, or no aggregate left at it: nothing happens (:129-132,138-139)
 #pragma unroll
     for (int c = 0; c < NCH; c++) { m[c] = __ballot_sync(FULL_MASK, c * 32 + lane < n_own && (int)k[c].x == price && k[c].y == LOBSIM_REF_AGGREGATE); any |= m[c]; }
-    if (!any) return true;
+    if (!any) return;
     aggregate = true;
   }
   const int i = flat_first(m);
@@ -203,28 +205,30 @@ __device__ __forceinline__ bool flat_order(unsigned char* blob, int lane, FastSt
   if (vol < cur) {                                                         // partial: reduce in place
     if (lane == 0) own[i].z = (unsigned)(cur - vol);
     if (TR && is_agent && !aggregate) { __syncwarp(); fast_agent_reduce(fb, S, ref & 0x7fffffffu, vol, false); }
-    return true;
+    return;
   }
   // full removal (over-size requests remove the resting volume, :142-146): the last order of the pool fills the hole
   if (price == best_own) best_own = flat_best_of<S>(k, n_own, lane, i);
   if (lane == 0) own[i] = own[n_own - 1];
   n_own -= 1;
   if (TR && is_agent && !aggregate) { __syncwarp(); fast_agent_reduce(fb, S, ref & 0x7fffffffu, cur, true); }
-  return true;
+  return;
 }
 
 // the replay form: a packed historical message
 template <class LT>
-__device__ __forceinline__ bool flat_message(unsigned char* blob, int lane, FastState& f, FlatState& st, int price, int vol, uint32_t ref, uint32_t meta) {
+__device__ __forceinline__ void flat_message(unsigned char* blob, int lane, FastState& f, FlatState& st, int price, int vol, uint32_t ref, uint32_t meta) {
   const int type = (int)(meta & 7u);
-  if (meta & 8u) return flat_order<LT, 1, false>(blob, lane, f, st, type, price, vol, ref, false);
-  return flat_order<LT, 0, false>(blob, lane, f, st, type, price, vol, ref, false);
+  if (meta & 8u) flat_order<LT, 1, false>(blob, lane, f, st, type, price, vol, ref, false);
+  else flat_order<LT, 0, false>(blob, lane, f, st, type, price, vol, ref, false);
 }
-// the tracked form (env kernels): historical messages and the agent's own orders
+// the tracked form (env kernels): historical messages and the agent's own orders; false: pool full (see flat_order)
 template <class LT>
 __device__ __forceinline__ bool flat_order_tracked(unsigned char* blob, int lane, FastState& f, FlatState& st, int type, int side, int price, int vol, uint32_t ref, bool is_agent) {
-  if (side) return flat_order<LT, 1, true>(blob, lane, f, st, type, price, vol, ref, is_agent);
-  return flat_order<LT, 0, true>(blob, lane, f, st, type, price, vol, ref, is_agent);
+  if (side) flat_order<LT, 1, true>(blob, lane, f, st, type, price, vol, ref, is_agent);
+  else flat_order<LT, 0, true>(blob, lane, f, st, type, price, vol, ref, is_agent);
+  if (f.bail) { f.bail = 0; return false; }
+  return true;
 }
 
 // volume resting at the best price of side S (Orderbook.best_buy_volume / best_sell_volume, models.py:80-85)

@@ -653,10 +653,10 @@ __global__ void __launch_bounds__(128, 7) k_replay_flat(const __grid_constant__ 
 #pragma unroll 1
         for (; i < cnt; i++) {
           const uint4 m = mp[i];
-          if (!flat_message<LT>(base, lane, f, fs, (int)m.x, (int)m.y, m.z, m.w)) break;   // pool full: this message runs on the sorted book
-          if (f.dead) break;
+          flat_message<LT>(base, lane, f, fs, (int)m.x, (int)m.y, m.z, m.w);
+          if (f.bail | f.dead) break;                                                      // pool full (this message runs on the sorted book) / EmptyOrderbookError
         }
-        if (i < cnt && !f.dead) { flat_leave(fb, fs); flat = false; }
+        if (f.bail) { f.bail = 0; flat_leave(fb, fs); flat = false; }
       }
       if (!flat && !f.dead) {
 #pragma unroll 1
