@@ -493,14 +493,14 @@ def run_rollout(ctx: Ctx, stream):
     obs = sim.reset(0, starts)
     torch.manual_seed(0)
     policy = torch.nn.Sequential(torch.nn.Linear(obs.shape[1], 64), torch.nn.Tanh(), torch.nn.Linear(64, 64), torch.nn.Tanh(),
-                                 torch.nn.Linear(64, 4)).to(dev).double()
+                                 torch.nn.Linear(64, 4)).to(dev)          # fp32, like the reference's RLlib torch policy
     scale = torch.tensor([1e-2, 1e-2, 1e-2, 1e3, 1e3, 1e-2, 1.0, 0.1, 1.0, 1.0], device=dev, dtype=torch.float64)
     box = {"obs": obs}
     kev = []      # CUDA events around every lobsim_step launch of the timed region (the kernel's own duration)
 
     def act(o):
         with torch.no_grad():
-            return torch.sigmoid(policy(o * scale)) * 10.0
+            return (torch.sigmoid(policy((o * scale).float())) * 10.0).double()   # env actions are fp64 (Python floats in the reference)
 
     def rollout(i, timed=False):
         o = box["obs"]
@@ -553,7 +553,7 @@ def run_rollout(ctx: Ctx, stream):
         "metric": "env_steps_per_sec", "value": env_steps / t_dev, "unit": "env steps/s", "n_gpus": world,
         "steps": steps, "warmup": warm, "ms_per_step": 1e3 * t_dev / steps, "higher_is_better": True,
         "scaling": "weak", "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "configs[2]: HistoricalOrderbookEnvironment rollouts, torch MLP Beta policy between steps, "
+        "config": {"workload": "configs[2]: HistoricalOrderbookEnvironment rollouts, torch MLP Beta policy (2 x 64 tanh, fp32) between steps, "
                                "PnL reward, default full_state features (F=10), %d envs per GPU, T=128 env steps per bench step" % n_envs,
                    "envs_per_gpu": n_envs, "n_levels": stream.n_levels, "T": T, "l2": "flushed between timed iterations (256 MiB write)"},
         "lob_messages_per_sec": msgs * world / t_dev,
@@ -661,7 +661,7 @@ def run_collect(ctx: Ctx, stream):
 def run_multiticker(ctx: Ctx):
     """BASELINE.json configs[4]: 8 synthetic tickers (seeds 0-7, mids $30-$500), 50 levels, heavy cancel / modify flow,
     deep queues; `multiticker_envs` books per GPU, ticker = book index mod 8, a random start second per book.  Replay
-    (messages/s, k_replay_flat / k_replay_fast<128,1536,64>) and a fused FixedActionAgent([1,2,1,2]) rollout (env steps/s)."""
+    (messages/s, k_replay_flat<128,1024,64>) and a fused FixedActionAgent([1,2,1,2]) rollout (env steps/s)."""
     args, torch = ctx.args, ctx.torch
     import ctypes
 
@@ -674,7 +674,9 @@ def run_multiticker(ctx: Ctx):
     steps, warm = args.sub_steps, 3
     feats = [abi.feature(abi.FEAT_SPREAD, 0, 100000, 0, 5000), abi.feature(abi.FEAT_BOOK_IMBALANCE, 0, 100000, -1, 1),
              abi.feature(abi.FEAT_INVENTORY, 0, 100000, -1e6, 1e6)]
-    cfg = abi.default_cfg(n_envs=n_envs, n_levels=50, outer_levels=20, max_levels_per_side=128, max_orders_per_side=1536,
+    # capacities: a side of these streams holds at most ~620 orders over the whole day (oracle replay) + ~45 agent orders: 1 024
+    # per side (compiled layout 128/1024/64) leaves 1.5x headroom and fits 12 books per SM instead of 8 with 1 536
+    cfg = abi.default_cfg(n_envs=n_envs, n_levels=50, outer_levels=20, max_levels_per_side=128, max_orders_per_side=1024,
                           max_agent_orders=64, features=feats, episode_steps=18000, warmup_steps=0,
                           step_reward=abi.Reward(abi.REWARD_PNL, 0, 0.0), terminal_reward=abi.Reward(abi.REWARD_PNL, 0, 0.0))
     sim = LobSim(cfg, ctx.local_rank)
@@ -711,9 +713,9 @@ def run_multiticker(ctx: Ctx):
                                "%d books per GPU, ticker = book mod %d, random start second per book, %d grid steps per bench step"
                                % (n_streams, args.multiticker_msgs, n_envs, n_streams, seg),
                    "envs_per_gpu": n_envs, "n_levels": 50, "n_streams": n_streams, "segment_steps": seg,
-                   "capacities": [128, 1536, 64]},
+                   "capacities": [128, 1024, 64]},
         "gpu_launches": int(launches), "clocks": clocks,
-        "roofline": roofline(algo, 1e3 * t_dev / steps, "k_replay_flat<StaticLayout<128,1536,64>> (deep books: its sorted-array path)",
+        "roofline": roofline(algo, 1e3 * t_dev / steps, "k_replay_flat<StaticLayout<128,1024,64>> (deep books: its sorted-array path)",
                              "k_replay_fast_L50" if n_envs == 8192 else None),
     }
     ctx.launches += launches
@@ -735,7 +737,7 @@ def run_multiticker(ctx: Ctx):
                   "ms_per_step": 1e3 * t_env / steps, "lob_messages_per_sec": msgs * world / t_env, "T": T,
                   "agent": "FixedActionAgent([1,2,1,2]) fused on the device", "features": "Spread, BookImbalance, Inventory; PnL",
                   "agent_overflow_envs": int((st["err"] & abi.ERR_AGENT_OVERFLOW != 0).sum()), "gpu_launches": int(launches),
-                  "roofline": roofline(algo, 1e3 * t_env / steps, "k_env_fast<StaticLayout<128,1536,64>> (one launch = 128 env steps)")}
+                  "roofline": roofline(algo, 1e3 * t_env / steps, "k_env_fast<StaticLayout<128,1024,64>> (one launch = 128 env steps)")}
     ctx.launches += launches
     if ctx.rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1

@@ -33,13 +33,14 @@
 // ---- the compiled straight-line layouts (layouts.h; one pair of translation units each, fast_layout.cu) -------------
 struct FastLayoutOps {
   int NL, NO, NA;
+  bool env_hot;
   cudaError_t (*attrs)(int dyn_replay, int dyn_env);
   cudaError_t (*attrs_rare)(int dyn_env);
   void (*replay)(int grid, int block, size_t dyn, cudaStream_t stream, const AdvParams& p, const EnvConst& ec);
   void (*replay_flat)(int grid, int block, size_t dyn, cudaStream_t stream, const AdvParams& p, const EnvConst& ec);
   void (*to_sorted)(unsigned char* blobs, int n_envs, cudaStream_t stream);
-  void (*env)(bool sync, int grid, int block, size_t dyn, cudaStream_t stream, const AdvParams& p, const EnvConst& ec);
-  void (*env_rare)(bool sync, int grid, int block, size_t dyn, cudaStream_t stream, const AdvParams& p, const EnvConst& ec);
+  void (*env)(int mode, bool sync, int grid, int block, size_t dyn, cudaStream_t stream, const AdvParams& p, const EnvConst& ec);
+  void (*env_rare)(int mode, bool sync, int grid, int block, size_t dyn, cudaStream_t stream, const AdvParams& p, const EnvConst& ec);
 };
 #define X(i, nl, no, na)                                                                                                   \
   cudaError_t lobsim_fast##i##_attrs(int, int);                                                                            \
@@ -47,11 +48,11 @@ struct FastLayoutOps {
   void lobsim_fast##i##_replay(int, int, size_t, cudaStream_t, const AdvParams&, const EnvConst&);                         \
   void lobsim_fast##i##_replay_flat(int, int, size_t, cudaStream_t, const AdvParams&, const EnvConst&);                    \
   void lobsim_fast##i##_to_sorted(unsigned char*, int, cudaStream_t);                                                      \
-  void lobsim_fast##i##_env(bool, int, int, size_t, cudaStream_t, const AdvParams&, const EnvConst&);                      \
-  void lobsim_fast##i##_env_rare(bool, int, int, size_t, cudaStream_t, const AdvParams&, const EnvConst&);
+  void lobsim_fast##i##_env(int, bool, int, int, size_t, cudaStream_t, const AdvParams&, const EnvConst&);                 \
+  void lobsim_fast##i##_env_rare(int, bool, int, int, size_t, cudaStream_t, const AdvParams&, const EnvConst&);
 LOBSIM_FAST_LAYOUTS(X)
 #undef X
-#define X(i, nl, no, na) {nl, no, na, lobsim_fast##i##_attrs, lobsim_fast##i##_attrs_rare, lobsim_fast##i##_replay, lobsim_fast##i##_replay_flat, lobsim_fast##i##_to_sorted, lobsim_fast##i##_env, lobsim_fast##i##_env_rare},
+#define X(i, nl, no, na) {nl, no, na, LOBSIM_LAYOUT_ENV_HOT(nl, no, na), lobsim_fast##i##_attrs, lobsim_fast##i##_attrs_rare, lobsim_fast##i##_replay, lobsim_fast##i##_replay_flat, lobsim_fast##i##_to_sorted, lobsim_fast##i##_env, lobsim_fast##i##_env_rare},
 static const FastLayoutOps g_fast_layouts[LOBSIM_N_FAST_LAYOUTS] = {LOBSIM_FAST_LAYOUTS(X)};
 #undef X
 static const FastLayoutOps* find_fast_layout(const Layout& L) {
@@ -209,6 +210,9 @@ struct lobsim {
   bool replay_flat = true;            // LOBSIM_REPLAY_FLAT=0: the replay fast path keeps every book in the sorted level arrays (A/B, testing)
   bool flat_blobs = true;             // LOBSIM_FLAT_BLOBS=0: the fast kernels never keep a book in the flat order pools across launches
                                       // (env kernels: sorted path only; replay: converts back at the end of every launch)
+  lobsim_order_t* po_orders = nullptr; uint32_t* po_refs = nullptr; lobsim_fill_t* po_fills = nullptr; int32_t* po_nf = nullptr;   // lobsim_process_orders staging
+  int po_cap = 0, po_fill_cap = 0;
+  int32_t* defer_count = nullptr; int2* defer_list = nullptr;   // env HOT kernel -> DEFERRED kernel hand-over (kernels.cuh ENV_HOT)
   bool blob_in_global = false;        // deep-book mode: the blob exceeds the shared memory of an SM and is worked on in place in HBM
   bool maybe_flat = false;            // some blob in HBM may be in the flat form: ensure_sorted() before anything that reads level arrays
   bool agent_orders_possible = false; // an agent order may rest in some book (disables the replay fast path)
@@ -326,6 +330,10 @@ int lobsim_create(const lobsim_cfg_t* cfg, int device, lobsim_t** out) {
   CUDA_TRY((cudaFuncSetAttribute(k_advance<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->warps_per_cta * h->warp_smem)));
   CUDA_TRY((cudaFuncSetAttribute(k_advance<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->warps_per_cta * h->warp_smem)));
   h->fast = h->force_general ? nullptr : find_fast_layout(h->L);
+  if (h->fast && h->fast->env_hot) {   // (allocated here, not at the first launch: that one may be inside a CUDA-graph capture)
+    CUDA_TRY(cudaMalloc(&h->defer_count, sizeof(int32_t)));
+    CUDA_TRY(cudaMalloc(&h->defer_list, (size_t)cfg->n_envs * sizeof(int2)));
+  }
   if (h->fast) {
     CUDA_TRY(h->fast->attrs(h->replay_warps_per_cta * h->replay_warp_smem, h->env_warps_per_cta * h->warp_smem));
     if (h->rare_paths) CUDA_TRY(h->fast->attrs_rare(h->env_warps_per_cta * h->warp_smem));
@@ -417,6 +425,7 @@ int lobsim_destroy(lobsim_t* h) {
   cudaFree(h->blobs); cudaFree(h->fstate); cudaFree(h->nstate); cudaFree(h->beta_tab); cudaFree(h->rings); cudaFree(h->rs_ring); cudaFree(h->rs_state); cudaFree(h->fill_log); cudaFree(h->fill_count); cudaFree(h->agents_dev);
   cudaFree(h->streams_dev); cudaFree(h->st_actions); cudaFree(h->st_obs); cudaFree(h->st_rew); cudaFree(h->st_done);
   cudaFree(h->st_state); cudaFree(h->st_msgs);
+  cudaFree(h->po_orders); cudaFree(h->po_refs); cudaFree(h->po_fills); cudaFree(h->po_nf); cudaFree(h->defer_count); cudaFree(h->defer_list);
   delete h;
   return LOBSIM_OK;
 }
@@ -507,17 +516,31 @@ static int launch_env(lobsim* h, const AdvParams& p, cudaStream_t stream) {
   const size_t dyn = (size_t)wpc * h->warp_smem;
   const int full = p.n_sel / wpc, tail = p.n_sel % wpc;
   auto launch = h->rare_paths ? h->fast->env_rare : h->fast->env;
-  if (p.allow_flat && LOBSIM_ENV_FLAT) h->maybe_flat = true;
-  else { int rc = ensure_sorted(h, stream); if (rc) return rc; }
+  // Step / rollout launches of an ENV_HOT layout: the flat-only kernel for every env, then the deferred (sorted) kernel for the env
+  // steps it handed over (usually none).  Resets, fill-logged handles and LOBSIM_FLAT_BLOBS=0 take the classic kernel, which reads both
+  // book forms and stores the sorted one.
+  const bool hot = h->fast->env_hot && h->defer_list && p.allow_flat && p.reset_mode == 0 && !h->fill_log && p.T > 0;
+  AdvParams q = p;
+  if (hot) {
+    CUDA_TRY(cudaMemsetAsync(h->defer_count, 0, sizeof(int32_t), stream));
+    q.defer_count = h->defer_count; q.defer_list = h->defer_list;
+    h->maybe_flat = true;
+  }
+  const int mode = hot ? ENV_HOT : ENV_CLASSIC;
   if (full > 0) { // full CTAs: phase-synchronous
-    launch(true, full, wpc * 32, dyn, stream, p, h->ec);
+    launch(mode, true, full, wpc * 32, dyn, stream, q, h->ec);
     CUDA_TRY(cudaGetLastError());
     h->launches++;
   }
   if (tail > 0) { // the remaining n_sel % wpc envs: one partially filled CTA without block-level barriers
-    AdvParams pt = p;
+    AdvParams pt = q;
     pt.sel_offset = full * wpc;
-    launch(false, 1, wpc * 32, dyn, stream, pt, h->ec);
+    launch(mode, false, 1, wpc * 32, dyn, stream, pt, h->ec);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+  }
+  if (hot) {
+    launch(ENV_DEFERRED, false, (p.n_sel + wpc - 1) / wpc, wpc * 32, dyn, stream, q, h->ec);
     CUDA_TRY(cudaGetLastError());
     h->launches++;
   }
@@ -744,11 +767,22 @@ int lobsim_process_orders(lobsim_t* h, const lobsim_order_t* orders, int32_t n, 
   CUDA_TRY(cudaSetDevice(h->device));
   if (n_fills_out) *n_fills_out = 0;
   if (n == 0) return LOBSIM_OK;
-  lobsim_order_t* d_orders = nullptr; lobsim_fill_t* d_fills = nullptr; int32_t* d_nf = nullptr; uint32_t* d_refs = nullptr;
-  CUDA_TRY(cudaMalloc(&d_orders, (size_t)n * sizeof(lobsim_order_t)));
-  CUDA_TRY(cudaMalloc(&d_fills, (size_t)(max_fills > 0 ? max_fills : 1) * sizeof(lobsim_fill_t)));
-  CUDA_TRY(cudaMalloc(&d_nf, sizeof(int32_t)));
-  CUDA_TRY(cudaMalloc(&d_refs, (size_t)n * sizeof(uint32_t)));
+  // device staging buffers, kept in the handle and grown on demand (a façade Exchange.process_order call is one order per call)
+  if (n > h->po_cap) {
+    cudaFree(h->po_orders); cudaFree(h->po_refs); h->po_orders = nullptr; h->po_refs = nullptr; h->po_cap = 0;
+    const int cap = n < 64 ? 64 : 2 * n;
+    CUDA_TRY(cudaMalloc(&h->po_orders, (size_t)cap * sizeof(lobsim_order_t)));
+    CUDA_TRY(cudaMalloc(&h->po_refs, (size_t)cap * sizeof(uint32_t)));
+    h->po_cap = cap;
+  }
+  if (max_fills > h->po_fill_cap || !h->po_fills) {
+    cudaFree(h->po_fills); h->po_fills = nullptr; h->po_fill_cap = 0;
+    const int cap = max_fills < 256 ? 256 : 2 * max_fills;
+    CUDA_TRY(cudaMalloc(&h->po_fills, (size_t)cap * sizeof(lobsim_fill_t)));
+    h->po_fill_cap = cap;
+  }
+  if (!h->po_nf) CUDA_TRY(cudaMalloc(&h->po_nf, sizeof(int32_t)));
+  lobsim_order_t* d_orders = h->po_orders; lobsim_fill_t* d_fills = h->po_fills; int32_t* d_nf = h->po_nf; uint32_t* d_refs = h->po_refs;
   CUDA_TRY(cudaMemcpy(d_orders, orders, (size_t)n * sizeof(lobsim_order_t), cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemset(d_nf, 0, sizeof(int32_t)));
   OrdParams p; p.blobs = h->blobs; p.L = h->L; p.n_envs = h->cfg.n_envs; p.blob_in_global = h->blob_in_global ? 1 : 0; p.orders = d_orders; p.n = n;
@@ -763,7 +797,6 @@ int lobsim_process_orders(lobsim_t* h, const lobsim_order_t* orders, int32_t n, 
   if (e == cudaSuccess) e = cudaMemcpy(&nf, d_nf, sizeof nf, cudaMemcpyDeviceToHost);
   if (e == cudaSuccess && fills_out && nf > 0) e = cudaMemcpy(fills_out, d_fills, (size_t)nf * sizeof(lobsim_fill_t), cudaMemcpyDeviceToHost);
   if (e == cudaSuccess && refs_out) e = cudaMemcpy(refs_out, d_refs, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost);
-  cudaFree(d_orders); cudaFree(d_fills); cudaFree(d_nf); cudaFree(d_refs);
   if (e != cudaSuccess) return fail(LOBSIM_E_CUDA, cudaGetErrorString(e));
   if (n_fills_out) *n_fills_out = nf;
   return LOBSIM_OK;
@@ -833,10 +866,11 @@ int lobsim_get_fills(lobsim_t* h, int32_t env, lobsim_fill_t* out, int32_t capac
 
 int lobsim_errors(lobsim_t* h, uint32_t* err_out) {
   if (!h || !err_out) return fail(LOBSIM_E_INVALID, "null argument");
-  std::vector<lobsim_env_state_t> st(h->cfg.n_envs);
-  int rc = lobsim_get_state(h, 0, h->cfg.n_envs, st.data());
-  if (rc) return rc;
-  for (int i = 0; i < h->cfg.n_envs; i++) err_out[i] = st[i].err;
+  // one strided device-to-host copy of the 4-byte error word of every blob header (both book forms keep it in place): no
+  // kernel, no state summary
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaMemcpy2D(err_out, sizeof(uint32_t), h->blobs + offsetof(BookHdr, err), (size_t)h->L.blob_bytes, sizeof(uint32_t), (size_t)h->cfg.n_envs,
+                        cudaMemcpyDeviceToHost));
   return LOBSIM_OK;
 }
 

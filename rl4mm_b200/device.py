@@ -216,7 +216,11 @@ class LobSim:
         return out[: min(n.value, cap)]
 
     def errors(self) -> np.ndarray:
-        return self.state()["err"].copy()
+        """Per-env error bits (lobsim_errors: one strided device-to-host copy of the header words, no state summary)."""
+        out = np.zeros(self.n_envs, np.uint32)
+        torch.cuda.synchronize(self.device)
+        check(lib().lobsim_errors(self._h, np_ptr(out)))
+        return out
 
     @property
     def kernel_path(self) -> str:

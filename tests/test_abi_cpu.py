@@ -32,6 +32,21 @@ def test_header_symbols_are_exported(lobsim_lib):
         assert hasattr(lobsim_lib, name), f"{name} declared in include/lobsim.h but not exported by liblobsim.so"
 
 
+def test_ingest_header_symbols_are_exported():
+    """include/lobingest.h <-> libingest.so (the LOBSTER packer's C ABI)."""
+    import ctypes
+
+    from rl4mm_b200.build import build_ingest
+
+    header = (ROOT / "include" / "lobingest.h").read_text()
+    declared = sorted(set(re.findall(r"\b(lobingest_[a-z_]+)\s*\(", header)))
+    assert declared == ["lobingest_count_lines", "lobingest_count_rows", "lobingest_pack_close", "lobingest_pack_copy", "lobingest_pack_open",
+                        "lobingest_pack_sizes", "lobingest_parse_book_rows", "lobingest_parse_messages"]
+    lib = ctypes.CDLL(str(build_ingest()))
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
 def test_abi_version_and_dims(lobsim_lib):
     assert lobsim_lib.lobsim_abi_version() == abi.ABI_VERSION
     cfg = abi.default_cfg(features=[abi.feature(abi.FEAT_SPREAD, 0, 100000, 0, 5000)] * 3, inc_prev_action_in_obs=1)

@@ -109,7 +109,7 @@ def test_config5_multi_ticker_heavy_cancel_general_path():
 @pytest.mark.fast_only
 def test_config5_full_size_8_tickers_8192_books():
     """BASELINE configs[4] at size: 8 synthetic tickers x 5e6 messages (50 levels, heavy cancel / modify flow, mean queue 12),
-    8 192 books per GPU, ticker = book mod 8, a random start second per book, on the straight-line kernels of the 128/1536/64
+    8 192 books per GPU, ticker = book mod 8, a random start second per book, on the straight-line kernels of the 128/1024/64
     layout (kernel_path "fast").  Replay, then a fused FixedActionAgent rollout; a sample of books against the oracle."""
     import ctypes
 
@@ -123,7 +123,7 @@ def test_config5_full_size_8_tickers_8192_books():
              abi.feature(abi.FEAT_INVENTORY, 0, 100000, -1e6, 1e6)]
     kw = dict(n_levels=50, outer_levels=20, features=feats, episode_steps=18000, warmup_steps=0,
               step_reward=abi.Reward(abi.REWARD_PNL, 0, 0.0), terminal_reward=abi.Reward(abi.REWARD_PNL, 0, 0.0))
-    cfg = abi.default_cfg(n_envs=n, max_levels_per_side=128, max_orders_per_side=1536, max_agent_orders=64, **kw)
+    cfg = abi.default_cfg(n_envs=n, max_levels_per_side=128, max_orders_per_side=1024, max_agent_orders=64, **kw)   # as bench.py
     sim = _sim(cfg, streams)
     assert sim.kernel_path == "fast"
     rng = np.random.default_rng(7)
@@ -178,7 +178,7 @@ def test_config3_rollout_65536_envs():
              abi.feature(abi.FEAT_TRADE_VOL_IMBALANCE, 100, 100000, -1, 1)]
     cfg = abi.default_cfg(n_envs=n, n_levels=10, episode_steps=64, warmup_steps=100, features=feats,
                           step_reward=abi.Reward(abi.REWARD_PNL, 0, 0), terminal_reward=abi.Reward(abi.REWARD_PNL, 0, 0),
-                          max_levels_per_side=64, max_orders_per_side=256, max_agent_orders=64, portfolio_carryover=0)
+                          max_levels_per_side=128, max_orders_per_side=256, max_agent_orders=64, portfolio_carryover=0)
     sim = _sim(cfg, [s])
     # pairs of replicas: env 2k and 2k+1 share the start; starts are spread over the first hour
     starts = (100 + (np.arange(n) // 2) % 3000).astype(np.int32) * 10

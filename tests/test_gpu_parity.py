@@ -256,9 +256,11 @@ def rollout_features():
     ]
 
 
+@pytest.mark.parametrize("levels_cap", [64, 128])
 @pytest.mark.parametrize("agent_kind", ["fixed", "teradactyl", "external", "random"])
-def test_synthetic_rollout_vs_oracle(agent_kind, torch_cuda):
-    """Full env path (agent orders, fills, portfolio, features, rewards, resync) on a synthetic SPY-shaped stream."""
+def test_synthetic_rollout_vs_oracle(agent_kind, levels_cap, torch_cuda):
+    """Full env path (agent orders, fills, portfolio, features, rewards, resync) on a synthetic SPY-shaped stream.  levels_cap 128
+    = the 128/256/64 layout, whose step / rollout launches run on the flat-only HOT kernel + the DEFERRED kernel (kernels.cuh)."""
     torch = torch_cuda
     from oracle.oracle import Oracle
     from rl4mm_b200 import synthetic
@@ -269,7 +271,7 @@ def test_synthetic_rollout_vs_oracle(agent_kind, torch_cuda):
     starts = [200, 1000, 3000, 3010]
     kw = dict(n_levels=10, episode_steps=200, warmup_steps=warm, outer_levels=20, features=rollout_features(),
               step_reward=abi.Reward(abi.REWARD_INV_ADJ_PNL, 0, 1e-4), terminal_reward=abi.Reward(abi.REWARD_PNL, 0, 0),
-              max_levels_per_side=64, max_orders_per_side=256, max_agent_orders=64,
+              max_levels_per_side=levels_cap, max_orders_per_side=256, max_agent_orders=64,
               market_order_clearing=1 if agent_kind == "teradactyl" else 0,
               market_order_fraction_of_inventory=0.25 if agent_kind == "teradactyl" else 0.0)
     sim = make_sim(abi.default_cfg(n_envs=len(starts), **kw), [s])
