@@ -326,7 +326,9 @@ int lobsim_create(const lobsim_cfg_t* cfg, int device, lobsim_t** out) {
   };
   h->warps_per_cta = best_wpc(4, 1.0, h->warp_smem);
   h->replay_warps_per_cta = best_wpc(4, 1.0, h->replay_warp_smem);
-  h->env_warps_per_cta = best_wpc(LOBSIM_ENVFAST_WARPS, 0.8, h->warp_smem);
+  h->env_warps_per_cta = best_wpc(LOBSIM_ENVFAST_WARPS, 0.95, h->warp_smem);   // (deep 128/1024/64 books: 5 warps x 2 CTAs = 10 resident, +11 % over 8 x 1)
+  { const char* e = getenv("LOBSIM_ENV_WPC"); const int w = e ? atoi(e) : 0;   // A/B override (tools/)
+    if (w >= 1 && w <= LOBSIM_ENVFAST_WARPS && (long long)w * h->warp_smem <= max_smem - 1024) h->env_warps_per_cta = w; }
   CUDA_TRY((cudaFuncSetAttribute(k_advance<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->warps_per_cta * h->warp_smem)));
   CUDA_TRY((cudaFuncSetAttribute(k_advance<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->warps_per_cta * h->warp_smem)));
   h->fast = h->force_general ? nullptr : find_fast_layout(h->L);
