@@ -413,8 +413,8 @@ __device__ __forceinline__ void fast_find_any(const FastBook<LT>& fb, unsigned c
   const int sm = -side;
   const int tkey = (price ^ sm) - sm;
   j = 0; jeq = -1;
-#pragma unroll
-  for (int q = 0; q < LT::NL / 32; q++) {
+#pragma unroll 1
+  for (int q = 0; q * 32 < nlv; q++) {                       // only the chunks that hold levels (deep books: 40-60 of 128)
     const int i = q * 32 + fb.lane;
     int k = INT32_MAX;
     if (i < nlv) k = (fb.P(sb)[i] ^ sm) - sm;
@@ -472,8 +472,8 @@ __device__ __forceinline__ void fast_rest_any(const FastBook<LT>& fb, FastState&
     if (base + lane < nord) fb.O(sb)[base + lane + 1] = v;
     __syncwarp();
   }
-#pragma unroll
-  for (int q = 0; q < LT::NL / 32 + 1; q++) {               // (+1: nlv2 may be NL)
+#pragma unroll 1
+  for (int q = j >> 5; q * 32 < nlv2; q++) {                 // level ends from the touched level on
     const int i = q * 32 + lane;
     if (i >= j && i < nlv2) fb.LE(sb)[i] = (uint16_t)(fb.LE(sb)[i] + 1);
   }
@@ -522,8 +522,8 @@ __device__ __forceinline__ void fast_remove_any(const FastBook<LT>& fb, FastStat
   }
   const bool level_gone = end - start == 1;
   if (!level_gone) {
-#pragma unroll
-    for (int q = 0; q < LT::NL / 32; q++) {
+#pragma unroll 1
+    for (int q = jeq >> 5; q * 32 < nlv; q++) {
       const int i = q * 32 + lane;
       if (i >= jeq && i < nlv) fb.LE(sb)[i] = (uint16_t)(fb.LE(sb)[i] - 1);
     }
