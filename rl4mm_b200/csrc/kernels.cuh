@@ -692,6 +692,7 @@ __global__ void __launch_bounds__(128, 7) k_replay_flat(const __grid_constant__ 
           }
         }
       }
+      if (flat && fs.seq > 0xE0000000u) { flat_leave(fb, fs); flat = false; }   // renumber the time-priority stamps long before they wrap
       if (!flat && flat_fits(fb, 8)) { flat_enter(fb, fs); flat = true; }   // back to the flat pools once the book has shrunk
     }
   }
