@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <string>
 #include <thread>
+#include <chrono>
 #include <vector>
 #include <fcntl.h>
 #include <sys/mman.h>
@@ -135,11 +136,8 @@ int64_t lobingest_count_rows(const char* path) {
 }
 
 // columns 0-5 of a LOBSTER message file: time, type, order id, size, price, direction (populate_database.py:71-78)
-int lobingest_parse_messages(const char* path, int64_t max_rows, int64_t* time_ns, int32_t* type, int64_t* order_id, int64_t* size,
-                             int64_t* price, int32_t* direction, int64_t* n_out) {
-  Map m;
-  if (!m.open(path)) return -1;
-  const Ranges r = split_rows(m);
+static int parse_messages_ranges(const Ranges& r, int64_t max_rows, int64_t* time_ns, int32_t* type, int64_t* order_id, int64_t* size,
+                                 int64_t* price, int32_t* direction, int64_t* n_out) {
   std::vector<int> rcs((size_t)r.parts(), 0);
   parallel_parts(r.parts(), [&](int part) {
     const char* s = r.cut[(size_t)part]; const char* e = r.cut[(size_t)part + 1];
@@ -166,12 +164,15 @@ int lobingest_parse_messages(const char* path, int64_t max_rows, int64_t* time_n
   *n_out = r.row0.back() < max_rows ? r.row0.back() : max_rows;
   return 0;
 }
-
-// rows `row_idx` (ascending, duplicates allowed) of an orderbook file with n_cols integer columns
-int lobingest_parse_book_rows(const char* path, const int64_t* row_idx, int64_t n_rows, int32_t n_cols, int64_t* out) {
+int lobingest_parse_messages(const char* path, int64_t max_rows, int64_t* time_ns, int32_t* type, int64_t* order_id, int64_t* size,
+                             int64_t* price, int32_t* direction, int64_t* n_out) {
   Map m;
   if (!m.open(path)) return -1;
-  const Ranges r = split_rows(m);
+  return parse_messages_ranges(split_rows(m), max_rows, time_ns, type, order_id, size, price, direction, n_out);
+}
+
+// rows `row_idx` (ascending, duplicates allowed) of an orderbook file with n_cols integer columns
+static int parse_book_rows_ranges(const Ranges& r, const int64_t* row_idx, int64_t n_rows, int32_t n_cols, int64_t* out) {
   if (n_rows > 0 && row_idx[n_rows - 1] >= r.row0.back()) return -3;
   std::vector<int> rcs((size_t)r.parts(), 0);
   parallel_parts(r.parts(), [&](int part) {
@@ -200,6 +201,11 @@ int lobingest_parse_book_rows(const char* path, const int64_t* row_idx, int64_t 
   });
   for (int rc : rcs) if (rc) return rc;
   return 0;
+}
+int lobingest_parse_book_rows(const char* path, const int64_t* row_idx, int64_t n_rows, int32_t n_cols, int64_t* out) {
+  Map m;
+  if (!m.open(path)) return -1;
+  return parse_book_rows_ranges(split_rows(m), row_idx, n_rows, n_cols, out);
 }
 
 // ====================================================================================================================
@@ -243,21 +249,30 @@ int pack_files(Pack& P, const char* msg_csv, const char* book_csv, int n_levels,
                int64_t db_batch, int64_t max_rows) {
   if (n_levels <= 0 || step_us <= 0 || 1000000 % step_us) { P.err = "step_us must divide one second"; return -10; }
   if (db_batch <= 0) db_batch = 1000000;
-  int64_t n = lobingest_count_rows(msg_csv);
-  if (n < 0) { P.err = std::string("cannot open ") + msg_csv; return -1; }
+  const bool timing = getenv("LOBINGEST_TIMING") != nullptr;
+  auto t_prev = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!timing) return;
+    auto t = std::chrono::steady_clock::now();
+    fprintf(stderr, "lobingest: %-28s %.3f s\n", what, std::chrono::duration<double>(t - t_prev).count());
+    t_prev = t;
+  };
+  Map mm, mb;                                                   // each file is mapped and split into row ranges ONCE
+  if (!mm.open(msg_csv)) { P.err = std::string("cannot open ") + msg_csv; return -1; }
+  if (!mb.open(book_csv)) { P.err = std::string("cannot open ") + book_csv; return -1; }
+  const Ranges rm = split_rows(mm), rb = split_rows(mb);
+  lap("map + split rows (both files)");
+  int64_t n = rm.row0.back();
   const bool truncated = max_rows >= 0 && max_rows < n;
   if (truncated) n = max_rows;
   if (n == 0) { P.err = "empty message file"; return -11; }
   std::vector<int64_t> time_ns((size_t)n), oid((size_t)n), size((size_t)n), price((size_t)n);
   std::vector<int32_t> type((size_t)n), dir((size_t)n);
   int64_t got = 0;
-  int rc = lobingest_parse_messages(msg_csv, n, time_ns.data(), type.data(), oid.data(), size.data(), price.data(), dir.data(), &got);
+  int rc = parse_messages_ranges(rm, n, time_ns.data(), type.data(), oid.data(), size.data(), price.data(), dir.data(), &got);
   if (rc != 0 || got != n) { P.err = "malformed LOBSTER message file"; return -2; }
-  if (!truncated) {
-    const int64_t nb = lobingest_count_rows(book_csv);
-    if (nb < 0) { P.err = std::string("cannot open ") + book_csv; return -1; }
-    if (nb != n) { P.err = "message file and orderbook file have different row counts"; return -12; }
-  }
+  lap("parse messages");
+  if (!truncated && rb.row0.back() != n) { P.err = "message file and orderbook file have different row counts"; return -12; }
   P.n_rows = n;
   for (int64_t i = 1; i < n; i++) if (time_ns[(size_t)i] < time_ns[(size_t)i - 1]) { P.err = "LOBSTER messages must be time ordered"; return -13; }
   auto ts_us = [&](int64_t i) { return time_ns[(size_t)i] / 1000; };
@@ -283,6 +298,7 @@ int pack_files(Pack& P, const char* msg_csv, const char* book_csv, int n_levels,
       a = b;
     }
   }
+  lap("tie order");
   // ---- keep: inside the replay range, not hidden; reject what the reference rejects ----------------------------------------------
   std::vector<int64_t> keep;
   keep.reserve((size_t)n);
@@ -296,32 +312,56 @@ int pack_files(Pack& P, const char* msg_csv, const char* book_csv, int n_levels,
     if (t < 1 || t > 4) { P.err = "unknown LOBSTER message type"; return -16; }
     if (price[(size_t)i] >= (1LL << 31) || size[(size_t)i] >= (1LL << 31)) { P.err = "price / size does not fit int32"; return -17; }
   }
+  lap("filter + checks");
   // ---- dense order references: rank among the distinct external ids (np.unique order), + 1 -------------------------------------
+  // (threads: chunk sorts + pairwise merges for the distinct ids, then the per-message rank lookups and record fills in parallel)
+  const int nthr = keep.size() > (size_t)(1 << 18) ? ingest_threads() : 1;
+  auto chunk = [&](int part, size_t total) { return std::pair<size_t, size_t>(total * (size_t)part / (size_t)nthr, total * (size_t)(part + 1) / (size_t)nthr); };
   std::vector<int64_t> uniq(keep.size());
-  for (size_t k = 0; k < keep.size(); k++) uniq[k] = oid[(size_t)keep[k]];
-  std::sort(uniq.begin(), uniq.end());
+  parallel_parts(nthr, [&](int part) {
+    const auto [a, b] = chunk(part, keep.size());
+    for (size_t k = a; k < b; k++) uniq[k] = oid[(size_t)keep[k]];
+    std::sort(uniq.begin() + (ptrdiff_t)a, uniq.begin() + (ptrdiff_t)b);
+  });
+  for (int width = 1; width < nthr; width *= 2) {                    // merge sorted runs [part, part + width) pairwise
+    const int pairs = (nthr + 2 * width - 1) / (2 * width);
+    parallel_parts(pairs, [&](int pr) {
+      const int lo = pr * 2 * width, mid = lo + width, hi = std::min(nthr, lo + 2 * width);
+      if (mid >= hi) return;
+      std::inplace_merge(uniq.begin() + (ptrdiff_t)chunk(lo, keep.size()).first, uniq.begin() + (ptrdiff_t)chunk(mid, keep.size()).first,
+                         uniq.begin() + (ptrdiff_t)chunk(hi - 1, keep.size()).second);
+    });
+  }
   uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
   if ((int64_t)uniq.size() + 1 >= (1LL << 31)) { P.err = "too many distinct order ids"; return -18; }
   P.ext_ids.assign(1, 0);
   P.ext_ids.insert(P.ext_ids.end(), uniq.begin(), uniq.end());
   P.msgs.resize(keep.size());
   P.step_off.assign((size_t)n_grid + 1, 0u);
-  for (size_t k = 0; k < keep.size(); k++) {
-    const int64_t i = keep[k];
-    const int t = type[(size_t)i];
-    int side = dir[(size_t)i] == 1 ? 0 : 1;          // +1 buy / otherwise sell
-    if (t == 4) side ^= 1;                             // executions carry the direction of the RESTING order: flip to the aggressor's
-    PackedMsg& m = P.msgs[k];
-    m.price = (int32_t)price[(size_t)i];
-    m.volume = (int32_t)size[(size_t)i];
-    m.ref = (uint32_t)(std::lower_bound(uniq.begin(), uniq.end(), oid[(size_t)i]) - uniq.begin()) + 1u;
-    m.meta = (uint32_t)t | ((uint32_t)side << 3);
-    const int64_t step = ceil_div(ts_us(i) - t0, step_us) - 1;       // ts in (t0 + k*step, t0 + (k+1)*step]  =>  k
-    if (step < 0 || step >= n_grid) { P.err = "internal: step index out of range"; return -19; }
-    P.step_off[(size_t)step + 1] += 1u;
-  }
+  std::vector<int> bad((size_t)nthr, 0);
+  std::vector<int64_t> steps(keep.size());
+  parallel_parts(nthr, [&](int part) {
+    const auto [a, b] = chunk(part, keep.size());
+    for (size_t k = a; k < b; k++) {
+      const int64_t i = keep[k];
+      const int t = type[(size_t)i];
+      int side = dir[(size_t)i] == 1 ? 0 : 1;          // +1 buy / otherwise sell
+      if (t == 4) side ^= 1;                             // executions carry the direction of the RESTING order: flip to the aggressor's
+      PackedMsg& m = P.msgs[k];
+      m.price = (int32_t)price[(size_t)i];
+      m.volume = (int32_t)size[(size_t)i];
+      m.ref = (uint32_t)(std::lower_bound(uniq.begin(), uniq.end(), oid[(size_t)i]) - uniq.begin()) + 1u;
+      m.meta = (uint32_t)t | ((uint32_t)side << 3);
+      const int64_t step = ceil_div(ts_us(i) - t0, step_us) - 1;       // ts in (t0 + k*step, t0 + (k+1)*step]  =>  k
+      if (step < 0 || step >= n_grid) { bad[(size_t)part] = 1; return; }
+      steps[k] = step;
+    }
+  });
+  for (int b : bad) if (b) { P.err = "internal: step index out of range"; return -19; }
+  for (size_t k = 0; k < keep.size(); k++) P.step_off[(size_t)steps[k] + 1] += 1u;
   for (int64_t k = 0; k < n_grid; k++) P.step_off[(size_t)k + 1] += P.step_off[(size_t)k];
 
+  lap("refs + records + offsets");
   // ---- per-second snapshots: the orderbook row of the last message with time <= T ------------------------------------------------
   const int64_t ns = n_seconds + 1;
   std::vector<int64_t> need((size_t)ns);
@@ -334,8 +374,9 @@ int pack_files(Pack& P, const char* msg_csv, const char* book_csv, int n_levels,
   }
   const int ncol = 4 * n_levels;
   std::vector<int64_t> rows((size_t)ns * ncol);
-  rc = lobingest_parse_book_rows(book_csv, need.data(), ns, ncol, rows.data());
+  rc = parse_book_rows_ranges(rb, need.data(), ns, ncol, rows.data());
   if (rc != 0) { P.err = "could not read the snapshot rows of the orderbook file"; return -3; }
+  lap("snapshot rows");
   P.snapshots.assign((size_t)ns * 2 * n_levels * 2, 0);
   for (int64_t k = 0; k < ns; k++)
     for (int l = 0; l < n_levels; l++) {
