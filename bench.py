@@ -661,7 +661,7 @@ def run_collect(ctx: Ctx, stream):
 def run_multiticker(ctx: Ctx):
     """BASELINE.json configs[4]: 8 synthetic tickers (seeds 0-7, mids $30-$500), 50 levels, heavy cancel / modify flow,
     deep queues; `multiticker_envs` books per GPU, ticker = book index mod 8, a random start second per book.  Replay
-    (messages/s, k_replay_flat<128,1024,64>) and a fused FixedActionAgent([1,2,1,2]) rollout (env steps/s)."""
+    (messages/s, k_replay_hyb<128,1024,64>: hot order pool near the touch + cold level arrays) and a fused FixedActionAgent([1,2,1,2]) rollout (env steps/s)."""
     args, torch = ctx.args, ctx.torch
     import ctypes
 
@@ -715,8 +715,11 @@ def run_multiticker(ctx: Ctx):
                    "envs_per_gpu": n_envs, "n_levels": 50, "n_streams": n_streams, "segment_steps": seg,
                    "capacities": [128, 1024, 64]},
         "gpu_launches": int(launches), "clocks": clocks,
-        "roofline": roofline(algo, 1e3 * t_dev / steps, "k_replay_flat<StaticLayout<128,1024,64>> (deep books: its sorted-array path)",
-                             "k_replay_fast_L50" if n_envs == 8192 else None),
+        "roofline": roofline(algo, 1e3 * t_dev / steps,
+                             "k_replay_hyb<StaticLayout<128,1024,64>> (hot order pool + cold level arrays, book_hybrid.cuh)"
+                             if os.environ.get("LOBSIM_REPLAY_HYBRID", "1") != "0" and os.environ.get("LOBSIM_REPLAY_FLAT", "1") != "0"
+                             else "k_replay_flat<StaticLayout<128,1024,64>> (deep books: its sorted-array path)",
+                             "k_replay_hyb_L50" if n_envs == 8192 else None),
     }
     ctx.launches += launches
     # ---- fused FixedActionAgent rollout --------------------------------------------------------------------------------

@@ -59,6 +59,7 @@ static void env_launch(int mode, bool sync, int grid, int block, size_t dyn, cud
 cudaError_t FN(_attrs)(int dyn_replay, int dyn_env) {
   cudaError_t e = set_attr((const void*)k_replay_fast<LT>, dyn_replay);
   if (e == cudaSuccess) e = set_attr((const void*)k_replay_flat<LT>, dyn_replay);
+  if constexpr (hyb_layout<LT>()) { if (e == cudaSuccess) e = set_attr((const void*)k_replay_hyb<LT>, dyn_replay); }
   if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)k_to_sorted<LT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * LT::blob_bytes <= 227 * 1024 ? 4 * LT::blob_bytes : LT::blob_bytes);
   if (e == cudaSuccess) e = env_attrs<false>(dyn_env);
   return e;
@@ -67,6 +68,9 @@ void FN(_replay)(int grid, int block, size_t dyn, cudaStream_t stream, const Adv
   k_replay_fast<LT><<<grid, block, dyn, stream>>>(p, ec);
 }
 void FN(_replay_flat)(int grid, int block, size_t dyn, cudaStream_t stream, const AdvParams& p, const EnvConst& ec) {
+  if constexpr (hyb_layout<LT>()) {
+    if (p.hybrid) { k_replay_hyb<LT><<<grid, block, dyn, stream>>>(p, ec); return; }
+  }
   k_replay_flat<LT><<<grid, block, dyn, stream>>>(p, ec);
 }
 void FN(_to_sorted)(unsigned char* blobs, int n_envs, cudaStream_t stream) {

@@ -14,6 +14,7 @@
 #include <stdint.h>
 
 #include "book_flat.cuh"
+#include "book_hybrid.cuh"
 #include "env.cuh"
 #include "lobsim.h"
 
@@ -102,6 +103,7 @@ struct AdvParams {
   int32_t blob_in_global;           // deep books: the blob does not fit in the shared memory of an SM and is worked on in place in HBM / L2
   int32_t* defer_count;             // env HOT kernel: number of (env, step) items handed to the deferred kernel
   int2* defer_list;                 // [n_sel] {selection index, env step to resume at}
+  int32_t hybrid;                   // deep layouts: the replay launch runs k_replay_hyb (book_hybrid.cuh); blobs stay sorted in HBM
   int32_t allow_flat;               // fast kernels: books that fit run on -- and are stored in -- the flat order pools (book_flat.cuh)
   const double* actions_in;         // EXTERNAL: [T][n_sel][action_dim]
   double* obs; double* act; double* rew; uint8_t* done; // [T][n_sel][...] (any may be null)
@@ -508,9 +510,153 @@ __global__ void __launch_bounds__(128, 7) k_replay_fast(const __grid_constant__ 
   __syncwarp();
 }
 
+__device__ __forceinline__ bool hdr_is_flat(const BookHdr* h) { return h->cnt[0][0] < 0; }
+// ====================================================================================================================
+//  the replay HYBRID kernel (deep layouts): k_replay_fast with the hybrid book of book_hybrid.cuh -- the levels near the touch in
+//  a flat order pool, the rest in the sorted arrays -- for every book that can take that form, the sorted straight-line path for
+//  the others.  The blob in HBM is the canonical sorted layout on entry and on exit.
+// ====================================================================================================================
+template <class LT>
+__global__ void __launch_bounds__(128, 3) k_replay_hyb(const __grid_constant__ AdvParams p, const __grid_constant__ EnvConst ec) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int env = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (env >= p.n_sel) return;
+  const lobsim_cfg_t& c = ec.cfg;
+  unsigned char* base = warp_smem_base(smem, warp, p.warp_smem);
+  unsigned char* msgbuf = base + LT::agent_off;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(msgbuf + 2 * MSG_TILE_BYTES);
+  unsigned char* gblob = p.blobs + (size_t)env * LT::blob_bytes;
+  if (lane == 0) {
+    mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
+    fence_mbar_init();
+    mbar_expect_tx(&bars[2], (uint32_t)LT::agent_off);
+    tma_load(base, gblob, (uint32_t)LT::agent_off, &bars[2]);
+  }
+  __syncwarp();
+  mbar_wait(&bars[2], 0);
+
+  FastBook<LT> fb; fb.blob = base; fb.lane = lane;
+  BookHdr* h = reinterpret_cast<BookHdr*>(base);
+  FastState f; f.err = h->err; f.dead = h->dead; f.bail = 0; f.bail_vol = 0;
+  if (hdr_is_flat(h)) flat_leave_fn<LT>(base, lane, h->cnt[0][1], h->cnt[1][1]);   // (a blob stored by the flat kernels)
+  fast_refresh_best(fb, f);
+  HybState hs; hs.n0 = hs.n1 = 0; hs.floor0 = INT32_MIN; hs.floor1 = INT32_MAX; hs.seq = 0;
+  bool hyb = false;
+  const lobsim_stream_t* stp = &p.streams[h->stream_id];
+  const lobsim_msg_t* __restrict__ st_msgs = stp->msgs;
+  const uint32_t* __restrict__ st_step_off = stp->step_off;
+  int now_step = h->now_step;
+  const int T = p.T;
+  const int n_grid = (int)stp->n_grid_steps;
+  if ((now_step < 0 || now_step > n_grid) && !f.dead && T > 0) { f.err |= LOBSIM_ERR_END_OF_STREAM; f.dead = 1; }
+  unsigned g = 0, g_end_all = 0;
+  if (!f.dead && T > 0) { g = __ldg(&st_step_off[now_step]); g_end_all = __ldg(&st_step_off[min((long long)now_step + T, (long long)n_grid)]); }
+  auto try_enter = [&]() {
+    if (hyb_enter(fb, f, hs)) hyb = true;
+    else if (hs.n0 | hs.n1) { hyb_leave(fb, f, hs); hs.n0 = hs.n1 = 0; }      // one side was moved, the other could not be: put it back
+  };
+  if (g < g_end_all) try_enter();
+  const unsigned tile0 = g / MSG_TILE;
+  unsigned next_issue = 0, next_wait = 0;
+  auto issue_tile = [&]() {
+    const unsigned first = (tile0 + next_issue) * MSG_TILE;
+    if (first >= g_end_all) return;
+    if (lane == 0) {
+      const unsigned n_total = (unsigned)stp->n_msgs;
+      const unsigned cnt = n_total - first < MSG_TILE ? n_total - first : MSG_TILE;
+      uint64_t* bar = &bars[next_issue & 1];
+      mbar_expect_tx(bar, cnt * 16);
+      tma_load(msgbuf + (next_issue & 1) * MSG_TILE_BYTES, st_msgs + first, cnt * 16, bar);
+    }
+    next_issue++;
+  };
+  auto wait_tile = [&]() { mbar_wait(&bars[next_wait & 1], (next_wait >> 1) & 1); next_wait++; };
+  if (g < g_end_all) { issue_tile(); issue_tile(); }
+  __syncwarp();
+  const int steps_per_sec = ec.steps_per_sec;
+  int sub = now_step >= 0 ? now_step % steps_per_sec : 0;
+
+#pragma unroll 1
+  for (int t = 0; t < T && !f.dead; t++) {
+    if (now_step >= n_grid) { f.err |= LOBSIM_ERR_END_OF_STREAM; f.dead = 1; break; }
+    const unsigned g_step_end = __ldg(&st_step_off[now_step + 1]);
+#pragma unroll 1
+    while (g < g_step_end) {
+      const unsigned tile = g / MSG_TILE - tile0;
+      if (tile == next_wait) wait_tile();
+      const unsigned tile_end = (g / MSG_TILE + 1) * MSG_TILE;
+      const unsigned lim = g_step_end < tile_end ? g_step_end : tile_end;
+      const uint4* mp = reinterpret_cast<const uint4*>(msgbuf + (tile & 1) * MSG_TILE_BYTES) + (g % MSG_TILE);
+      const unsigned cnt = lim - g;
+      unsigned i = 0;
+      int redo_vol = 0;
+      if (hyb) {
+#pragma unroll 1
+        for (; i < cnt; i++) {
+          const uint4 m = mp[i];
+          hyb_message<LT>(fb, f, hs, (int)m.x, (int)m.y, m.z, m.w);
+          if (f.bail | f.dead) break;
+        }
+        if (f.bail) {                                        // this book cannot stay hybrid: back to the sorted form
+          const int why = f.bail, rest = f.bail_vol;
+          f.bail = 0; f.bail_vol = 0;
+          hyb_leave(fb, f, hs); hyb = false; hs.n0 = hs.n1 = 0;
+          if (why == FLAT_BAIL_FULL) redo_vol = rest;        // the unfinished part of message i runs on the sorted book
+          else i++;
+        }
+      }
+      if (!hyb && !f.dead) {
+#pragma unroll 1
+        for (; i < cnt; i++) {
+          const uint4 m = mp[i];
+          const int v = redo_vol ? redo_vol : (int)m.y;
+          redo_vol = 0;
+          fast_message(fb, f, (int)m.x, v, m.z, m.w);
+          if (f.dead) break;
+        }
+      }
+      if (f.dead) break;
+      g = lim;
+      if (g == tile_end) { __syncwarp(); issue_tile(); }
+    }
+    if (f.dead) break;
+    now_step++;
+    if (hyb) hyb_top_up(fb, f, hs);
+    if (++sub == steps_per_sec) {                            // whole second: outer-level resync, OrderbookSimulator.py:86-87
+      sub = 0;
+      if (c.resync && (!p.resync_last_only || t == T - 1)) {
+        const double prop = ec.outer_prop;
+        const double bb = f.best0 == INT32_MIN ? 0.0 : (double)f.best0;
+        const double bs = f.best1 == INT32_MAX ? (double)INFINITY : (double)f.best1;
+        if (bb < (double)h->min_buy + prop * (double)h->init_buy_range || bs > (double)h->max_sell - prop * (double)h->init_sell_range) {
+          const int sec = now_step / steps_per_sec;
+          if (sec <= (int)stp->n_seconds && stp->snap_valid[sec]) {
+            const int32_t* row = stp->snapshots + (size_t)sec * 2 * c.n_levels * 2;
+            if (hyb && !flat_resync_needed(h, row, c.n_levels, lane)) hyb_update_trackers(fb, hs);
+            else {
+              if (hyb) { hyb_leave(fb, f, hs); hyb = false; hs.n0 = hs.n1 = 0; }
+              fast_resync(fb, f, row, c.n_levels);
+            }
+          }
+        }
+      }
+      if (!hyb) try_enter();
+    }
+  }
+  if (hyb) hyb_leave(fb, f, hs);
+  while (next_wait < next_issue) wait_tile();
+  __syncwarp();
+  if (lane == 0) { h->now_step = now_step; h->err = f.err; h->dead = f.dead; }
+  __syncwarp();
+  fence_proxy_async();
+  __syncwarp();
+  if (lane == 0) { tma_store(gblob, base, (uint32_t)LT::agent_off); tma_store_wait(); }
+  __syncwarp();
+}
+
 // ---- the flat form of a blob in HBM (book_flat.cuh): header with cnt[0] = {-1, n0}, cnt[1] = {seq, n1}; per side the order pool
 //      (n x 16 B at the start of the side's order array); the agent tables as always.  Parts: lanes 0-1 the pools, 2-7 the agent tables.
-__device__ __forceinline__ bool hdr_is_flat(const BookHdr* h) { return h->cnt[0][0] < 0; }
 template <class LT, bool LOAD>
 __device__ __forceinline__ uint32_t flat_body_copy(unsigned char* sm, unsigned char* gm, uint64_t* bar, int lane, int n0, int n1) {
   const BookHdr* h = reinterpret_cast<const BookHdr*>(sm);

@@ -207,6 +207,8 @@ struct lobsim {
   lobsim_msg_t* st_msgs = nullptr; uint64_t st_msgs_cap = 0;
   bool has_reset = false;
   bool force_general = false;         // LOBSIM_FORCE_GENERAL=1: always use the runtime-layout kernels (testing)
+  int replay_hybrid = -1;             // k_replay_hyb (book_hybrid.cuh) as the replay launch of a deep compiled layout (NL >= 64, NO >= 512):
+                                      // -1 (default) when NO >= 1024, LOBSIM_REPLAY_HYBRID=1 on every such layout, =0 never
   bool replay_flat = true;            // LOBSIM_REPLAY_FLAT=0: the replay fast path keeps every book in the sorted level arrays (A/B, testing)
   bool flat_blobs = true;             // LOBSIM_FLAT_BLOBS=0: the fast kernels never keep a book in the flat order pools across launches
                                       // (env kernels: sorted path only; replay: converts back at the end of every launch)
@@ -283,6 +285,7 @@ int lobsim_create(const lobsim_cfg_t* cfg, int device, lobsim_t** out) {
   h->cfg = *cfg; h->device = device;
   { const char* e = getenv("LOBSIM_FORCE_GENERAL"); h->force_general = e && e[0] == '1'; }
   { const char* e = getenv("LOBSIM_REPLAY_FLAT"); h->replay_flat = !(e && e[0] == '0'); }
+  { const char* e = getenv("LOBSIM_REPLAY_HYBRID"); h->replay_hybrid = e && e[0] == '1' ? 1 : e && e[0] == '0' ? 0 : -1; }
   { const char* e = getenv("LOBSIM_FLAT_BLOBS"); h->flat_blobs = !(e && e[0] == '0'); }
   h->rare_paths = cfg->step_reward.kind == LOBSIM_REWARD_ROLLING_SHARPE || cfg->terminal_reward.kind == LOBSIM_REWARD_ROLLING_SHARPE;
   for (int i = 0; i < cfg->n_features; i++) h->rare_paths = h->rare_paths || cfg->features[i].norm_len > 0;
@@ -500,7 +503,9 @@ static int launch_replay_fast(lobsim* h, const AdvParams& p, cudaStream_t stream
   if (grid <= 0) return LOBSIM_OK;
   AdvParams pr = p;
   pr.warp_smem = h->replay_warp_smem;
-  if (!h->replay_flat) { int rc = ensure_sorted(h, stream); if (rc) return rc; }
+  pr.hybrid = h->replay_flat && h->fast->NL >= 64 && h->fast->NO >= 512 && (h->replay_hybrid > 0 || (h->replay_hybrid < 0 && h->fast->NO >= 1024)) ? 1 : 0;
+  if (pr.hybrid) pr.allow_flat = 0;
+  if (!h->replay_flat || pr.hybrid) { int rc = ensure_sorted(h, stream); if (rc) return rc; }
   else if (p.allow_flat) h->maybe_flat = true;
   (h->replay_flat ? h->fast->replay_flat : h->fast->replay)(grid, wpc * 32, (size_t)wpc * h->replay_warp_smem, stream, pr, h->ec);
   CUDA_TRY(cudaGetLastError());

@@ -20,9 +20,12 @@ def pytest_generate_tests(metafunc):
     """Every GPU test runs on three independent implementations of the order semantics: "fast" = the straight-line static-layout
     kernels with every book that fits in the flat order pools of book_flat.cuh (in shared memory and in HBM); "sorted" = the same
     kernels on the sorted level arrays only (LOBSIM_REPLAY_FLAT=0, LOBSIM_FLAT_BLOBS=0); "general" = the runtime-layout kernel
-    (LOBSIM_FORCE_GENERAL=1)."""
+    (LOBSIM_FORCE_GENERAL=1).  Tests marked `replay_path` run a fourth time, "hybrid": the hot-pool / cold-level-array book of
+    book_hybrid.cuh forced on for every layout that can hold it (LOBSIM_REPLAY_HYBRID=1; by default only the NO >= 1024 layouts)."""
     if "kernel_family" in metafunc.fixturenames and metafunc.definition.get_closest_marker("gpu"):
         fams = ["fast"] if metafunc.definition.get_closest_marker("fast_only") else ["fast", "sorted", "general"]
+        if metafunc.definition.get_closest_marker("replay_path") and len(fams) > 1:
+            fams.append("hybrid")
         metafunc.parametrize("kernel_family", fams, indirect=True)
 
 
@@ -33,6 +36,10 @@ def kernel_family(request, monkeypatch):
         monkeypatch.setenv("LOBSIM_FORCE_GENERAL", "1" if fam == "general" else "0")
         monkeypatch.setenv("LOBSIM_REPLAY_FLAT", "0" if fam == "sorted" else "1")
         monkeypatch.setenv("LOBSIM_FLAT_BLOBS", "0" if fam == "sorted" else "1")
+        if fam == "hybrid":
+            monkeypatch.setenv("LOBSIM_REPLAY_HYBRID", "1")
+        else:
+            monkeypatch.delenv("LOBSIM_REPLAY_HYBRID", raising=False)
     return fam
 
 

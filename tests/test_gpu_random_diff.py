@@ -101,8 +101,9 @@ def test_random_env_case(seed):
 @pytest.mark.fast_only          # the test itself runs both kernel families
 @pytest.mark.parametrize("seed", range(SEED0, SEED0 + N_REPLAY_CASES))
 def test_random_replay_case(seed, monkeypatch):
-    """Pure replay on all three implementations -- the flat order pools (k_replay_flat), the sorted level arrays
-    (k_replay_fast, LOBSIM_REPLAY_FLAT=0) and, forced, the general k_advance -- vs the oracle."""
+    """Pure replay on all four implementations -- the flat order pools (k_replay_flat), the hybrid hot-pool / cold-array book
+    (k_replay_hyb, LOBSIM_REPLAY_HYBRID=1 on the layouts that can hold it), the sorted level arrays (k_replay_fast,
+    LOBSIM_REPLAY_FLAT=0) and, forced, the general k_advance -- vs the oracle."""
     from oracle.oracle import Oracle
     from rl4mm_b200 import synthetic
     from test_gpu_parity import compare_books, make_sim
@@ -111,8 +112,9 @@ def test_random_replay_case(seed, monkeypatch):
     s = synthetic.generate(c["synth"])
     n = c["n_envs"]
     okw = {k: v for k, v in c["cfg_kw"].items() if not k.startswith("max_")}
-    for force_general, flat in (("0", "1"), ("0", "0"), ("1", "1")):
+    for force_general, flat, hyb in (("0", "1", "0"), ("0", "1", "1"), ("0", "0", "0"), ("1", "1", "0")):
         monkeypatch.setenv("LOBSIM_FORCE_GENERAL", force_general)
+        monkeypatch.setenv("LOBSIM_REPLAY_HYBRID", hyb)
         monkeypatch.setenv("LOBSIM_REPLAY_FLAT", flat)
         monkeypatch.setenv("LOBSIM_FLAT_BLOBS", flat)
         sim = make_sim(abi.default_cfg(n_envs=n, **c["cfg_kw"]), [s])
@@ -124,7 +126,7 @@ def test_random_replay_case(seed, monkeypatch):
             sim.replay(chunk)
             st = sim.state()
             for env, o in enumerate(oracles):
-                what = f"replay seed {seed} general={force_general} flat={flat} env {env} chunk {chunk}"
+                what = f"replay seed {seed} general={force_general} flat={flat} hybrid={hyb} env {env} chunk {chunk}"
                 o.replay(chunk)
                 os_ = o.state()
                 overflow = int(st["err"][env]) & (abi.ERR_LEVEL_OVERFLOW | abi.ERR_ORDER_OVERFLOW)
@@ -195,3 +197,60 @@ def test_per_env_agents_match_oracle_and_sweep_table():
     starts2 = env.episode_start_steps.reshape(len(grid), 6)
     assert (starts2 == starts2[0]).all()                      # every agent saw the same six episodes
     assert len({round(r["episode_reward_mean"], 6) for r in table}) > 1
+
+
+HYBRID_STRESS = {
+    # queues far longer than the 128-order pool at very few prices: the best level cannot become hot (enter fails / bails)
+    "long_queues": dict(geom_p=0.6, max_offset_ticks=2, target_orders=700, mean_queue=12, p_sweep=0.01, no=1024),
+    # a book around the cold capacity of the 128/512/64 layout (256 cold + 128 hot orders per side): bail on a full cold part
+    "cold_full": dict(geom_p=0.1, max_offset_ticks=70, target_orders=760, mean_queue=4, p_sweep=0.0005, no=512),
+    # many sweeps through several levels: the pool runs empty inside an execution and is refilled from the cold levels
+    "sweeps": dict(geom_p=0.12, max_offset_ticks=70, target_orders=500, mean_queue=1, p_sweep=0.05, no=1024),
+    # everything near the touch: the pool fills up and spills its worst level again and again
+    "spills": dict(geom_p=0.5, max_offset_ticks=12, target_orders=400, mean_queue=12, p_sweep=0.002, no=1536),
+}
+
+
+@pytest.mark.fast_only
+@pytest.mark.parametrize("name", sorted(HYBRID_STRESS))
+def test_hybrid_book_stress(name, monkeypatch):
+    """k_replay_hyb (book_hybrid.cuh) on streams shaped to hit its conversions: hot <-> cold level moves, pool full, cold part
+    full, a best level longer than the pool.  Books, trackers and error flags vs the oracle after every chunk."""
+    from oracle.oracle import Oracle
+    from rl4mm_b200 import synthetic
+    from test_gpu_parity import compare_books, make_sim
+
+    k = HYBRID_STRESS[name]
+    sc = synthetic.SynthConfig(seed=77, n_msgs=120_000, duration_s=120, n_levels=50, mid0=2_000_000, p_limit=0.40, p_cancel=0.2,
+                               p_delete=0.3, p_exec=0.1, geom_p=k["geom_p"], init_levels=55, mean_queue=k["mean_queue"],
+                               target_orders=k["target_orders"], max_offset_ticks=k["max_offset_ticks"], p_sweep=k["p_sweep"])
+    s = synthetic.generate(sc)
+    monkeypatch.setenv("LOBSIM_FORCE_GENERAL", "0")
+    monkeypatch.setenv("LOBSIM_REPLAY_FLAT", "1")
+    monkeypatch.setenv("LOBSIM_REPLAY_HYBRID", "1")
+    n = 4
+    kw = dict(n_levels=50, outer_levels=20, resync=1)
+    sim = make_sim(abi.default_cfg(n_envs=n, max_levels_per_side=128, max_orders_per_side=k["no"], **kw), [s])
+    assert sim.kernel_path == "fast"
+    oracles = [Oracle(abi.default_cfg(n_envs=1, **kw), s) for _ in range(n)]
+    starts = np.array([0, 100, 300, 500], np.int32)
+    sim.reset_book(0, starts)
+    for o, st in zip(oracles, starts):
+        o.reset_book(int(st))
+    compared = 0
+    for chunk in (1, 9, 90, 250, 250):
+        sim.replay(chunk)
+        st = sim.state()
+        for env, o in enumerate(oracles):
+            what = f"hybrid stress {name} env {env} chunk {chunk}"
+            o.replay(chunk)
+            os_ = o.state()
+            if int(st["err"][env]) & (abi.ERR_LEVEL_OVERFLOW | abi.ERR_ORDER_OVERFLOW):
+                continue
+            assert int(st["err"][env]) == int(os_["err"]), (what, int(st["err"][env]), int(os_["err"]))
+            for f in ("now_step", "min_buy_price", "max_sell_price", "best_buy", "best_sell", "best_buy_volume", "best_sell_volume"):
+                assert st[f][env] == os_[f], (what, f, st[f][env], os_[f])
+            compare_books(sim, env, o, what)
+            compared += 1
+    assert compared >= 8, (name, compared)
+    sim.close()
