@@ -46,6 +46,18 @@ class DeviceDatabase:
         s.ticker, s.date = ticker, trading_date.strftime("%Y-%m-%d")
         return self.add_stream(ticker, trading_date, s)
 
+    def has_day(self, ticker: str, day: datetime) -> bool:
+        """utils.daterange_in_db for one ticker-day (rl4mm/utils/utils.py:65-73)."""
+        day = datetime.combine(day.date(), datetime.min.time())
+        return any(t == ticker and d == day for t, d in zip(self.tickers, self.dates))
+
+    def populate_from_archives(self, path_to_lobster_data, **kw) -> List[int]:
+        """LOBSTER month archives (``*.7z``) of a folder, oldest first (run_populate_database_from_zipped.py:50-109); see
+        ``rl4mm_b200.archives.populate_from_archives``."""
+        from .archives import populate_from_archives
+
+        return populate_from_archives(self, path_to_lobster_data, **kw)
+
     def stream_id(self, ticker: str, day: datetime) -> int:
         day = datetime.combine(day.date(), datetime.min.time())
         for i, (t, d) in enumerate(zip(self.tickers, self.dates)):

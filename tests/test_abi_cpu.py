@@ -534,3 +534,64 @@ def test_reference_seeded_episode_starts():
         got = [reference_random_start_time(lo, hi, timedelta(seconds=c["min_start_s"]), timedelta(seconds=c["max_end_s"]),
                                            timedelta(seconds=c["episode_s"]), timedelta(seconds=0.1), days).isoformat() for _ in range(4)]
         assert got == c["starts"], c
+
+
+def test_month_archives_are_ingested_in_date_order(tmp_path, monkeypatch):
+    """run_populate_database_from_zipped.py:50-109: archives ordered by the dates behind `__` (not the download number), ticker /
+    dates / levels from the file name, one stream per trading day inside, extracted CSVs removed afterwards, days that are
+    already loaded skipped, and a loud error when there is no 7z executable."""
+    import shutil
+    from datetime import datetime
+
+    from rl4mm_b200 import archives
+    from rl4mm_b200.simulation import DeviceDatabase
+
+    # the reference's own example (its comment lists this folder): sorting whole names would put May first
+    names = ["_data_dwn_50_385__KO_2018-04-01_2018-04-30_3.7z", "_data_dwn_50_389__KO_2018-02-01_2018-02-28_3.7z",
+             "_data_dwn_50_386__KO_2018-03-01_2018-03-31_3.7z", "_data_dwn_50_384__KO_2018-05-01_2018-05-31_3.7z"]
+    assert [n.split("_")[-3] for n in archives.archive_order(names)] == ["2018-02-01", "2018-03-01", "2018-04-01", "2018-05-01"]
+    tk, d0, d1, L = archives.parse_archive_name("/data/KO/" + names[0])
+    assert (tk, d0, d1, L) == ("KO", datetime(2018, 4, 1), datetime(2018, 4, 30), 3)
+    with pytest.raises(ValueError):
+        archives.parse_archive_name("/data/readme.7z")
+
+    def write_day(folder, ticker, day, n=200, L=3, seed=0):
+        rng = np.random.default_rng(seed)
+        t = np.sort(rng.integers(34_200_000_000_000, 34_206_000_000_000, size=n))
+        with open(folder / f"{ticker}_{day}_34200000_57600000_message_{L}.csv", "w") as f:
+            for i in range(n):
+                sec, ns = divmod(int(t[i]), 10**9)
+                f.write(f"{sec}.{ns:09d},{rng.choice([1, 3, 4])},{rng.integers(1, 10**6)},{rng.integers(1, 500)},"
+                        f"{3_000_000 + 100 * int(rng.integers(0, 50))},{rng.choice([-1, 1])}\n")
+        rows = np.zeros((n, 4 * L), np.int64)
+        for lv in range(L):
+            rows[:, 4 * lv: 4 * lv + 4] = (3_050_100 + 100 * lv, 10 + lv, 3_050_000 - 100 * lv, 20 + lv)
+        np.savetxt(folder / f"{ticker}_{day}_34200000_57600000_orderbook_{L}.csv", rows, fmt="%d", delimiter=",")
+
+    content = {names[0]: ["2018-04-02", "2018-04-03"], names[1]: ["2018-02-01"], names[2]: ["2018-03-01", "2018-03-02"], names[3]: []}
+    folder = tmp_path / "KO"
+    folder.mkdir()
+    for n_ in names:
+        (folder / n_).write_bytes(b"7z\xbc\xaf\x27\x1c")          # only the name matters to the fake extractor below
+    (folder / "notes.csv").write_text("keep me\n")                 # not created by an extraction: must survive
+    seen = []
+
+    def fake_extract(fpath, out_dir):
+        seen.append(Path(fpath).name)
+        for k, day in enumerate(content[Path(fpath).name]):
+            write_day(Path(out_dir), "KO", day, seed=len(seen) * 10 + k)
+
+    db = DeviceDatabase()
+    ids = db.populate_from_archives(folder, extractor=fake_extract)
+    assert seen == [names[1], names[2], names[0], names[3]]
+    assert ids == [0, 1, 2, 3, 4]
+    assert [d.strftime("%Y-%m-%d") for d in db.dates] == ["2018-02-01", "2018-03-01", "2018-03-02", "2018-04-02", "2018-04-03"]
+    assert set(db.tickers) == {"KO"} and all(s.n_levels == 3 and len(s.msgs) > 0 for s in db.streams)
+    assert sorted(p.name for p in folder.glob("*.csv")) == ["notes.csv"]
+    assert db.stream_id("KO", datetime(2018, 3, 2)) == 2
+    # a second pass adds nothing: every day is already there
+    assert db.populate_from_archives(folder, extractor=fake_extract) == []
+    # the default extractor is the reference's `7z x`: without the executable it must fail loudly, not skip
+    monkeypatch.setattr(shutil, "which", lambda exe: None)
+    with pytest.raises(RuntimeError, match="7z"):
+        DeviceDatabase().populate_from_archives(folder)
