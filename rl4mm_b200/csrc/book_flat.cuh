@@ -55,6 +55,13 @@ __device__ __forceinline__ void flat_keys(const uint4* pool, int n, int lane, ui
     if (c * 32 + lane < n) k[c] = *reinterpret_cast<const uint2*>(&pool[c * 32 + lane]);
   }
 }
+// the same without the sentinel: every lane loads its slot (always inside the pool, CAP = 32 x NCH), slots beyond n hold stale
+// orders -- every use must test `c * 32 + lane < n` itself (saves the per-search register initialisation)
+template <int NCH>
+__device__ __forceinline__ void flat_keys_raw(const uint4* pool, int lane, uint2 (&k)[NCH]) {
+#pragma unroll
+  for (int c = 0; c < NCH; c++) k[c] = *reinterpret_cast<const uint2*>(&pool[c * 32 + lane]);
+}
 // first set bit of a per-chunk ballot array -> order index (the array is not all zero)
 template <int NCH>
 __device__ __forceinline__ int flat_first(const unsigned (&m)[NCH]) {
@@ -84,11 +91,12 @@ __device__ __forceinline__ int flat_best_scan(unsigned char* blob, int lane, int
 // One order of side S (0 buy, 1 sell) through the flat book.  Same results as fast_order_full<LT,TR> on the sorted book; TR: fills /
 // flows / the agent's order tables are tracked (env kernels), exactly as in book_fast.cuh.
 // Sets f.bail = FLAT_BAIL_FULL -- with the book untouched -- when the order may have to rest and the pool of its side is full: the
-// caller converts the book to the sorted form and runs the order there.  (A status in FastState instead of a return value: the hot
-// loop tests `f.bail | f.dead` once per message.)
+// caller converts the book to the sorted form and runs the order there.  Returns true when the caller's message loop has to stop
+// (f.bail or f.dead set) -- a constant per return site, so the compiler threads the rare exits straight out of the loop and the
+// common paths carry no status register.
 #define FLAT_BAIL_FULL 3
-template <class LT, int S, bool TR>
-__device__ __forceinline__ void flat_order(unsigned char* blob, int lane, FastState& f, FlatState& st, int type, int price, int vol, uint32_t ref, bool is_agent) {
+template <class LT, int S, bool TR, bool VCHK = true>
+__device__ __forceinline__ bool flat_order(unsigned char* blob, int lane, FastState& f, FlatState& st, int type, int price, int vol, uint32_t ref, bool is_agent) {
   constexpr int OPP = S ^ 1;
   constexpr int NCH = flat_nch<LT>();
   if (!TR) is_agent = false;
@@ -99,18 +107,44 @@ __device__ __forceinline__ void flat_order(unsigned char* blob, int lane, FastSt
   uint4* own = flat_pool<LT>(blob, S);
   uint4* opp = flat_pool<LT>(blob, OPP);
   FastBook<LT> fb; fb.blob = blob; fb.lane = lane;
-  if (__builtin_expect(vol <= 0, 0)) { f.err |= LOBSIM_ERR_BAD_VOLUME; return; }   // assert order.volume > 0, Exchange.py:59-60
-  __syncwarp();                                                             // the previous order's stores are visible
-  if (type == LOBSIM_MSG_LIMIT || type == LOBSIM_MSG_MARKET) {
-    int rem = vol;
-    if (type == LOBSIM_MSG_LIMIT && n_own >= flat_cap<LT>()) { f.bail = FLAT_BAIL_FULL; return; }
+  if (VCHK && __builtin_expect(vol <= 0, 0)) { f.err |= LOBSIM_ERR_BAD_VOLUME; return false; }   // assert order.volume > 0, Exchange.py:59-60
+  __syncwarp();                                                             // (!VCHK: the caller has checked the volume)
+  // ---- the order rests at the back of its price's queue (Exchange.py:74-83) --------------------------------------------
+  auto rest = [&](int rem) -> bool {
+    if (TR && is_agent) {   // OrderIdConvertor.add_internal_id_to_order_and_track + internal book append
+      BookHdr* h = reinterpret_cast<BookHdr*>(blob);
+      const int nag = h->nag[S];
+      if (nag >= LT::NA) { f.err |= LOBSIM_ERR_AGENT_OVERFLOW; return false; }
+      const uint32_t id = h->next_agent_id;
+      ref = LOBSIM_REF_AGENT | id;
+      __syncwarp();
+      if (lane == 0) {
+        int32_t* ap = reinterpret_cast<int32_t*>(blob + LT::agent_off + S * LT::NA * 12);
+        ap[nag] = price; ap[LT::NA + nag] = rem; reinterpret_cast<uint32_t*>(ap)[2 * LT::NA + nag] = id;
+        h->nag[S] = nag + 1; h->next_agent_id = id + 1;
+      }
+    }
+    if (lane == 0) own[n_own] = make_uint4((unsigned)price, ref, (unsigned)rem, st.seq);
+    n_own += 1; st.seq += 1;
+    if (S ? price < best_own : price > best_own) best_own = price;
+    return false;
+  };
+  // dispatch, the common cases first: a limit order that does not cross (3 tests), a cancellation / deletion (2 tests)
+  bool exec;                                                                // the previous order's stores are visible (above)
+  if (type == LOBSIM_MSG_LIMIT) {
+    if (n_own >= flat_cap<LT>()) { f.bail = FLAT_BAIL_FULL; return true; }
     const bool crosses = S ? price <= best_opp : price >= best_opp;        // empty opposite side: INT32_MIN / INT32_MAX
-    if (type == LOBSIM_MSG_MARKET || crosses) {
+    if (!crosses) return rest(vol);
+    exec = true;
+  } else exec = type == LOBSIM_MSG_MARKET;
+  if (exec) {
+    int rem = vol;
+    {
       // ---- execution against the opposite side, best price first, oldest order first (Exchange.py:85-120) -------------
 #pragma unroll 1
       while (rem > 0) {
         if (n_opp == 0) {
-          if (type == LOBSIM_MSG_MARKET) { f.err |= LOBSIM_ERR_EMPTY_BOOK; f.dead = 1; }   // EmptyOrderbookError :183-186
+          if (type == LOBSIM_MSG_MARKET) { f.err |= LOBSIM_ERR_EMPTY_BOOK; f.dead = 1; return true; }   // EmptyOrderbookError :183-186
           break;
         }
         const int bp = best_opp;
@@ -162,41 +196,23 @@ __device__ __forceinline__ void flat_order(unsigned char* blob, int lane, FastSt
         __syncwarp();
         if (TR && hagent) fast_agent_reduce(fb, OPP, href & 0x7fffffffu, 0, true);   // the resting agent order is gone
       }
-      if (!(rem > 0 && type == LOBSIM_MSG_LIMIT && !f.dead)) return;
-      // the remainder of a crossing limit order rests (Exchange.py:116-119)
     }
-    // ---- the order rests at the back of its price's queue (Exchange.py:74-83) ------------------------------------------
-    if (TR && is_agent) {   // OrderIdConvertor.add_internal_id_to_order_and_track + internal book append
-      BookHdr* h = reinterpret_cast<BookHdr*>(blob);
-      const int nag = h->nag[S];
-      if (nag >= LT::NA) { f.err |= LOBSIM_ERR_AGENT_OVERFLOW; return; }
-      const uint32_t id = h->next_agent_id;
-      ref = LOBSIM_REF_AGENT | id;
-      __syncwarp();
-      if (lane == 0) {
-        int32_t* ap = reinterpret_cast<int32_t*>(blob + LT::agent_off + S * LT::NA * 12);
-        ap[nag] = price; ap[LT::NA + nag] = rem; reinterpret_cast<uint32_t*>(ap)[2 * LT::NA + nag] = id;
-        h->nag[S] = nag + 1; h->next_agent_id = id + 1;
-      }
-    }
-    if (lane == 0) own[n_own] = make_uint4((unsigned)price, ref, (unsigned)rem, st.seq);
-    n_own += 1; st.seq += 1;
-    if (S ? price < best_own : price > best_own) best_own = price;
-    return;
+    if (!(rem > 0 && type == LOBSIM_MSG_LIMIT)) return false;
+    return rest(rem);                                                       // the remainder of a crossing limit order rests (:116-119)
   }
   // ---- cancellation / deletion (Exchange.py:122-147) ----------------------------------------------------------------------
   uint2 k[NCH];
-  flat_keys(own, n_own, lane, k);
+  flat_keys_raw(own, lane, k);
   unsigned m[NCH], any = 0;
 #pragma unroll
-  for (int c = 0; c < NCH; c++) { m[c] = __ballot_sync(FULL_MASK, (int)k[c].x == price && k[c].y == ref); any |= m[c]; }
+  for (int c = 0; c < NCH; c++) { m[c] = __ballot_sync(FULL_MASK, c * 32 + lane < n_own && (int)k[c].x == price && k[c].y == ref); any |= m[c]; }
   bool aggregate = false;
   if (!any) {
     // unknown id: the level's snapshot aggregate (internal_id -1, always the head of its level) takes the hit (:133-137);
     // no such level, or no aggregate left at it: nothing happens (:129-132,138-139)
 #pragma unroll
     for (int c = 0; c < NCH; c++) { m[c] = __ballot_sync(FULL_MASK, c * 32 + lane < n_own && (int)k[c].x == price && k[c].y == LOBSIM_REF_AGGREGATE); any |= m[c]; }
-    if (!any) return;
+    if (!any) return false;
     aggregate = true;
   }
   const int i = flat_first(m);
@@ -205,22 +221,23 @@ __device__ __forceinline__ void flat_order(unsigned char* blob, int lane, FastSt
   if (vol < cur) {                                                         // partial: reduce in place
     if (lane == 0) own[i].z = (unsigned)(cur - vol);
     if (TR && is_agent && !aggregate) { __syncwarp(); fast_agent_reduce(fb, S, ref & 0x7fffffffu, vol, false); }
-    return;
+    return false;
   }
   // full removal (over-size requests remove the resting volume, :142-146): the last order of the pool fills the hole
   if (price == best_own) best_own = flat_best_of<S>(k, n_own, lane, i);
   if (lane == 0) own[i] = own[n_own - 1];
   n_own -= 1;
   if (TR && is_agent && !aggregate) { __syncwarp(); fast_agent_reduce(fb, S, ref & 0x7fffffffu, cur, true); }
-  return;
+  return false;
 }
 
 // the replay form: a packed historical message
-template <class LT>
-__device__ __forceinline__ void flat_message(unsigned char* blob, int lane, FastState& f, FlatState& st, int price, int vol, uint32_t ref, uint32_t meta) {
+// (VCHK = false: the caller has looked at the volumes of the whole message tile at once)
+template <class LT, bool VCHK = true>
+__device__ __forceinline__ bool flat_message(unsigned char* blob, int lane, FastState& f, FlatState& st, int price, int vol, uint32_t ref, uint32_t meta) {
   const int type = (int)(meta & 7u);
-  if (meta & 8u) flat_order<LT, 1, false>(blob, lane, f, st, type, price, vol, ref, false);
-  else flat_order<LT, 0, false>(blob, lane, f, st, type, price, vol, ref, false);
+  if (meta & 8u) return flat_order<LT, 1, false, VCHK>(blob, lane, f, st, type, price, vol, ref, false);
+  return flat_order<LT, 0, false, VCHK>(blob, lane, f, st, type, price, vol, ref, false);
 }
 // the tracked form (env kernels): historical messages and the agent's own orders; false: pool full (see flat_order)
 template <class LT>

@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
 #include "book_flat.cuh"
 #include "book_hybrid.cuh"
 #include "env.cuh"
@@ -725,8 +726,11 @@ __global__ void __launch_bounds__(128) k_to_sorted(unsigned char* blobs, int n_e
 //  FLAT_CAP resting orders per side), the sorted straight-line path for the others -- per book, re-decided every second.
 //  The blob in HBM is the canonical sorted layout on entry and on exit.
 // ====================================================================================================================
+#ifndef LOBSIM_REPLAY_FLAT_MIN_BLOCKS
+#define LOBSIM_REPLAY_FLAT_MIN_BLOCKS 7      // 72 registers: 28 resident warps per SM with the 64/256/32 blob (8 = 64 registers: A/B in profiles/)
+#endif
 template <class LT>
-__global__ void __launch_bounds__(128, 7) k_replay_flat(const __grid_constant__ AdvParams p, const __grid_constant__ EnvConst ec) {
+__global__ void __launch_bounds__(128, LOBSIM_REPLAY_FLAT_MIN_BLOCKS) k_replay_flat(const __grid_constant__ AdvParams p, const __grid_constant__ EnvConst ec) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int env = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -798,13 +802,20 @@ __global__ void __launch_bounds__(128, 7) k_replay_flat(const __grid_constant__ 
       const unsigned cnt = lim - g;
       unsigned i = 0;
       if (flat) {
+        // the volumes of the whole segment (<= 32 messages, one per lane) are checked at once; the per-message test is one predicate
+        const bool bad_vol = __any_sync(FULL_MASK, (unsigned)lane < cnt && mp[(unsigned)lane < cnt ? lane : 0].y <= 0);
+        auto run = [&](auto vchk) {                          // (two copies of the loop: the one that runs has no volume test)
 #pragma unroll 1
-        for (; i < cnt; i++) {
-          const uint4 m = mp[i];
-          flat_message<LT>(base, lane, f, fs, (int)m.x, (int)m.y, m.z, m.w);
-          if (f.bail | f.dead) break;                                                      // pool full (this message runs on the sorted book) / EmptyOrderbookError
-        }
-        if (f.bail) { f.bail = 0; flat_leave(fb, fs); flat = false; }
+          for (; i < cnt; i++) {
+            const uint4 m = mp[i];
+            if (flat_message<LT, decltype(vchk)::value>(base, lane, f, fs, (int)m.x, (int)m.y, m.z, m.w)) return true;   // pool full
+                                                             // (this message runs on the sorted book) or f.dead: EmptyOrderbookError
+          }
+          return false;
+        };
+        const bool stopped = __builtin_expect(bad_vol, 0) ? run(std::true_type{}) : run(std::false_type{});
+        f.bail = 0;                                          // (not read: `stopped` without f.dead is the full pool)
+        if (stopped && !f.dead) { flat_leave(fb, fs); flat = false; }
       }
       if (!flat && !f.dead) {
 #pragma unroll 1
