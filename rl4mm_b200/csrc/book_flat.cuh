@@ -203,19 +203,22 @@ __device__ __forceinline__ bool flat_order(unsigned char* blob, int lane, FastSt
   // ---- cancellation / deletion (Exchange.py:122-147) ----------------------------------------------------------------------
   uint2 k[NCH];
   flat_keys_raw(own, lane, k);
-  unsigned m[NCH], any = 0;
+  // (price, ref) names at most one resting order: the lane that holds it announces its index (one warp reduction)
+  int mine = -1;
 #pragma unroll
-  for (int c = 0; c < NCH; c++) { m[c] = __ballot_sync(FULL_MASK, c * 32 + lane < n_own && (int)k[c].x == price && k[c].y == ref); any |= m[c]; }
+  for (int c = 0; c < NCH; c++) if (c * 32 + lane < n_own && (int)k[c].x == price && k[c].y == ref) mine = c * 32 + lane;
+  int i = __reduce_max_sync(FULL_MASK, mine);
   bool aggregate = false;
-  if (!any) {
+  if (i < 0) {
     // unknown id: the level's snapshot aggregate (internal_id -1, always the head of its level) takes the hit (:133-137);
     // no such level, or no aggregate left at it: nothing happens (:129-132,138-139)
+    mine = INT32_MAX;
 #pragma unroll
-    for (int c = 0; c < NCH; c++) { m[c] = __ballot_sync(FULL_MASK, c * 32 + lane < n_own && (int)k[c].x == price && k[c].y == LOBSIM_REF_AGGREGATE); any |= m[c]; }
-    if (!any) return false;
+    for (int c = NCH - 1; c >= 0; c--) if (c * 32 + lane < n_own && (int)k[c].x == price && k[c].y == LOBSIM_REF_AGGREGATE) mine = c * 32 + lane;
+    i = __reduce_min_sync(FULL_MASK, mine);
+    if (i == INT32_MAX) return false;
     aggregate = true;
   }
-  const int i = flat_first(m);
   const int cur = (int)own[i].z;
   __syncwarp();
   if (vol < cur) {                                                         // partial: reduce in place
