@@ -277,7 +277,7 @@ __device__ __forceinline__ void hyb_order(const FastBook<LT>& fb, FastState& f, 
   const int floor_own = S ? hs.floor1 : hs.floor0;
   uint4* own = hyb_pool<LT>(fb.blob, S);
   uint4* opp = hyb_pool<LT>(fb.blob, OPP);
-  if (__builtin_expect(vol <= 0, 0)) { f.err |= LOBSIM_ERR_BAD_VOLUME; return; }
+  // (vol > 0: the caller looks at the volumes of a whole message segment at once and runs a segment with a bad one on the sorted book)
   __syncwarp();
   const bool hot = S ? price <= floor_own : price >= floor_own;
   if (type == LOBSIM_MSG_LIMIT || type == LOBSIM_MSG_MARKET) {
@@ -364,16 +364,18 @@ __device__ __forceinline__ void hyb_order(const FastBook<LT>& fb, FastState& f, 
     return;
   }
   uint2 k[HYB_NCH];
-  flat_keys(own, n_own, lane, k);
-  unsigned m[HYB_NCH], any = 0;
+  flat_keys_raw(own, lane, k);                               // (slots beyond n_own are stale: every test below checks the index)
+  int mine = -1;                                             // (price, ref) names at most one order: its lane announces the index
 #pragma unroll
-  for (int c = 0; c < HYB_NCH; c++) { m[c] = __ballot_sync(FULL_MASK, (int)k[c].x == price && k[c].y == ref); any |= m[c]; }
-  if (!any) {
+  for (int c = 0; c < HYB_NCH; c++) if (c * 32 + lane < n_own && (int)k[c].x == price && k[c].y == ref) mine = c * 32 + lane;
+  int i = __reduce_max_sync(FULL_MASK, mine);
+  if (i < 0) {                                               // unknown id: the level's snapshot aggregate, if it is still there
+    mine = INT32_MAX;
 #pragma unroll
-    for (int c = 0; c < HYB_NCH; c++) { m[c] = __ballot_sync(FULL_MASK, c * 32 + lane < n_own && (int)k[c].x == price && k[c].y == LOBSIM_REF_AGGREGATE); any |= m[c]; }
-    if (!any) return;
+    for (int c = HYB_NCH - 1; c >= 0; c--) if (c * 32 + lane < n_own && (int)k[c].x == price && k[c].y == LOBSIM_REF_AGGREGATE) mine = c * 32 + lane;
+    i = __reduce_min_sync(FULL_MASK, mine);
+    if (i == INT32_MAX) return;
   }
-  const int i = flat_first(m);
   const int cur = (int)own[i].z;
   __syncwarp();
   if (vol < cur) { if (lane == 0) own[i].z = (unsigned)(cur - vol); return; }

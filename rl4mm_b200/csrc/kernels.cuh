@@ -592,6 +592,11 @@ __global__ void __launch_bounds__(128, 3) k_replay_hyb(const __grid_constant__ A
       const unsigned cnt = lim - g;
       unsigned i = 0;
       int redo_vol = 0;
+      // the volumes of the whole segment (<= 32 messages, one per lane) at once: a segment with a bad one (never in valid data) runs on
+      // the sorted book, whose routines test every order (assert order.volume > 0, Exchange.py:59-60)
+      if (hyb && __any_sync(FULL_MASK, (unsigned)lane < cnt && (int)mp[(unsigned)lane < cnt ? lane : 0].y <= 0)) {
+        hyb_leave(fb, f, hs); hyb = false; hs.n0 = hs.n1 = 0;
+      }
       if (hyb) {
 #pragma unroll 1
         for (; i < cnt; i++) {
@@ -803,7 +808,7 @@ __global__ void __launch_bounds__(128, LOBSIM_REPLAY_FLAT_MIN_BLOCKS) k_replay_f
       unsigned i = 0;
       if (flat) {
         // the volumes of the whole segment (<= 32 messages, one per lane) are checked at once; the per-message test is one predicate
-        const bool bad_vol = __any_sync(FULL_MASK, (unsigned)lane < cnt && mp[(unsigned)lane < cnt ? lane : 0].y <= 0);
+        const bool bad_vol = __any_sync(FULL_MASK, (unsigned)lane < cnt && (int)mp[(unsigned)lane < cnt ? lane : 0].y <= 0);
         auto run = [&](auto vchk) {                          // (two copies of the loop: the one that runs has no volume test)
 #pragma unroll 1
           for (; i < cnt; i++) {

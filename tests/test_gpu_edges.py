@@ -197,3 +197,41 @@ def test_deep_books_in_hbm_match_oracle():
         oo, oa, orw, od = o.rollout(50, agent)
         assert np.allclose(obs[:, env], oo, rtol=1e-6, atol=1e-9) and np.allclose(rew[:, env], orw, rtol=1e-6, atol=1e-9)
         compare_books(sim, env, o, ("deep env", env))
+
+
+@pytest.mark.replay_path
+@pytest.mark.parametrize("deep", [False, True])
+def test_messages_with_nonpositive_volume_set_bad_volume_and_are_skipped(deep):
+    """`assert order.volume > 0` (Exchange.py:59-60): the reference raises; the device flags the env (LOBSIM_ERR_BAD_VOLUME), skips
+    the message and goes on -- on every replay implementation (the flat / hybrid loops look at the volumes of a whole message
+    segment at once), with the books still equal to the oracle's."""
+    from oracle.oracle import Oracle
+    from rl4mm_b200 import synthetic
+    from test_gpu_parity import compare_books
+
+    sc = synthetic.SynthConfig(seed=21, n_msgs=30_000, duration_s=60, n_levels=50 if deep else 10, target_orders=500 if deep else 50,
+                               mean_queue=8 if deep else 4, init_levels=55 if deep else 30)
+    s = synthetic.generate(sc)
+    rng = np.random.default_rng(3)
+    bad = rng.choice(np.arange(200, s.n_msgs), size=40, replace=False)
+    s.msgs["volume"][bad[:20]] = 0
+    s.msgs["volume"][bad[20:]] = -7
+    kw = dict(n_levels=sc.n_levels, outer_levels=5, resync=1)
+    cap = dict(max_levels_per_side=128, max_orders_per_side=1024) if deep else {}
+    n = 3
+    sim = _sim(abi.default_cfg(n_envs=n, **kw, **cap), [s])
+    starts = np.array([0, 100, 200], np.int32)
+    sim.reset_book(0, starts)
+    oracles = [Oracle(abi.default_cfg(n_envs=1, **kw), s) for _ in range(n)]
+    for o, st in zip(oracles, starts):
+        o.reset_book(int(st))
+    for chunk in (3, 150, 200):
+        sim.replay(chunk)
+        st = sim.state()
+        for env, o in enumerate(oracles):
+            o.replay(chunk)
+            os_ = o.state()
+            assert int(st["err"][env]) == int(os_["err"]), (env, chunk, int(st["err"][env]), int(os_["err"]))
+            compare_books(sim, env, o, f"bad volume env {env} chunk {chunk}")
+    assert all(int(e) & abi.ERR_BAD_VOLUME for e in sim.state()["err"])
+    sim.close()
