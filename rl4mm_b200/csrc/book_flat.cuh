@@ -132,9 +132,9 @@ __device__ __forceinline__ bool flat_order(unsigned char* blob, int lane, FastSt
   // dispatch, the common cases first: a limit order that does not cross (3 tests), a cancellation / deletion (2 tests)
   bool exec;                                                                // the previous order's stores are visible (above)
   if (type == LOBSIM_MSG_LIMIT) {
-    if (n_own >= flat_cap<LT>()) { f.bail = FLAT_BAIL_FULL; return true; }
     const bool crosses = S ? price <= best_opp : price >= best_opp;        // empty opposite side: INT32_MIN / INT32_MAX
-    if (!crosses) return rest(vol);
+    if (__builtin_expect(!crosses & (n_own < flat_cap<LT>()), 1)) return rest(vol);   // (one branch for the common case)
+    if (n_own >= flat_cap<LT>()) { f.bail = FLAT_BAIL_FULL; return true; }
     exec = true;
   } else exec = type == LOBSIM_MSG_MARKET;
   if (exec) {

@@ -809,16 +809,19 @@ __global__ void __launch_bounds__(128, LOBSIM_REPLAY_FLAT_MIN_BLOCKS) k_replay_f
       if (flat) {
         // the volumes of the whole segment (<= 32 messages, one per lane) are checked at once; the per-message test is one predicate
         const bool bad_vol = __any_sync(FULL_MASK, (unsigned)lane < cnt && (int)mp[(unsigned)lane < cnt ? lane : 0].y <= 0);
+        unsigned off = 0;                                    // (the loop walks a byte offset: no index arithmetic per message)
+        const unsigned off_end = cnt * 16u;
         auto run = [&](auto vchk) {                          // (two copies of the loop: the one that runs has no volume test)
 #pragma unroll 1
-          for (; i < cnt; i++) {
-            const uint4 m = mp[i];
+          for (; off != off_end; off += 16u) {
+            const uint4 m = *reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(mp) + off);
             if (flat_message<LT, decltype(vchk)::value>(base, lane, f, fs, (int)m.x, (int)m.y, m.z, m.w)) return true;   // pool full
                                                              // (this message runs on the sorted book) or f.dead: EmptyOrderbookError
           }
           return false;
         };
         const bool stopped = __builtin_expect(bad_vol, 0) ? run(std::true_type{}) : run(std::false_type{});
+        i = off >> 4;
         f.bail = 0;                                          // (not read: `stopped` without f.dead is the full pool)
         if (stopped && !f.dead) { flat_leave(fb, fs); flat = false; }
       }
