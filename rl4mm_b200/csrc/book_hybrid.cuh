@@ -264,10 +264,11 @@ __device__ __forceinline__ void hyb_leave(const FastBook<LT>& fb, FastState& f, 
 }
 
 // ---- one historical message through the hybrid book (results == fast_order_full<LT,false> on the sorted book) -----------------
+// Returns true when the message loop has to stop (f.bail or f.dead set; a constant per return site, as in flat_order).
 // f.bail = FLAT_BAIL_FULL: leave the hybrid form and run a (type, side, price, f.bail_vol, ref) order on the sorted book (the
 // unfinished part of this one); f.bail = HYB_BAIL_DONE: leave the hybrid form, the order is complete.
 template <class LT, int S>
-__device__ __forceinline__ void hyb_order(const FastBook<LT>& fb, FastState& f, HybState& hs, int type, int price, int vol, uint32_t ref) {
+__device__ __forceinline__ bool hyb_order(const FastBook<LT>& fb, FastState& f, HybState& hs, int type, int price, int vol, uint32_t ref) {
   constexpr int OPP = S ^ 1;
   const int lane = fb.lane;
   int& n_own = S ? hs.n1 : hs.n0;
@@ -288,10 +289,10 @@ __device__ __forceinline__ void hyb_order(const FastBook<LT>& fb, FastState& f, 
       while (rem > 0) {
         if (n_opp == 0) {                                     // pool empty: more levels beyond the floor?
           if (fb.cnt(OPP)->x == 0) {
-            if (type == LOBSIM_MSG_MARKET) { f.err |= LOBSIM_ERR_EMPTY_BOOK; f.dead = 1; }   // EmptyOrderbookError :183-186
+            if (type == LOBSIM_MSG_MARKET) { f.err |= LOBSIM_ERR_EMPTY_BOOK; f.dead = 1; return true; }   // EmptyOrderbookError :183-186
             break;
           }
-          if (!hyb_refill_one<LT, OPP>(fb, f, hs)) { f.bail = FLAT_BAIL_FULL; f.bail_vol = rem; return; }   // a level longer than the pool
+          if (!hyb_refill_one<LT, OPP>(fb, f, hs)) { f.bail = FLAT_BAIL_FULL; f.bail_vol = rem; return true; }   // a level longer than the pool
         }
         const int bp = best_opp;
         if (type == LOBSIM_MSG_LIMIT && !(S ? price <= bp : price >= bp)) break;
@@ -328,40 +329,40 @@ __device__ __forceinline__ void hyb_order(const FastBook<LT>& fb, FastState& f, 
         n_opp -= 1;
         __syncwarp();
       }
-      if (n_opp == 0 && fb.cnt(OPP)->x != 0 && !f.dead) {     // keep the best price of the side in the pool
+      if (n_opp == 0 && fb.cnt(OPP)->x != 0) {     // keep the best price of the side in the pool
         if (!hyb_refill_one<LT, OPP>(fb, f, hs)) {
           if (rem > 0 && type == LOBSIM_MSG_LIMIT) { f.bail = FLAT_BAIL_FULL; f.bail_vol = rem; }   // the remainder rests on the sorted book
           else f.bail = HYB_BAIL_DONE;
-          return;
+          return true;
         }
       }
-      if (!(rem > 0 && type == LOBSIM_MSG_LIMIT && !f.dead)) return;
+      if (!(rem > 0 && type == LOBSIM_MSG_LIMIT)) return false;
       // the remainder of a crossing limit order rests: it is the new best of its side => hot
     } else if (!hot) {
       // ---- beyond the floor: the any-depth routine on the cold arrays ------------------------------------------------------
-      if (fb.cnt(S)->y >= hyb_cold_max<LT>()) { f.bail = FLAT_BAIL_FULL; f.bail_vol = rem; return; }
+      if (fb.cnt(S)->y >= hyb_cold_max<LT>()) { f.bail = FLAT_BAIL_FULL; f.bail_vol = rem; return true; }
       f.err |= hyb_cold_rest_fn<LT>(fb.blob, lane, S, price, rem, ref);
-      if (n_own == 0) { if (!hyb_refill_one<LT, S>(fb, f, hs)) f.bail = HYB_BAIL_DONE; }   // (the side was empty: its best must be hot)
-      return;
+      if (n_own == 0) { if (!hyb_refill_one<LT, S>(fb, f, hs)) { f.bail = HYB_BAIL_DONE; return true; } }   // (the side was empty: its best must be hot)
+      return false;
     }
-    if (n_own >= HYB_CAP && !hyb_spill_one<LT, S>(fb, hs)) { f.bail = FLAT_BAIL_FULL; f.bail_vol = rem; return; }
+    if (n_own >= HYB_CAP && !hyb_spill_one<LT, S>(fb, hs)) { f.bail = FLAT_BAIL_FULL; f.bail_vol = rem; return true; }
     const int floor_now = S ? hs.floor1 : hs.floor0;          // the spill may have moved the floor past this price
     if (!(S ? price <= floor_now : price >= floor_now)) {
-      if (fb.cnt(S)->y >= hyb_cold_max<LT>()) { f.bail = FLAT_BAIL_FULL; f.bail_vol = rem; return; }
+      if (fb.cnt(S)->y >= hyb_cold_max<LT>()) { f.bail = FLAT_BAIL_FULL; f.bail_vol = rem; return true; }
       f.err |= hyb_cold_rest_fn<LT>(fb.blob, lane, S, price, rem, ref);
-      if (n_own == 0) { if (!hyb_refill_one<LT, S>(fb, f, hs)) f.bail = HYB_BAIL_DONE; }
-      return;
+      if (n_own == 0) { if (!hyb_refill_one<LT, S>(fb, f, hs)) { f.bail = HYB_BAIL_DONE; return true; } }
+      return false;
     }
     __syncwarp();
     if (lane == 0) own[n_own] = make_uint4((unsigned)price, ref, (unsigned)rem, hs.seq);
     n_own += 1; hs.seq += 1;
     if (S ? price < best_own : price > best_own) best_own = price;
-    return;
+    return false;
   }
   // ---- cancellation / deletion ---------------------------------------------------------------------------------------------
   if (!hot) {
     f.err |= hyb_cold_remove_fn<LT>(fb.blob, lane, S, price, vol, ref);
-    return;
+    return false;
   }
   uint2 k[HYB_NCH];
   flat_keys_raw(own, lane, k);                               // (slots beyond n_own are stale: every test below checks the index)
@@ -374,22 +375,23 @@ __device__ __forceinline__ void hyb_order(const FastBook<LT>& fb, FastState& f, 
 #pragma unroll
     for (int c = HYB_NCH - 1; c >= 0; c--) if (c * 32 + lane < n_own && (int)k[c].x == price && k[c].y == LOBSIM_REF_AGGREGATE) mine = c * 32 + lane;
     i = __reduce_min_sync(FULL_MASK, mine);
-    if (i == INT32_MAX) return;
+    if (i == INT32_MAX) return false;
   }
   const int cur = (int)own[i].z;
   __syncwarp();
-  if (vol < cur) { if (lane == 0) own[i].z = (unsigned)(cur - vol); return; }
+  if (vol < cur) { if (lane == 0) own[i].z = (unsigned)(cur - vol); return false; }
   if (price == best_own) best_own = flat_best_of<S>(k, n_own, lane, i);
   if (lane == 0) own[i] = own[n_own - 1];
   n_own -= 1;
-  if (n_own == 0 && fb.cnt(S)->x != 0) { if (!hyb_refill_one<LT, S>(fb, f, hs)) f.bail = HYB_BAIL_DONE; }
+  if (n_own == 0 && fb.cnt(S)->x != 0) { if (!hyb_refill_one<LT, S>(fb, f, hs)) { f.bail = HYB_BAIL_DONE; return true; } }
+  return false;
 }
 
 template <class LT>
-__device__ __forceinline__ void hyb_message(const FastBook<LT>& fb, FastState& f, HybState& hs, int price, int vol, uint32_t ref, uint32_t meta) {
+__device__ __forceinline__ bool hyb_message(const FastBook<LT>& fb, FastState& f, HybState& hs, int price, int vol, uint32_t ref, uint32_t meta) {
   const int type = (int)(meta & 7u);
-  if (meta & 8u) hyb_order<LT, 1>(fb, f, hs, type, price, vol, ref);
-  else hyb_order<LT, 0>(fb, f, hs, type, price, vol, ref);
+  if (meta & 8u) return hyb_order<LT, 1>(fb, f, hs, type, price, vol, ref);
+  return hyb_order<LT, 0>(fb, f, hs, type, price, vol, ref);
 }
 // step boundary: top the pools up from the cold levels when they run low (keeps most of the flow on the flat path)
 template <class LT>

@@ -601,8 +601,7 @@ __global__ void __launch_bounds__(128, 3) k_replay_hyb(const __grid_constant__ A
 #pragma unroll 1
         for (; i < cnt; i++) {
           const uint4 m = mp[i];
-          hyb_message<LT>(fb, f, hs, (int)m.x, (int)m.y, m.z, m.w);
-          if (f.bail | f.dead) break;
+          if (hyb_message<LT>(fb, f, hs, (int)m.x, (int)m.y, m.z, m.w)) break;
         }
         if (f.bail) {                                        // this book cannot stay hybrid: back to the sorted form
           const int why = f.bail, rest = f.bail_vol;
