@@ -129,15 +129,51 @@ __device__ __forceinline__ bool flat_order(unsigned char* blob, int lane, FastSt
     if (S ? price < best_own : price > best_own) best_own = price;
     return false;
   };
-  // dispatch, the common cases first: a limit order that does not cross (3 tests), a cancellation / deletion (2 tests)
-  bool exec;                                                                // the previous order's stores are visible (above)
-  if (type == LOBSIM_MSG_LIMIT) {
+  auto remove = [&]() -> bool {
+    // ---- cancellation / deletion (Exchange.py:122-147) ----------------------------------------------------------------------
+    uint2 k[NCH];
+    flat_keys_raw(own, lane, k);
+    // (price, ref) names at most one resting order: the lane that holds it announces its index (one warp reduction)
+    int mine = -1;
+#pragma unroll
+    for (int c = 0; c < NCH; c++) if (c * 32 + lane < n_own && (int)k[c].x == price && k[c].y == ref) mine = c * 32 + lane;
+    int i = __reduce_max_sync(FULL_MASK, mine);
+    bool aggregate = false;
+    if (i < 0) {
+      // unknown id: the level's snapshot aggregate (internal_id -1, always the head of its level) takes the hit (:133-137);
+      // no such level, or no aggregate left at it: nothing happens (:129-132,138-139)
+      mine = INT32_MAX;
+#pragma unroll
+      for (int c = NCH - 1; c >= 0; c--) if (c * 32 + lane < n_own && (int)k[c].x == price && k[c].y == LOBSIM_REF_AGGREGATE) mine = c * 32 + lane;
+      i = __reduce_min_sync(FULL_MASK, mine);
+      if (i == INT32_MAX) return false;
+      aggregate = true;
+    }
+    const int cur = (int)own[i].z;
+    __syncwarp();
+    if (vol < cur) {                                                         // partial: reduce in place
+      if (lane == 0) own[i].z = (unsigned)(cur - vol);
+      if (TR && is_agent && !aggregate) { __syncwarp(); fast_agent_reduce(fb, S, ref & 0x7fffffffu, vol, false); }
+      return false;
+    }
+    // full removal (over-size requests remove the resting volume, :142-146): the last order of the pool fills the hole
+    if (price == best_own) best_own = flat_best_of<S>(k, n_own, lane, i);
+    if (lane == 0) own[i] = own[n_own - 1];
+    n_own -= 1;
+    if (TR && is_agent && !aggregate) { __syncwarp(); fast_agent_reduce(fb, S, ref & 0x7fffffffu, cur, true); }
+    return false;
+  };
+  // dispatch, the common cases first: a limit order that neither crosses nor finds the pool full, then cancellations / deletions.
+  // (The second test reads an opaque copy of `type`: two plain tests of one variable become a jump table -- LDC + BRX, measured
+  // 8 % slower than the two compares.)
+  int type2 = type;
+  asm volatile("" : "+r"(type2));
+  if (__builtin_expect(type == LOBSIM_MSG_LIMIT, 1)) {                     // (the previous order's stores are visible: above)
     const bool crosses = S ? price <= best_opp : price >= best_opp;        // empty opposite side: INT32_MIN / INT32_MAX
     if (__builtin_expect(!crosses & (n_own < flat_cap<LT>()), 1)) return rest(vol);   // (one branch for the common case)
     if (n_own >= flat_cap<LT>()) { f.bail = FLAT_BAIL_FULL; return true; }
-    exec = true;
-  } else exec = type == LOBSIM_MSG_MARKET;
-  if (exec) {
+  } else if (type2 != LOBSIM_MSG_MARKET) return remove();
+  {
     int rem = vol;
     {
       // ---- execution against the opposite side, best price first, oldest order first (Exchange.py:85-120) -------------
@@ -200,38 +236,7 @@ __device__ __forceinline__ bool flat_order(unsigned char* blob, int lane, FastSt
     if (!(rem > 0 && type == LOBSIM_MSG_LIMIT)) return false;
     return rest(rem);                                                       // the remainder of a crossing limit order rests (:116-119)
   }
-  // ---- cancellation / deletion (Exchange.py:122-147) ----------------------------------------------------------------------
-  uint2 k[NCH];
-  flat_keys_raw(own, lane, k);
-  // (price, ref) names at most one resting order: the lane that holds it announces its index (one warp reduction)
-  int mine = -1;
-#pragma unroll
-  for (int c = 0; c < NCH; c++) if (c * 32 + lane < n_own && (int)k[c].x == price && k[c].y == ref) mine = c * 32 + lane;
-  int i = __reduce_max_sync(FULL_MASK, mine);
-  bool aggregate = false;
-  if (i < 0) {
-    // unknown id: the level's snapshot aggregate (internal_id -1, always the head of its level) takes the hit (:133-137);
-    // no such level, or no aggregate left at it: nothing happens (:129-132,138-139)
-    mine = INT32_MAX;
-#pragma unroll
-    for (int c = NCH - 1; c >= 0; c--) if (c * 32 + lane < n_own && (int)k[c].x == price && k[c].y == LOBSIM_REF_AGGREGATE) mine = c * 32 + lane;
-    i = __reduce_min_sync(FULL_MASK, mine);
-    if (i == INT32_MAX) return false;
-    aggregate = true;
-  }
-  const int cur = (int)own[i].z;
-  __syncwarp();
-  if (vol < cur) {                                                         // partial: reduce in place
-    if (lane == 0) own[i].z = (unsigned)(cur - vol);
-    if (TR && is_agent && !aggregate) { __syncwarp(); fast_agent_reduce(fb, S, ref & 0x7fffffffu, vol, false); }
-    return false;
-  }
-  // full removal (over-size requests remove the resting volume, :142-146): the last order of the pool fills the hole
-  if (price == best_own) best_own = flat_best_of<S>(k, n_own, lane, i);
-  if (lane == 0) own[i] = own[n_own - 1];
-  n_own -= 1;
-  if (TR && is_agent && !aggregate) { __syncwarp(); fast_agent_reduce(fb, S, ref & 0x7fffffffu, cur, true); }
-  return false;
+  return remove();
 }
 
 // the replay form: a packed historical message
