@@ -193,13 +193,13 @@ __device__ __forceinline__ bool flat_order(unsigned char* blob, int lane, FastSt
           qmin = min(qmin, q[c]);
         }
         const unsigned head_seq = __reduce_min_sync(FULL_MASK, qmin);
-        unsigned hm[NCH]; int at_best = 0;
+        int at_best = 0, head = -1;                                         // seq is unique: the head's lane announces its index
 #pragma unroll
         for (int c = 0; c < NCH; c++) {
-          hm[c] = __ballot_sync(FULL_MASK, q[c] == head_seq);
+          if (q[c] == head_seq) head = c * 32 + lane;
           at_best += __popc(__ballot_sync(FULL_MASK, q[c] != 0xffffffffu));
         }
-        const int i = flat_first(hm);                                       // the head of the best queue
+        const int i = __reduce_max_sync(FULL_MASK, head);                                       // the head of the best queue
         const uint4 he = opp[i];
         const int hv = (int)he.z;
         const uint32_t href = he.y;

@@ -304,13 +304,13 @@ __device__ __forceinline__ bool hyb_order(const FastBook<LT>& fb, FastState& f, 
           qmin = min(qmin, q[c]);
         }
         const unsigned head_seq = __reduce_min_sync(FULL_MASK, qmin);
-        unsigned hm[HYB_NCH]; int at_best = 0;
+        int at_best = 0, head = -1;                                         // seq is unique: the head's lane announces its index
 #pragma unroll
         for (int c = 0; c < HYB_NCH; c++) {
-          hm[c] = __ballot_sync(FULL_MASK, q[c] == head_seq);
+          if (q[c] == head_seq) head = c * 32 + lane;
           at_best += __popc(__ballot_sync(FULL_MASK, q[c] != 0xffffffffu));
         }
-        const int i = flat_first(hm);
+        const int i = __reduce_max_sync(FULL_MASK, head);
         const int hv = (int)opp[i].z;
         __syncwarp();
         if (rem < hv) {
