@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """SASS listings of the hot kernels + mnemonic counts (what proves TMA bulk copies / no calls / no tensor cores):
 
-    python tools/sass_summary.py            # writes profiles/r02_sass_{replay_flat,replay_sorted,env}.txt
+    python tools/sass_summary.py            # writes profiles/r02_sass_{replay_flat,replay_sorted,env,replay_flat_L50,replay_hyb_L50}.txt
 
 Reads the object files of the in-tree build (rl4mm_b200/_native/obj), i.e. exactly what liblobsim.so was linked from."""
 import re
@@ -38,7 +38,8 @@ def main():
     round_tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
     targets = [("replay_flat", "fast0_0.o", lambda n: "k_replay_flat" in n), ("replay_sorted", "fast0_0.o", lambda n: "k_replay_fast" in n),
                ("env", "fast2_0.o", lambda n: "k_env_fast" in n and "Lb1ELb0" in n),
-               ("replay_flat_L50", "fast3_0.o", lambda n: "k_replay_flat" in n)]
+               ("replay_flat_L50", "fast3_0.o", lambda n: "k_replay_flat" in n),
+               ("replay_hyb_L50", "fast4_0.o", lambda n: "k_replay_hyb" in n)]          # layouts.h entry 4 = 128/1024/64
     for tag, obj, pred in targets:
         for name, lines in functions(OBJ / obj):
             if not pred(name):
