@@ -595,3 +595,25 @@ def test_month_archives_are_ingested_in_date_order(tmp_path, monkeypatch):
     monkeypatch.setattr(shutil, "which", lambda exe: None)
     with pytest.raises(RuntimeError, match="7z"):
         DeviceDatabase().populate_from_archives(folder)
+
+
+def test_extract_7z_calls_the_tool_like_the_reference(tmp_path, monkeypatch):
+    """run_populate_database_from_zipped.py:99 runs `7z x <archive> -o<folder>`: the default extractor builds the same command line
+    (plus -y so that a re-run does not prompt) and fails loudly when the tool fails."""
+    import os
+    import stat
+    import subprocess
+
+    from rl4mm_b200 import archives
+
+    bindir = tmp_path / "bin"
+    bindir.mkdir()
+    log = tmp_path / "args.txt"
+    tool = bindir / "7z"
+    tool.write_text(f"#!/bin/sh\necho \"$@\" > {log}\ncase \"$2\" in *broken*) exit 2;; esac\nexit 0\n")
+    tool.chmod(tool.stat().st_mode | stat.S_IEXEC)
+    monkeypatch.setenv("PATH", f"{bindir}{os.pathsep}{os.environ['PATH']}")
+    archives.extract_7z(tmp_path / "a__KO_2018-02-01_2018-02-28_10.7z", tmp_path / "out")
+    assert log.read_text().split() == ["x", str(tmp_path / "a__KO_2018-02-01_2018-02-28_10.7z"), "-o" + str(tmp_path / "out"), "-y"]
+    with pytest.raises(subprocess.CalledProcessError):
+        archives.extract_7z(tmp_path / "broken__KO_2018-02-01_2018-02-28_10.7z", tmp_path / "out")
