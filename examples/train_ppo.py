@@ -54,6 +54,15 @@ def main(argv=None):
                          use_cuda_graph={"auto": None, "on": True, "off": False}[args.cuda_graph])
     hist = trainer.train(args.iterations, log=(lambda s: print(json.dumps(s))) if rank == 0 else None)
     if world > 1:
+        # DDP keeps the replicas identical: the parameter checksum must be the same number on every rank
+        chk = torch.stack([p.detach().double().sum() for p in trainer.policy.parameters()]).sum().reshape(1)
+        lo, hi = chk.clone(), chk.clone()
+        torch.distributed.all_reduce(lo, op=torch.distributed.ReduceOp.MIN)
+        torch.distributed.all_reduce(hi, op=torch.distributed.ReduceOp.MAX)
+        if rank == 0:
+            print(json.dumps({"world_size": world, "param_checksum_min": float(lo), "param_checksum_max": float(hi),
+                              "replicas_in_sync": bool(lo == hi)}))
+        assert bool(lo == hi), "DDP replicas diverged"
         torch.distributed.destroy_process_group()
     return hist
 

@@ -335,3 +335,37 @@ def test_batched_env_auto_reset_and_per_env_error_flags():
     with pytest.raises(RuntimeError, match="AGENT_OVERFLOW"):
         for t in range(10):
             env2.step(a)
+
+
+@pytest.mark.fast_only
+def test_ppo_update_improves_its_own_batch():
+    """A learning check for the policy-update loop (the reference delegates this to RLlib): on the batch it was computed
+    from, one PPO update must lower the value loss, raise the surrogate objective above its starting point (ratio = 1, normalised
+    advantages: exactly 0) and move the policy (KL > 0) -- i.e. gradients flow from the device env's rewards into the Beta head."""
+    import torch
+
+    from rl4mm_b200.ppo import PPOConfig, PPOTrainer
+
+    env = _ppo_env(512)
+    tr = PPOTrainer(env, PPOConfig(rollout_steps=32, epochs=4, minibatches=2, reward_scale=1e-3), seed=0)
+    batch = tr.collect()
+    keep = batch["valid"].flatten()
+    obs = batch["obs_n"].flatten(0, 1)[keep]
+    x = batch["x"].flatten(0, 1).clamp(1e-6, 1 - 1e-6)[keep]
+    logp0, adv, ret = batch["logp"].flatten()[keep], batch["adv"].flatten()[keep], batch["ret"].flatten()[keep]
+    adv = (adv - adv.mean()) / (adv.std() + 1e-8)
+
+    def metrics():
+        with torch.no_grad():
+            dist, val = tr.module(obs)
+            logp = dist.log_prob(x).sum(-1)
+            return float((torch.exp(logp - logp0) * adv).mean()), float(0.5 * (val - ret).pow(2).mean()), float((logp0 - logp).mean())
+
+    s0, v0, k0 = metrics()
+    assert abs(s0) < 1e-4 and abs(k0) < 1e-6, (s0, k0)         # unchanged parameters: ratio exactly 1
+    stats = tr.update(batch)
+    s1, v1, k1 = metrics()
+    assert np.isfinite([s1, v1, k1]).all() and np.isfinite(stats["loss"])
+    assert v1 < v0, (v0, v1)
+    assert s1 > s0 + 1e-4, (s0, s1)
+    assert k1 > 0, k1
